@@ -1,0 +1,107 @@
+"""Pins the oracle (oracle/yolo_oracle.py, oracle/nms_oracle.c) against the golden vectors that
+tests/golden/make_golden.py recorded from the reference itself.  CPU only."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import nms_oracle, yolo_oracle
+from yolo_infer_pt_b200 import synth
+from yolo_infer_pt_b200.nets import nn
+
+ARCH = {s: getattr(nn, f"yolo_v11_{s}") for s in "ntsmlx"}
+
+
+def _state(size, fused):
+    m = ARCH[size](80)
+    synth.load_synth(m, 0)
+    if fused:
+        m.fuse()
+    return {k: v.float() for k, v in m.state_dict().items()}, m._arch
+
+
+@pytest.mark.parametrize("size", list("ntsmlx"))
+def test_forward_matches_reference_64(size, golden_dir):
+    g = np.load(os.path.join(golden_dir, f"fwd_{size}_64.npz"))
+    x = synth.synth_images(2, 64, 64, seed=1)
+    for fused, key in ((True, "out"), (False, "out_unfused")):
+        sd, (width, depth, csp, nc) = _state(size, fused)
+        with torch.no_grad():
+            maps = yolo_oracle.forward_raw(sd, width, depth, csp, nc, x)
+            y = yolo_oracle.decode(maps, nc)
+        ref = torch.from_numpy(g[key])
+        assert y.shape == ref.shape
+        # unfused: same ATen kernels in the same order -> fp32 noise only.  fused: the product's BN
+        # fold is written per channel instead of as the reference's diag matmul, and that fp32
+        # round-off travels through up to 174 convs (the reference's own fused-vs-unfused outputs
+        # differ by more than this).
+        box_tol, cls_tol = (0.15, 2e-3) if fused else (1e-3, 1e-5)
+        assert (y[:, :4] - ref[:, :4]).abs().max() < box_tol, "boxes (pixels)"
+        assert (y[:, 4:] - ref[:, 4:]).abs().max() < cls_tol, "scores"
+        if fused:
+            for i in range(3):
+                r = torch.from_numpy(g[f"raw{i}"])
+                assert (maps[i] - r).abs().max() < 5e-3 * max(1.0, r.abs().max().item())
+
+
+@pytest.mark.parametrize("size", ["n", "s"])
+def test_forward_matches_reference_640(size, golden_dir):
+    g = np.load(os.path.join(golden_dir, f"fwd_{size}_640.npz"))
+    sd, (width, depth, csp, nc) = _state(size, True)
+    x = synth.synth_images(1, 640, 640, seed=0)
+    with torch.no_grad():
+        y = yolo_oracle.forward(sd, width, depth, csp, nc, x)
+    assert y.shape == (1, 84, 8400)
+    sub = y[:, :, torch.from_numpy(g["idx"])]
+    ref = torch.from_numpy(g["out_sub"])
+    assert (sub[:, :4] - ref[:, :4]).abs().max() < 0.15
+    assert (sub[:, 4:] - ref[:, 4:]).abs().max() < 2e-3
+
+
+def test_fold_bn_matches_reference_fuse():
+    torch.manual_seed(0)
+    w = torch.randn(8, 4, 3, 3)
+    gamma, beta, mean, var = torch.rand(8) + 0.5, torch.randn(8), torch.randn(8), torch.rand(8) + 0.1
+    wf, bf = yolo_oracle.fold_bn(w, None, gamma, beta, mean, var)
+    x = torch.randn(2, 4, 9, 9)
+    a = torch.nn.functional.conv2d(x, wf, bf, 1, 1)
+    b = torch.nn.functional.batch_norm(torch.nn.functional.conv2d(x, w, None, 1, 1), mean, var, gamma, beta,
+                                       False, 0.0, 1e-3)
+    assert (a - b).abs().max() < 1e-5
+
+
+NMS_CASES = ["sparse_640", "sparse_640_iou07", "dense_640", "sparse_1280", "nc1_320", "conf25_640", "few_640",
+             "empty"]
+
+
+def load_nms_case(golden_dir, name):
+    g = np.load(os.path.join(golden_dir, f"nms_{name}.npz"))
+    kw = {k[3:]: g[k].item() for k in g.files if k.startswith("kw_")}
+    pred = synth.synth_predictions(**kw)
+    return g, pred
+
+
+@pytest.mark.parametrize("name", NMS_CASES)
+def test_nms_oracle_matches_reference(name, golden_dir):
+    g, pred = load_nms_case(golden_dir, name)
+    out = nms_oracle.non_max_suppression(pred, float(g["conf"]), float(g["iou"]))
+    assert [len(o) for o in out] == g["counts"].tolist()
+    for b, o in enumerate(out):
+        assert np.array_equal(o, g["det"][b, :len(o)]), f"image {b} differs from the reference output"
+
+
+def test_nms_oracle_full_scan_equals_early_stop():
+    pred = synth.synth_predictions(1, 80, 2100, img=320, mode="sparse", seed=11)
+    a = nms_oracle.non_max_suppression(pred, 0.001, 0.65, full_scan=True)
+    b = nms_oracle.non_max_suppression(pred, 0.001, 0.65, full_scan=False)
+    assert np.array_equal(a[0], b[0])
+
+
+def test_nms_threshold_is_compared_in_double():
+    # fp32 IoU of these boxes is fl32(1/3) > double(1/3): torchvision's CPU kernel suppresses
+    pred = np.zeros((1, 5, 2), dtype=np.float32)
+    pred[0, :, 0] = [1.0, 0.5, 2.0, 1.0, 0.9]   # [0,0,2,1]
+    pred[0, :, 1] = [2.0, 0.5, 2.0, 1.0, 0.8]   # [1,0,3,1]
+    assert len(nms_oracle.non_max_suppression(pred, 0.1, 1.0 / 3.0)[0]) == 1
+    assert len(nms_oracle.non_max_suppression(pred, 0.1, float(np.float32(1.0 / 3.0)))[0]) == 2

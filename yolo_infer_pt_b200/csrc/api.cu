@@ -1,0 +1,374 @@
+// extern "C" surface of libyolob200.so (see include/yolob200.h).
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <atomic>
+#include <new>
+
+#include "yb_internal.h"
+
+namespace yb {
+
+static thread_local char g_err[512] = "";
+static std::atomic<unsigned long long> g_launches{0};
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+
+size_t nms_workspace_bytes(int B, int nc, int A, int max_nms);
+int nms_run(const float* pred, int B, int nc, int A, float conf, double iou, int max_det, int max_nms,
+            float max_wh, float* out, int* out_counts, void* ws, size_t ws_bytes, cudaStream_t st);
+
+static int check_device(int device) {
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess || n <= 0) {
+    set_error("no CUDA device available (%s); libyolob200 has no CPU path",
+              e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    return YB_ERR_CUDA;
+  }
+  if (device < 0 || device >= n) {
+    set_error("device %d out of range (%d devices)", device, n);
+    return YB_ERR_ARG;
+  }
+  cudaDeviceProp prop;
+  YB_CUDA(cudaGetDeviceProperties(&prop, device));
+  if (prop.major != 10) {
+    set_error("device %d is sm_%d%d; this library contains sm_100a code only", device, prop.major,
+              prop.minor);
+    return YB_ERR_UNSUPPORTED;
+  }
+  return YB_OK;
+}
+
+static int run_ops(yb_plan* p, const void* in, int in_dtype, float* out, int raw, cudaStream_t st) {
+  int rc = YB_OK;
+  for (const Op& op : p->ops) {
+    switch (op.kind) {
+      case OP_STEM:
+        rc = launch_stem(p, op, in, in_dtype, st);
+        break;
+      case OP_CONV:
+        rc = p->conv_impl == 1 ? launch_conv_naive(p, op, st) : launch_conv_tc(p, op, st);
+        break;
+      case OP_DW:
+        rc = launch_dw(p, op, st);
+        break;
+      case OP_POOL:
+        rc = launch_pool(p, op, st);
+        break;
+      case OP_ATTN:
+        rc = launch_attn(p, op, st);
+        break;
+      case OP_DECODE: {
+        const Buf& lb = p->bufs[p->logits_buf];
+        const float* logits = reinterpret_cast<const float*>(buf_ptr(p, p->logits_buf));
+        if (raw) {
+          size_t rows = (size_t)p->B * p->A;
+          YB_CUDA(cudaMemcpy2DAsync(out, (size_t)p->no * 4, logits, (size_t)lb.C * 4, (size_t)p->no * 4,
+                                    rows, cudaMemcpyDeviceToDevice, st));
+        } else {
+          rc = launch_decode(p, logits, out, st);
+        }
+        break;
+      }
+    }
+    if (rc) return rc;
+  }
+  return YB_OK;
+}
+
+static int forward_impl(yb_plan* p, const void* in, int in_dtype, float* out, int raw, void* stream) {
+  if (!p || !in || !out) {
+    set_error("yb_forward: null argument");
+    return YB_ERR_ARG;
+  }
+  if (!p->bound) {
+    set_error("yb_forward: plan has no weights/workspace bound (call yb_plan_bind)");
+    return YB_ERR_STATE;
+  }
+  YB_CUDA(cudaSetDevice(p->device));
+  cudaStream_t st = (cudaStream_t)stream;
+  if (!p->use_graph) return run_ops(p, in, in_dtype, out, raw, st);
+  for (GraphEntry& g : p->graphs) {
+    if (g.in == in && g.out == out && g.stream == stream && g.dtype == in_dtype && g.raw == raw &&
+        g.impl == p->conv_impl) {
+      YB_CUDA(cudaGraphLaunch(g.exec, st));
+      g_launches.fetch_add((unsigned long long)yb_plan_num_launches(p), std::memory_order_relaxed);
+      return YB_OK;
+    }
+  }
+  cudaGraph_t graph = nullptr;
+  unsigned long long before = g_launches.load();
+  YB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  int rc = run_ops(p, in, in_dtype, out, raw, st);
+  cudaError_t e = cudaStreamEndCapture(st, &graph);
+  g_launches.store(before);
+  if (rc) {
+    if (graph) cudaGraphDestroy(graph);
+    return rc;
+  }
+  if (e != cudaSuccess) {
+    set_error("cudaStreamEndCapture failed: %s", cudaGetErrorString(e));
+    return YB_ERR_CUDA;
+  }
+  GraphEntry g;
+  g.in = in;
+  g.out = out;
+  g.stream = stream;
+  g.dtype = in_dtype;
+  g.raw = raw;
+  g.impl = p->conv_impl;
+  e = cudaGraphInstantiate(&g.exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) {
+    set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(e));
+    return YB_ERR_CUDA;
+  }
+  if (p->graphs.size() >= 8) {
+    cudaGraphExecDestroy(p->graphs.front().exec);
+    p->graphs.erase(p->graphs.begin());
+  }
+  p->graphs.push_back(g);
+  YB_CUDA(cudaGraphLaunch(g.exec, st));
+  g_launches.fetch_add((unsigned long long)yb_plan_num_launches(p), std::memory_order_relaxed);
+  return YB_OK;
+}
+
+static void drop_graphs(yb_plan* p) {
+  for (GraphEntry& g : p->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  p->graphs.clear();
+}
+
+}  // namespace yb
+
+using namespace yb;
+
+extern "C" {
+
+int yb_plan_create(const yb_arch_desc* arch, int batch, int height, int width, int device,
+                   yb_plan** out) {
+  if (!arch || !out || batch <= 0) {
+    set_error("yb_plan_create: bad argument");
+    return YB_ERR_ARG;
+  }
+  *out = nullptr;
+  int rc = YB_OK;
+  if (device >= 0) {  // device < 0: host-only plan (op list, weight layout); it can never be bound
+    rc = check_device(device);
+    if (rc) return rc;
+  }
+  yb_plan* p = new (std::nothrow) yb_plan();
+  if (!p) {
+    set_error("out of host memory");
+    return YB_ERR_ARG;
+  }
+  p->arch = *arch;
+  p->B = batch;
+  p->H = height;
+  p->W = width;
+  p->device = device;
+  cudaDeviceProp prop;
+  if (device >= 0 && cudaGetDeviceProperties(&prop, device) == cudaSuccess)
+    p->num_sms = prop.multiProcessorCount;
+  rc = build_plan(p);
+  if (rc) {
+    delete p;
+    return rc;
+  }
+  *out = p;
+  return YB_OK;
+}
+
+void yb_plan_destroy(yb_plan* plan) {
+  if (!plan) return;
+  drop_graphs(plan);
+  delete plan;
+}
+
+size_t yb_plan_workspace_bytes(const yb_plan* plan) { return plan ? plan->workspace_bytes : 0; }
+size_t yb_plan_weight_bytes(const yb_plan* plan) { return plan ? plan->weight_bytes : 0; }
+int yb_plan_num_anchors(const yb_plan* plan) { return plan ? plan->A : 0; }
+int yb_plan_num_outputs(const yb_plan* plan) { return plan ? 4 + plan->nc : 0; }
+int yb_plan_num_convs(const yb_plan* plan) { return plan ? (int)plan->convs.size() : 0; }
+int yb_plan_num_launches(const yb_plan* plan) { return plan ? (int)plan->ops.size() : 0; }
+
+int yb_plan_conv_info(const yb_plan* plan, int index, yb_conv_info* out) {
+  if (!plan || !out || index < 0 || index >= (int)plan->convs.size()) {
+    set_error("yb_plan_conv_info: bad argument");
+    return YB_ERR_ARG;
+  }
+  *out = plan->convs[index].info;
+  return YB_OK;
+}
+
+int yb_plan_pack_conv(const yb_plan* plan, int index, const float* w, const float* bias,
+                      void* host_blob) {
+  if (!plan || !w || !host_blob || index < 0 || index >= (int)plan->convs.size()) {
+    set_error("yb_plan_pack_conv: bad argument");
+    return YB_ERR_ARG;
+  }
+  const ConvW& cw = plan->convs[index];
+  const Op& op = plan->ops[cw.op];
+  uint8_t* dst = reinterpret_cast<uint8_t*>(host_blob) + cw.info.blob_offset;
+  memset(dst, 0, cw.info.blob_bytes);
+  const int cout = cw.info.cout, cin = cw.info.cin, k = cw.info.ksize;
+  if (cw.info.kind == 1) {
+    __nv_bfloat16* W = reinterpret_cast<__nv_bfloat16*>(dst);
+    float* B = reinterpret_cast<float*>(dst + (size_t)op.N_pad * op.K_pad * 2);
+    int per_tap = 0;
+    for (int s = 0; s < op.nseg; s++) per_tap += cpad8(op.src[s].C);
+    for (int co = 0; co < cout; co++) {
+      __nv_bfloat16* row = W + (size_t)co * op.K_pad;
+      for (int tap = 0; tap < k * k; tap++) {
+        int kpos = op.a_tma ? 0 : tap * per_tap;
+        int ci0 = 0;
+        for (int s = 0; s < op.nseg; s++) {
+          for (int c = 0; c < op.src[s].C; c++) {
+            float v = w[((size_t)co * cin + (ci0 + c)) * k * k + tap];
+            row[kpos + c] = __float2bfloat16(v);
+          }
+          ci0 += op.src[s].C;
+          kpos += op.a_tma ? op.seg_kpad[s] : cpad8(op.src[s].C);
+        }
+      }
+      B[co] = bias ? bias[co] : 0.f;
+    }
+  } else if (cw.info.kind == 0) {
+    int Cp = cpad8(cout);
+    float* W = reinterpret_cast<float*>(dst);
+    for (int co = 0; co < cout; co++) {
+      for (int t = 0; t < 27; t++) W[(size_t)t * Cp + co] = w[(size_t)co * 27 + t];
+      W[(size_t)27 * Cp + co] = bias ? bias[co] : 0.f;
+    }
+  } else {
+    int Cp = cpad8(cout);
+    float* W = reinterpret_cast<float*>(dst);
+    for (int co = 0; co < cout; co++) {
+      for (int t = 0; t < 9; t++) W[(size_t)t * Cp + co] = w[(size_t)co * 9 + t];
+      W[(size_t)9 * Cp + co] = bias ? bias[co] : 0.f;
+    }
+  }
+  return YB_OK;
+}
+
+int yb_plan_bind(yb_plan* plan, const void* dev_weights, void* dev_workspace) {
+  if (!plan || !dev_weights || !dev_workspace) {
+    set_error("yb_plan_bind: null argument");
+    return YB_ERR_ARG;
+  }
+  if (plan->device < 0) {
+    set_error("yb_plan_bind: host-only plan (created with device < 0) cannot run");
+    return YB_ERR_STATE;
+  }
+  YB_CUDA(cudaSetDevice(plan->device));
+  drop_graphs(plan);
+  plan->d_weights = reinterpret_cast<const uint8_t*>(dev_weights);
+  plan->d_ws = reinterpret_cast<uint8_t*>(dev_workspace);
+  for (Op& op : plan->ops) {
+    if (op.kind == OP_CONV) {
+      int rc = conv_tc_prepare(plan, op);
+      if (rc) return rc;
+    }
+  }
+  plan->bound = true;
+  return YB_OK;
+}
+
+int yb_forward(yb_plan* plan, const void* in_nchw, int in_dtype, float* out, void* cuda_stream) {
+  return forward_impl(plan, in_nchw, in_dtype, out, 0, cuda_stream);
+}
+
+int yb_forward_raw(yb_plan* plan, const void* in_nchw, int in_dtype, float* raw, void* cuda_stream) {
+  return forward_impl(plan, in_nchw, in_dtype, raw, 1, cuda_stream);
+}
+
+int yb_plan_use_graph(yb_plan* plan, int enable) {
+  if (!plan) return YB_ERR_ARG;
+  plan->use_graph = enable ? 1 : 0;
+  if (!enable) drop_graphs(plan);
+  return YB_OK;
+}
+
+int yb_plan_set_conv_impl(yb_plan* plan, int impl) {
+  if (!plan || impl < 0 || impl > 1) {
+    set_error("yb_plan_set_conv_impl: bad argument");
+    return YB_ERR_ARG;
+  }
+  plan->conv_impl = impl;
+  return YB_OK;
+}
+
+long long yb_plan_debug_read(yb_plan* plan, const char* conv_name, float* host_out,
+                             size_t host_capacity_floats, int* out_h, int* out_w, int* out_c) {
+  if (!plan || !conv_name || !host_out || !plan->bound) {
+    set_error("yb_plan_debug_read: bad argument or unbound plan");
+    return YB_ERR_ARG;
+  }
+  for (const Op& op : plan->ops) {
+    if (op.name != conv_name) continue;
+    if (op.kind == OP_DECODE) break;
+    const Buf& b = plan->bufs[op.dst.buf];
+    int C = op.dst.C;
+    if (op.kind == OP_POOL) C = op.dst.C;
+    size_t rows = (size_t)plan->B * b.rows_per_img;
+    size_t n = rows * C;
+    if (n > host_capacity_floats) {
+      set_error("yb_plan_debug_read: host buffer too small (%zu floats needed)", n);
+      return YB_ERR_ARG;
+    }
+    YB_CUDA(cudaSetDevice(plan->device));
+    YB_CUDA(cudaDeviceSynchronize());
+    size_t row_bytes = (size_t)b.C * b.elem_bytes;
+    std::vector<uint8_t> tmp(rows * row_bytes);
+    YB_CUDA(cudaMemcpy(tmp.data(), buf_ptr(plan, op.dst.buf), tmp.size(), cudaMemcpyDeviceToHost));
+    for (size_t r = 0; r < rows; r++) {
+      const uint8_t* rp = tmp.data() + r * row_bytes + (size_t)op.dst.c_off * b.elem_bytes;
+      for (int c = 0; c < C; c++) {
+        float v;
+        if (b.elem_bytes == 4) {
+          v = reinterpret_cast<const float*>(rp)[c];
+        } else {
+          uint32_t bits = (uint32_t)reinterpret_cast<const uint16_t*>(rp)[c] << 16;
+          memcpy(&v, &bits, 4);
+        }
+        host_out[r * C + c] = v;
+      }
+    }
+    if (out_h) *out_h = b.H;
+    if (out_w) *out_w = b.rows_per_img / (b.H ? b.H : 1);
+    if (out_c) *out_c = C;
+    return (long long)n;
+  }
+  set_error("yb_plan_debug_read: no op named %s", conv_name);
+  return YB_ERR_ARG;
+}
+
+size_t yb_nms_workspace_bytes(int batch, int num_classes, int num_anchors, int max_nms) {
+  return nms_workspace_bytes(batch, num_classes, num_anchors, max_nms);
+}
+
+int yb_nms(const float* pred, int batch, int num_classes, int num_anchors, float conf, double iou,
+           int max_det, int max_nms, float max_wh, float* out, int* out_counts, void* workspace,
+           size_t workspace_bytes, void* cuda_stream) {
+  if (!pred || !out || !out_counts) {
+    set_error("yb_nms: null argument");
+    return YB_ERR_ARG;
+  }
+  return nms_run(pred, batch, num_classes, num_anchors, conf, iou, max_det, max_nms, max_wh, out,
+                 out_counts, workspace, workspace_bytes, (cudaStream_t)cuda_stream);
+}
+
+const char* yb_last_error(void) { return g_err; }
+unsigned long long yb_launch_count(void) { return g_launches.load(); }
+int yb_version(void) { return 100; }
+
+}  // extern "C"

@@ -1,0 +1,592 @@
+// Dense convolution (1x1 / 3x3, stride 1 / 2, groups = 1) as an implicit GEMM on the sm_100a
+// 5th-generation tensor cores.  Stands in for every `Conv.fuse_forward` / bare Conv2d call of the
+// reference (nets/nn.py:38-39, 246, 252) together with the SiLU, residual add (nn.py:49,135,136),
+// torch.cat (nn.py:63,80,94,148,205-208,257) and Upsample (nn.py:195) around it.
+//
+//   D[m, n] = sum_k A[m, k] * W[n, k]       m = flattened (image, oy, ox) output pixel
+//                                           n = output channel
+//                                           k = (tap, source slice, channel)
+//
+//   A : NHWC bf16 activations.  1x1/stride-1 convs over plain slices fetch 128x64 tiles with TMA
+//       (one 2-D tensor map per source slice of the concat).  3x3, stride-2 and upsampled sources
+//       use a software im2col producer: 128 threads gather 16-byte channel granules and store
+//       them in the 128B-swizzled K-major layout the UMMA descriptor expects.
+//   W : packed bf16 [N_pad][K_pad], K-major, fetched with TMA (SWIZZLE_128B).
+//   D : fp32 accumulators in TMEM (128 lanes x BN columns), tcgen05.mma cta_group::1 kind::f16,
+//       issued by one thread; tcgen05.commit releases smem stages and signals the epilogue.
+//   Epilogue: tcgen05.ld -> +bias -> SiLU -> +residual -> bf16 (or fp32 head logits) stored
+//       straight into the channel slice of the consumer's buffer.
+//
+// Warp roles (192 threads): warps 0-3 im2col producers, then epilogue (TMEM lane = output row);
+// warp 4 TMEM allocator + MMA issuer; warp 5 TMA producer.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "yb_internal.h"
+
+namespace yb {
+
+static constexpr int BM = 128;
+static constexpr int BK = 64;
+static constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
+static constexpr int MAX_STAGES = 8;
+
+struct ConvParams {
+  const __nv_bfloat16* src[4];
+  int src_cp[4];      // padded channels of the slice (multiple of 8): its K extent per tap
+  int src_ld[4];      // row stride of the source buffer, elements
+  int src_up[4];
+  int nseg;
+  int ksize, stride, pad;
+  int Hin, Win, Hout, Wout;
+  int M;              // B * Hout * Wout
+  int K, num_kb;
+  int per_tap;        // sum of src_cp
+  int seg_kb[4];      // a_tma: k-blocks per segment
+  void* dst;
+  int dst_ld;         // elements
+  int dst_rows_per_img, dst_row_off, hw_out;
+  int cout_store;     // channels actually stored (padded to 8 for bf16, 4 for fp32)
+  int out_f32;
+  const float* bias;
+  const __nv_bfloat16* res;
+  int res_ld;
+  int act;
+  int BN, stages, a_tma, tmem_cols;
+  // naive path only
+  const __nv_bfloat16* w;
+  int K_pad, cout;
+  int src_c[4];       // real channels
+  int seg_kpad[4];
+};
+
+// ------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (surfacing as a CUDA error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try(bar, parity)) {
+    if (++spins > (1u << 27)) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1,
+                                            uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, "
+      "%3}], [%4];" ::"r"(dst),
+      "l"((uint64_t)map), "r"(c0), "r"(c1), "r"(bar)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  // K-major, SWIZZLE_128B canonical layout: 8-row x 128B atoms, SBO = 1024 B, LBO = 1 (unused),
+  // descriptor version 1 (sm_100), layout type 2.
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t db, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, "
+      "[%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr));
+}
+__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.f + __expf(-x)); }
+
+__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+// ------------------------------------------------------------------------------------------
+// The kernel
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(192, 1)
+    conv_gemm_tcgen05_kernel(const ConvParams P, const __grid_constant__ CUtensorMap tmap_b,
+                             const __grid_constant__ CUtensorMap tmap_a0,
+                             const __grid_constant__ CUtensorMap tmap_a1,
+                             const __grid_constant__ CUtensorMap tmap_a2,
+                             const __grid_constant__ CUtensorMap tmap_a3) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t raw_addr = smem_u32(smem_raw);
+  const uint32_t base = (raw_addr + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024 B alignment
+  uint8_t* smem = smem_raw + (base - raw_addr);
+
+  const int S = P.stages;
+  const int BN = P.BN;
+  const uint32_t b_stage_bytes = (uint32_t)BN * 128u;
+  const uint32_t a_base = base;
+  const uint32_t b_base = base + (uint32_t)S * A_STAGE_BYTES;
+  uint8_t* tail = smem + (size_t)S * (A_STAGE_BYTES + b_stage_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);  // full[0..S), empty[0..S), tmem_full
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + (2 * MAX_STAGES + 1) * 8);
+  float* bias_s = reinterpret_cast<float*>(tail + (2 * MAX_STAGES + 1) * 8 + 16);
+  const uint32_t bar0 = smem_u32(bars);
+  auto full_bar = [&](int s) { return bar0 + 8u * s; };
+  auto empty_bar = [&](int s) { return bar0 + 8u * (MAX_STAGES + s); };
+  const uint32_t tmem_full_bar = bar0 + 8u * (2 * MAX_STAGES);
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const int m0 = blockIdx.x * BM;
+  const int n0 = blockIdx.y * BN;
+  const int num_kb = P.num_kb;
+
+  if (tid == 0) {
+    for (int s = 0; s < S; s++) {
+      mbar_init(full_bar(s), P.a_tma ? 1u : 129u);
+      mbar_init(empty_bar(s), 1u);
+    }
+    mbar_init(tmem_full_bar, 1u);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  for (int i = tid; i < BN; i += blockDim.x) bias_s[i] = P.bias[n0 + i];
+  if (warp == 4) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
+                     smem_u32(tmem_slot)),
+                 "r"((uint32_t)P.tmem_cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp < 4) {
+    // ============================ im2col producer (skipped when A comes by TMA) ============
+    if (!P.a_tma) {
+      const int g = tid & 7;       // 16-byte granule (8 channels) inside the 128-byte K row
+      const int rbase = tid >> 3;  // rows rbase + 16*i
+      const uint32_t sw_off = (uint32_t)((g ^ (rbase & 7)) << 4);
+      int row_n[8], row_y[8], row_x[8];
+#pragma unroll
+      for (int i = 0; i < 8; i++) {
+        int m = m0 + rbase + 16 * i;
+        if (m < P.M) {
+          int n = m / P.hw_out;
+          int r = m - n * P.hw_out;
+          int oy = r / P.Wout;
+          row_n[i] = n;
+          row_y[i] = oy * P.stride - P.pad;
+          row_x[i] = (r - oy * P.Wout) * P.stride - P.pad;
+        } else {
+          row_n[i] = -1;
+          row_y[i] = 0;
+          row_x[i] = 0;
+        }
+      }
+      int tap = 0;
+      int rem = g * 8;  // position inside the tap's [seg0 | seg1 | ...] channel run
+      while (rem >= P.per_tap) {
+        rem -= P.per_tap;
+        tap++;
+      }
+      for (int kb = 0; kb < num_kb; kb++) {
+        const int s = kb % S;
+        const uint32_t ph = (uint32_t)(kb / S) & 1u;
+        uint4 v[8];
+        const bool k_ok = (kb * BK + g * 8) < P.K;
+        int seg = 0, c = rem;
+        while (seg + 1 < P.nseg && c >= P.src_cp[seg]) {
+          c -= P.src_cp[seg];
+          seg++;
+        }
+        const int up = P.src_up[seg];
+        const int Hs = P.Hin >> up, Ws = P.Win >> up;
+        const int ld = P.src_ld[seg];
+        const __nv_bfloat16* sp = P.src[seg] + c;
+        int dy = 0, dx = 0;
+        if (P.ksize == 3) {
+          dy = tap / 3;
+          dx = tap - dy * 3;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          int iy = row_y[i] + dy, ix = row_x[i] + dx;
+          bool ok = k_ok && row_n[i] >= 0 && (unsigned)iy < (unsigned)P.Hin &&
+                    (unsigned)ix < (unsigned)P.Win;
+          v[i] = make_uint4(0u, 0u, 0u, 0u);
+          if (ok) {
+            size_t off = ((size_t)(row_n[i] * Hs + (iy >> up)) * Ws + (ix >> up)) * (size_t)ld;
+            v[i] = __ldg(reinterpret_cast<const uint4*>(sp + off));
+          }
+        }
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        const uint32_t a_s = a_base + (uint32_t)s * A_STAGE_BYTES + sw_off;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          uint32_t addr = a_s + (uint32_t)(rbase + 16 * i) * 128u;
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v[i].x),
+                       "r"(v[i].y), "r"(v[i].z), "r"(v[i].w)
+                       : "memory");
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        mbar_arrive(full_bar(s));
+        rem += BK;
+        while (rem >= P.per_tap) {
+          rem -= P.per_tap;
+          tap++;
+        }
+      }
+    }
+    // ============================ epilogue ================================================
+    mbar_wait(tmem_full_bar, 0u);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const int m = m0 + tid;
+    const bool row_ok = m < P.M;
+    size_t drow = 0;
+    if (row_ok) {
+      int n_img = m / P.hw_out;
+      int r = m - n_img * P.hw_out;
+      drow = (size_t)n_img * P.dst_rows_per_img + P.dst_row_off + r;
+    }
+    const __nv_bfloat16* resp = P.res ? P.res + (size_t)m * P.res_ld : nullptr;
+    for (int c0 = 0; c0 < BN; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      const int nb = n0 + c0;
+      if (!row_ok || nb >= P.cout_store) continue;
+      float f[16];
+#pragma unroll
+      for (int j = 0; j < 16; j++) {
+        float x = __uint_as_float(v[j]) + bias_s[c0 + j];
+        f[j] = P.act ? silu_f(x) : x;
+      }
+      if (P.out_f32) {
+        float* dp = reinterpret_cast<float*>(P.dst) + drow * (size_t)P.dst_ld + nb;
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+          if (nb + 4 * q < P.cout_store)
+            *reinterpret_cast<float4*>(dp + 4 * q) =
+                make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+        }
+      } else {
+        __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(P.dst) + drow * (size_t)P.dst_ld + nb;
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          if (nb + 8 * h < P.cout_store) {
+            if (resp) {
+              uint4 rv = __ldg(reinterpret_cast<const uint4*>(resp + nb + 8 * h));
+              const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+              for (int j = 0; j < 4; j++) {
+                float2 rf = __bfloat1622float2(r2[j]);
+                f[8 * h + 2 * j] += rf.x;
+                f[8 * h + 2 * j + 1] += rf.y;
+              }
+            }
+            uint4 o;
+            o.x = pack_bf16(f[8 * h + 0], f[8 * h + 1]);
+            o.y = pack_bf16(f[8 * h + 2], f[8 * h + 3]);
+            o.z = pack_bf16(f[8 * h + 4], f[8 * h + 5]);
+            o.w = pack_bf16(f[8 * h + 6], f[8 * h + 7]);
+            *reinterpret_cast<uint4*>(dp + 8 * h) = o;
+          }
+        }
+      }
+    }
+  } else if (warp == 4) {
+    // ============================ MMA issuer ==============================================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                             ((uint32_t)(BM >> 4) << 24);
+      for (int kb = 0; kb < num_kb; kb++) {
+        const int s = kb % S;
+        const uint32_t ph = (uint32_t)(kb / S) & 1u;
+        mbar_wait(full_bar(s), ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t a_s = a_base + (uint32_t)s * A_STAGE_BYTES;
+        const uint32_t b_s = b_base + (uint32_t)s * b_stage_bytes;
+#pragma unroll
+        for (int k = 0; k < BK / 16; k++) {
+          umma_bf16(tmem_base, umma_desc_sw128(a_s + k * 32), umma_desc_sw128(b_s + k * 32), idesc,
+                    (uint32_t)((kb | k) != 0));
+        }
+        umma_commit(empty_bar(s));  // frees the smem stage once these MMAs have read it
+      }
+      umma_commit(tmem_full_bar);   // accumulator complete -> epilogue
+    }
+  } else {
+    // ============================ TMA producer ============================================
+    if (lane == 0) {
+      const uint32_t tx = b_stage_bytes + (P.a_tma ? (uint32_t)A_STAGE_BYTES : 0u);
+      int seg = 0, kk = 0;
+      for (int kb = 0; kb < num_kb; kb++) {
+        const int s = kb % S;
+        const uint32_t ph = (uint32_t)(kb / S) & 1u;
+        mbar_wait(empty_bar(s), ph ^ 1u);
+        mbar_expect_tx(full_bar(s), tx);
+        tma_load_2d(b_base + (uint32_t)s * b_stage_bytes, &tmap_b, kb * BK, n0, full_bar(s));
+        if (P.a_tma) {
+          const CUtensorMap* ma = seg == 0 ? &tmap_a0 : seg == 1 ? &tmap_a1 : seg == 2 ? &tmap_a2 : &tmap_a3;
+          tma_load_2d(a_base + (uint32_t)s * A_STAGE_BYTES, ma, kk * BK, m0, full_bar(s));
+          if (++kk == P.seg_kb[seg]) {
+            kk = 0;
+            seg++;
+          }
+        }
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 4) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"((uint32_t)P.tmem_cols)
+                 : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Scalar cross-check kernel (validation only; selected with yb_plan_set_conv_impl(plan, 1)).
+// One thread per (output row, output channel), same packed weights, fp32 accumulation.
+// ------------------------------------------------------------------------------------------
+__global__ void conv_direct_check_kernel(const ConvParams P) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int cs = P.cout_store;
+  if (idx >= (long long)P.M * cs) return;
+  int m = (int)(idx / cs);
+  int n = (int)(idx - (long long)m * cs);
+  int img = m / P.hw_out;
+  int r = m - img * P.hw_out;
+  int oy = r / P.Wout, ox = r - oy * P.Wout;
+  float acc = 0.f;
+  const __nv_bfloat16* wrow = P.w + (size_t)n * P.K_pad;
+  int taps = P.ksize * P.ksize;
+  for (int tap = 0; tap < taps; tap++) {
+    int dy = P.ksize == 3 ? tap / 3 : 0, dx = P.ksize == 3 ? tap % 3 : 0;
+    int iy = oy * P.stride - P.pad + dy, ix = ox * P.stride - P.pad + dx;
+    bool ok = (unsigned)iy < (unsigned)P.Hin && (unsigned)ix < (unsigned)P.Win;
+    int kpos = P.a_tma ? 0 : tap * P.per_tap;
+    for (int s = 0; s < P.nseg; s++) {
+      if (ok) {
+        int up = P.src_up[s];
+        int Hs = P.Hin >> up, Ws = P.Win >> up;
+        const __nv_bfloat16* sp =
+            P.src[s] + ((size_t)(img * Hs + (iy >> up)) * Ws + (ix >> up)) * (size_t)P.src_ld[s];
+        for (int c = 0; c < P.src_c[s]; c++)
+          acc += __bfloat162float(sp[c]) * __bfloat162float(wrow[kpos + c]);
+      }
+      kpos += P.a_tma ? P.seg_kpad[s] : P.src_cp[s];
+    }
+  }
+  float x = acc + P.bias[n];
+  if (P.act) x = x / (1.f + expf(-x));
+  size_t drow = (size_t)img * P.dst_rows_per_img + P.dst_row_off + r;
+  if (P.out_f32) {
+    reinterpret_cast<float*>(P.dst)[drow * (size_t)P.dst_ld + n] = x;
+  } else {
+    if (P.res) x += __bfloat162float(P.res[(size_t)m * P.res_ld + n]);
+    reinterpret_cast<__nv_bfloat16*>(P.dst)[drow * (size_t)P.dst_ld + n] = __float2bfloat16(x);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Host side
+// ------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_encodeTiled get_encode() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (PFN_encodeTiled)p;
+  }
+  return fn;
+}
+
+static int make_tmap_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows,
+                        uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_rows) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled driver entry point not available");
+    return YB_ERR_CUDA;
+  }
+  cuuint64_t dims[2] = {inner, rows};
+  cuuint64_t strides[1] = {row_stride_bytes};
+  cuuint32_t box[2] = {box_inner, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed with %d (inner=%llu rows=%llu stride=%llu box=%ux%u)",
+              (int)r, (unsigned long long)inner, (unsigned long long)rows,
+              (unsigned long long)row_stride_bytes, box_inner, box_rows);
+    return YB_ERR_CUDA;
+  }
+  return YB_OK;
+}
+
+static size_t conv_smem_bytes(int stages, int BN) {
+  return 1024 + (size_t)stages * (A_STAGE_BYTES + (size_t)BN * 128) + (2 * MAX_STAGES + 1) * 8 + 16 +
+         256 * 4;
+}
+
+int conv_tc_prepare(yb_plan* p, Op& op) {
+  const ConvW& cw = p->convs[op.conv_index];
+  const uint8_t* wbase = p->d_weights + cw.info.blob_offset;
+  int num_kb = op.K_pad / BK;
+  // stage count: enough to cover the K loop, capped so that small-N layers keep 2-3 CTAs per SM
+  size_t stage_bytes = A_STAGE_BYTES + (size_t)op.BN * 128;
+  int st = std::min(num_kb, 4);
+  while (st > 2 && conv_smem_bytes(st, op.BN) > 200 * 1024) st--;
+  if (const char* e = getenv("YB_STAGES")) st = std::max(1, std::min(MAX_STAGES, atoi(e)));
+  (void)stage_bytes;
+  op.stages = std::max(1, st);
+  op.smem_bytes = conv_smem_bytes(op.stages, op.BN);
+  int rc = make_tmap_2d(&op.tmap_b, wbase, (uint64_t)op.K_pad, (uint64_t)op.N_pad,
+                        (uint64_t)op.K_pad * 2, BK, (uint32_t)op.BN);
+  if (rc) return rc;
+  for (int i = 0; i < 4; i++) op.tmap_a[i] = op.tmap_b;
+  if (op.a_tma) {
+    for (int i = 0; i < op.nseg; i++) {
+      const Buf& b = p->bufs[op.src[i].buf];
+      const uint8_t* base = buf_ptr(p, op.src[i].buf) + (size_t)op.src[i].c_off * 2;
+      rc = make_tmap_2d(&op.tmap_a[i], base, (uint64_t)cpad8(op.src[i].C),
+                        (uint64_t)p->B * b.rows_per_img, (uint64_t)b.C * 2, BK, BM);
+      if (rc) return rc;
+    }
+  }
+  static bool attr_set = false;
+  if (!attr_set) {
+    YB_CUDA(cudaFuncSetAttribute(conv_gemm_tcgen05_kernel,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  return YB_OK;
+}
+
+static void fill_params(const yb_plan* p, const Op& op, ConvParams& P) {
+  memset(&P, 0, sizeof(P));
+  const ConvW& cw = p->convs[op.conv_index];
+  P.nseg = op.nseg;
+  int per_tap = 0;
+  for (int i = 0; i < op.nseg; i++) {
+    const Buf& b = p->bufs[op.src[i].buf];
+    P.src[i] = reinterpret_cast<const __nv_bfloat16*>(buf_ptr(p, op.src[i].buf)) + op.src[i].c_off;
+    P.src_cp[i] = cpad8(op.src[i].C);
+    P.src_c[i] = op.src[i].C;
+    P.src_ld[i] = b.C;
+    P.src_up[i] = op.src[i].up;
+    P.seg_kb[i] = op.seg_kpad[i] / BK;
+    P.seg_kpad[i] = op.seg_kpad[i];
+    per_tap += P.src_cp[i];
+  }
+  P.per_tap = per_tap;
+  P.ksize = op.k;
+  P.stride = op.stride;
+  P.pad = op.k / 2;
+  P.Hin = op.Hin;
+  P.Win = op.Win;
+  P.Hout = op.Hout;
+  P.Wout = op.Wout;
+  P.hw_out = op.Hout * op.Wout;
+  P.M = p->B * P.hw_out;
+  P.K = op.K;
+  P.K_pad = op.K_pad;
+  P.num_kb = op.K_pad / BK;
+  const Buf& db = p->bufs[op.dst.buf];
+  P.dst = buf_ptr(p, op.dst.buf) + (size_t)op.dst.c_off * db.elem_bytes;
+  P.dst_ld = db.C;
+  P.dst_rows_per_img = db.rows_per_img;
+  P.dst_row_off = op.dst_row_off;
+  P.out_f32 = op.out_f32;
+  P.cout = op.dst.C;
+  P.cout_store = op.out_f32 ? round_up(op.dst.C, 4) : cpad8(op.dst.C);
+  const uint8_t* wbase = p->d_weights + cw.info.blob_offset;
+  P.w = reinterpret_cast<const __nv_bfloat16*>(wbase);
+  P.bias = reinterpret_cast<const float*>(wbase + (size_t)op.N_pad * op.K_pad * 2);
+  if (op.has_res) {
+    const Buf& rb = p->bufs[op.res.buf];
+    P.res = reinterpret_cast<const __nv_bfloat16*>(buf_ptr(p, op.res.buf)) + op.res.c_off;
+    P.res_ld = rb.C;
+  }
+  P.act = op.act;
+  P.BN = op.BN;
+  P.stages = op.stages;
+  P.a_tma = op.a_tma;
+  int cols = 32;
+  while (cols < op.BN) cols <<= 1;
+  P.tmem_cols = cols;
+}
+
+int launch_conv_tc(const yb_plan* p, const Op& op, cudaStream_t st) {
+  ConvParams P;
+  fill_params(p, op, P);
+  dim3 grid((P.M + BM - 1) / BM, op.N_pad / op.BN);
+  conv_gemm_tcgen05_kernel<<<grid, 192, op.smem_bytes, st>>>(P, op.tmap_b, op.tmap_a[0], op.tmap_a[1],
+                                                            op.tmap_a[2], op.tmap_a[3]);
+  count_launch();
+  YB_CUDA(cudaGetLastError());
+  return YB_OK;
+}
+
+int launch_conv_naive(const yb_plan* p, const Op& op, cudaStream_t st) {
+  ConvParams P;
+  fill_params(p, op, P);
+  long long total = (long long)P.M * P.cout_store;
+  int threads = 256;
+  long long blocks = (total + threads - 1) / threads;
+  conv_direct_check_kernel<<<(unsigned)blocks, threads, 0, st>>>(P);
+  count_launch();
+  YB_CUDA(cudaGetLastError());
+  return YB_OK;
+}
+
+}  // namespace yb

@@ -1,0 +1,524 @@
+// Memory-bound kernels of the YOLOv11 forward: stem conv, depthwise 3x3, SPPF pooling, the C2PSA
+// attention core and the DFL box decode.  All activations are NHWC bf16; arithmetic is fp32.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <cuda_fp16.h>
+
+#include "yb_internal.h"
+
+namespace yb {
+
+__device__ __forceinline__ float silu_acc(float x) { return __fdividef(x, 1.f + __expf(-x)); }
+
+__device__ __forceinline__ void bf16x8_to_float(const uint4& v, float* f) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    float2 t = __bfloat1622float2(h[j]);
+    f[2 * j] = t.x;
+    f[2 * j + 1] = t.y;
+  }
+}
+__device__ __forceinline__ uint4 float_to_bf16x8(const float* f) {
+  uint4 o;
+  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+  for (int j = 0; j < 4; j++) h[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
+  return o;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stem: net.p1.0 = Conv(3 -> w1, k3, s2, p1) + SiLU (nets/nn.py:161).  Reads the caller's NCHW
+// image (fp32 / fp16 / bf16 / uint8), writes NHWC bf16.  K = 27 is far below the tensor-core
+// ridge (AI ~ 23 flop/B), so this is a direct convolution: one thread per output pixel, the 27
+// input taps held in registers, weights broadcast from shared memory.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ float load_px(const T* p);
+template <>
+__device__ __forceinline__ float load_px<float>(const float* p) { return __ldg(p); }
+template <>
+__device__ __forceinline__ float load_px<__half>(const __half* p) { return __half2float(__ldg(p)); }
+template <>
+__device__ __forceinline__ float load_px<__nv_bfloat16>(const __nv_bfloat16* p) {
+  return __bfloat162float(__ldg(p));
+}
+template <>
+__device__ __forceinline__ float load_px<uint8_t>(const uint8_t* p) { return (float)__ldg(p); }
+
+template <typename T>
+__global__ void __launch_bounds__(128)
+    stem_conv_kernel(const T* __restrict__ in, __nv_bfloat16* __restrict__ out,
+                     const float* __restrict__ wgt, int B, int H, int W, int Ho, int Wo, int Cp,
+                     int out_ld, float in_scale) {
+  extern __shared__ float ws[];  // [27][Cp] weights then [Cp] bias
+  for (int i = threadIdx.x; i < 28 * Cp; i += blockDim.x) ws[i] = wgt[i];
+  __syncthreads();
+  const float* bs = ws + 27 * Cp;
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long total = (long long)B * Ho * Wo;
+  if (idx >= total) return;
+  int ox = (int)(idx % Wo);
+  int oy = (int)((idx / Wo) % Ho);
+  int b = (int)(idx / ((long long)Wo * Ho));
+  float x[27];
+#pragma unroll
+  for (int ci = 0; ci < 3; ci++) {
+    const T* plane = in + ((size_t)b * 3 + ci) * H * W;
+#pragma unroll
+    for (int ky = 0; ky < 3; ky++) {
+      int iy = 2 * oy - 1 + ky;
+#pragma unroll
+      for (int kx = 0; kx < 3; kx++) {
+        int ix = 2 * ox - 1 + kx;
+        float v = 0.f;
+        if ((unsigned)iy < (unsigned)H && (unsigned)ix < (unsigned)W)
+          v = load_px<T>(plane + (size_t)iy * W + ix) * in_scale;
+        x[(ci * 3 + ky) * 3 + kx] = v;
+      }
+    }
+  }
+  __nv_bfloat16* op = out + (size_t)idx * out_ld;
+  for (int c0 = 0; c0 < Cp; c0 += 8) {
+    float acc[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[j] = bs[c0 + j];
+#pragma unroll
+    for (int t = 0; t < 27; t++) {
+      const float4 w0 = *reinterpret_cast<const float4*>(ws + t * Cp + c0);
+      const float4 w1 = *reinterpret_cast<const float4*>(ws + t * Cp + c0 + 4);
+      acc[0] = fmaf(x[t], w0.x, acc[0]);
+      acc[1] = fmaf(x[t], w0.y, acc[1]);
+      acc[2] = fmaf(x[t], w0.z, acc[2]);
+      acc[3] = fmaf(x[t], w0.w, acc[3]);
+      acc[4] = fmaf(x[t], w1.x, acc[4]);
+      acc[5] = fmaf(x[t], w1.y, acc[5]);
+      acc[6] = fmaf(x[t], w1.z, acc[6]);
+      acc[7] = fmaf(x[t], w1.w, acc[7]);
+    }
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[j] = silu_acc(acc[j]);
+    *reinterpret_cast<uint4*>(op + c0) = float_to_bf16x8(acc);
+  }
+}
+
+int launch_stem(const yb_plan* p, const Op& op, const void* in, int in_dtype, cudaStream_t st) {
+  const ConvW& cw = p->convs[op.conv_index];
+  const float* w = reinterpret_cast<const float*>(p->d_weights + cw.info.blob_offset);
+  const Buf& db = p->bufs[op.dst.buf];
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(buf_ptr(p, op.dst.buf)) + op.dst.c_off;
+  int Cp = cpad8(op.dst.C);
+  long long total = (long long)p->B * op.Hout * op.Wout;
+  int threads = 128;
+  unsigned blocks = (unsigned)((total + threads - 1) / threads);
+  size_t smem = (size_t)28 * Cp * 4;
+  switch (in_dtype) {
+    case YB_F32:
+      stem_conv_kernel<float><<<blocks, threads, smem, st>>>((const float*)in, out, w, p->B, p->H, p->W,
+                                                            op.Hout, op.Wout, Cp, db.C, 1.f);
+      break;
+    case YB_F16:
+      stem_conv_kernel<__half><<<blocks, threads, smem, st>>>((const __half*)in, out, w, p->B, p->H,
+                                                             p->W, op.Hout, op.Wout, Cp, db.C, 1.f);
+      break;
+    case YB_BF16:
+      stem_conv_kernel<__nv_bfloat16><<<blocks, threads, smem, st>>>(
+          (const __nv_bfloat16*)in, out, w, p->B, p->H, p->W, op.Hout, op.Wout, Cp, db.C, 1.f);
+      break;
+    case YB_U8:
+      stem_conv_kernel<uint8_t><<<blocks, threads, smem, st>>>((const uint8_t*)in, out, w, p->B, p->H,
+                                                              p->W, op.Hout, op.Wout, Cp, db.C,
+                                                              1.f / 255.f);
+      break;
+    default:
+      set_error("unsupported input dtype %d", in_dtype);
+      return YB_ERR_ARG;
+  }
+  count_launch();
+  YB_CUDA(cudaGetLastError());
+  return YB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Depthwise 3x3, stride 1, pad 1 (+ folded BN bias, optional SiLU): head cls branches
+// (nets/nn.py:248,250) and the attention positional conv `pe` on v (nn.py:109,122).
+// One thread = one pixel x 8 channels (16 B); taps hit L1/L2.  `gsz/gstride/goff` gather the
+// source channels (v rows of the per-head [q k v] interleave); `add` accumulates into dst.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    dwconv3x3_kernel(const __nv_bfloat16* __restrict__ src, int src_ld, __nv_bfloat16* dst, int dst_ld,
+                     const float* __restrict__ wgt, int Cp, int B, int H, int W, int C, int gsz,
+                     int gstride, int goff, int act, int add) {
+  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  int cgs = C >> 3;
+  long long total = (long long)B * H * W * cgs;
+  if (idx >= total) return;
+  int cg = (int)(idx % cgs);
+  long long pix = idx / cgs;
+  int x = (int)(pix % W);
+  int y = (int)((pix / W) % H);
+  int b = (int)(pix / ((long long)W * H));
+  int c = cg * 8;
+  int sc = (c / gsz) * gstride + goff + (c % gsz);
+  float acc[8];
+  const float* bias = wgt + 9 * Cp;
+#pragma unroll
+  for (int j = 0; j < 8; j++) acc[j] = bias[c + j];
+#pragma unroll
+  for (int ky = 0; ky < 3; ky++) {
+    int iy = y - 1 + ky;
+    if ((unsigned)iy >= (unsigned)H) continue;
+#pragma unroll
+    for (int kx = 0; kx < 3; kx++) {
+      int ix = x - 1 + kx;
+      if ((unsigned)ix >= (unsigned)W) continue;
+      uint4 v = __ldg(reinterpret_cast<const uint4*>(src + ((size_t)(b * H + iy) * W + ix) * src_ld + sc));
+      float f[8];
+      bf16x8_to_float(v, f);
+      const float* wp = wgt + (ky * 3 + kx) * Cp + c;
+#pragma unroll
+      for (int j = 0; j < 8; j++) acc[j] = fmaf(f[j], wp[j], acc[j]);
+    }
+  }
+  if (act) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[j] = silu_acc(acc[j]);
+  }
+  __nv_bfloat16* dp = dst + (size_t)pix * dst_ld + c;
+  if (add) {
+    float f[8];
+    bf16x8_to_float(*reinterpret_cast<const uint4*>(dp), f);
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[j] += f[j];
+  }
+  *reinterpret_cast<uint4*>(dp) = float_to_bf16x8(acc);
+}
+
+int launch_dw(const yb_plan* p, const Op& op, cudaStream_t st) {
+  const ConvW& cw = p->convs[op.conv_index];
+  const float* w = reinterpret_cast<const float*>(p->d_weights + cw.info.blob_offset);
+  const Buf& sb = p->bufs[op.src[0].buf];
+  const Buf& db = p->bufs[op.dst.buf];
+  const __nv_bfloat16* src =
+      reinterpret_cast<const __nv_bfloat16*>(buf_ptr(p, op.src[0].buf)) + op.src[0].c_off;
+  __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(buf_ptr(p, op.dst.buf)) + op.dst.c_off;
+  int C = op.dst.C;
+  long long total = (long long)p->B * op.Hout * op.Wout * (C >> 3);
+  int threads = 256;
+  unsigned blocks = (unsigned)((total + threads - 1) / threads);
+  dwconv3x3_kernel<<<blocks, threads, 0, st>>>(src, sb.C, dst, db.C, w, cpad8(C), p->B, op.Hout, op.Wout,
+                                               C, op.dw_gsz, op.dw_gstride, op.dw_goff, op.act,
+                                               op.dw_add);
+  count_launch();
+  YB_CUDA(cudaGetLastError());
+  return YB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// SPPF pooling (nets/nn.py:88,92-94): three cascaded MaxPool2d(5,1,2).  One CTA holds an
+// (image, 8-channel group) plane in shared memory and runs the cascade as separable row/column
+// 5-max passes; slice 0 of the concat buffer is read once, slices 1..3 are written once.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 max_bf16x8(const uint4& a, const uint4& b) {
+  uint4 o;
+  const __nv_bfloat162* x = reinterpret_cast<const __nv_bfloat162*>(&a);
+  const __nv_bfloat162* y = reinterpret_cast<const __nv_bfloat162*>(&b);
+  __nv_bfloat162* z = reinterpret_cast<__nv_bfloat162*>(&o);
+#pragma unroll
+  for (int j = 0; j < 4; j++) z[j] = __hmax2(x[j], y[j]);
+  return o;
+}
+
+__global__ void __launch_bounds__(256)
+    sppf_pool_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* dst, int ld, int H, int W,
+                     int Chalf) {
+  extern __shared__ uint4 pl[];  // cur[HW], tmp[HW]
+  const int HW = H * W;
+  uint4* cur = pl;
+  uint4* tmp = pl + HW;
+  const int cgs = Chalf >> 3;
+  const int b = blockIdx.x / cgs;
+  const int cg = blockIdx.x % cgs;
+  const size_t img_base = (size_t)b * HW * ld + cg * 8;
+  for (int i = threadIdx.x; i < HW; i += blockDim.x)
+    cur[i] = __ldg(reinterpret_cast<const uint4*>(src + img_base + (size_t)i * ld));
+  __syncthreads();
+  for (int stage = 0; stage < 3; stage++) {
+    for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+      int y = i / W, x = i - y * W;
+      uint4 m = cur[i];
+#pragma unroll
+      for (int d = -2; d <= 2; d++) {
+        int xx = x + d;
+        if (d != 0 && (unsigned)xx < (unsigned)W) m = max_bf16x8(m, cur[y * W + xx]);
+      }
+      tmp[i] = m;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < HW; i += blockDim.x) {
+      int y = i / W, x = i - y * W;
+      uint4 m = tmp[i];
+#pragma unroll
+      for (int d = -2; d <= 2; d++) {
+        int yy = y + d;
+        if (d != 0 && (unsigned)yy < (unsigned)H) m = max_bf16x8(m, tmp[yy * W + x]);
+      }
+      // dst points at slice 1 of the concat buffer; slices are Chalf channels apart
+      *reinterpret_cast<uint4*>(dst + img_base + (size_t)i * ld + (size_t)stage * Chalf) = m;
+      cur[i] = m;  // each thread rewrites only the pixels it owns; tmp is the read set
+    }
+    __syncthreads();
+  }
+}
+
+int launch_pool(const yb_plan* p, const Op& op, cudaStream_t st) {
+  const Buf& sb = p->bufs[op.src[0].buf];
+  const __nv_bfloat16* src =
+      reinterpret_cast<const __nv_bfloat16*>(buf_ptr(p, op.src[0].buf)) + op.src[0].c_off;
+  __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(buf_ptr(p, op.dst.buf)) + op.dst.c_off;
+  int Chalf = op.src[0].C;
+  int HW = op.Hin * op.Win;
+  size_t smem = (size_t)2 * HW * 16;
+  if (smem > 200 * 1024) {
+    set_error("SPPF plane %dx%d does not fit shared memory", op.Hin, op.Win);
+    return YB_ERR_UNSUPPORTED;
+  }
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && smem > attr) {
+    YB_CUDA(cudaFuncSetAttribute(sppf_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem));
+    attr = smem;
+  }
+  // src (slice 0) and dst (slices 1..3) live in the same concat buffer
+  unsigned blocks = (unsigned)(p->B * (Chalf >> 3));
+  sppf_pool_kernel<<<blocks, 256, smem, st>>>(src, dst, sb.C, op.Hin, op.Win,
+                                              Chalf);
+  count_launch();
+  YB_CUDA(cudaGetLastError());
+  return YB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// C2PSA attention core (nets/nn.py:112-122): per (image, head)
+//     out[:, i] = sum_j softmax_j( (q_i . k_j) * dk^-1/2 ) v_j
+// qkv rows are tokens; channels of head h are [q(32) | k(32) | v(64)] at h*128 (the reference's
+// view(b, heads, 2*dk+dh, N) split).  One thread owns one query: q and the 64-wide accumulator
+// stay in registers, K/V tiles are staged once per CTA in shared memory as fp32 and read as
+// broadcasts; softmax is computed online in base 2.
+// ---------------------------------------------------------------------------------------------
+static constexpr int ATT_Q = 128;  // queries per CTA
+static constexpr int ATT_KT = 64;  // keys per shared-memory tile
+
+__global__ void __launch_bounds__(ATT_Q)
+    attention_kernel(const __nv_bfloat16* __restrict__ qkv, int qkv_ld, __nv_bfloat16* __restrict__ out,
+                     int out_ld, int N, int heads, float scale_log2e) {
+  __shared__ __align__(16) float Ks[ATT_KT][32];
+  __shared__ __align__(16) float Vs[ATT_KT][64];
+  const int qt = blockIdx.x;
+  const int h = blockIdx.y;
+  const int b = blockIdx.z;
+  const int tid = threadIdx.x;
+  const int qi = qt * ATT_Q + tid;
+  const bool q_ok = qi < N;
+  const __nv_bfloat16* base = qkv + (size_t)b * N * qkv_ld + h * 128;
+  float q[32];
+  {
+    const __nv_bfloat16* qp = base + (size_t)(q_ok ? qi : 0) * qkv_ld;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      float f[8];
+      bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(qp + 8 * j)), f);
+#pragma unroll
+      for (int t = 0; t < 8; t++) q[8 * j + t] = f[t] * scale_log2e;
+    }
+  }
+  float acc[64];
+#pragma unroll
+  for (int d = 0; d < 64; d++) acc[d] = 0.f;
+  float mrun = -INFINITY, lrun = 0.f;
+
+  for (int k0 = 0; k0 < N; k0 += ATT_KT) {
+    __syncthreads();
+    // stage K (64 x 32) and V (64 x 64): 12 granules of 8 channels per key
+    for (int i = tid; i < ATT_KT * 12; i += ATT_Q) {
+      int key = i / 12, gr = i - key * 12;
+      float f[8];
+      if (k0 + key < N) {
+        bf16x8_to_float(
+            __ldg(reinterpret_cast<const uint4*>(base + (size_t)(k0 + key) * qkv_ld + 32 + gr * 8)), f);
+      } else {
+#pragma unroll
+        for (int t = 0; t < 8; t++) f[t] = 0.f;
+      }
+      float* dp = gr < 4 ? &Ks[key][gr * 8] : &Vs[key][(gr - 4) * 8];
+      *reinterpret_cast<float4*>(dp) = make_float4(f[0], f[1], f[2], f[3]);
+      *reinterpret_cast<float4*>(dp + 4) = make_float4(f[4], f[5], f[6], f[7]);
+    }
+    __syncthreads();
+    const int kmax = min(ATT_KT, N - k0);
+    for (int c0 = 0; c0 < kmax; c0 += 8) {
+      float s[8];
+      float cmax = -INFINITY;
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        float a = 0.f;
+#pragma unroll
+        for (int d4 = 0; d4 < 8; d4++) {
+          float4 kk = *reinterpret_cast<const float4*>(&Ks[c0 + u][4 * d4]);
+          a = fmaf(q[4 * d4], kk.x, a);
+          a = fmaf(q[4 * d4 + 1], kk.y, a);
+          a = fmaf(q[4 * d4 + 2], kk.z, a);
+          a = fmaf(q[4 * d4 + 3], kk.w, a);
+        }
+        s[u] = (c0 + u < kmax) ? a : -INFINITY;
+        cmax = fmaxf(cmax, s[u]);
+      }
+      float mnew = fmaxf(mrun, cmax);
+      float corr = exp2f(mrun - mnew);
+      lrun *= corr;
+#pragma unroll
+      for (int d = 0; d < 64; d++) acc[d] *= corr;
+      mrun = mnew;
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        float pj = exp2f(s[u] - mnew);
+        lrun += pj;
+#pragma unroll
+        for (int d4 = 0; d4 < 16; d4++) {
+          float4 vv = *reinterpret_cast<const float4*>(&Vs[c0 + u][4 * d4]);
+          acc[4 * d4] = fmaf(pj, vv.x, acc[4 * d4]);
+          acc[4 * d4 + 1] = fmaf(pj, vv.y, acc[4 * d4 + 1]);
+          acc[4 * d4 + 2] = fmaf(pj, vv.z, acc[4 * d4 + 2]);
+          acc[4 * d4 + 3] = fmaf(pj, vv.w, acc[4 * d4 + 3]);
+        }
+      }
+    }
+  }
+  if (q_ok) {
+    float inv = 1.f / lrun;
+    __nv_bfloat16* op = out + ((size_t)b * N + qi) * out_ld + h * 64;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      float f[8];
+#pragma unroll
+      for (int t = 0; t < 8; t++) f[t] = acc[8 * j + t] * inv;
+      *reinterpret_cast<uint4*>(op + 8 * j) = float_to_bf16x8(f);
+    }
+  }
+}
+
+int launch_attn(const yb_plan* p, const Op& op, cudaStream_t st) {
+  const Buf& sb = p->bufs[op.src[0].buf];
+  const Buf& db = p->bufs[op.dst.buf];
+  const __nv_bfloat16* qkv =
+      reinterpret_cast<const __nv_bfloat16*>(buf_ptr(p, op.src[0].buf)) + op.src[0].c_off;
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(buf_ptr(p, op.dst.buf)) + op.dst.c_off;
+  int N = op.Hin * op.Win;
+  dim3 grid((N + ATT_Q - 1) / ATT_Q, op.heads, p->B);
+  attention_kernel<<<grid, ATT_Q, 0, st>>>(qkv, sb.C, out, db.C, N, op.heads,
+                                           op.scale * 1.4426950408889634f);
+  count_launch();
+  YB_CUDA(cudaGetLastError());
+  return YB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Head decode (nets/nn.py:261-270 + DFL nn.py:222-225 + make_anchors utils/util.py:85-96):
+// logits (B, A, 64+nc) fp32 -> out (B, 4+nc, A) fp32.  Anchor points and strides are computed
+// from the anchor index, never materialised.  Tiles of 64 anchors are transposed through shared
+// memory so that both the logits read and the plane-major write are coalesced.
+// ---------------------------------------------------------------------------------------------
+struct DecodeParams {
+  int B, A, nc, ld;
+  int lvl_off[3], lvl_w[3];
+  float lvl_stride[3];
+};
+
+static constexpr int DEC_T = 64;
+
+__global__ void __launch_bounds__(256)
+    head_decode_kernel(const float* __restrict__ logits, float* __restrict__ out, const DecodeParams D) {
+  extern __shared__ float tile[];  // [DEC_T][ldp]
+  const int no = 64 + D.nc;
+  const int ldp = no | 1;  // odd row pitch: conflict-free column access
+  float* dist = tile + DEC_T * ldp;  // [DEC_T][4]
+  const long long row0 = (long long)blockIdx.x * DEC_T;
+  const long long rows_total = (long long)D.B * D.A;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < DEC_T * no; i += blockDim.x) {
+    int r = i / no, c = i - r * no;
+    long long row = row0 + r;
+    tile[r * ldp + c] = row < rows_total ? __ldg(logits + row * D.ld + c) : 0.f;
+  }
+  __syncthreads();
+  {  // DFL: softmax over 16 bins, expectation with weights 0..15 (nn.py:218-225)
+    int r = tid & (DEC_T - 1), side = tid >> 6;  // 64 anchors x 4 sides = 256 threads
+    const float* lp = tile + r * ldp + side * 16;
+    float mx = lp[0];
+#pragma unroll
+    for (int j = 1; j < 16; j++) mx = fmaxf(mx, lp[j]);
+    float se = 0.f, sw = 0.f;
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+      float e = expf(lp[j] - mx);
+      se += e;
+      sw = fmaf((float)j, e, sw);
+    }
+    dist[r * 4 + side] = sw / se;
+  }
+  __syncthreads();
+  const int r = tid & (DEC_T - 1);
+  const long long row = row0 + r;
+  if (row >= rows_total) return;
+  const int b = (int)(row / D.A);
+  const int a = (int)(row - (long long)b * D.A);
+  float* ob = out + (size_t)b * (4 + D.nc) * D.A + a;
+  const int part = tid >> 6;
+  if (part == 0) {
+    int lvl = a >= D.lvl_off[2] ? 2 : (a >= D.lvl_off[1] ? 1 : 0);
+    int i = a - D.lvl_off[lvl];
+    int y = i / D.lvl_w[lvl], x = i - y * D.lvl_w[lvl];
+    float ax = (float)x + 0.5f, ay = (float)y + 0.5f, s = D.lvl_stride[lvl];
+    float x1 = ax - dist[r * 4 + 0], y1 = ay - dist[r * 4 + 1];
+    float x2 = ax + dist[r * 4 + 2], y2 = ay + dist[r * 4 + 3];
+    ob[0] = (x1 + x2) / 2.f * s;
+    ob[(size_t)D.A] = (y1 + y2) / 2.f * s;
+    ob[(size_t)2 * D.A] = (x2 - x1) * s;
+    ob[(size_t)3 * D.A] = (y2 - y1) * s;
+  }
+  for (int j = part; j < D.nc; j += 4) {
+    float z = tile[r * ldp + 64 + j];
+    ob[(size_t)(4 + j) * D.A] = 1.f / (1.f + expf(-z));
+  }
+}
+
+int launch_decode(const yb_plan* p, const float* logits, float* out, cudaStream_t st) {
+  DecodeParams D;
+  D.B = p->B;
+  D.A = p->A;
+  D.nc = p->nc;
+  D.ld = p->bufs[p->logits_buf].C;
+  for (int i = 0; i < 3; i++) {
+    D.lvl_off[i] = p->lvl_off[i];
+    D.lvl_w[i] = p->lvl_w[i];
+    D.lvl_stride[i] = p->lvl_stride[i];
+  }
+  int no = 64 + p->nc;
+  size_t smem = ((size_t)DEC_T * (no | 1) + DEC_T * 4) * 4;
+  static size_t attr = 0;
+  if (smem > 48 * 1024 && smem > attr) {
+    YB_CUDA(cudaFuncSetAttribute(head_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)smem));
+    attr = smem;
+  }
+  long long rows = (long long)p->B * p->A;
+  unsigned blocks = (unsigned)((rows + DEC_T - 1) / DEC_T);
+  head_decode_kernel<<<blocks, 256, smem, st>>>(logits, out, D);
+  count_launch();
+  YB_CUDA(cudaGetLastError());
+  return YB_OK;
+}
+
+}  // namespace yb

@@ -1,0 +1,135 @@
+// Internal structures shared by the plan builder and the kernel launchers of libyolob200.so.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/yolob200.h"
+
+namespace yb {
+
+void set_error(const char* fmt, ...);
+void count_launch();
+
+#define YB_CUDA(expr)                                                                  \
+  do {                                                                                 \
+    cudaError_t _e = (expr);                                                           \
+    if (_e != cudaSuccess) {                                                           \
+      yb::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,  \
+                    __LINE__);                                                         \
+      return YB_ERR_CUDA;                                                              \
+    }                                                                                  \
+  } while (0)
+
+static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
+static inline int cpad8(int c) { return round_up(c, 8); }
+
+// ---------------------------------------------------------------------------------------------
+// Activation buffers: NHWC bf16 (or fp32 for the head logits) inside one workspace arena.
+// A "slice" is a channel range [c_off, c_off + C) of a buffer; producers write straight into the
+// slice of their consumer's concat buffer, so torch.cat / chunk never exist as kernels.
+// ---------------------------------------------------------------------------------------------
+struct Buf {
+  int H = 0, W = 0, C = 0;  // C = total (padded) channels = row stride in elements
+  int elem_bytes = 2;
+  int rows_per_img = 0;     // H*W, or A for the logits buffer
+  size_t offset = 0;        // byte offset in the workspace arena
+  size_t bytes = 0;
+  int first_def = 1 << 30, last_use = -1;  // liveness (op indices) for arena reuse
+  std::string tag;
+};
+
+struct Slice {
+  int buf = -1;
+  int c_off = 0;
+  int C = 0;      // real channels
+  int up = 0;     // 1: consumer reads this source nearest-upsampled x2 (nn.py:195,205-206)
+};
+
+enum OpKind { OP_STEM = 0, OP_CONV = 1, OP_DW = 2, OP_POOL = 3, OP_ATTN = 4, OP_DECODE = 5 };
+
+struct Op {
+  OpKind kind = OP_CONV;
+  std::string name;
+  // geometry
+  int k = 1, stride = 1;
+  int Hin = 0, Win = 0;    // input spatial dims at the conv's own resolution (after upsample)
+  int Hout = 0, Wout = 0;
+  int nseg = 0;
+  Slice src[4];
+  Slice dst;               // dst.C = real cout
+  int dst_row_off = 0;     // row offset inside an image of the dst buffer (anchor offset of a level)
+  int has_res = 0;
+  Slice res;
+  int act = 1;
+  int out_f32 = 0;         // epilogue writes fp32 (head logits)
+  int conv_index = -1;     // index into Plan::convs
+  // tensor-core GEMM parameters (OP_CONV)
+  int a_tma = 0;           // A operand via TMA tiled loads (1x1, no upsample), else software im2col
+  int K = 0, K_pad = 0;    // GEMM K (real, padded to 64)
+  int seg_kpad[4] = {0, 0, 0, 0};  // per-segment padded K (a_tma mode)
+  int N_pad = 0, BN = 0;   // padded Cout, N tile
+  int stages = 0;
+  size_t smem_bytes = 0;
+  CUtensorMap tmap_b;
+  CUtensorMap tmap_a[4];
+  // depthwise: channel gather of the source (attention `pe` conv reads the v rows of qkv)
+  int dw_gsz = 0, dw_gstride = 0, dw_goff = 0, dw_add = 0;
+  // attention
+  int heads = 0, dk = 0, dh = 0;
+  float scale = 0.f;
+};
+
+struct ConvW {
+  yb_conv_info info;
+  int op = -1;
+};
+
+struct GraphEntry {
+  const void* in = nullptr;
+  void* out = nullptr;
+  void* stream = nullptr;
+  int dtype = 0, raw = 0, impl = 0;
+  cudaGraphExec_t exec = nullptr;
+};
+
+}  // namespace yb
+
+struct yb_plan {
+  yb_arch_desc arch;
+  int B = 0, H = 0, W = 0, device = 0;
+  int nc = 0, no = 0, A = 0;
+  int lvl_h[3], lvl_w[3], lvl_off[3];
+  float lvl_stride[3];
+  std::vector<yb::Buf> bufs;
+  std::vector<yb::Op> ops;
+  std::vector<yb::ConvW> convs;
+  size_t workspace_bytes = 0, weight_bytes = 0;
+  int logits_buf = -1;
+  const uint8_t* d_weights = nullptr;
+  uint8_t* d_ws = nullptr;
+  bool bound = false;
+  int conv_impl = 0;
+  int use_graph = 0;
+  int num_sms = 148;
+  std::vector<yb::GraphEntry> graphs;
+};
+
+namespace yb {
+// plan.cu
+int build_plan(yb_plan* p);
+// launchers (each enqueues exactly one kernel on `st`)
+int launch_conv_tc(const yb_plan* p, const Op& op, cudaStream_t st);
+int launch_conv_naive(const yb_plan* p, const Op& op, cudaStream_t st);
+int launch_stem(const yb_plan* p, const Op& op, const void* in, int in_dtype, cudaStream_t st);
+int launch_dw(const yb_plan* p, const Op& op, cudaStream_t st);
+int launch_pool(const yb_plan* p, const Op& op, cudaStream_t st);
+int launch_attn(const yb_plan* p, const Op& op, cudaStream_t st);
+int launch_decode(const yb_plan* p, const float* logits, float* out, cudaStream_t st);
+int conv_tc_prepare(yb_plan* p, Op& op);  // tensor maps + smem attribute, needs bound buffers
+
+inline uint8_t* buf_ptr(const yb_plan* p, int buf) { return p->d_ws + p->bufs[buf].offset; }
+}  // namespace yb

@@ -1,0 +1,170 @@
+"""Host-side driver of one libyolob200 execution plan.
+
+An Engine owns, for one (architecture, batch, height, width, device):
+  * the C-side plan (op list, buffer aliasing, TMA descriptors),
+  * the packed weight blob (BN folded as the reference's fuse_conv does, nets/nn.py:8-25),
+  * the activation workspace arena and the static (B, 4+nc, A) fp32 output tensor.
+PyTorch is used for device memory and streams only; every kernel on the path lives in the .so.
+"""
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_DTYPES = {torch.float32: _lib.YB_F32, torch.float16: _lib.YB_F16, torch.bfloat16: _lib.YB_BF16,
+           torch.uint8: _lib.YB_U8}
+
+
+def fold_conv_bn(conv, norm=None):
+    """Fold an eval-mode BatchNorm into the preceding conv: the arithmetic of fuse_conv
+    (reference nets/nn.py:8-25) written per output channel instead of as a diag matmul."""
+    w = conv.weight.detach().float().cpu()
+    b = conv.bias.detach().float().cpu() if conv.bias is not None else torch.zeros(w.shape[0])
+    if norm is None:
+        return w.contiguous(), b.contiguous()
+    scale = norm.weight.detach().float().cpu() / torch.sqrt(norm.eps + norm.running_var.detach().float().cpu())
+    w = w * scale.view(-1, 1, 1, 1)
+    b = scale * b + (norm.bias.detach().float().cpu()
+                     - norm.weight.detach().float().cpu() * norm.running_mean.detach().float().cpu()
+                     / torch.sqrt(norm.running_var.detach().float().cpu() + norm.eps))
+    return w.contiguous(), b.contiguous()
+
+
+class Engine:
+    def __init__(self, width, depth, csp, num_classes, batch, height, width_px, device=None,
+                 host_only=False):
+        L = _lib.lib()
+        self.L = L
+        arch = _lib.ArchDesc()
+        arch.width[:] = list(width)
+        arch.depth[:] = list(depth)
+        arch.csp[:] = [int(bool(c)) for c in csp]
+        arch.num_classes = int(num_classes)
+        self.arch = arch
+        self.batch, self.height, self.width = int(batch), int(height), int(width_px)
+        self.host_only = host_only
+        if host_only:
+            dev_index = -1
+            self.device = None
+        else:
+            self.device = torch.device(device if device is not None else "cuda")
+            if self.device.type != "cuda":
+                raise RuntimeError("yolo_infer_pt_b200 runs on CUDA (sm_100a) only; there is no CPU path")
+            dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+            self.device = torch.device("cuda", dev_index)
+        handle = ctypes.c_void_p()
+        _lib.check(L.yb_plan_create(ctypes.byref(arch), self.batch, self.height, self.width, dev_index,
+                                    ctypes.byref(handle)), "yb_plan_create")
+        self.plan = handle
+        self.num_anchors = L.yb_plan_num_anchors(self.plan)
+        self.num_outputs = L.yb_plan_num_outputs(self.plan)
+        self.num_launches = L.yb_plan_num_launches(self.plan)
+        self.weight_bytes = L.yb_plan_weight_bytes(self.plan)
+        self.workspace_bytes = L.yb_plan_workspace_bytes(self.plan)
+        self.convs = []
+        info = _lib.ConvInfo()
+        for i in range(L.yb_plan_num_convs(self.plan)):
+            _lib.check(L.yb_plan_conv_info(self.plan, i, ctypes.byref(info)), "yb_plan_conv_info")
+            self.convs.append(dict(index=i, name=info.name.decode(), cout=info.cout, cin=info.cin,
+                                   ksize=info.ksize, stride=info.stride, groups=info.groups, act=info.act,
+                                   wrapped=info.wrapped, kind=info.kind, blob_offset=info.blob_offset,
+                                   blob_bytes=info.blob_bytes))
+        self.host_blob = None
+        self.dev_weights = None
+        self.workspace = None
+        self.out = None
+        self.raw = None
+        self.graph = False
+
+    def __del__(self):
+        try:
+            if getattr(self, "plan", None):
+                self.L.yb_plan_destroy(self.plan)
+                self.plan = None
+        except Exception:
+            pass
+
+    # ---- weights -------------------------------------------------------------------------
+    def pack_from_model(self, model):
+        """Fold + pack every conv of `model` (a nets.nn.YOLO, fused or not) into the kernel layout."""
+        blob = np.zeros(self.weight_bytes, dtype=np.uint8)
+        for c in self.convs:
+            mod = model.get_submodule(c["name"])
+            if c["wrapped"]:
+                w, b = fold_conv_bn(mod.conv, getattr(mod, "norm", None))
+            else:
+                w, b = fold_conv_bn(mod, None)
+            exp = (c["cout"], c["cin"], c["ksize"], c["ksize"])
+            if tuple(w.shape) != exp:
+                raise RuntimeError(f"conv {c['name']}: weight shape {tuple(w.shape)} != plan {exp}")
+            wn = np.ascontiguousarray(w.numpy(), dtype=np.float32)
+            bn = np.ascontiguousarray(b.numpy(), dtype=np.float32)
+            _lib.check(self.L.yb_plan_pack_conv(self.plan, c["index"], wn.ctypes.data, bn.ctypes.data,
+                                                blob.ctypes.data), "yb_plan_pack_conv")
+        self.host_blob = blob
+        if not self.host_only:
+            self._bind()
+        return blob
+
+    def _bind(self):
+        dev = self.device
+        self.dev_weights = torch.from_numpy(self.host_blob).to(dev)
+        if self.workspace is None:
+            self.workspace = torch.zeros(self.workspace_bytes, dtype=torch.uint8, device=dev)
+            self.out = torch.empty(self.batch, self.num_outputs, self.num_anchors, dtype=torch.float32,
+                                   device=dev)
+        torch.cuda.synchronize(dev)
+        _lib.check(self.L.yb_plan_bind(self.plan, self.dev_weights.data_ptr(), self.workspace.data_ptr()),
+                   "yb_plan_bind")
+
+    # ---- execution -----------------------------------------------------------------------
+    def use_graph(self, enable=True):
+        self.graph = bool(enable)
+        _lib.check(self.L.yb_plan_use_graph(self.plan, int(self.graph)), "yb_plan_use_graph")
+
+    def set_conv_impl(self, impl):
+        _lib.check(self.L.yb_plan_set_conv_impl(self.plan, int(impl)), "yb_plan_set_conv_impl")
+
+    def _check_input(self, x):
+        if self.dev_weights is None:
+            raise RuntimeError("Engine has no weights bound; call pack_from_model first")
+        if not x.is_cuda or x.device != self.device:
+            raise RuntimeError(f"input must live on {self.device}; the inference path has no CPU fallback")
+        if tuple(x.shape) != (self.batch, 3, self.height, self.width):
+            raise RuntimeError(f"input shape {tuple(x.shape)} != plan {(self.batch, 3, self.height, self.width)}")
+        if x.dtype not in _DTYPES:
+            raise RuntimeError(f"unsupported input dtype {x.dtype}")
+        return x if x.is_contiguous() else x.contiguous()
+
+    def forward(self, x):
+        """(B,3,H,W) image tensor -> the engine's static (B, 4+nc, A) fp32 prediction tensor
+        (layout of reference nets/nn.py:262-270). The returned tensor is overwritten by the next call."""
+        x = self._check_input(x)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self.L.yb_forward(self.plan, x.data_ptr(), _DTYPES[x.dtype], self.out.data_ptr(),
+                                     ctypes.c_void_p(stream)), "yb_forward")
+        return self.out
+
+    def forward_raw(self, x):
+        """Pre-decode head logits (B, A, 64+nc) fp32 (reference training-mode output, nn.py:256-259)."""
+        x = self._check_input(x)
+        if self.raw is None:
+            self.raw = torch.empty(self.batch, self.num_anchors, self.num_outputs + 60, dtype=torch.float32,
+                                   device=self.device)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self.L.yb_forward_raw(self.plan, x.data_ptr(), _DTYPES[x.dtype], self.raw.data_ptr(),
+                                         ctypes.c_void_p(stream)), "yb_forward_raw")
+        return self.raw
+
+    def debug_read(self, conv_name):
+        """Activation written by op `conv_name` as an (B, H, W, C) fp32 CPU tensor (layer parity tests;
+        meaningful only when the plan was created with YB_NO_REUSE=1)."""
+        cap = self.batch * self.height * self.width * 8
+        buf = np.empty(cap, dtype=np.float32)
+        h, w, c = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+        n = self.L.yb_plan_debug_read(self.plan, conv_name.encode(), buf.ctypes.data, cap, ctypes.byref(h),
+                                      ctypes.byref(w), ctypes.byref(c))
+        _lib.check(int(n), "yb_plan_debug_read")
+        return torch.from_numpy(buf[:n].copy()).view(self.batch, -1, c.value)

@@ -1,0 +1,98 @@
+"""Drop-in for the hot-path functions of the reference's `utils.util`
+(t0saki/YOLO-Infer-pt utils/util.py:76-96, 123-169): `wh2xy`, `make_anchors`, `non_max_suppression`.
+
+`non_max_suppression` keeps the reference signature and return type but runs entirely on the
+device through libyolob200.so (`yb_nms`): one D2H copy of the per-image counts at the end instead of
+several host synchronisations per image.  It raises for CPU tensors — there is no CPU fallback.
+"""
+import ctypes
+import os
+import sys
+
+import numpy
+import torch
+
+MAX_WH = 7680      # utils/util.py:124
+MAX_DET = 300      # utils/util.py:125
+MAX_NMS = 30000    # utils/util.py:126
+
+
+def _lib_module():
+    try:
+        from yolo_infer_pt_b200 import _lib
+    except ImportError:
+        root = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        sys.path.insert(0, root)
+        from yolo_infer_pt_b200 import _lib
+    return _lib
+
+
+def wh2xy(x):
+    """(cx, cy, w, h) rows -> (x1, y1, x2, y2) rows; tensor or numpy (reference util.py:76-82)."""
+    y = x.clone() if isinstance(x, torch.Tensor) else numpy.copy(x)
+    half_w, half_h = x[:, 2] / 2, x[:, 3] / 2
+    y[:, 0] = x[:, 0] - half_w
+    y[:, 1] = x[:, 1] - half_h
+    y[:, 2] = x[:, 0] + half_w
+    y[:, 3] = x[:, 1] + half_h
+    return y
+
+
+def make_anchors(x, strides, offset=0.5):
+    """Anchor centres (A,2) as (x+offset, y+offset) and strides (A,1) for a list of feature maps
+    (reference util.py:85-96). The CUDA forward computes these from the anchor index instead;
+    this helper remains for the training loss (util.py:864)."""
+    assert x is not None
+    points, scales = [], []
+    for fmap, stride in zip(x, strides):
+        h, w = fmap.shape[-2:]
+        ys = torch.arange(h, device=fmap.device, dtype=fmap.dtype) + offset
+        xs = torch.arange(w, device=fmap.device, dtype=fmap.dtype) + offset
+        gy, gx = torch.meshgrid(ys, xs, indexing="ij")
+        points.append(torch.stack((gx, gy), -1).view(-1, 2))
+        scales.append(torch.full((h * w, 1), float(stride), dtype=fmap.dtype, device=fmap.device))
+    return torch.cat(points), torch.cat(scales)
+
+
+_workspaces = {}
+
+
+def nms_padded(outputs, confidence_threshold=0.001, iou_threshold=0.65, max_det=MAX_DET, max_nms=MAX_NMS,
+               max_wh=MAX_WH):
+    """Device-resident NMS: returns (det, counts) with det (B, max_det, 6) fp32 rows
+    [x1, y1, x2, y2, score, class] and counts (B,) int32 — no host synchronisation."""
+    if not (isinstance(outputs, torch.Tensor) and outputs.is_cuda):
+        raise RuntimeError("yolo_infer_pt_b200.non_max_suppression needs a CUDA tensor; "
+                           "there is no CPU fallback on the inference path")
+    if outputs.dim() != 3 or outputs.shape[1] < 5:
+        raise RuntimeError(f"expected (B, 4+nc, A) predictions, got {tuple(outputs.shape)}")
+    _lib = _lib_module()
+    L = _lib.lib()
+    pred = outputs if outputs.dtype == torch.float32 else outputs.float()
+    pred = pred.contiguous()
+    B, no, A = pred.shape
+    nc = no - 4
+    dev = pred.device
+    key = (dev.index, B, nc, A, max_nms)
+    ws = _workspaces.get(key)
+    if ws is None:
+        nbytes = L.yb_nms_workspace_bytes(B, nc, A, max_nms)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        _workspaces.clear()
+        _workspaces[key] = ws
+    det = torch.zeros(B, max_det, 6, dtype=torch.float32, device=dev)
+    counts = torch.zeros(B, dtype=torch.int32, device=dev)
+    conf32 = float(numpy.float32(confidence_threshold))  # torch compares an fp32 tensor in fp32
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    _lib.check(L.yb_nms(pred.data_ptr(), B, nc, A, conf32, float(iou_threshold), max_det, max_nms,
+                        float(max_wh), det.data_ptr(), counts.data_ptr(), ws.data_ptr(), ws.numel(),
+                        ctypes.c_void_p(stream)), "yb_nms")
+    return det, counts
+
+
+def non_max_suppression(outputs, confidence_threshold=0.001, iou_threshold=0.65):
+    """Reference signature and result (util.py:123-169): list of B tensors (k<=300, 6) fp32
+    [x1, y1, x2, y2, confidence, class] on outputs.device, score-descending."""
+    det, counts = nms_padded(outputs, confidence_threshold, iou_threshold)
+    counts = counts.cpu().tolist()  # the single host synchronisation of the call
+    return [det[i, :k] for i, k in enumerate(counts)]
