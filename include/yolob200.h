@@ -119,6 +119,11 @@ int yb_plan_set_conv_impl(yb_plan* plan, int impl);
 long long yb_plan_debug_read(yb_plan* plan, const char* conv_name, float* host_out,
                              size_t host_capacity_floats, int* out_h, int* out_w, int* out_c);
 
+/* Writes a JSON description of the plan (buffers, ops, slices, GEMM shapes) into buf; returns the
+ * number of bytes needed (call with capacity 0 to size the buffer). Used by the host-logic tests
+ * to replay the dataflow on the CPU. */
+long long yb_plan_describe(const yb_plan* plan, char* buf, size_t capacity);
+
 /* ---- NMS: stands in for utils.util.non_max_suppression, utils/util.py:123-169 ---- */
 
 size_t yb_nms_workspace_bytes(int batch, int num_classes, int num_anchors, int max_nms);

@@ -35,9 +35,9 @@ ref_util.time = lambda: 0.0  # neutralise the wall-clock bail-out, utils/util.py
 torch.set_num_threads(8)
 
 
-def ref_model(size, nc=80, seed=0):
+def ref_model(size, nc=80, seed=0, recipe="calibrated"):
     m = getattr(ref_nn, f"yolo_v11_{size}")(nc)
-    m.load_state_dict(synth.synth_state_dict(m, seed))
+    m.load_state_dict(synth.synth_state_dict(m, seed, recipe))
     return m
 
 
@@ -61,9 +61,16 @@ def main():
             fused = m.fuse().eval()(x)
         save(f"fwd_{size}_64.npz", out=fused.numpy(), out_unfused=unfused.numpy(),
              raw0=raw[0].numpy(), raw1=raw[1].numpy(), raw2=raw[2].numpy())
+    # ---- forward on the SURVEY §8(d) recipe (the tolerance gate's weights) -----------------------
+    for size in "nx":
+        m = ref_model(size, recipe="survey").fuse().eval()
+        x = synth.synth_images(2, 64, 64, seed=1)
+        with torch.no_grad():
+            y = m(x)
+        save(f"fwdsv_{size}_64.npz", out=y.numpy())
     # ---- forward, n and s at 640 (BASELINE config 1), sub-sampled anchors ----------------------
     for size in "ns":
-        m = ref_model(size).fuse().eval()
+        m = ref_model(size, recipe="survey").fuse().eval()
         x = synth.synth_images(1, 640, 640, seed=0)
         with torch.no_grad():
             y = m(x)

@@ -1,0 +1,188 @@
+"""Host-logic tests (CPU only): C-ABI surface, plan builder, buffer aliasing, weight packer, and the
+Python drop-in boundary.  The plan is replayed on the CPU by oracle/plan_replay.py (test
+infrastructure) and compared with the oracle forward; no CUDA kernel runs here."""
+import copy
+import io
+import os
+import pickle
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import yolo_oracle
+from oracle.plan_replay import PlanReplay
+from yolo_infer_pt_b200 import _lib, synth
+from yolo_infer_pt_b200.engine import Engine
+from yolo_infer_pt_b200.nets import nn
+from yolo_infer_pt_b200.utils import util
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "yolob200.h")).read()
+    declared = set(re.findall(r"\b(yb_[a-z_0-9]+)\s*\(", header))
+    assert declared, "no declarations parsed"
+    lib = _lib.lib()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/yolob200.h but not exported"
+    assert declared == set(_lib.SYMBOLS), "ctypes table and header disagree"
+    assert lib.yb_version() >= 100
+
+
+def test_no_cpu_fallback():
+    m = nn.yolo_v11_n(80).eval()
+    with pytest.raises(RuntimeError, match="no CPU"):
+        m(torch.zeros(1, 3, 64, 64))
+    with pytest.raises(RuntimeError, match="no CPU"):
+        util.non_max_suppression(torch.zeros(1, 84, 84))
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="no CUDA device|no CPU"):
+            Engine(*nn.yolo_v11_n(80)._arch, 1, 64, 64, device="cuda:0")
+
+
+def test_training_mode_and_state_dict_contract():
+    m = nn.yolo_v11_n(80)
+    assert m.training
+    maps = m(torch.zeros(1, 3, 64, 64))
+    assert [tuple(t.shape) for t in maps] == [(1, 144, 8, 8), (1, 144, 4, 4), (1, 144, 2, 2)]
+    sd = m.state_dict()
+    assert len(sd) == 499  # 499 keys unfused for n
+    for k in ("net.p1.0.conv.weight", "net.p1.0.norm.running_mean", "head.box.0.2.bias", "head.dfl.conv.weight",
+              "net.p5.3.res_m.0.conv1.qkv.conv.weight", "fpn.h6.res_m.0.res_m.1.conv2.conv.weight"):
+        assert k in sd
+    assert torch.equal(m.stride, torch.tensor([8.0, 16.0, 32.0]))
+    assert m.head.nc == 80 and m.head.no == 144 and m.head.ch == 16 and m.head.nl == 3
+    m.fuse()
+    assert len(m.state_dict()) == 175  # 175 keys fused
+    assert not hasattr(m.net.p1[0], "norm")
+    # pickling / deepcopy must not drag engine handles along
+    m2 = pickle.load(io.BytesIO(pickle.dumps(m)))
+    m3 = copy.deepcopy(m)
+    for a, b in zip(m.state_dict().values(), m2.state_dict().values()):
+        assert torch.equal(a, b)
+    assert len(m3.state_dict()) == 175
+
+
+def test_fuse_matches_batchnorm():
+    torch.manual_seed(0)
+    c = nn.Conv(8, 16, torch.nn.SiLU(), k=3, p=1)
+    c.norm.running_mean.normal_()
+    c.norm.running_var.uniform_(0.5, 2.0)
+    c.norm.weight.data.uniform_(0.5, 1.5)
+    c.norm.bias.data.normal_()
+    c.eval()
+    x = torch.randn(2, 8, 12, 12)
+    ref = c(x)
+    fused = nn.fuse_conv(c.conv, c.norm)
+    assert (torch.nn.functional.silu(fused(x)) - ref).abs().max() < 1e-5
+
+
+def bf16_weight_state(model):
+    """Fused state_dict whose dense-conv weights are rounded to bf16 — what the packed blob holds
+    (stem and depthwise weights stay fp32 in the blob)."""
+    m = copy.deepcopy(model).fuse()
+    sd = {k: v.float().clone() for k, v in m.state_dict().items()}
+    for name, mod in m.named_modules():
+        if isinstance(mod, torch.nn.Conv2d) and mod.groups == 1 and name not in ("net.p1.0.conv", "head.dfl.conv"):
+            sd[name + ".weight"] = sd[name + ".weight"].to(torch.bfloat16).float()
+    return sd
+
+
+@pytest.mark.parametrize("size,hw", [("n", 64), ("t", 64), ("s", 64), ("m", 64), ("x", 64), ("n", 96)])
+def test_plan_replay_matches_oracle(size, hw):
+    """Plan + aliasing + packed weights, replayed in fp32 on the CPU, reproduce the oracle forward
+    run on the same bf16-rounded weights — layer by layer and end to end."""
+    model = getattr(nn, f"yolo_v11_{size}")(80)
+    synth.load_synth(model, 0)
+    eng = Engine(*model._arch, 2, hw, hw, host_only=True)
+    blob = eng.pack_from_model(model)
+    desc = eng.describe()
+    x = synth.synth_images(2, hw, hw, seed=1)
+    taps_o, taps_r = {}, {}
+    sd = bf16_weight_state(model)
+    with torch.no_grad():
+        ref = yolo_oracle.forward(sd, *model._arch, x, taps=taps_o)
+        rep = PlanReplay(desc, eng.convs, blob, emulate_bf16=False)
+        out = rep.run(x, taps=taps_r)
+    assert not torch.isnan(out).any(), "an op read channels nobody wrote"
+    checked = 0
+    for name in [o["name"] for o in desc["ops"] if o["kind"] != 5]:
+        if name not in taps_o:
+            continue
+        a = taps_r[name]                                             # (B, rows, C)
+        b = taps_o[name].permute(0, 2, 3, 1).reshape(a.shape[0], -1, taps_o[name].shape[1])
+        assert a.shape == b.shape, name
+        err = (a - b).abs().max().item()
+        assert err <= 2e-3 * max(1.0, b.abs().max().item()), f"{name}: max err {err}"
+        checked += 1
+    assert checked >= 80
+    assert (out[:, :4] - ref[:, :4]).abs().max() < 0.2   # fp32 summation-order noise on ~700 px boxes
+    assert (out[:, 4:] - ref[:, 4:]).abs().max() < 2e-3
+
+
+def test_conv_names_resolve_to_modules_of_every_size():
+    for size in "ntsmlx":
+        model = getattr(nn, f"yolo_v11_{size}")(80)
+        eng = Engine(*model._arch, 1, 64, 64, host_only=True)
+        seen = set()
+        for c in eng.convs:
+            mod = model.get_submodule(c["name"])
+            conv = mod.conv if c["wrapped"] else mod
+            assert tuple(conv.weight.shape) == (c["cout"], c["cin"], c["ksize"], c["ksize"]), c["name"]
+            assert conv.groups == c["groups"] and conv.stride[0] == c["stride"], c["name"]
+            seen.add(c["name"])
+        convs_in_model = {n for n, m in model.named_modules()
+                          if isinstance(m, torch.nn.Conv2d) and not n.startswith("head.dfl")}
+        convs_in_model = {n[:-5] if n.endswith(".conv") else n for n in convs_in_model}
+        assert seen == convs_in_model, f"{size}: plan misses {convs_in_model - seen} / extra {seen - convs_in_model}"
+
+
+@pytest.mark.parametrize("size,batch,hw", [("n", 256, 640), ("x", 64, 640), ("s", 1, 1280)])
+def test_arena_reuse_never_overlaps_live_buffers(size, batch, hw):
+    model_arch = getattr(nn, f"yolo_v11_{size}")(80)._arch
+    eng = Engine(*model_arch, batch, hw, hw, host_only=True)
+    d = eng.describe()
+    # recompute liveness from the op list
+    first, last = {}, {}
+    for i, op in enumerate(d["ops"]):
+        slices = list(op["src"]) + ([op["dst"]] if op["kind"] != 5 else []) + ([op["res"]] if op["has_res"] else [])
+        if op["kind"] == 5:
+            slices.append({"buf": d["logits_buf"]})
+        for s in slices:
+            if s["buf"] < 0:
+                continue
+            first[s["buf"]] = min(first.get(s["buf"], i), i)
+            last[s["buf"]] = max(last.get(s["buf"], i), i)
+    bufs = d["bufs"]
+    total = 0
+    for i, a in enumerate(bufs):
+        assert a["first_def"] <= first[i] and a["last_use"] >= last[i], a["tag"]
+        assert a["offset"] % 1024 == 0 and a["offset"] + a["bytes"] <= d["workspace_bytes"]
+        total += a["bytes"]
+        for j in range(i):
+            b = bufs[j]
+            mem_overlap = a["offset"] < b["offset"] + b["bytes"] and b["offset"] < a["offset"] + a["bytes"]
+            live_overlap = not (a["last_use"] < b["first_def"] or b["last_use"] < a["first_def"])
+            assert not (mem_overlap and live_overlap), f"{a['tag']} and {b['tag']} alias while both live"
+    assert d["workspace_bytes"] < total  # reuse actually happens
+    assert d["workspace_bytes"] < 170e9
+
+
+def test_unsupported_configs_fail_loudly():
+    with pytest.raises(RuntimeError, match="multiple of 32"):
+        Engine(*nn.yolo_v11_n(80)._arch, 1, 100, 100, host_only=True)
+    with pytest.raises(RuntimeError):
+        Engine([3, 16, 32, 64, 128, 200], [1] * 6, [False, True], 80, 1, 64, 64, host_only=True)
+
+
+def test_wh2xy_and_make_anchors():
+    x = torch.tensor([[10.0, 20.0, 4.0, 6.0]])
+    assert torch.equal(util.wh2xy(x), torch.tensor([[8.0, 17.0, 12.0, 23.0]]))
+    assert np.array_equal(util.wh2xy(x.numpy()), np.array([[8.0, 17.0, 12.0, 23.0]], dtype=np.float32))
+    maps = [torch.zeros(1, 1, 2, 3), torch.zeros(1, 1, 1, 1)]
+    pts, st = util.make_anchors(maps, [8, 16])
+    assert pts.tolist() == [[0.5, 0.5], [1.5, 0.5], [2.5, 0.5], [0.5, 1.5], [1.5, 1.5], [2.5, 1.5], [0.5, 0.5]]
+    assert st.view(-1).tolist() == [8.0] * 6 + [16.0]

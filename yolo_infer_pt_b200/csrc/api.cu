@@ -352,6 +352,49 @@ long long yb_plan_debug_read(yb_plan* plan, const char* conv_name, float* host_o
   return YB_ERR_ARG;
 }
 
+long long yb_plan_describe(const yb_plan* plan, char* buf, size_t capacity) {
+  if (!plan) return YB_ERR_ARG;
+  std::string j;
+  char t[512];
+  auto slice = [&](const Slice& s) {
+    snprintf(t, sizeof(t), "{\"buf\":%d,\"c_off\":%d,\"C\":%d,\"up\":%d}", s.buf, s.c_off, s.C, s.up);
+    return std::string(t);
+  };
+  snprintf(t, sizeof(t), "{\"B\":%d,\"H\":%d,\"W\":%d,\"nc\":%d,\"A\":%d,\"logits_buf\":%d,"
+           "\"workspace_bytes\":%zu,\"weight_bytes\":%zu,\"lvl_off\":[%d,%d,%d],\"bufs\":[",
+           plan->B, plan->H, plan->W, plan->nc, plan->A, plan->logits_buf, plan->workspace_bytes,
+           plan->weight_bytes, plan->lvl_off[0], plan->lvl_off[1], plan->lvl_off[2]);
+  j += t;
+  for (size_t i = 0; i < plan->bufs.size(); i++) {
+    const Buf& b = plan->bufs[i];
+    snprintf(t, sizeof(t), "%s{\"H\":%d,\"W\":%d,\"C\":%d,\"elem_bytes\":%d,\"rows_per_img\":%d,"
+             "\"offset\":%zu,\"bytes\":%zu,\"first_def\":%d,\"last_use\":%d,\"tag\":\"%s\"}",
+             i ? "," : "", b.H, b.W, b.C, b.elem_bytes, b.rows_per_img, b.offset, b.bytes, b.first_def,
+             b.last_use, b.tag.c_str());
+    j += t;
+  }
+  j += "],\"ops\":[";
+  for (size_t i = 0; i < plan->ops.size(); i++) {
+    const Op& o = plan->ops[i];
+    snprintf(t, sizeof(t), "%s{\"kind\":%d,\"name\":\"%s\",\"k\":%d,\"stride\":%d,\"Hin\":%d,\"Win\":%d,"
+             "\"Hout\":%d,\"Wout\":%d,\"act\":%d,\"out_f32\":%d,\"dst_row_off\":%d,\"conv_index\":%d,"
+             "\"a_tma\":%d,\"K\":%d,\"K_pad\":%d,\"N_pad\":%d,\"BN\":%d,\"has_res\":%d,",
+             i ? "," : "", (int)o.kind, o.name.c_str(), o.k, o.stride, o.Hin, o.Win, o.Hout, o.Wout, o.act,
+             o.out_f32, o.dst_row_off, o.conv_index, o.a_tma, o.K, o.K_pad, o.N_pad, o.BN, o.has_res);
+    j += t;
+    snprintf(t, sizeof(t), "\"seg_kpad\":[%d,%d,%d,%d],\"dw\":[%d,%d,%d,%d],\"heads\":%d,\"scale\":%.9g,",
+             o.seg_kpad[0], o.seg_kpad[1], o.seg_kpad[2], o.seg_kpad[3], o.dw_gsz, o.dw_gstride, o.dw_goff,
+             o.dw_add, o.heads, o.scale);
+    j += t;
+    j += "\"src\":[";
+    for (int s = 0; s < o.nseg; s++) j += (s ? "," : "") + slice(o.src[s]);
+    j += "],\"dst\":" + slice(o.dst) + ",\"res\":" + slice(o.res) + "}";
+  }
+  j += "]}";
+  if (buf && capacity > j.size()) memcpy(buf, j.c_str(), j.size() + 1);
+  return (long long)j.size() + 1;
+}
+
 size_t yb_nms_workspace_bytes(int batch, int num_classes, int num_anchors, int max_nms) {
   return nms_workspace_bytes(batch, num_classes, num_anchors, max_nms);
 }

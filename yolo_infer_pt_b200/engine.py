@@ -158,6 +158,14 @@ class Engine:
                                          ctypes.c_void_p(stream)), "yb_forward_raw")
         return self.raw
 
+    def describe(self):
+        """The plan as a dict (buffers, ops, slices) — host-logic tests replay it on the CPU."""
+        import json
+        n = self.L.yb_plan_describe(self.plan, None, 0)
+        buf = ctypes.create_string_buffer(int(n) + 16)
+        _lib.check(int(self.L.yb_plan_describe(self.plan, buf, len(buf))), "yb_plan_describe")
+        return json.loads(buf.value.decode())
+
     def debug_read(self, conv_name):
         """Activation written by op `conv_name` as an (B, H, W, C) fp32 CPU tensor (layer parity tests;
         meaningful only when the plan was created with YB_NO_REUSE=1)."""

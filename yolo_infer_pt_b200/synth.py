@@ -29,16 +29,26 @@ def _variant_name(model):
     return table.get((width[0], width[1], depth))
 
 
-def synth_state_dict(model, seed=0, calibrated=True):
-    """Seeded weights for `model` (reference or product YOLO, same state_dict keys).  With
-    calibrated=True the BatchNorm running statistics come from tests/golden/synth_bn_<size>.npz:
-    per-channel batch statistics recorded by tests/golden/make_synth_bn.py on a calibration batch,
-    stored as fp16 so that every machine loads bit-identical values."""
+def synth_state_dict(model, seed=0, recipe="calibrated", calibrated=True):
+    """Seeded weights for `model` (reference or product YOLO, same state_dict keys).
+
+    recipe="survey"      SURVEY.md §8(d) `synth_weights`: torch-default conv init range
+                         U(+-1/sqrt(fan_in)), arbitrary BatchNorm statistics.  Activations shrink
+                         with depth, so round-off is barely amplified: this is the recipe the
+                         0.5 px / 1e-2 tolerance of the north star was probed on.
+    recipe="calibrated"  variance-preserving conv init and BatchNorm running statistics taken from
+                         tests/golden/synth_bn_<size>_seed<seed>.npz (per-channel batch statistics
+                         recorded by tests/golden/make_synth_bn.py, stored as fp16 so every machine
+                         loads identical values).  Every layer keeps unit scale and spatial
+                         structure — the recipe for layer-level parity (a tap-order or slice bug is
+                         invisible on a collapsed network) and a round-off stress test.
+    """
     rng = np.random.RandomState(seed)
     out = {}
     bn = None
     size = _variant_name(model)
-    if calibrated and size is not None:
+    survey = recipe == "survey"
+    if not survey and calibrated and size is not None:
         path = os.path.join(_BN_DIR, f"synth_bn_{size}_seed{seed}.npz")
         if os.path.exists(path):
             bn = np.load(path)
@@ -58,13 +68,14 @@ def synth_state_dict(model, seed=0, calibrated=True):
             val = rng.normal(0.0, 0.1, shape)
         elif key.endswith(".weight"):  # conv weight OIHW, variance preserving: std = 1/sqrt(fan_in)
             fan_in = int(np.prod(shape[1:]))
-            bound = np.sqrt(3.0 / fan_in)
+            bound = np.sqrt((1.0 if survey else 3.0) / fan_in)
             val = rng.uniform(-bound, bound, shape)
         elif key.endswith(".bias"):
             if key.startswith("head.box."):
                 val = np.full(shape, 1.0)
             elif key.startswith("head.cls."):
-                val = np.full(shape, CLS_BIAS) + rng.normal(0.0, 0.5, shape)
+                val = (np.full(shape, -8.0) + rng.normal(0.0, 1.0, shape)) if survey else \
+                    (np.full(shape, CLS_BIAS) + rng.normal(0.0, 0.5, shape))
             else:
                 val = rng.normal(0.0, 0.1, shape)
         else:
@@ -75,8 +86,8 @@ def synth_state_dict(model, seed=0, calibrated=True):
     return out
 
 
-def load_synth(model, seed=0):
-    model.load_state_dict(synth_state_dict(model, seed))
+def load_synth(model, seed=0, recipe="calibrated"):
+    model.load_state_dict(synth_state_dict(model, seed, recipe))
     return model
 
 
