@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""Benchmark of the YOLO-Infer-pt inference hot path (YOLO.forward + non_max_suppression).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--model n|x|...]
+                    [--batch B] [--size 640]
+
+One step = forward + decode + NMS over one batch of synthetic images (random-init synthetic weights,
+SURVEY.md §8(d) recipe).  Default workload (N=1): BASELINE.json configs[1] — YOLO11n, bf16
+activations, batch 256 per GPU, 640x640.  Under torchrun every rank runs its own batch on its own
+GPU (weak scaling, no data-path collective); times are CUDA-event times, max over ranks.
+
+Prints ONE JSON line on rank 0 (see DESIGN.md §Measurement for every field).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+METRIC = "images/sec YOLO11n 640x640 forward+NMS (bf16 activations)"
+
+
+def read_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=float(p["hbm_gbs"]), tf_burst=float(p["bf16_tflops"]),
+                    tf_sustained=float(p.get("bf16_tflops_sustained", p["bf16_tflops"])), source="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._pump, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# -------------------------------------------------------------------------------------------------
+def conv_algorithmic_work(desc, batch):
+    """Per op of the plan: algorithmic FLOPs (2*MAC) and bytes (input read once + output written once
+    + weights once) for the whole batch."""
+    work = []
+    for op in desc["ops"]:
+        flops = bytes_ = 0.0
+        m = batch * op["Hout"] * op["Wout"]
+        cout = op["dst"]["C"]
+        if op["kind"] == 1:
+            cin = sum(s["C"] for s in op["src"])
+            flops = 2.0 * m * cout * cin * op["k"] ** 2
+            in_elems = sum(batch * (op["Hin"] >> s["up"]) * (op["Win"] >> s["up"]) * s["C"] for s in op["src"])
+            bytes_ = 2.0 * in_elems + (4.0 if op["out_f32"] else 2.0) * m * cout + 2.0 * cout * cin * op["k"] ** 2
+            if op["has_res"]:
+                bytes_ += 2.0 * m * cout
+        work.append((flops, bytes_))
+    return work
+
+
+def run_ours(args, rank, world, local_rank):
+    from oracle import nms_oracle, yolo_oracle  # checker / CPU baseline only
+    from yolo_infer_pt_b200 import _lib, synth
+    from yolo_infer_pt_b200.nets import nn
+    from yolo_infer_pt_b200.utils import util
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    peaks = read_peaks()
+    model = getattr(nn, f"yolo_v11_{args.model}")(80)
+    synth.load_synth(model, 0, "survey")
+    model = model.fuse().eval().to(dev)
+    B, S = args.batch, args.size
+    # synthetic uint8 images (what the reference's loader yields, main.py:265-267); /255 is fused in the stem
+    base = (synth.synth_images(min(B, 8), S, S, seed=rank) * 255).round().to(torch.uint8)
+    host = base.repeat((B + base.shape[0] - 1) // base.shape[0], 1, 1, 1)[:B].contiguous().pin_memory()
+    x_dev = host.to(dev)
+    L = _lib.lib()
+
+    def step_resident():
+        y = model(x_dev)
+        return util.nms_padded(y, 0.001, 0.65)
+
+    def step_e2e():
+        x = host.to(dev, non_blocking=True)
+        y = model(x)
+        det, counts = util.nms_padded(y, 0.001, 0.65)
+        return det.to("cpu", non_blocking=False), counts.to("cpu", non_blocking=False)
+
+    for _ in range(max(3, args.warmup)):
+        step_resident()
+    torch.cuda.synchronize(dev)
+    eng = model._engine_for(x_dev)
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+
+    def timed(fn, steps, profile=False):
+        sampler = ClockSampler(local_rank)
+        if profile:
+            eng.profile(True)
+        barrier()
+        torch.cuda.synchronize(dev)
+        sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        before = L.yb_launch_count()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize(dev)
+        barrier()
+        clocks = sampler.stop()
+        ms = e0.elapsed_time(e1)
+        launches = L.yb_launch_count() - before
+        op_ms = None
+        if profile:
+            op_ms, _ = eng.profile_read()
+            eng.profile(False)
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+            ms = t.item()
+        return ms, launches, clocks, op_ms
+
+    ms, launches, clocks, op_ms = timed(step_resident, args.steps, profile=True)
+    ms_per_step = ms / args.steps
+    value = world * B * args.steps / (ms / 1e3)
+    for _ in range(2):
+        step_e2e()
+    ms_e, _, _, _ = timed(step_e2e, args.steps)
+    e2e_value = world * B * args.steps / (ms_e / 1e3)
+
+    # ---- roofline of the dominant kernel (the tcgen05 implicit-GEMM conv, all its launches) -------
+    desc = eng.describe()
+    work = conv_algorithmic_work(desc, B)
+    conv_ms = sum(float(op_ms[i]) for i, op in enumerate(desc["ops"]) if op["kind"] == 1)
+    conv_flops = sum(w[0] for w in work)
+    conv_bytes = sum(w[1] for w in work)
+    fwd_ms = float(op_ms.sum())
+    t_flops = conv_flops / (peaks["tf_sustained"] * 1e12)
+    t_bytes = conv_bytes / (peaks["hbm"] * 1e9)
+    bound = "tensor" if t_flops > t_bytes else "hbm"
+    if bound == "hbm":
+        achieved = conv_bytes / (conv_ms / 1e3) / 1e9
+        peak, unit = peaks["hbm"], "GB/s"
+    else:
+        achieved = conv_flops / (conv_ms / 1e3) / 1e12
+        peak, unit = peaks["tf_sustained"], "TFLOP/s"
+    n_conv = sum(1 for op in desc["ops"] if op["kind"] == 1)
+    roofline = {"bound": bound, "achieved": round(achieved, 2), "peak": peak, "unit": unit,
+                "frac": round(achieved / peak, 4), "traffic": None, "kernel": "conv_gemm_tcgen05_kernel",
+                "launches_per_step": n_conv, "kernel_ms_per_step": round(conv_ms, 4),
+                "kernel_share_of_step": round(conv_ms / ms_per_step, 4),
+                "algorithmic_gbytes_per_step": round(conv_bytes / 1e9, 4),
+                "algorithmic_tflop_per_step": round(conv_flops / 1e12, 4),
+                "tensor_tflops_achieved": round(conv_flops / (conv_ms / 1e3) / 1e12, 2),
+                "peak_source": peaks["source"] + (" (sustained)" if bound == "tensor" else "")}
+    if rank == 0 and args.profile_json:
+        rows = [dict(name=op["name"], kind=op["kind"], ms=float(op_ms[i]), gflop=work[i][0] / 1e9,
+                     mbytes=work[i][1] / 1e6) for i, op in enumerate(desc["ops"])]
+        json.dump(dict(model=args.model, batch=B, size=S, forward_ms=fwd_ms, step_ms=ms_per_step, ops=rows),
+                  open(args.profile_json, "w"), indent=1)
+
+    # ---- CPU baseline: the oracle port on the host cores, bounded sample --------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline(args.model, S, budget_s=12.0)
+    out = {
+        "metric": METRIC.replace("YOLO11n", f"YOLO11{args.model}"), "value": round(value, 2), "unit": "images/sec",
+        "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": round(ms_per_step, 4),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"YOLO11{args.model} fused, bf16 activations, batch {B} per GPU, {S}x{S}, "
+                               "forward + DFL decode + NMS (conf 0.001, IoU 0.65, max_det 300)",
+                   "weights": "random-init synthetic (SURVEY.md 8d recipe, seed 0)",
+                   "input": "uint8 NCHW resident in HBM, /255 fused into the stem kernel",
+                   "l2": f"inputs larger than L2 ({host.numel() / 1e6:.0f} MB images + "
+                         f"{eng.workspace_bytes / 1e9:.1f} GB activation arena per step)",
+                   "parallelism": f"image-sharded x{world}, no collective on the data path"},
+        "roofline": roofline,
+        "e2e": {"value": round(e2e_value, 2), "unit": "images/sec", "h2d_bytes_per_step": int(host.numel()),
+                "d2h_bytes_per_step": int(B * (300 * 6 * 4 + 4)), "ms_per_step": round(ms_e / args.steps, 4)},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "forward_ms_per_step": round(fwd_ms, 4),
+    }
+    if cpu is not None:
+        out["cpu_baseline"] = cpu
+    return out
+
+
+def cpu_baseline(model_size, size, budget_s=12.0, batch=8):
+    """Oracle port (plain fp32 PyTorch CPU ops + C NMS) timed on the host cores: forward + NMS on
+    batches of `batch` synthetic images until ~budget_s seconds of work were done."""
+    from oracle import nms_oracle, yolo_oracle
+    from yolo_infer_pt_b200 import synth
+    from yolo_infer_pt_b200.nets import nn
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    m = getattr(nn, f"yolo_v11_{model_size}")(80)
+    synth.load_synth(m, 0, "survey")
+    m.fuse()
+    sd = {k: v.float() for k, v in m.state_dict().items()}
+    x = synth.synth_images(batch, size, size, seed=0)
+    done, t_total = 0, 0.0
+    with torch.no_grad():
+        yolo_oracle.forward(sd, *m._arch, x[:1])  # warm-up
+        while t_total < budget_s:
+            t0 = time.perf_counter()
+            y = yolo_oracle.forward(sd, *m._arch, x)
+            nms_oracle.non_max_suppression(y.numpy(), 0.001, 0.65)
+            t_total += time.perf_counter() - t0
+            done += batch
+    return {"value": round(done / t_total, 3), "unit": "images/sec", "cores": torch.get_num_threads(),
+            "kind": "port", "sample": f"{done} images in batches of {batch}, {size}x{size}, fp32 oracle "
+                                      f"(torch CPU ops + C NMS), {t_total:.1f} s"}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path.  The reference is pure Python
+    on torch ops and cannot travel to the GPU box (no /root/reference there), so this times the oracle
+    port of it (same ATen kernels, same algorithm) with all host threads."""
+    if rank != 0:
+        return None
+    batch = 8
+    per_step_budget = max(2.0, 60.0 / max(1, args.steps + args.warmup))
+    cb = None
+    for _ in range(max(0, min(args.warmup, 1))):
+        cpu_baseline(args.model, args.size, budget_s=0.5, batch=batch)
+    vals = []
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cb = cpu_baseline(args.model, args.size, budget_s=per_step_budget, batch=batch)
+        vals.append(cb["value"])
+    v = float(np.mean(vals))
+    cb["value"] = round(v, 3)
+    return {
+        "impl": "reference", "metric": METRIC.replace("YOLO11n", f"YOLO11{args.model}"), "value": round(v, 3),
+        "unit": "images/sec", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round((time.perf_counter() - t0) * 1e3 / max(1, args.steps), 2), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"YOLO11{args.model} fused fp32 on host CPU, {args.size}x{args.size}, forward + NMS; "
+                               f"each step = a bounded sample (~{per_step_budget:.0f} s) in batches of {batch}"},
+        "cpu_baseline": cb,
+        "e2e": {"value": round(v, 3), "unit": "images/sec", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="n")
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--size", type=int, default=640)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-json", default="")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        out = run_reference(args, rank, world)
+        if out is not None:
+            print(json.dumps(out), flush=True)
+        return
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        torch.distributed.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    out = run_ours(args, rank, world, local_rank)
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -110,6 +110,13 @@ int yb_forward_raw(yb_plan* plan, const void* in_nchw, int in_dtype, float* raw,
  * with the same pointers. enable = 0 returns to plain stream launches. */
 int yb_plan_use_graph(yb_plan* plan, int enable);
 
+/* Per-op device timing for bench.py's roofline: while enabled (and graphs are off), every forward
+ * brackets each op with CUDA events on the caller's stream. yb_plan_profile_read synchronises,
+ * writes the mean milliseconds of each op over the forwards recorded since the last read into
+ * op_ms[0 .. num_launches) and returns how many forwards were averaged. */
+int yb_plan_profile(yb_plan* plan, int enable);
+int yb_plan_profile_read(yb_plan* plan, float* op_ms, int capacity);
+
 /* Debug / validation switch: 0 = tcgen05 tensor-core convolutions (the product path),
  * 1 = scalar direct-convolution CUDA kernel used only to cross-check the tensor-core kernel. */
 int yb_plan_set_conv_impl(yb_plan* plan, int impl);

@@ -59,6 +59,8 @@ SYMBOLS = {
     "yb_forward_raw": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
                                       ctypes.c_void_p]),
     "yb_plan_use_graph": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "yb_plan_profile": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+    "yb_plan_profile_read": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]),
     "yb_plan_set_conv_impl": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
     "yb_plan_debug_read": (ctypes.c_longlong, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p,
                                                ctypes.c_size_t, ctypes.POINTER(ctypes.c_int),

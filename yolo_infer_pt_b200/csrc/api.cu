@@ -50,6 +50,19 @@ static int check_device(int device) {
 
 static int run_ops(yb_plan* p, const void* in, int in_dtype, float* out, int raw, cudaStream_t st) {
   int rc = YB_OK;
+  std::vector<cudaEvent_t>* ev = nullptr;
+  if (p->profiling && !p->use_graph) {
+    if (p->prof_used == (int)p->prof_events.size()) {
+      if (p->prof_events.size() < 256) {
+        std::vector<cudaEvent_t> v(p->ops.size() + 1);
+        for (auto& e : v) YB_CUDA(cudaEventCreate(&e));
+        p->prof_events.push_back(v);
+      }
+    }
+    if (p->prof_used < (int)p->prof_events.size()) ev = &p->prof_events[p->prof_used++];
+  }
+  size_t op_i = 0;
+  if (ev) YB_CUDA(cudaEventRecord((*ev)[0], st));
   for (const Op& op : p->ops) {
     switch (op.kind) {
       case OP_STEM:
@@ -81,6 +94,8 @@ static int run_ops(yb_plan* p, const void* in, int in_dtype, float* out, int raw
       }
     }
     if (rc) return rc;
+    op_i++;
+    if (ev) YB_CUDA(cudaEventRecord((*ev)[op_i], st));
   }
   return YB_OK;
 }
@@ -191,6 +206,8 @@ int yb_plan_create(const yb_arch_desc* arch, int batch, int height, int width, i
 void yb_plan_destroy(yb_plan* plan) {
   if (!plan) return;
   drop_graphs(plan);
+  for (auto& v : plan->prof_events)
+    for (auto& e : v) cudaEventDestroy(e);
   delete plan;
 }
 
@@ -296,6 +313,33 @@ int yb_plan_use_graph(yb_plan* plan, int enable) {
   plan->use_graph = enable ? 1 : 0;
   if (!enable) drop_graphs(plan);
   return YB_OK;
+}
+
+int yb_plan_profile(yb_plan* plan, int enable) {
+  if (!plan) return YB_ERR_ARG;
+  plan->profiling = enable ? 1 : 0;
+  plan->prof_used = 0;
+  return YB_OK;
+}
+
+int yb_plan_profile_read(yb_plan* plan, float* op_ms, int capacity) {
+  if (!plan || !op_ms || capacity < (int)plan->ops.size()) {
+    set_error("yb_plan_profile_read: bad argument");
+    return YB_ERR_ARG;
+  }
+  YB_CUDA(cudaSetDevice(plan->device));
+  YB_CUDA(cudaDeviceSynchronize());
+  int n = plan->prof_used;
+  for (size_t i = 0; i < plan->ops.size(); i++) op_ms[i] = 0.f;
+  for (int f = 0; f < n; f++) {
+    for (size_t i = 0; i < plan->ops.size(); i++) {
+      float ms = 0.f;
+      YB_CUDA(cudaEventElapsedTime(&ms, plan->prof_events[f][i], plan->prof_events[f][i + 1]));
+      op_ms[i] += ms / (float)n;
+    }
+  }
+  plan->prof_used = 0;
+  return n;
 }
 
 int yb_plan_set_conv_impl(yb_plan* plan, int impl) {

@@ -124,6 +124,15 @@ class Engine:
         self.graph = bool(enable)
         _lib.check(self.L.yb_plan_use_graph(self.plan, int(self.graph)), "yb_plan_use_graph")
 
+    def profile(self, enable=True):
+        _lib.check(self.L.yb_plan_profile(self.plan, int(enable)), "yb_plan_profile")
+
+    def profile_read(self):
+        """(mean ms per op over the forwards recorded since the last read, number of forwards)."""
+        ms = np.zeros(self.num_launches, dtype=np.float32)
+        n = _lib.check(self.L.yb_plan_profile_read(self.plan, ms.ctypes.data, len(ms)), "yb_plan_profile_read")
+        return ms, n
+
     def set_conv_impl(self, impl):
         _lib.check(self.L.yb_plan_set_conv_impl(self.plan, int(impl)), "yb_plan_set_conv_impl")
 

@@ -74,7 +74,7 @@ def synth_state_dict(model, seed=0, recipe="calibrated", calibrated=True):
             if key.startswith("head.box."):
                 val = np.full(shape, 1.0)
             elif key.startswith("head.cls."):
-                val = (np.full(shape, -8.0) + rng.normal(0.0, 1.0, shape)) if survey else \
+                val = (np.full(shape, -9.0) + rng.normal(0.0, 1.0, shape)) if survey else \
                     (np.full(shape, CLS_BIAS) + rng.normal(0.0, 0.5, shape))
             else:
                 val = rng.normal(0.0, 0.1, shape)
