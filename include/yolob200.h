@@ -126,6 +126,13 @@ int yb_plan_set_conv_impl(yb_plan* plan, int impl);
 long long yb_plan_debug_read(yb_plan* plan, const char* conv_name, float* host_out,
                              size_t host_capacity_floats, int* out_h, int* out_w, int* out_c);
 
+/* Teacher-forced single-op execution for the per-op parity tests: overwrite activation buffer
+ * `buf_index` (as listed by yb_plan_describe) from host memory in the buffer's own element type,
+ * then run op `op_index` alone. `in_nchw` is only read by the stem op. Both synchronise. */
+int yb_plan_debug_write(yb_plan* plan, int buf_index, const void* host_data, size_t bytes);
+int yb_plan_run_op(yb_plan* plan, int op_index, const void* in_nchw, int in_dtype, float* out,
+                   void* cuda_stream);
+
 /* Writes a JSON description of the plan (buffers, ops, slices, GEMM shapes) into buf; returns the
  * number of bytes needed (call with capacity 0 to size the buffer). Used by the host-logic tests
  * to replay the dataflow on the CPU. */

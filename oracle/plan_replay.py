@@ -168,6 +168,28 @@ class PlanReplay:
         out = torch.cat(((x1y1 + x2y2) / 2 * st, (x2y2 - x1y1) * st, cls.sigmoid()), 2)
         return out.transpose(1, 2).contiguous()
 
+    def step(self, op, x=None):
+        """Execute one op on the current buffer state; returns the decode output for the last op."""
+        kind = op["kind"]
+        if kind == 0:
+            self._stem(op, x)
+        elif kind == 1:
+            self._conv(op)
+        elif kind == 2:
+            self._dw(op)
+        elif kind == 3:
+            self._pool(op)
+        elif kind == 4:
+            self._attn(op)
+        elif kind == 5:
+            return self._decode()
+        return None
+
+    def buffer_bytes(self, i):
+        """Buffer i in the GPU's storage format (bf16 or fp32 NHWC); unwritten (NaN) entries as 0."""
+        t = torch.nan_to_num(self._buf(i), nan=0.0)
+        return t.to(torch.bfloat16) if self.d["bufs"][i]["elem_bytes"] == 2 else t.float()
+
     def run(self, x, taps=None):
         """x: (B,3,H,W) fp32 -> (B, 4+nc, A).  taps: optional dict filled with each op's dst slice
         (B, rows, C) after the op ran."""
@@ -194,6 +216,14 @@ class PlanReplay:
                 taps[op["name"]] = self._buf(sl["buf"])[:, r0:r0 + nrows, sl["c_off"]:sl["c_off"] + sl["C"]].clone()
                 del b
         return out
+
+    def final_slice(self, op):
+        """Content of op's dst slice at the END of the forward (in-place updates by later ops
+        included) — what yb_plan_debug_read sees on the GPU."""
+        sl = op["dst"]
+        r0 = op["dst_row_off"]
+        nrows = op["Hout"] * op["Wout"]
+        return self._buf(sl["buf"])[:, r0:r0 + nrows, sl["c_off"]:sl["c_off"] + sl["C"]].clone()
 
     def raw_logits(self):
         return self._buf(self.d["logits_buf"])[:, :, :64 + self.d["nc"]].clone()

@@ -40,10 +40,14 @@ def _taps_from_engine(eng, desc):
     return out
 
 
-@pytest.mark.parametrize("size,hw", [("n", 64), ("n", 160), ("x", 64)])
+@pytest.mark.parametrize("size,hw", [("n", 64)])
 def test_layers_tensor_core_vs_direct_vs_cpu_replay(size, hw, monkeypatch):
-    """Layer-level parity on the calibrated recipe (every layer has unit-scale, spatially varying
-    activations): tcgen05 kernel == scalar cross-check kernel == bf16-faithful CPU replay of the plan."""
+    """Whole-forward layer parity on the calibrated recipe (every layer has unit-scale, spatially
+    varying activations): tcgen05 kernel == scalar cross-check kernel == bf16-faithful CPU replay.
+    Only the shallow n model at 64x64 is usable this way: a unit-gain random network is chaotic, and
+    on deeper ones two *correct* bf16 implementations drift tens of % apart by the head (measured:
+    x@64 rel-rms 0.45 between the tcgen05 and the scalar kernel).  test_every_op_teacher_forced is
+    the strict per-op check for every size."""
     monkeypatch.setenv("YB_NO_REUSE", "1")
     model = _model(size, "calibrated")
     dev = torch.device("cuda:0")
@@ -51,9 +55,11 @@ def test_layers_tensor_core_vs_direct_vs_cpu_replay(size, hw, monkeypatch):
     eng = Engine(*model._arch, 2, hw, hw, dev)
     blob = eng.pack_from_model(model)
     desc = eng.describe()
-    cpu_taps = {}
     with torch.no_grad():
-        PlanReplay(desc, eng.convs, blob, emulate_bf16=True).run(x, taps=cpu_taps)
+        rep = PlanReplay(desc, eng.convs, blob, emulate_bf16=True)
+        rep.run(x)
+    # buffers are compared in their END-of-forward state (PSA updates its y slice in place)
+    cpu_taps = {op["name"]: rep.final_slice(op) for op in desc["ops"] if op["kind"] in (1, 2, 4)}
     xg = x.to(dev)
     eng.set_conv_impl(1)
     y_direct = eng.forward(xg).clone()
@@ -62,22 +68,23 @@ def test_layers_tensor_core_vs_direct_vs_cpu_replay(size, hw, monkeypatch):
     y_tc = eng.forward(xg).clone()
     tc = _taps_from_engine(eng, desc)
     torch.cuda.synchronize()
+
+    def rel_rms(a, b):
+        return ((a - b).pow(2).mean().sqrt() / b.pow(2).mean().sqrt().clamp_min(1e-6)).item()
+
     worst = []
     for name, ref in cpu_taps.items():
-        if name not in tc:
-            continue
-        scale = max(1.0, ref.abs().max().item())
-        e_tc = (tc[name] - ref).abs().max().item() / scale
-        e_dir = (direct[name] - ref).abs().max().item() / scale
-        e_x = (tc[name] - direct[name]).abs().max().item() / scale
+        e_tc, e_dir, e_x = rel_rms(tc[name], ref), rel_rms(direct[name], ref), rel_rms(tc[name], direct[name])
         worst.append((max(e_tc, e_dir, e_x), name, e_tc, e_dir, e_x))
     worst.sort(reverse=True)
-    report = "\n".join(f"{n:42s} tc-cpu {a:.4f} direct-cpu {b:.4f} tc-direct {c:.4f}" for _, n, a, b, c in worst[:12])
+    report = "\n".join(f"{n:42s} rel-rms: tc-cpu {a:.4f} direct-cpu {b:.4f} tc-direct {c:.4f}"
+                       for _, n, a, b, c in worst[:8])
     print(report)
-    # bf16 stores differ by at most a few ulp (0.4 % each) between summation orders; errors compound
-    # slowly with depth, a real bug shows up as O(1)
-    assert worst[0][0] < 0.08, report
-    assert (y_tc - y_direct).abs().max().item() < 0.1 * max(1.0, y_direct.abs().max().item())
+    # The three implementations sum in different orders, so bf16 stores flip by an ulp (0.4 %) here
+    # and there and the unit-gain random network amplifies that with depth (a few % rel-rms at the
+    # head); a real bug (wrong tap, slice, swizzle, K order) is O(100 %) at the layer where it happens.
+    assert worst[0][0] < 0.06, report
+    assert rel_rms(y_tc, y_direct) < 0.05
 
 
 @pytest.mark.parametrize("size,hw,batch", [("n", 64, 2), ("t", 64, 1), ("s", 64, 1), ("m", 64, 1), ("l", 64, 1),
@@ -124,8 +131,8 @@ def test_forward_640_matches_golden_subsample(golden_dir):
 
 
 def test_calibrated_recipe_round_off_report():
-    """Round-off stress: unit-gain random weights amplify bf16 rounding ~10x more than the survey
-    recipe.  Asserted against the bf16-faithful CPU replay (tight) and reported against fp32."""
+    """Round-off stress, report only: unit-gain random weights make the network chaotic, so any two
+    bf16 evaluation orders diverge (the CPU replay differs from the GPU as much as from fp32)."""
     model = _model("n", "calibrated")
     x = synth.synth_images(1, 320, 320, seed=2)
     eng = Engine(*model._arch, 1, 320, 320, "cuda:0")
@@ -137,8 +144,7 @@ def test_calibrated_recipe_round_off_report():
     print(f"calibrated n@320 vs fp32 oracle: box {(y[:, :4] - ref[:, :4]).abs().max():.3f} px, "
           f"score {(y[:, 4:] - ref[:, 4:]).abs().max():.4f}; vs bf16 CPU replay: "
           f"box {(y[:, :4] - rep[:, :4]).abs().max():.3f} px, score {(y[:, 4:] - rep[:, 4:]).abs().max():.4f}")
-    assert (y[:, 4:] - rep[:, 4:]).abs().max() < 0.1
-    assert (y[:, :4] - rep[:, :4]).abs().median() < 1.0
+    assert torch.isfinite(y).all()
 
 
 def test_raw_logits_and_input_dtypes():
@@ -184,3 +190,49 @@ def test_batch_independence():
     y3 = e3.forward(x).clone()
     for i in range(3):
         assert torch.equal(e1.forward(x[i:i + 1].contiguous())[0], y3[i])
+
+
+@pytest.mark.parametrize("size,hw", [("n", 64), ("n", 160), ("t", 64), ("x", 64), ("s", 96)])
+def test_every_op_teacher_forced(size, hw, monkeypatch):
+    """Per-op parity with identical inputs: before each op the GPU buffers are overwritten with the CPU
+    replay's (bf16-exact) state, the op runs alone through both conv implementations, and its output
+    slice is compared with the replay's.  No error can accumulate, so the tolerance is a couple of
+    bf16 ulps: a wrong tap order, slice offset, swizzle, K layout, N tile or residual shows at once."""
+    monkeypatch.setenv("YB_NO_REUSE", "1")
+    model = _model(size, "calibrated")
+    x = synth.synth_images(2, hw, hw, seed=1)
+    eng = Engine(*model._arch, 2, hw, hw, "cuda:0")
+    blob = eng.pack_from_model(model)
+    desc = eng.describe()
+    rep = PlanReplay(desc, eng.convs, blob, emulate_bf16=True)
+    xg = x.to("cuda:0")
+    report, worst = [], 0.0
+    with torch.no_grad():
+        for i, op in enumerate(desc["ops"]):
+            if op["kind"] == 5:
+                break
+            touched = {s["buf"] for s in op["src"]} | {op["dst"]["buf"]} | ({op["res"]["buf"]} if op["has_res"] else set())
+            before = {b: rep.buffer_bytes(b) for b in touched if b >= 0}
+            rep.step(op, x)
+            want = rep.final_slice(op) if op["kind"] != 3 else None
+            if op["kind"] == 3:
+                sl = op["dst"]
+                want = rep._buf(sl["buf"])[:, :, sl["c_off"]:sl["c_off"] + sl["C"]].clone()
+            for impl in ((0, 1) if op["kind"] == 1 else (0,)):
+                for b, t in before.items():
+                    eng.debug_write(b, t)
+                eng.set_conv_impl(impl)
+                eng.run_op(i, xg)
+                got = eng.debug_read(op["name"])
+                if op["kind"] != 3:
+                    r0 = op["dst_row_off"]
+                    got = got[:, r0:r0 + op["Hout"] * op["Wout"]]
+                scale = max(1.0, want.abs().max().item())
+                err = (got - want).abs().max().item() / scale
+                worst = max(worst, err)
+                if err > 0.01:
+                    report.append(f"{op['name']} impl={impl} k{op['k']} s{op['stride']} tma{op['a_tma']} "
+                                  f"K{op['K_pad']} N{op['N_pad']}/BN{op['BN']}: max err {err:.4f} of max |x|")
+            eng.set_conv_impl(0)
+    print(f"{size}@{hw}: worst per-op error {worst:.5f} of the layer's max |activation|")
+    assert not report, "\n".join(report)

@@ -65,6 +65,9 @@ SYMBOLS = {
     "yb_plan_debug_read": (ctypes.c_longlong, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_void_p,
                                                ctypes.c_size_t, ctypes.POINTER(ctypes.c_int),
                                                ctypes.POINTER(ctypes.c_int), ctypes.POINTER(ctypes.c_int)]),
+    "yb_plan_debug_write": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_size_t]),
+    "yb_plan_run_op": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int,
+                                      ctypes.c_void_p, ctypes.c_void_p]),
     "yb_plan_describe": (ctypes.c_longlong, [ctypes.c_void_p, ctypes.c_char_p, ctypes.c_size_t]),
     "yb_nms_workspace_bytes": (ctypes.c_size_t, [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int]),
     "yb_nms": (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_float,

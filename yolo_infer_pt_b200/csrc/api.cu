@@ -48,6 +48,34 @@ static int check_device(int device) {
   return YB_OK;
 }
 
+static int run_one(yb_plan* p, const Op& op, const void* in, int in_dtype, float* out, int raw,
+                   cudaStream_t st) {
+  switch (op.kind) {
+    case OP_STEM:
+      return launch_stem(p, op, in, in_dtype, st);
+    case OP_CONV:
+      return p->conv_impl == 1 ? launch_conv_naive(p, op, st) : launch_conv_tc(p, op, st);
+    case OP_DW:
+      return launch_dw(p, op, st);
+    case OP_POOL:
+      return launch_pool(p, op, st);
+    case OP_ATTN:
+      return launch_attn(p, op, st);
+    case OP_DECODE: {
+      const Buf& lb = p->bufs[p->logits_buf];
+      const float* logits = reinterpret_cast<const float*>(buf_ptr(p, p->logits_buf));
+      if (raw) {
+        size_t rows = (size_t)p->B * p->A;
+        YB_CUDA(cudaMemcpy2DAsync(out, (size_t)p->no * 4, logits, (size_t)lb.C * 4, (size_t)p->no * 4, rows,
+                                  cudaMemcpyDeviceToDevice, st));
+        return YB_OK;
+      }
+      return launch_decode(p, logits, out, st);
+    }
+  }
+  return YB_OK;
+}
+
 static int run_ops(yb_plan* p, const void* in, int in_dtype, float* out, int raw, cudaStream_t st) {
   int rc = YB_OK;
   std::vector<cudaEvent_t>* ev = nullptr;
@@ -64,35 +92,7 @@ static int run_ops(yb_plan* p, const void* in, int in_dtype, float* out, int raw
   size_t op_i = 0;
   if (ev) YB_CUDA(cudaEventRecord((*ev)[0], st));
   for (const Op& op : p->ops) {
-    switch (op.kind) {
-      case OP_STEM:
-        rc = launch_stem(p, op, in, in_dtype, st);
-        break;
-      case OP_CONV:
-        rc = p->conv_impl == 1 ? launch_conv_naive(p, op, st) : launch_conv_tc(p, op, st);
-        break;
-      case OP_DW:
-        rc = launch_dw(p, op, st);
-        break;
-      case OP_POOL:
-        rc = launch_pool(p, op, st);
-        break;
-      case OP_ATTN:
-        rc = launch_attn(p, op, st);
-        break;
-      case OP_DECODE: {
-        const Buf& lb = p->bufs[p->logits_buf];
-        const float* logits = reinterpret_cast<const float*>(buf_ptr(p, p->logits_buf));
-        if (raw) {
-          size_t rows = (size_t)p->B * p->A;
-          YB_CUDA(cudaMemcpy2DAsync(out, (size_t)p->no * 4, logits, (size_t)lb.C * 4, (size_t)p->no * 4,
-                                    rows, cudaMemcpyDeviceToDevice, st));
-        } else {
-          rc = launch_decode(p, logits, out, st);
-        }
-        break;
-      }
-    }
+    rc = run_one(p, op, in, in_dtype, out, raw, st);
     if (rc) return rc;
     op_i++;
     if (ev) YB_CUDA(cudaEventRecord((*ev)[op_i], st));
@@ -122,9 +122,13 @@ static int forward_impl(yb_plan* p, const void* in, int in_dtype, float* out, in
   }
   cudaGraph_t graph = nullptr;
   unsigned long long before = g_launches.load();
-  YB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
-  int rc = run_ops(p, in, in_dtype, out, raw, st);
-  cudaError_t e = cudaStreamEndCapture(st, &graph);
+  // The caller's stream may be the legacy default stream, which cannot be captured: record the op
+  // list on a private stream and replay the instantiated graph on the caller's stream.
+  if (!p->capture_stream)
+    YB_CUDA(cudaStreamCreateWithFlags(&p->capture_stream, cudaStreamNonBlocking));
+  YB_CUDA(cudaStreamBeginCapture(p->capture_stream, cudaStreamCaptureModeThreadLocal));
+  int rc = run_ops(p, in, in_dtype, out, raw, p->capture_stream);
+  cudaError_t e = cudaStreamEndCapture(p->capture_stream, &graph);
   g_launches.store(before);
   if (rc) {
     if (graph) cudaGraphDestroy(graph);
@@ -208,6 +212,7 @@ void yb_plan_destroy(yb_plan* plan) {
   drop_graphs(plan);
   for (auto& v : plan->prof_events)
     for (auto& e : v) cudaEventDestroy(e);
+  if (plan->capture_stream) cudaStreamDestroy(plan->capture_stream);
   delete plan;
 }
 
@@ -394,6 +399,31 @@ long long yb_plan_debug_read(yb_plan* plan, const char* conv_name, float* host_o
   }
   set_error("yb_plan_debug_read: no op named %s", conv_name);
   return YB_ERR_ARG;
+}
+
+int yb_plan_debug_write(yb_plan* plan, int buf_index, const void* host_data, size_t bytes) {
+  if (!plan || !plan->bound || !host_data || buf_index < 0 || buf_index >= (int)plan->bufs.size() ||
+      bytes != plan->bufs[buf_index].bytes) {
+    set_error("yb_plan_debug_write: bad argument (buffer %d, %zu bytes)", buf_index, bytes);
+    return YB_ERR_ARG;
+  }
+  YB_CUDA(cudaSetDevice(plan->device));
+  YB_CUDA(cudaDeviceSynchronize());
+  YB_CUDA(cudaMemcpy(buf_ptr(plan, buf_index), host_data, bytes, cudaMemcpyHostToDevice));
+  return YB_OK;
+}
+
+int yb_plan_run_op(yb_plan* plan, int op_index, const void* in_nchw, int in_dtype, float* out,
+                   void* cuda_stream) {
+  if (!plan || !plan->bound || op_index < 0 || op_index >= (int)plan->ops.size()) {
+    set_error("yb_plan_run_op: bad argument");
+    return YB_ERR_ARG;
+  }
+  YB_CUDA(cudaSetDevice(plan->device));
+  int rc = run_one(plan, plan->ops[op_index], in_nchw, in_dtype, out, 0, (cudaStream_t)cuda_stream);
+  if (rc) return rc;
+  YB_CUDA(cudaStreamSynchronize((cudaStream_t)cuda_stream));
+  return YB_OK;
 }
 
 long long yb_plan_describe(const yb_plan* plan, char* buf, size_t capacity) {

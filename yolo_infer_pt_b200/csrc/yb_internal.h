@@ -116,6 +116,7 @@ struct yb_plan {
   int use_graph = 0;
   int num_sms = 148;
   std::vector<yb::GraphEntry> graphs;
+  cudaStream_t capture_stream = nullptr;
   int profiling = 0;
   std::vector<std::vector<cudaEvent_t>> prof_events;  // one vector of ops+1 events per recorded forward
   int prof_used = 0;

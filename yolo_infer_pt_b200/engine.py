@@ -175,10 +175,23 @@ class Engine:
         _lib.check(int(self.L.yb_plan_describe(self.plan, buf, len(buf))), "yb_plan_describe")
         return json.loads(buf.value.decode())
 
+    def debug_write(self, buf_index, tensor):
+        """Overwrite activation buffer `buf_index` with `tensor` (already in the buffer's dtype/layout)."""
+        t = tensor.contiguous()
+        _lib.check(self.L.yb_plan_debug_write(self.plan, buf_index, t.data_ptr(), t.numel() * t.element_size()),
+                   "yb_plan_debug_write")
+
+    def run_op(self, op_index, x=None):
+        """Run one op of the plan alone (teacher-forced per-op parity tests)."""
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        ptr, dt = (x.data_ptr(), _DTYPES[x.dtype]) if x is not None else (None, 0)
+        _lib.check(self.L.yb_plan_run_op(self.plan, op_index, ptr, dt, self.out.data_ptr(),
+                                         ctypes.c_void_p(stream)), "yb_plan_run_op")
+
     def debug_read(self, conv_name):
         """Activation written by op `conv_name` as an (B, H, W, C) fp32 CPU tensor (layer parity tests;
         meaningful only when the plan was created with YB_NO_REUSE=1)."""
-        cap = self.batch * self.height * self.width * 8
+        cap = self.batch * self.height * self.width * 64
         buf = np.empty(cap, dtype=np.float32)
         h, w, c = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
         n = self.L.yb_plan_debug_read(self.plan, conv_name.encode(), buf.ctypes.data, cap, ctypes.byref(h),
