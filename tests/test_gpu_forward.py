@@ -160,10 +160,30 @@ def test_raw_logits_and_input_dtypes():
         yu8 = model((x * 255).round().to(torch.uint8).to("cuda:0")).clone()
     ref_rows = yolo_oracle.raw_to_rows(maps)
     assert raw.shape == ref_rows.shape
+    # the decode fused into the head tails' epilogues == the oracle's decode of the GPU's own logits
+    dec = yolo_oracle.decode([raw[:, o:o + h * h].transpose(1, 2).reshape(2, 144, h, h)
+                              for o, h in ((0, 12), (144, 6), (180, 3))], 80)
+    assert (dec[:, :4] - y32.cpu()[:, :4]).abs().max() < 2e-2
+    assert (dec[:, 4:] - y32.cpu()[:, 4:]).abs().max() < 1e-5
     assert (raw - ref_rows).abs().max() < 0.05 * max(1.0, ref_rows.abs().max().item())
     assert (y16[:, :4] - y32[:, :4]).abs().max() < 1.0 and (ybf[:, :4] - y32[:, :4]).abs().max() < 2.0
     assert (yu8[:, :4] - y32[:, :4]).abs().max() < 2.0
     assert (y16[:, 4:] - y32[:, 4:]).abs().max() < 1e-2
+
+
+def test_fused_decode_equals_separate_decode_kernel(monkeypatch):
+    model = _model("n", "survey")
+    x = synth.synth_images(2, 128, 128, seed=7).to("cuda:0")
+    fused = Engine(*model._arch, 2, 128, 128, "cuda:0")
+    fused.pack_from_model(model)
+    a = fused.forward(x).clone()
+    monkeypatch.setenv("YB_NO_FUSE_DECODE", "1")
+    plain = Engine(*model._arch, 2, 128, 128, "cuda:0")
+    plain.pack_from_model(model)
+    b = plain.forward(x).clone()
+    assert plain.num_launches == fused.num_launches + 1
+    assert (a[:, :4] - b[:, :4]).abs().max() < 2e-2      # __expf vs expf in the DFL softmax
+    assert (a[:, 4:] - b[:, 4:]).abs().max() < 1e-5
 
 
 def test_cuda_graph_replay_equals_stream_launch():

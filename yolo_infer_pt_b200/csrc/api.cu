@@ -53,8 +53,11 @@ static int run_one(yb_plan* p, const Op& op, const void* in, int in_dtype, float
   switch (op.kind) {
     case OP_STEM:
       return launch_stem(p, op, in, in_dtype, st);
-    case OP_CONV:
-      return p->conv_impl == 1 ? launch_conv_naive(p, op, st) : launch_conv_tc(p, op, st);
+    case OP_CONV: {
+      if (p->conv_impl == 1) return launch_conv_naive(p, op, st);
+      bool fuse = p->fuse_decode && !raw && op.head_part;
+      return launch_conv_tc(p, op, st, fuse ? out : nullptr);
+    }
     case OP_DW:
       return launch_dw(p, op, st);
     case OP_POOL:
@@ -70,6 +73,7 @@ static int run_one(yb_plan* p, const Op& op, const void* in, int in_dtype, float
                                   cudaMemcpyDeviceToDevice, st));
         return YB_OK;
       }
+      if (p->fuse_decode && p->conv_impl == 0) return YB_OK;  // decoded in the head tails' epilogues
       return launch_decode(p, logits, out, st);
     }
   }
@@ -221,7 +225,10 @@ size_t yb_plan_weight_bytes(const yb_plan* plan) { return plan ? plan->weight_by
 int yb_plan_num_anchors(const yb_plan* plan) { return plan ? plan->A : 0; }
 int yb_plan_num_outputs(const yb_plan* plan) { return plan ? 4 + plan->nc : 0; }
 int yb_plan_num_convs(const yb_plan* plan) { return plan ? (int)plan->convs.size() : 0; }
-int yb_plan_num_launches(const yb_plan* plan) { return plan ? (int)plan->ops.size() : 0; }
+int yb_plan_num_launches(const yb_plan* plan) {
+  if (!plan) return 0;
+  return (int)plan->ops.size() - (plan->fuse_decode && plan->conv_impl == 0 ? 1 : 0);
+}
 
 int yb_plan_conv_info(const yb_plan* plan, int index, yb_conv_info* out) {
   if (!plan || !out || index < 0 || index >= (int)plan->convs.size()) {
@@ -420,7 +427,10 @@ int yb_plan_run_op(yb_plan* plan, int op_index, const void* in_nchw, int in_dtyp
     return YB_ERR_ARG;
   }
   YB_CUDA(cudaSetDevice(plan->device));
+  int saved = plan->fuse_decode;
+  plan->fuse_decode = 0;  // head tails write their logits slice, so the test can read it back
   int rc = run_one(plan, plan->ops[op_index], in_nchw, in_dtype, out, 0, (cudaStream_t)cuda_stream);
+  plan->fuse_decode = saved;
   if (rc) return rc;
   YB_CUDA(cudaStreamSynchronize((cudaStream_t)cuda_stream));
   return YB_OK;

@@ -17,11 +17,19 @@
 //   Epilogue: tcgen05.ld -> +bias -> SiLU -> +residual -> bf16 (or fp32 head logits) stored
 //       straight into the channel slice of the consumer's buffer.
 //
-// Warp roles (192 threads): warps 0-3 im2col producers, then epilogue (TMEM lane = output row);
-// warp 4 TMEM allocator + MMA issuer; warp 5 TMA producer.
+// The kernel is persistent: grid = SMs x resident CTAs, each CTA walks tiles t = blockIdx.x + i*grid.
+// Warp roles (320 threads): warps 0-3 epilogue (TMEM lane = output row), warps 4-7 im2col
+// producers, warp 8 TMEM allocator + MMA issuer, warp 9 TMA producer.  Two accumulator stages in
+// TMEM (2 x BN columns) let the epilogue of tile i overlap the main loop of tile i+1; the smem
+// stage ring runs continuously across tiles.
+// Epilogue modes: bf16 NHWC slice (+residual) | fp32 head logits | fused DFL box decode
+// (nets/nn.py:222-225,265-268 + make_anchors utils/util.py:85-96) | fused class sigmoid (nn.py:270),
+// the last two writing the final (B, 4+nc, A) fp32 tensor directly.
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+
+#include <algorithm>
 
 #include "yb_internal.h"
 
@@ -54,6 +62,11 @@ struct ConvParams {
   int res_ld;
   int act;
   int BN, stages, a_tma, tmem_cols;
+  int n_tiles, total_tiles;
+  // fused head decode (out_mode 2 / 3): dst is the (B, 4+nc, A) fp32 output tensor
+  int out_mode;       // 0 bf16 slice, 1 fp32 logits, 2 DFL box decode, 3 class sigmoid
+  int A_total, nc;
+  float lvl_stride;
   // naive path only
   const __nv_bfloat16* w;
   int K_pad, cout;
@@ -146,7 +159,13 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 // ------------------------------------------------------------------------------------------
 // The kernel
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(192, 1)
+static constexpr int NUM_THREADS = 320;
+static constexpr int EPI_WARPS = 4;      // warps 0-3
+static constexpr int PROD_WARP0 = 4;     // warps 4-7
+static constexpr int MMA_WARP = 8;
+static constexpr int TMA_WARP = 9;
+
+__global__ void __launch_bounds__(NUM_THREADS, 2)
     conv_gemm_tcgen05_kernel(const ConvParams P, const __grid_constant__ CUtensorMap tmap_b,
                              const __grid_constant__ CUtensorMap tmap_a0,
                              const __grid_constant__ CUtensorMap tmap_a1,
@@ -163,19 +182,18 @@ __global__ void __launch_bounds__(192, 1)
   const uint32_t a_base = base;
   const uint32_t b_base = base + (uint32_t)S * A_STAGE_BYTES;
   uint8_t* tail = smem + (size_t)S * (A_STAGE_BYTES + b_stage_bytes);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);  // full[0..S), empty[0..S), tmem_full
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + (2 * MAX_STAGES + 1) * 8);
-  float* bias_s = reinterpret_cast<float*>(tail + (2 * MAX_STAGES + 1) * 8 + 16);
+  // barriers: full[MAX_STAGES], empty[MAX_STAGES], tmem_full[2], tmem_empty[2]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + (2 * MAX_STAGES + 4) * 8);
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (MAX_STAGES + s); };
-  const uint32_t tmem_full_bar = bar0 + 8u * (2 * MAX_STAGES);
+  auto tmem_full_bar = [&](int a) { return bar0 + 8u * (2 * MAX_STAGES + a); };
+  auto tmem_empty_bar = [&](int a) { return bar0 + 8u * (2 * MAX_STAGES + 2 + a); };
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
   const int lane = tid & 31;
-  const int m0 = blockIdx.x * BM;
-  const int n0 = blockIdx.y * BN;
   const int num_kb = P.num_kb;
 
   if (tid == 0) {
@@ -183,12 +201,14 @@ __global__ void __launch_bounds__(192, 1)
       mbar_init(full_bar(s), P.a_tma ? 1u : 129u);
       mbar_init(empty_bar(s), 1u);
     }
-    mbar_init(tmem_full_bar, 1u);
+    for (int a = 0; a < 2; a++) {
+      mbar_init(tmem_full_bar(a), 1u);
+      mbar_init(tmem_empty_bar(a), 128u);
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
-  for (int i = tid; i < BN; i += blockDim.x) bias_s[i] = P.bias[n0 + i];
-  if (warp == 4) {
+  if (warp == MMA_WARP) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(
                      smem_u32(tmem_slot)),
                  "r"((uint32_t)P.tmem_cols)
@@ -200,178 +220,239 @@ __global__ void __launch_bounds__(192, 1)
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < 4) {
-    // ============================ im2col producer (skipped when A comes by TMA) ============
-    if (!P.a_tma) {
-      const int g = tid & 7;       // 16-byte granule (8 channels) inside the 128-byte K row
-      const int rbase = tid >> 3;  // rows rbase + 16*i
-      const uint32_t sw_off = (uint32_t)((g ^ (rbase & 7)) << 4);
-      int row_n[8], row_y[8], row_x[8];
+  if (warp < EPI_WARPS) {
+    // ============================ epilogue =================================================
+    int ti = 0;
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ti++) {
+      const int m0 = (tile / P.n_tiles) * BM;
+      const int n0 = (tile % P.n_tiles) * BN;
+      const int acc = ti & 1;
+      mbar_wait(tmem_full_bar(acc), (uint32_t)(ti >> 1) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const int m = m0 + tid;
+      const bool row_ok = m < P.M;
+      int n_img = 0, r = 0;
+      if (row_ok) {
+        n_img = m / P.hw_out;
+        r = m - n_img * P.hw_out;
+      }
+      const size_t drow = (size_t)n_img * P.dst_rows_per_img + P.dst_row_off + r;
+      const __nv_bfloat16* resp = P.res ? P.res + (size_t)m * P.res_ld : nullptr;
+      const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN);
+      float dist[4];
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld16(t_row + (uint32_t)c0, v);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        const int nb = n0 + c0;
+        if (!row_ok || nb >= P.cout_store) continue;
+        float f[16];
 #pragma unroll
-      for (int i = 0; i < 8; i++) {
-        int m = m0 + rbase + 16 * i;
-        if (m < P.M) {
-          int n = m / P.hw_out;
-          int r = m - n * P.hw_out;
-          int oy = r / P.Wout;
-          row_n[i] = n;
-          row_y[i] = oy * P.stride - P.pad;
-          row_x[i] = (r - oy * P.Wout) * P.stride - P.pad;
+        for (int j = 0; j < 16; j++) {
+          float x = __uint_as_float(v[j]) + __ldg(P.bias + nb + j);
+          f[j] = P.act ? silu_f(x) : x;
+        }
+        if (P.out_mode == 0) {
+          __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(P.dst) + drow * (size_t)P.dst_ld + nb;
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+            if (nb + 8 * h < P.cout_store) {
+              if (resp) {
+                uint4 rv = __ldg(reinterpret_cast<const uint4*>(resp + nb + 8 * h));
+                const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                  float2 rf = __bfloat1622float2(r2[j]);
+                  f[8 * h + 2 * j] += rf.x;
+                  f[8 * h + 2 * j + 1] += rf.y;
+                }
+              }
+              uint4 o;
+              o.x = pack_bf16(f[8 * h + 0], f[8 * h + 1]);
+              o.y = pack_bf16(f[8 * h + 2], f[8 * h + 3]);
+              o.z = pack_bf16(f[8 * h + 4], f[8 * h + 5]);
+              o.w = pack_bf16(f[8 * h + 6], f[8 * h + 7]);
+              *reinterpret_cast<uint4*>(dp + 8 * h) = o;
+            }
+          }
+        } else if (P.out_mode == 1) {
+          float* dp = reinterpret_cast<float*>(P.dst) + drow * (size_t)P.dst_ld + nb;
+#pragma unroll
+          for (int q = 0; q < 4; q++) {
+            if (nb + 4 * q < P.cout_store)
+              *reinterpret_cast<float4*>(dp + 4 * q) =
+                  make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
+          }
+        } else if (P.out_mode == 2) {
+          // one 16-column chunk = the 16 DFL bins of one box side: softmax expectation
+          float mx = f[0];
+#pragma unroll
+          for (int j = 1; j < 16; j++) mx = fmaxf(mx, f[j]);
+          float se = 0.f, sw = 0.f;
+#pragma unroll
+          for (int j = 0; j < 16; j++) {
+            float e = __expf(f[j] - mx);
+            se += e;
+            sw = fmaf((float)j, e, sw);
+          }
+          dist[(c0 >> 4) & 3] = sw / se;
         } else {
-          row_n[i] = -1;
-          row_y[i] = 0;
-          row_x[i] = 0;
-        }
-      }
-      int tap = 0;
-      int rem = g * 8;  // position inside the tap's [seg0 | seg1 | ...] channel run
-      while (rem >= P.per_tap) {
-        rem -= P.per_tap;
-        tap++;
-      }
-      for (int kb = 0; kb < num_kb; kb++) {
-        const int s = kb % S;
-        const uint32_t ph = (uint32_t)(kb / S) & 1u;
-        uint4 v[8];
-        const bool k_ok = (kb * BK + g * 8) < P.K;
-        int seg = 0, c = rem;
-        while (seg + 1 < P.nseg && c >= P.src_cp[seg]) {
-          c -= P.src_cp[seg];
-          seg++;
-        }
-        const int up = P.src_up[seg];
-        const int Hs = P.Hin >> up, Ws = P.Win >> up;
-        const int ld = P.src_ld[seg];
-        const __nv_bfloat16* sp = P.src[seg] + c;
-        int dy = 0, dx = 0;
-        if (P.ksize == 3) {
-          dy = tap / 3;
-          dx = tap - dy * 3;
-        }
+          // class scores: plane-major fp32 stores, one anchor per lane -> 128 B per warp store
+          float* ob = reinterpret_cast<float*>(P.dst) + ((size_t)n_img * (4 + P.nc) + 4 + nb) * P.A_total +
+                      P.dst_row_off + r;
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-          int iy = row_y[i] + dy, ix = row_x[i] + dx;
-          bool ok = k_ok && row_n[i] >= 0 && (unsigned)iy < (unsigned)P.Hin &&
-                    (unsigned)ix < (unsigned)P.Win;
-          v[i] = make_uint4(0u, 0u, 0u, 0u);
-          if (ok) {
-            size_t off = ((size_t)(row_n[i] * Hs + (iy >> up)) * Ws + (ix >> up)) * (size_t)ld;
-            v[i] = __ldg(reinterpret_cast<const uint4*>(sp + off));
+          for (int j = 0; j < 16; j++) {
+            if (nb + j < P.nc) ob[(size_t)j * P.A_total] = 1.f / (1.f + __expf(-f[j]));
           }
         }
-        mbar_wait(empty_bar(s), ph ^ 1u);
-        const uint32_t a_s = a_base + (uint32_t)s * A_STAGE_BYTES + sw_off;
+      }
+      if (P.out_mode == 2 && row_ok) {
+        const int y = r / P.Wout, x = r - y * P.Wout;
+        const float ax = (float)x + 0.5f, ay = (float)y + 0.5f, st = P.lvl_stride;
+        const float x1 = ax - dist[0], y1 = ay - dist[1], x2 = ax + dist[2], y2 = ay + dist[3];
+        float* ob = reinterpret_cast<float*>(P.dst) + (size_t)n_img * (4 + P.nc) * P.A_total + P.dst_row_off + r;
+        ob[0] = (x1 + x2) / 2.f * st;
+        ob[(size_t)P.A_total] = (y1 + y2) / 2.f * st;
+        ob[(size_t)2 * P.A_total] = (x2 - x1) * st;
+        ob[(size_t)3 * P.A_total] = (y2 - y1) * st;
+      }
+      // accumulator stage drained: hand it back to the MMA warp
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      mbar_arrive(tmem_empty_bar(acc));
+    }
+  } else if (warp < MMA_WARP) {
+    // ============================ im2col producer (idle when A comes by TMA) ================
+    if (!P.a_tma) {
+      const int ptid = tid - PROD_WARP0 * 32;
+      const int g = ptid & 7;       // 16-byte granule (8 channels) inside the 128-byte K row
+      const int rbase = ptid >> 3;  // rows rbase + 16*i
+      const uint32_t sw_off = (uint32_t)((g ^ (rbase & 7)) << 4);
+      int it = 0;
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+        const int m0 = (tile / P.n_tiles) * BM;
+        int row_n[8], row_y[8], row_x[8];
 #pragma unroll
         for (int i = 0; i < 8; i++) {
-          uint32_t addr = a_s + (uint32_t)(rbase + 16 * i) * 128u;
-          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v[i].x),
-                       "r"(v[i].y), "r"(v[i].z), "r"(v[i].w)
-                       : "memory");
+          int m = m0 + rbase + 16 * i;
+          if (m < P.M) {
+            int n = m / P.hw_out;
+            int r = m - n * P.hw_out;
+            int oy = r / P.Wout;
+            row_n[i] = n;
+            row_y[i] = oy * P.stride - P.pad;
+            row_x[i] = (r - oy * P.Wout) * P.stride - P.pad;
+          } else {
+            row_n[i] = -1;
+            row_y[i] = 0;
+            row_x[i] = 0;
+          }
         }
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        mbar_arrive(full_bar(s));
-        rem += BK;
+        int tap = 0;
+        int rem = g * 8;  // position inside the tap's [seg0 | seg1 | ...] channel run
         while (rem >= P.per_tap) {
           rem -= P.per_tap;
           tap++;
         }
-      }
-    }
-    // ============================ epilogue ================================================
-    mbar_wait(tmem_full_bar, 0u);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int m = m0 + tid;
-    const bool row_ok = m < P.M;
-    size_t drow = 0;
-    if (row_ok) {
-      int n_img = m / P.hw_out;
-      int r = m - n_img * P.hw_out;
-      drow = (size_t)n_img * P.dst_rows_per_img + P.dst_row_off + r;
-    }
-    const __nv_bfloat16* resp = P.res ? P.res + (size_t)m * P.res_ld : nullptr;
-    for (int c0 = 0; c0 < BN; c0 += 16) {
-      uint32_t v[16];
-      tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0, v);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      const int nb = n0 + c0;
-      if (!row_ok || nb >= P.cout_store) continue;
-      float f[16];
+        for (int kb = 0; kb < num_kb; kb++, it++) {
+          const int s = it % S;
+          const uint32_t ph = (uint32_t)(it / S) & 1u;
+          uint4 v[8];
+          const bool k_ok = (kb * BK + g * 8) < P.K;
+          int seg = 0, c = rem;
+          while (seg + 1 < P.nseg && c >= P.src_cp[seg]) {
+            c -= P.src_cp[seg];
+            seg++;
+          }
+          const int up = P.src_up[seg];
+          const int Hs = P.Hin >> up, Ws = P.Win >> up;
+          const int ld = P.src_ld[seg];
+          const __nv_bfloat16* sp = P.src[seg] + c;
+          int dy = 0, dx = 0;
+          if (P.ksize == 3) {
+            dy = tap / 3;
+            dx = tap - dy * 3;
+          }
 #pragma unroll
-      for (int j = 0; j < 16; j++) {
-        float x = __uint_as_float(v[j]) + bias_s[c0 + j];
-        f[j] = P.act ? silu_f(x) : x;
-      }
-      if (P.out_f32) {
-        float* dp = reinterpret_cast<float*>(P.dst) + drow * (size_t)P.dst_ld + nb;
-#pragma unroll
-        for (int q = 0; q < 4; q++) {
-          if (nb + 4 * q < P.cout_store)
-            *reinterpret_cast<float4*>(dp + 4 * q) =
-                make_float4(f[4 * q], f[4 * q + 1], f[4 * q + 2], f[4 * q + 3]);
-        }
-      } else {
-        __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(P.dst) + drow * (size_t)P.dst_ld + nb;
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-          if (nb + 8 * h < P.cout_store) {
-            if (resp) {
-              uint4 rv = __ldg(reinterpret_cast<const uint4*>(resp + nb + 8 * h));
-              const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
-#pragma unroll
-              for (int j = 0; j < 4; j++) {
-                float2 rf = __bfloat1622float2(r2[j]);
-                f[8 * h + 2 * j] += rf.x;
-                f[8 * h + 2 * j + 1] += rf.y;
-              }
+          for (int i = 0; i < 8; i++) {
+            int iy = row_y[i] + dy, ix = row_x[i] + dx;
+            bool ok = k_ok && row_n[i] >= 0 && (unsigned)iy < (unsigned)P.Hin &&
+                      (unsigned)ix < (unsigned)P.Win;
+            v[i] = make_uint4(0u, 0u, 0u, 0u);
+            if (ok) {
+              size_t off = ((size_t)(row_n[i] * Hs + (iy >> up)) * Ws + (ix >> up)) * (size_t)ld;
+              v[i] = __ldg(reinterpret_cast<const uint4*>(sp + off));
             }
-            uint4 o;
-            o.x = pack_bf16(f[8 * h + 0], f[8 * h + 1]);
-            o.y = pack_bf16(f[8 * h + 2], f[8 * h + 3]);
-            o.z = pack_bf16(f[8 * h + 4], f[8 * h + 5]);
-            o.w = pack_bf16(f[8 * h + 6], f[8 * h + 7]);
-            *reinterpret_cast<uint4*>(dp + 8 * h) = o;
+          }
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          const uint32_t a_s = a_base + (uint32_t)s * A_STAGE_BYTES + sw_off;
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            uint32_t addr = a_s + (uint32_t)(rbase + 16 * i) * 128u;
+            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v[i].x),
+                         "r"(v[i].y), "r"(v[i].z), "r"(v[i].w)
+                         : "memory");
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbar_arrive(full_bar(s));
+          rem += BK;
+          while (rem >= P.per_tap) {
+            rem -= P.per_tap;
+            tap++;
           }
         }
       }
     }
-  } else if (warp == 4) {
+  } else if (warp == MMA_WARP) {
     // ============================ MMA issuer ==============================================
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
                              ((uint32_t)(BM >> 4) << 24);
-      for (int kb = 0; kb < num_kb; kb++) {
-        const int s = kb % S;
-        const uint32_t ph = (uint32_t)(kb / S) & 1u;
-        mbar_wait(full_bar(s), ph);
+      int it = 0, ti = 0;
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ti++) {
+        const int acc = ti & 1;
+        mbar_wait(tmem_empty_bar(acc), ((uint32_t)(ti >> 1) & 1u) ^ 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t a_s = a_base + (uint32_t)s * A_STAGE_BYTES;
-        const uint32_t b_s = b_base + (uint32_t)s * b_stage_bytes;
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int kb = 0; kb < num_kb; kb++, it++) {
+          const int s = it % S;
+          const uint32_t ph = (uint32_t)(it / S) & 1u;
+          mbar_wait(full_bar(s), ph);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t a_s = a_base + (uint32_t)s * A_STAGE_BYTES;
+          const uint32_t b_s = b_base + (uint32_t)s * b_stage_bytes;
 #pragma unroll
-        for (int k = 0; k < BK / 16; k++) {
-          umma_bf16(tmem_base, umma_desc_sw128(a_s + k * 32), umma_desc_sw128(b_s + k * 32), idesc,
-                    (uint32_t)((kb | k) != 0));
+          for (int k = 0; k < BK / 16; k++) {
+            umma_bf16(d_tmem, umma_desc_sw128(a_s + k * 32), umma_desc_sw128(b_s + k * 32), idesc,
+                      (uint32_t)((kb | k) != 0));
+          }
+          umma_commit(empty_bar(s));  // frees the smem stage once these MMAs have read it
         }
-        umma_commit(empty_bar(s));  // frees the smem stage once these MMAs have read it
+        umma_commit(tmem_full_bar(acc));  // accumulator complete -> epilogue
       }
-      umma_commit(tmem_full_bar);   // accumulator complete -> epilogue
     }
   } else {
     // ============================ TMA producer ============================================
     if (lane == 0) {
       const uint32_t tx = b_stage_bytes + (P.a_tma ? (uint32_t)A_STAGE_BYTES : 0u);
-      int seg = 0, kk = 0;
-      for (int kb = 0; kb < num_kb; kb++) {
-        const int s = kb % S;
-        const uint32_t ph = (uint32_t)(kb / S) & 1u;
-        mbar_wait(empty_bar(s), ph ^ 1u);
-        mbar_expect_tx(full_bar(s), tx);
-        tma_load_2d(b_base + (uint32_t)s * b_stage_bytes, &tmap_b, kb * BK, n0, full_bar(s));
-        if (P.a_tma) {
-          const CUtensorMap* ma = seg == 0 ? &tmap_a0 : seg == 1 ? &tmap_a1 : seg == 2 ? &tmap_a2 : &tmap_a3;
-          tma_load_2d(a_base + (uint32_t)s * A_STAGE_BYTES, ma, kk * BK, m0, full_bar(s));
-          if (++kk == P.seg_kb[seg]) {
-            kk = 0;
-            seg++;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+        const int m0 = (tile / P.n_tiles) * BM;
+        const int n0 = (tile % P.n_tiles) * BN;
+        int seg = 0, kk = 0;
+        for (int kb = 0; kb < num_kb; kb++, it++) {
+          const int s = it % S;
+          const uint32_t ph = (uint32_t)(it / S) & 1u;
+          mbar_wait(empty_bar(s), ph ^ 1u);
+          mbar_expect_tx(full_bar(s), tx);
+          tma_load_2d(b_base + (uint32_t)s * b_stage_bytes, &tmap_b, kb * BK, n0, full_bar(s));
+          if (P.a_tma) {
+            const CUtensorMap* ma =
+                seg == 0 ? &tmap_a0 : seg == 1 ? &tmap_a1 : seg == 2 ? &tmap_a2 : &tmap_a3;
+            tma_load_2d(a_base + (uint32_t)s * A_STAGE_BYTES, ma, kk * BK, m0, full_bar(s));
+            if (++kk == P.seg_kb[seg]) {
+              kk = 0;
+              seg++;
+            }
           }
         }
       }
@@ -379,7 +460,7 @@ __global__ void __launch_bounds__(192, 1)
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 4) {
+  if (warp == MMA_WARP) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                  "r"((uint32_t)P.tmem_cols)
                  : "memory");
@@ -474,22 +555,35 @@ static int make_tmap_2d(CUtensorMap* map, const void* base, uint64_t inner, uint
 }
 
 static size_t conv_smem_bytes(int stages, int BN) {
-  return 1024 + (size_t)stages * (A_STAGE_BYTES + (size_t)BN * 128) + (2 * MAX_STAGES + 1) * 8 + 16 +
-         256 * 4;
+  return 1024 + (size_t)stages * (A_STAGE_BYTES + (size_t)BN * 128) + (2 * MAX_STAGES + 4) * 8 + 64;
+}
+
+static int tmem_cols_for(int BN) {
+  int cols = 32;
+  while (cols < 2 * BN) cols <<= 1;  // two accumulator stages
+  return cols;
 }
 
 int conv_tc_prepare(yb_plan* p, Op& op) {
   const ConvW& cw = p->convs[op.conv_index];
   const uint8_t* wbase = p->d_weights + cw.info.blob_offset;
-  int num_kb = op.K_pad / BK;
-  // stage count: enough to cover the K loop, capped so that small-N layers keep 2-3 CTAs per SM
-  size_t stage_bytes = A_STAGE_BYTES + (size_t)op.BN * 128;
-  int st = std::min(num_kb, 4);
-  while (st > 2 && conv_smem_bytes(st, op.BN) > 200 * 1024) st--;
-  if (const char* e = getenv("YB_STAGES")) st = std::max(1, std::min(MAX_STAGES, atoi(e)));
-  (void)stage_bytes;
-  op.stages = std::max(1, st);
-  op.smem_bytes = conv_smem_bytes(op.stages, op.BN);
+  // Resident CTAs per SM: bounded by TMEM (512 columns per SM, 2 accumulator stages per CTA) and
+  // capped at 2.  The shared-memory request is sized so that exactly `occ` CTAs fit, which keeps
+  // tcgen05.alloc from ever waiting on a co-resident persistent CTA.
+  const size_t SMEM_MAX = 227 * 1024;
+  int occ = std::min(2, 512 / tmem_cols_for(op.BN));
+  if (const char* e = getenv("YB_OCC")) occ = std::max(1, std::min(occ, atoi(e)));
+  size_t budget = SMEM_MAX / occ;
+  int st = MAX_STAGES;
+  while (st > 2 && conv_smem_bytes(st, op.BN) > budget) st--;
+  if (const char* e = getenv("YB_STAGES")) st = std::max(1, std::min(st, atoi(e)));
+  op.stages = st;
+  op.smem_bytes = std::max(conv_smem_bytes(st, op.BN), SMEM_MAX / (occ + 1) + 1024);
+  if (op.smem_bytes > SMEM_MAX) {
+    set_error("conv %s: tile needs %zu bytes of shared memory", op.name.c_str(), op.smem_bytes);
+    return YB_ERR_UNSUPPORTED;
+  }
+  op.occ = occ;
   int rc = make_tmap_2d(&op.tmap_b, wbase, (uint64_t)op.K_pad, (uint64_t)op.N_pad,
                         (uint64_t)op.K_pad * 2, BK, (uint32_t)op.BN);
   if (rc) return rc;
@@ -561,17 +655,28 @@ static void fill_params(const yb_plan* p, const Op& op, ConvParams& P) {
   P.BN = op.BN;
   P.stages = op.stages;
   P.a_tma = op.a_tma;
-  int cols = 32;
-  while (cols < op.BN) cols <<= 1;
-  P.tmem_cols = cols;
+  P.tmem_cols = tmem_cols_for(op.BN);
+  P.n_tiles = op.N_pad / op.BN;
+  P.total_tiles = ((P.M + BM - 1) / BM) * P.n_tiles;
+  P.out_mode = op.out_f32 ? 1 : 0;
+  P.A_total = p->A;
+  P.nc = p->nc;
 }
 
-int launch_conv_tc(const yb_plan* p, const Op& op, cudaStream_t st) {
+int launch_conv_tc(const yb_plan* p, const Op& op, cudaStream_t st, float* fused_out) {
   ConvParams P;
   fill_params(p, op, P);
-  dim3 grid((P.M + BM - 1) / BM, op.N_pad / op.BN);
-  conv_gemm_tcgen05_kernel<<<grid, 192, op.smem_bytes, st>>>(P, op.tmap_b, op.tmap_a[0], op.tmap_a[1],
-                                                            op.tmap_a[2], op.tmap_a[3]);
+  if (fused_out && op.head_part) {
+    // head tails write the final (B, 4+nc, A) tensor: DFL box decode (part 1) / class sigmoid (part 2)
+    P.out_mode = op.head_part == 1 ? 2 : 3;
+    P.dst = fused_out;
+    P.cout_store = op.head_part == 1 ? 64 : round_up(p->nc, 16);
+    int lvl = op.dst_row_off == p->lvl_off[2] ? 2 : op.dst_row_off == p->lvl_off[1] ? 1 : 0;
+    P.lvl_stride = p->lvl_stride[lvl];
+  }
+  int grid = std::min(P.total_tiles, p->num_sms * op.occ);
+  conv_gemm_tcgen05_kernel<<<grid, NUM_THREADS, op.smem_bytes, st>>>(P, op.tmap_b, op.tmap_a[0],
+                                                                    op.tmap_a[1], op.tmap_a[2], op.tmap_a[3]);
   count_launch();
   YB_CUDA(cudaGetLastError());
   return YB_OK;

@@ -32,8 +32,9 @@ __device__ __forceinline__ uint4 float_to_bf16x8(const float* f) {
 // ---------------------------------------------------------------------------------------------
 // Stem: net.p1.0 = Conv(3 -> w1, k3, s2, p1) + SiLU (nets/nn.py:161).  Reads the caller's NCHW
 // image (fp32 / fp16 / bf16 / uint8), writes NHWC bf16.  K = 27 is far below the tensor-core
-// ridge (AI ~ 23 flop/B), so this is a direct convolution: one thread per output pixel, the 27
-// input taps held in registers, weights broadcast from shared memory.
+// ridge (AI ~ 23 flop/B), so this is a direct convolution: a CTA stages the (2*8+1) x (2*32+1) x 3
+// input patch of an 8 x 32 output tile in shared memory with coalesced loads, then one thread per
+// output pixel keeps its 27 taps in registers and reads the weights as shared-memory broadcasts.
 // ---------------------------------------------------------------------------------------------
 template <typename T>
 __device__ __forceinline__ float load_px(const T* p);
@@ -48,39 +49,49 @@ __device__ __forceinline__ float load_px<__nv_bfloat16>(const __nv_bfloat16* p) 
 template <>
 __device__ __forceinline__ float load_px<uint8_t>(const uint8_t* p) { return (float)__ldg(p); }
 
+static constexpr int STEM_TW = 32, STEM_TH = 8;              // output tile per CTA (256 threads)
+static constexpr int STEM_IW = 2 * STEM_TW + 1, STEM_IH = 2 * STEM_TH + 1;
+static constexpr int STEM_PITCH = STEM_IW + 1;
+
 template <typename T>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
     stem_conv_kernel(const T* __restrict__ in, __nv_bfloat16* __restrict__ out,
                      const float* __restrict__ wgt, int B, int H, int W, int Ho, int Wo, int Cp,
                      int out_ld, float in_scale) {
-  extern __shared__ float ws[];  // [27][Cp] weights then [Cp] bias
+  extern __shared__ float ws[];  // [27][Cp] weights, [Cp] bias, then the input tile [3][IH][PITCH]
+  float* tile = ws + 28 * Cp;
+  const int tiles_x = (Wo + STEM_TW - 1) / STEM_TW, tiles_y = (Ho + STEM_TH - 1) / STEM_TH;
+  int bid = blockIdx.x;
+  const int tx = bid % tiles_x;
+  bid /= tiles_x;
+  const int ty = bid % tiles_y;
+  const int b = bid / tiles_y;
   for (int i = threadIdx.x; i < 28 * Cp; i += blockDim.x) ws[i] = wgt[i];
+  const int gy0 = 2 * ty * STEM_TH - 1, gx0 = 2 * tx * STEM_TW - 1;
+  for (int i = threadIdx.x; i < 3 * STEM_IH * STEM_IW; i += blockDim.x) {
+    int ix = i % STEM_IW;
+    int iy = (i / STEM_IW) % STEM_IH;
+    int ci = i / (STEM_IW * STEM_IH);
+    int gy = gy0 + iy, gx = gx0 + ix;
+    float v = 0.f;
+    if ((unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W)
+      v = load_px<T>(in + (((size_t)b * 3 + ci) * H + gy) * W + gx) * in_scale;
+    tile[(ci * STEM_IH + iy) * STEM_PITCH + ix] = v;
+  }
   __syncthreads();
   const float* bs = ws + 27 * Cp;
-  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  long long total = (long long)B * Ho * Wo;
-  if (idx >= total) return;
-  int ox = (int)(idx % Wo);
-  int oy = (int)((idx / Wo) % Ho);
-  int b = (int)(idx / ((long long)Wo * Ho));
+  const int lx = threadIdx.x % STEM_TW, ly = threadIdx.x / STEM_TW;
+  const int ox = tx * STEM_TW + lx, oy = ty * STEM_TH + ly;
+  if (ox >= Wo || oy >= Ho) return;
   float x[27];
 #pragma unroll
-  for (int ci = 0; ci < 3; ci++) {
-    const T* plane = in + ((size_t)b * 3 + ci) * H * W;
+  for (int ci = 0; ci < 3; ci++)
 #pragma unroll
-    for (int ky = 0; ky < 3; ky++) {
-      int iy = 2 * oy - 1 + ky;
+    for (int ky = 0; ky < 3; ky++)
 #pragma unroll
-      for (int kx = 0; kx < 3; kx++) {
-        int ix = 2 * ox - 1 + kx;
-        float v = 0.f;
-        if ((unsigned)iy < (unsigned)H && (unsigned)ix < (unsigned)W)
-          v = load_px<T>(plane + (size_t)iy * W + ix) * in_scale;
-        x[(ci * 3 + ky) * 3 + kx] = v;
-      }
-    }
-  }
-  __nv_bfloat16* op = out + (size_t)idx * out_ld;
+      for (int kx = 0; kx < 3; kx++)
+        x[(ci * 3 + ky) * 3 + kx] = tile[(ci * STEM_IH + 2 * ly + ky) * STEM_PITCH + 2 * lx + kx];
+  __nv_bfloat16* op = out + (((size_t)b * Ho + oy) * Wo + ox) * out_ld;
   for (int c0 = 0; c0 < Cp; c0 += 8) {
     float acc[8];
 #pragma unroll
@@ -110,10 +121,9 @@ int launch_stem(const yb_plan* p, const Op& op, const void* in, int in_dtype, cu
   const Buf& db = p->bufs[op.dst.buf];
   __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(buf_ptr(p, op.dst.buf)) + op.dst.c_off;
   int Cp = cpad8(op.dst.C);
-  long long total = (long long)p->B * op.Hout * op.Wout;
-  int threads = 128;
-  unsigned blocks = (unsigned)((total + threads - 1) / threads);
-  size_t smem = (size_t)28 * Cp * 4;
+  int threads = 256;
+  unsigned blocks = (unsigned)(p->B * ((op.Hout + STEM_TH - 1) / STEM_TH) * ((op.Wout + STEM_TW - 1) / STEM_TW));
+  size_t smem = ((size_t)28 * Cp + 3 * STEM_IH * STEM_PITCH) * 4;
   switch (in_dtype) {
     case YB_F32:
       stem_conv_kernel<float><<<blocks, threads, smem, st>>>((const float*)in, out, w, p->B, p->H, p->W,
@@ -144,56 +154,76 @@ int launch_stem(const yb_plan* p, const Op& op, const void* in, int in_dtype, cu
 // ---------------------------------------------------------------------------------------------
 // Depthwise 3x3, stride 1, pad 1 (+ folded BN bias, optional SiLU): head cls branches
 // (nets/nn.py:248,250) and the attention positional conv `pe` on v (nn.py:109,122).
-// One thread = one pixel x 8 channels (16 B); taps hit L1/L2.  `gsz/gstride/goff` gather the
+// One thread = 4 pixels along x by 8 channels (16 B each): 18 tap loads feed 4 outputs.  `gsz/gstride/goff` gather the
 // source channels (v rows of the per-head [q k v] interleave); `add` accumulates into dst.
 // ---------------------------------------------------------------------------------------------
+static constexpr int DW_PX = 4;  // output pixels along x per thread: 18 tap loads for 4 outputs
+
 __global__ void __launch_bounds__(256)
     dwconv3x3_kernel(const __nv_bfloat16* __restrict__ src, int src_ld, __nv_bfloat16* dst, int dst_ld,
                      const float* __restrict__ wgt, int Cp, int B, int H, int W, int C, int gsz,
                      int gstride, int goff, int act, int add) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  int cgs = C >> 3;
-  long long total = (long long)B * H * W * cgs;
+  const int cgs = C >> 3;
+  const int xq = (W + DW_PX - 1) / DW_PX;
+  long long total = (long long)B * H * xq * cgs;
   if (idx >= total) return;
-  int cg = (int)(idx % cgs);
-  long long pix = idx / cgs;
-  int x = (int)(pix % W);
-  int y = (int)((pix / W) % H);
-  int b = (int)(pix / ((long long)W * H));
-  int c = cg * 8;
-  int sc = (c / gsz) * gstride + goff + (c % gsz);
-  float acc[8];
+  const int cg = (int)(idx % cgs);
+  long long t = idx / cgs;
+  const int x0 = (int)(t % xq) * DW_PX;
+  const int y = (int)((t / xq) % H);
+  const int b = (int)(t / ((long long)xq * H));
+  const int c = cg * 8;
+  const int sc = (c / gsz) * gstride + goff + (c % gsz);
+  float acc[DW_PX][8];
   const float* bias = wgt + 9 * Cp;
 #pragma unroll
-  for (int j = 0; j < 8; j++) acc[j] = bias[c + j];
+  for (int p = 0; p < DW_PX; p++)
+#pragma unroll
+    for (int j = 0; j < 8; j++) acc[p][j] = bias[c + j];
 #pragma unroll
   for (int ky = 0; ky < 3; ky++) {
-    int iy = y - 1 + ky;
+    const int iy = y - 1 + ky;
     if ((unsigned)iy >= (unsigned)H) continue;
+    float w[3][8];
 #pragma unroll
-    for (int kx = 0; kx < 3; kx++) {
-      int ix = x - 1 + kx;
+    for (int kx = 0; kx < 3; kx++)
+#pragma unroll
+      for (int j = 0; j < 8; j++) w[kx][j] = wgt[(ky * 3 + kx) * Cp + c + j];
+    const __nv_bfloat16* rowp = src + ((size_t)(b * H + iy) * W) * src_ld + sc;
+#pragma unroll
+    for (int col = 0; col < DW_PX + 2; col++) {
+      const int ix = x0 - 1 + col;
       if ((unsigned)ix >= (unsigned)W) continue;
-      uint4 v = __ldg(reinterpret_cast<const uint4*>(src + ((size_t)(b * H + iy) * W + ix) * src_ld + sc));
       float f[8];
-      bf16x8_to_float(v, f);
-      const float* wp = wgt + (ky * 3 + kx) * Cp + c;
+      bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(rowp + (size_t)ix * src_ld)), f);
 #pragma unroll
-      for (int j = 0; j < 8; j++) acc[j] = fmaf(f[j], wp[j], acc[j]);
+      for (int kx = 0; kx < 3; kx++) {
+        const int p = col - kx;  // output pixel this column feeds through tap kx
+        if (p >= 0 && p < DW_PX) {
+#pragma unroll
+          for (int j = 0; j < 8; j++) acc[p][j] = fmaf(f[j], w[kx][j], acc[p][j]);
+        }
+      }
     }
   }
-  if (act) {
 #pragma unroll
-    for (int j = 0; j < 8; j++) acc[j] = silu_acc(acc[j]);
-  }
-  __nv_bfloat16* dp = dst + (size_t)pix * dst_ld + c;
-  if (add) {
-    float f[8];
-    bf16x8_to_float(*reinterpret_cast<const uint4*>(dp), f);
+  for (int p = 0; p < DW_PX; p++) {
+    const int x = x0 + p;
+    if (x >= W) break;
+    if (act) {
 #pragma unroll
-    for (int j = 0; j < 8; j++) acc[j] += f[j];
+      for (int j = 0; j < 8; j++) acc[p][j] = silu_acc(acc[p][j]);
+    }
+    __nv_bfloat16* dp = dst + ((size_t)(b * H + y) * W + x) * dst_ld + c;
+    if (add) {
+      float f[8];
+      bf16x8_to_float(*reinterpret_cast<const uint4*>(dp), f);
+#pragma unroll
+      for (int j = 0; j < 8; j++) acc[p][j] += f[j];
+    }
+    *reinterpret_cast<uint4*>(dp) = float_to_bf16x8(acc[p]);
   }
-  *reinterpret_cast<uint4*>(dp) = float_to_bf16x8(acc);
 }
 
 int launch_dw(const yb_plan* p, const Op& op, cudaStream_t st) {
@@ -205,7 +235,7 @@ int launch_dw(const yb_plan* p, const Op& op, cudaStream_t st) {
       reinterpret_cast<const __nv_bfloat16*>(buf_ptr(p, op.src[0].buf)) + op.src[0].c_off;
   __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(buf_ptr(p, op.dst.buf)) + op.dst.c_off;
   int C = op.dst.C;
-  long long total = (long long)p->B * op.Hout * op.Wout * (C >> 3);
+  long long total = (long long)p->B * op.Hout * ((op.Wout + DW_PX - 1) / DW_PX) * (C >> 3);
   int threads = 256;
   unsigned blocks = (unsigned)((total + threads - 1) / threads);
   dwconv3x3_kernel<<<blocks, threads, 0, st>>>(src, sb.C, dst, db.C, w, cpad8(C), p->B, op.Hout, op.Wout,

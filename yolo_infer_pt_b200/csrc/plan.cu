@@ -392,12 +392,14 @@ int build_plan(yb_plan* p) {
     Slice b1 = b.conv(bi + ".1", {b0}, Bc, 3, 1, 1);
     Slice dbox = b.sub(p->logits_buf, 0, 64);
     b.conv(bi + ".2", {b1}, 64, 1, 1, 0, &dbox, nullptr, 0, 1, p->lvl_off[i]);
+    p->ops.back().head_part = 1;
     Slice c0 = b.dwconv(ci + ".0", x, x.C, 1);
     Slice c1 = b.conv(ci + ".1", {c0}, Cc, 1, 1, 1);
     Slice c2 = b.dwconv(ci + ".2", c1, Cc, 1);
     Slice c3 = b.conv(ci + ".3", {c2}, Cc, 1, 1, 1);
     Slice dcls = b.sub(p->logits_buf, 64, p->nc);
     b.conv(ci + ".4", {c3}, p->nc, 1, 1, 0, &dcls, nullptr, 0, 1, p->lvl_off[i]);
+    p->ops.back().head_part = 2;
   }
   if (b.err) return b.err;
   {
@@ -411,6 +413,7 @@ int build_plan(yb_plan* p) {
     p->ops.push_back(op);
   }
 
+  if (getenv("YB_NO_FUSE_DECODE")) p->fuse_decode = 0;
   // ---- weight blob layout ----
   size_t off = 0;
   for (auto& cw : p->convs) {

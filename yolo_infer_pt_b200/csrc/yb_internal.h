@@ -73,6 +73,8 @@ struct Op {
   int seg_kpad[4] = {0, 0, 0, 0};  // per-segment padded K (a_tma mode)
   int N_pad = 0, BN = 0;   // padded Cout, N tile
   int stages = 0;
+  int occ = 1;             // resident CTAs per SM of the persistent GEMM kernel
+  int head_part = 0;       // 1: box tail (fusable DFL decode), 2: cls tail (fusable sigmoid)
   size_t smem_bytes = 0;
   CUtensorMap tmap_b;
   CUtensorMap tmap_a[4];
@@ -114,6 +116,7 @@ struct yb_plan {
   bool bound = false;
   int conv_impl = 0;
   int use_graph = 0;
+  int fuse_decode = 1;     // head tails decode in their epilogue; the logits buffer is skipped
   int num_sms = 148;
   std::vector<yb::GraphEntry> graphs;
   cudaStream_t capture_stream = nullptr;
@@ -126,7 +129,7 @@ namespace yb {
 // plan.cu
 int build_plan(yb_plan* p);
 // launchers (each enqueues exactly one kernel on `st`)
-int launch_conv_tc(const yb_plan* p, const Op& op, cudaStream_t st);
+int launch_conv_tc(const yb_plan* p, const Op& op, cudaStream_t st, float* fused_out);
 int launch_conv_naive(const yb_plan* p, const Op& op, cudaStream_t st);
 int launch_stem(const yb_plan* p, const Op& op, const void* in, int in_dtype, cudaStream_t st);
 int launch_dw(const yb_plan* p, const Op& op, cudaStream_t st);

@@ -129,9 +129,9 @@ class Engine:
 
     def profile_read(self):
         """(mean ms per op over the forwards recorded since the last read, number of forwards)."""
-        ms = np.zeros(self.num_launches, dtype=np.float32)
+        ms = np.zeros(self.num_launches + 8, dtype=np.float32)   # one slot per op of the plan
         n = _lib.check(self.L.yb_plan_profile_read(self.plan, ms.ctypes.data, len(ms)), "yb_plan_profile_read")
-        return ms, n
+        return ms[:len(self.describe()["ops"])], n
 
     def set_conv_impl(self, impl):
         _lib.check(self.L.yb_plan_set_conv_impl(self.plan, int(impl)), "yb_plan_set_conv_impl")
