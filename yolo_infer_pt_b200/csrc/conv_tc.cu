@@ -39,6 +39,7 @@ static constexpr int BM = 128;
 static constexpr int BK = 64;
 static constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
 static constexpr int MAX_STAGES = 8;
+static constexpr int C_GROUP_BYTES = BM * 128;    // 128 rows x 64 bf16 output staging sub-tile
 
 struct ConvParams {
   const __nv_bfloat16* src[4];
@@ -170,7 +171,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
                              const __grid_constant__ CUtensorMap tmap_a0,
                              const __grid_constant__ CUtensorMap tmap_a1,
                              const __grid_constant__ CUtensorMap tmap_a2,
-                             const __grid_constant__ CUtensorMap tmap_a3) {
+                             const __grid_constant__ CUtensorMap tmap_a3,
+                             const __grid_constant__ CUtensorMap tmap_c) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024 B alignment
@@ -181,10 +183,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
   const uint32_t b_stage_bytes = (uint32_t)BN * 128u;
   const uint32_t a_base = base;
   const uint32_t b_base = base + (uint32_t)S * A_STAGE_BYTES;
-  uint8_t* tail = smem + (size_t)S * (A_STAGE_BYTES + b_stage_bytes);
+  // output staging for the TMA store: one 128 x 64 bf16 swizzled sub-tile (16 KB) per 64 channels
+  const uint32_t c_groups = (uint32_t)(BN + 63) / 64;
+  const uint32_t c_base = b_base + (uint32_t)S * b_stage_bytes;
+  uint8_t* tail = smem + (size_t)S * (A_STAGE_BYTES + b_stage_bytes) + (size_t)c_groups * C_GROUP_BYTES;
   // barriers: full[MAX_STAGES], empty[MAX_STAGES], tmem_full[2], tmem_empty[2]
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + (2 * MAX_STAGES + 4) * 8);
+  float* bias_s = reinterpret_cast<float*>(tail + (2 * MAX_STAGES + 4) * 8 + 16);
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (MAX_STAGES + s); };
@@ -229,6 +235,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
       const int acc = ti & 1;
       mbar_wait(tmem_full_bar(acc), (uint32_t)(ti >> 1) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      // the previous tile's TMA stores must have finished reading the staging buffer
+      if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      for (int i = tid; i < BN; i += 128) bias_s[i] = __ldg(P.bias + n0 + i);
+      asm volatile("bar.sync 1, 128;" ::: "memory");
       const int m = m0 + tid;
       const bool row_ok = m < P.M;
       int n_img = 0, r = 0;
@@ -245,19 +255,21 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
         tmem_ld16(t_row + (uint32_t)c0, v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         const int nb = n0 + c0;
-        if (!row_ok || nb >= P.cout_store) continue;
+        if (nb >= P.cout_store || (!row_ok && P.out_mode != 0)) continue;
         float f[16];
 #pragma unroll
         for (int j = 0; j < 16; j++) {
-          float x = __uint_as_float(v[j]) + __ldg(P.bias + nb + j);
+          float x = __uint_as_float(v[j]) + bias_s[c0 + j];
           f[j] = P.act ? silu_f(x) : x;
         }
         if (P.out_mode == 0) {
-          __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(P.dst) + drow * (size_t)P.dst_ld + nb;
+          // bf16 tile staged in shared memory in the TMA SWIZZLE_128B layout (16-byte chunk index
+          // XOR row%8 inside each 128-byte row), then written with one TMA store per 64 channels
+          const uint32_t srow = c_base + (uint32_t)(c0 >> 6) * C_GROUP_BYTES + (uint32_t)tid * 128u;
 #pragma unroll
           for (int h = 0; h < 2; h++) {
             if (nb + 8 * h < P.cout_store) {
-              if (resp) {
+              if (resp && row_ok) {
                 uint4 rv = __ldg(reinterpret_cast<const uint4*>(resp + nb + 8 * h));
                 const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
 #pragma unroll
@@ -267,12 +279,12 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
                   f[8 * h + 2 * j + 1] += rf.y;
                 }
               }
-              uint4 o;
-              o.x = pack_bf16(f[8 * h + 0], f[8 * h + 1]);
-              o.y = pack_bf16(f[8 * h + 2], f[8 * h + 3]);
-              o.z = pack_bf16(f[8 * h + 4], f[8 * h + 5]);
-              o.w = pack_bf16(f[8 * h + 6], f[8 * h + 7]);
-              *reinterpret_cast<uint4*>(dp + 8 * h) = o;
+              const uint32_t chunk = (uint32_t)(((c0 & 63) >> 3) + h);
+              const uint32_t addr = srow + ((chunk ^ (uint32_t)(tid & 7)) << 4);
+              asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
+                           "r"(pack_bf16(f[8 * h + 0], f[8 * h + 1])), "r"(pack_bf16(f[8 * h + 2], f[8 * h + 3])),
+                           "r"(pack_bf16(f[8 * h + 4], f[8 * h + 5])), "r"(pack_bf16(f[8 * h + 6], f[8 * h + 7]))
+                           : "memory");
             }
           }
         } else if (P.out_mode == 1) {
@@ -319,7 +331,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
       // accumulator stage drained: hand it back to the MMA warp
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(tmem_empty_bar(acc));
+      if (P.out_mode == 0) {
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (tid == 0) {
+          for (uint32_t g = 0; g < c_groups; g++) {
+            const int cg0 = n0 + (int)g * 64;
+            if (cg0 < P.cout_store) {
+              asm volatile(
+                  "cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
+                      (uint64_t)&tmap_c),
+                  "r"(cg0), "r"(m0), "r"(c_base + g * C_GROUP_BYTES)
+                  : "memory");
+            }
+          }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        }
+      }
     }
+    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   } else if (warp < MMA_WARP) {
     // ============================ im2col producer (idle when A comes by TMA) ================
     if (!P.a_tma) {
@@ -555,7 +585,8 @@ static int make_tmap_2d(CUtensorMap* map, const void* base, uint64_t inner, uint
 }
 
 static size_t conv_smem_bytes(int stages, int BN) {
-  return 1024 + (size_t)stages * (A_STAGE_BYTES + (size_t)BN * 128) + (2 * MAX_STAGES + 4) * 8 + 64;
+  return 1024 + (size_t)stages * (A_STAGE_BYTES + (size_t)BN * 128) + (size_t)((BN + 63) / 64) * C_GROUP_BYTES +
+         (2 * MAX_STAGES + 4) * 8 + 16 + 256 * 4 + 64;
 }
 
 static int tmem_cols_for(int BN) {
@@ -596,6 +627,14 @@ int conv_tc_prepare(yb_plan* p, Op& op) {
                         (uint64_t)p->B * b.rows_per_img, (uint64_t)b.C * 2, BK, BM);
       if (rc) return rc;
     }
+  }
+  op.tmap_c = op.tmap_b;
+  if (!op.out_f32) {
+    const Buf& db = p->bufs[op.dst.buf];
+    const uint8_t* dbase = buf_ptr(p, op.dst.buf) + (size_t)op.dst.c_off * 2;
+    rc = make_tmap_2d(&op.tmap_c, dbase, (uint64_t)cpad8(op.dst.C), (uint64_t)p->B * db.rows_per_img,
+                      (uint64_t)db.C * 2, 64, BM);
+    if (rc) return rc;
   }
   static bool attr_set = false;
   if (!attr_set) {
@@ -676,7 +715,8 @@ int launch_conv_tc(const yb_plan* p, const Op& op, cudaStream_t st, float* fused
   }
   int grid = std::min(P.total_tiles, p->num_sms * op.occ);
   conv_gemm_tcgen05_kernel<<<grid, NUM_THREADS, op.smem_bytes, st>>>(P, op.tmap_b, op.tmap_a[0],
-                                                                    op.tmap_a[1], op.tmap_a[2], op.tmap_a[3]);
+                                                                    op.tmap_a[1], op.tmap_a[2], op.tmap_a[3],
+                                                                    op.tmap_c);
   count_launch();
   YB_CUDA(cudaGetLastError());
   return YB_OK;

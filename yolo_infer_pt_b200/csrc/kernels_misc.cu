@@ -50,14 +50,47 @@ template <>
 __device__ __forceinline__ float load_px<uint8_t>(const uint8_t* p) { return (float)__ldg(p); }
 
 static constexpr int STEM_TW = 32, STEM_TH = 8;              // output tile per CTA (256 threads)
-static constexpr int STEM_IW = 2 * STEM_TW + 1, STEM_IH = 2 * STEM_TH + 1;
-static constexpr int STEM_PITCH = STEM_IW + 1;
+static constexpr int STEM_IH = 2 * STEM_TH + 1;
+static constexpr int STEM_PITCH = 2 * STEM_TW + 32 + 1;      // widest aligned window (uint8: 96) + 1
+
+template <typename T>
+__device__ __forceinline__ void unpack16(const uint4& v, float* f, float scale);
+template <>
+__device__ __forceinline__ void unpack16<float>(const uint4& v, float* f, float scale) {
+  f[0] = __uint_as_float(v.x) * scale;
+  f[1] = __uint_as_float(v.y) * scale;
+  f[2] = __uint_as_float(v.z) * scale;
+  f[3] = __uint_as_float(v.w) * scale;
+}
+template <>
+__device__ __forceinline__ void unpack16<__half>(const uint4& v, float* f, float scale) {
+  const __half2* h = reinterpret_cast<const __half2*>(&v);
+#pragma unroll
+  for (int j = 0; j < 4; j++) {
+    float2 t = __half22float2(h[j]);
+    f[2 * j] = t.x * scale;
+    f[2 * j + 1] = t.y * scale;
+  }
+}
+template <>
+__device__ __forceinline__ void unpack16<__nv_bfloat16>(const uint4& v, float* f, float scale) {
+  bf16x8_to_float(v, f);
+#pragma unroll
+  for (int j = 0; j < 8; j++) f[j] *= scale;
+}
+template <>
+__device__ __forceinline__ void unpack16<uint8_t>(const uint4& v, float* f, float scale) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int j = 0; j < 16; j++) f[j] = (float)((w[j >> 2] >> (8 * (j & 3))) & 0xFFu) * scale;
+}
 
 template <typename T>
 __global__ void __launch_bounds__(256)
     stem_conv_kernel(const T* __restrict__ in, __nv_bfloat16* __restrict__ out,
                      const float* __restrict__ wgt, int B, int H, int W, int Ho, int Wo, int Cp,
                      int out_ld, float in_scale) {
+  constexpr int EPV = 16 / (int)sizeof(T);  // elements per 16-byte vector (W % 32 == 0 keeps rows aligned)
   extern __shared__ float ws[];  // [27][Cp] weights, [Cp] bias, then the input tile [3][IH][PITCH]
   float* tile = ws + 28 * Cp;
   const int tiles_x = (Wo + STEM_TW - 1) / STEM_TW, tiles_y = (Ho + STEM_TH - 1) / STEM_TH;
@@ -67,16 +100,26 @@ __global__ void __launch_bounds__(256)
   const int ty = bid % tiles_y;
   const int b = bid / tiles_y;
   for (int i = threadIdx.x; i < 28 * Cp; i += blockDim.x) ws[i] = wgt[i];
-  const int gy0 = 2 * ty * STEM_TH - 1, gx0 = 2 * tx * STEM_TW - 1;
-  for (int i = threadIdx.x; i < 3 * STEM_IH * STEM_IW; i += blockDim.x) {
-    int ix = i % STEM_IW;
-    int iy = (i / STEM_IW) % STEM_IH;
-    int ci = i / (STEM_IW * STEM_IH);
-    int gy = gy0 + iy, gx = gx0 + ix;
-    float v = 0.f;
-    if ((unsigned)gy < (unsigned)H && (unsigned)gx < (unsigned)W)
-      v = load_px<T>(in + (((size_t)b * 3 + ci) * H + gy) * W + gx) * in_scale;
-    tile[(ci * STEM_IH + iy) * STEM_PITCH + ix] = v;
+  // aligned window of the input rows: starts at gxa <= 2*tx*TW - 1, a multiple of EPV
+  const int gy0 = 2 * ty * STEM_TH - 1;
+  const int gxa = 2 * tx * STEM_TW - EPV;
+  const int nvec = (2 * STEM_TW + 1 + EPV + EPV - 1) / EPV;  // covers [gxa, gxa + EPV + 2*TW + 1)
+  for (int i = threadIdx.x; i < 3 * STEM_IH * nvec; i += blockDim.x) {
+    const int vx = i % nvec;
+    const int iy = (i / nvec) % STEM_IH;
+    const int ci = i / (nvec * STEM_IH);
+    const int gy = gy0 + iy, gx = gxa + vx * EPV;
+    float f[EPV];
+    if ((unsigned)gy < (unsigned)H && gx >= 0 && gx < W) {
+      uint4 v = __ldg(reinterpret_cast<const uint4*>(in + (((size_t)b * 3 + ci) * H + gy) * W + gx));
+      unpack16<T>(v, f, in_scale);
+    } else {
+#pragma unroll
+      for (int j = 0; j < EPV; j++) f[j] = 0.f;
+    }
+    float* tp = tile + (ci * STEM_IH + iy) * STEM_PITCH + vx * EPV;
+#pragma unroll
+    for (int j = 0; j < EPV; j++) tp[j] = f[j];
   }
   __syncthreads();
   const float* bs = ws + 27 * Cp;
@@ -90,7 +133,7 @@ __global__ void __launch_bounds__(256)
     for (int ky = 0; ky < 3; ky++)
 #pragma unroll
       for (int kx = 0; kx < 3; kx++)
-        x[(ci * 3 + ky) * 3 + kx] = tile[(ci * STEM_IH + 2 * ly + ky) * STEM_PITCH + 2 * lx + kx];
+        x[(ci * 3 + ky) * 3 + kx] = tile[(ci * STEM_IH + 2 * ly + ky) * STEM_PITCH + EPV - 1 + 2 * lx + kx];
   __nv_bfloat16* op = out + (((size_t)b * Ho + oy) * Wo + ox) * out_ld;
   for (int c0 = 0; c0 < Cp; c0 += 8) {
     float acc[8];

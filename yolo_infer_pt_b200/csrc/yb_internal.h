@@ -78,6 +78,7 @@ struct Op {
   size_t smem_bytes = 0;
   CUtensorMap tmap_b;
   CUtensorMap tmap_a[4];
+  CUtensorMap tmap_c;      // bf16 output slice, written by the epilogue's TMA store
   // depthwise: channel gather of the source (attention `pe` conv reads the v rows of qkv)
   int dw_gsz = 0, dw_gstride = 0, dw_goff = 0, dw_add = 0;
   // attention
