@@ -64,6 +64,7 @@ struct ConvParams {
   int act;
   int BN, stages, a_tma, tmem_cols;
   int n_tiles, total_tiles;
+  uint32_t hw_mul, hw_shr, w_mul, w_shr;  // magic numbers: division by hw_out and by Wout
   // fused head decode (out_mode 2 / 3): dst is the (B, 4+nc, A) fp32 output tensor
   int out_mode;       // 0 bf16 slice, 1 fp32 logits, 2 DFL box decode, 3 class sigmoid
   int A_total, nc;
@@ -149,6 +150,26 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* v) {
         "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
         "=r"(v[14]), "=r"(v[15])
       : "r"(taddr));
+}
+// 16-byte global->shared async copy; src_bytes = 0 zero-fills the destination (out-of-image taps)
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_pending(int n) {
+  switch (n) {
+    case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+    case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+    case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+    case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+    case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
+    case 5: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
+    default: asm volatile("cp.async.wait_group 6;" ::: "memory"); break;
+  }
+}
+// q = n / d for n < 2^31 with host-computed (mul, shr): mul = ceil(2^(31+ceil_log2 d) / d)
+__device__ __forceinline__ int fast_div(int n, uint32_t mul, uint32_t shr, int d) {
+  return d == 1 ? n : (int)(__umulhi((uint32_t)n, mul) >> shr);
 }
 __device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.f + __expf(-x)); }
 
@@ -243,7 +264,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
       const bool row_ok = m < P.M;
       int n_img = 0, r = 0;
       if (row_ok) {
-        n_img = m / P.hw_out;
+        n_img = fast_div(m, P.hw_mul, P.hw_shr, P.hw_out);
         r = m - n_img * P.hw_out;
       }
       const size_t drow = (size_t)n_img * P.dst_rows_per_img + P.dst_row_off + r;
@@ -319,7 +340,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
         }
       }
       if (P.out_mode == 2 && row_ok) {
-        const int y = r / P.Wout, x = r - y * P.Wout;
+        const int y = fast_div(r, P.w_mul, P.w_shr, P.Wout), x = r - y * P.Wout;
         const float ax = (float)x + 0.5f, ay = (float)y + 0.5f, st = P.lvl_stride;
         const float x1 = ax - dist[0], y1 = ay - dist[1], x2 = ax + dist[2], y2 = ay + dist[3];
         float* ob = reinterpret_cast<float*>(P.dst) + (size_t)n_img * (4 + P.nc) * P.A_total + P.dst_row_off + r;
@@ -357,6 +378,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
       const int g = ptid & 7;       // 16-byte granule (8 channels) inside the 128-byte K row
       const int rbase = ptid >> 3;  // rows rbase + 16*i
       const uint32_t sw_off = (uint32_t)((g ^ (rbase & 7)) << 4);
+      // cp.async gathers need no staging registers and no wait in the producer: each thread's
+      // copies of a k-block arrive on the stage's full barrier by themselves when they land
+      // (cp.async.mbarrier.arrive.noinc), so a thread runs ahead as far as free stages allow.  The
+      // generic-proxy writes are made visible to the tensor core's async-proxy reads by the MMA
+      // thread's fence.proxy.async after it acquires the barrier.
+      // Address arithmetic is hoisted: per tile each row keeps the pixel index of its tap (0,0) and
+      // a 9-bit in-bounds mask; a k-block then costs one add + one wide multiply per row.
       int it = 0;
       for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
         const int m0 = (tile / P.n_tiles) * BM;
@@ -365,9 +393,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
         for (int i = 0; i < 8; i++) {
           int m = m0 + rbase + 16 * i;
           if (m < P.M) {
-            int n = m / P.hw_out;
+            int n = fast_div(m, P.hw_mul, P.hw_shr, P.hw_out);
             int r = m - n * P.hw_out;
-            int oy = r / P.Wout;
+            int oy = fast_div(r, P.w_mul, P.w_shr, P.Wout);
             row_n[i] = n;
             row_y[i] = oy * P.stride - P.pad;
             row_x[i] = (r - oy * P.Wout) * P.stride - P.pad;
@@ -377,16 +405,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
             row_x[i] = 0;
           }
         }
+        int pix[8];
+        uint32_t okmask[8];
+        int cur_seg = -1;
         int tap = 0;
         int rem = g * 8;  // position inside the tap's [seg0 | seg1 | ...] channel run
         while (rem >= P.per_tap) {
           rem -= P.per_tap;
           tap++;
         }
-        for (int kb = 0; kb < num_kb; kb++, it++) {
+        for (int kb = 0; kb < num_kb; kb++) {
           const int s = it % S;
           const uint32_t ph = (uint32_t)(it / S) & 1u;
-          uint4 v[8];
           const bool k_ok = (kb * BK + g * 8) < P.K;
           int seg = 0, c = rem;
           while (seg + 1 < P.nseg && c >= P.src_cp[seg]) {
@@ -394,36 +424,47 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
             seg++;
           }
           const int up = P.src_up[seg];
-          const int Hs = P.Hin >> up, Ws = P.Win >> up;
-          const int ld = P.src_ld[seg];
-          const __nv_bfloat16* sp = P.src[seg] + c;
-          int dy = 0, dx = 0;
-          if (P.ksize == 3) {
-            dy = tap / 3;
-            dx = tap - dy * 3;
-          }
+          const int Ws = P.Win >> up;
+          if (seg != cur_seg) {  // new tile, or the K walk crossed into the next source of a concat
+            cur_seg = seg;
+            const int Hs = P.Hin >> up;
 #pragma unroll
-          for (int i = 0; i < 8; i++) {
-            int iy = row_y[i] + dy, ix = row_x[i] + dx;
-            bool ok = k_ok && row_n[i] >= 0 && (unsigned)iy < (unsigned)P.Hin &&
-                      (unsigned)ix < (unsigned)P.Win;
-            v[i] = make_uint4(0u, 0u, 0u, 0u);
-            if (ok) {
-              size_t off = ((size_t)(row_n[i] * Hs + (iy >> up)) * Ws + (ix >> up)) * (size_t)ld;
-              v[i] = __ldg(reinterpret_cast<const uint4*>(sp + off));
+            for (int i = 0; i < 8; i++) {
+              uint32_t mk = 0;
+              if (row_n[i] >= 0) {
+                if (P.ksize == 3) {
+#pragma unroll
+                  for (int t = 0; t < 9; t++) {
+                    int iy = row_y[i] + t / 3, ix = row_x[i] + t % 3;
+                    if ((unsigned)iy < (unsigned)P.Hin && (unsigned)ix < (unsigned)P.Win) mk |= 1u << t;
+                  }
+                } else {
+                  mk = 1u;
+                }
+              }
+              okmask[i] = mk;
+              // ksize 3 never reads an upsampled source, so (y >> up) only matters for tap (0,0)
+              pix[i] = (row_n[i] * Hs + (row_y[i] >> up)) * Ws + (row_x[i] >> up);
             }
           }
+          int delta = 0, tbit = 0;
+          if (P.ksize == 3) {
+            int dy = tap / 3;
+            delta = dy * Ws + (tap - dy * 3);
+            tbit = tap;
+          }
+          const __nv_bfloat16* sp = P.src[seg] + c;
+          const int ld = P.src_ld[seg];
           mbar_wait(empty_bar(s), ph ^ 1u);
           const uint32_t a_s = a_base + (uint32_t)s * A_STAGE_BYTES + sw_off;
 #pragma unroll
           for (int i = 0; i < 8; i++) {
-            uint32_t addr = a_s + (uint32_t)(rbase + 16 * i) * 128u;
-            asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v[i].x),
-                         "r"(v[i].y), "r"(v[i].z), "r"(v[i].w)
-                         : "memory");
+            const bool ok = k_ok && ((okmask[i] >> tbit) & 1u);
+            const __nv_bfloat16* gp = ok ? sp + (long long)(pix[i] + delta) * ld : P.src[0];
+            cp_async16(a_s + (uint32_t)(rbase + 16 * i) * 128u, gp, ok ? 16u : 0u);
           }
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          mbar_arrive(full_bar(s));
+          asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full_bar(s)) : "memory");
+          it++;
           rem += BK;
           while (rem >= P.per_tap) {
             rem -= P.per_tap;
@@ -447,6 +488,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
           const int s = it % S;
           const uint32_t ph = (uint32_t)(it / S) & 1u;
           mbar_wait(full_bar(s), ph);
+          if (!P.a_tma) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t a_s = a_base + (uint32_t)s * A_STAGE_BYTES;
           const uint32_t b_s = b_base + (uint32_t)s * b_stage_bytes;
@@ -604,6 +646,8 @@ int conv_tc_prepare(yb_plan* p, Op& op) {
   const size_t SMEM_MAX = 227 * 1024;
   int occ = std::min(2, 512 / tmem_cols_for(op.BN));
   if (const char* e = getenv("YB_OCC")) occ = std::max(1, std::min(occ, atoi(e)));
+  if (!op.a_tma)
+    if (const char* e = getenv("YB_OCC_GATHER")) occ = std::max(1, std::min(occ, atoi(e)));
   size_t budget = SMEM_MAX / occ;
   int st = MAX_STAGES;
   while (st > 2 && conv_smem_bytes(st, op.BN) > budget) st--;
@@ -697,6 +741,20 @@ static void fill_params(const yb_plan* p, const Op& op, ConvParams& P) {
   P.tmem_cols = tmem_cols_for(op.BN);
   P.n_tiles = op.N_pad / op.BN;
   P.total_tiles = ((P.M + BM - 1) / BM) * P.n_tiles;
+  auto magic = [](int d, uint32_t& mul, uint32_t& shr) {
+    if (d <= 1) {
+      mul = 0;
+      shr = 0;
+      return;
+    }
+    int lg = 0;
+    while ((1u << lg) < (uint32_t)d) lg++;
+    int pshift = 31 + lg;
+    mul = (uint32_t)((((unsigned long long)1 << pshift) + (unsigned)d - 1) / (unsigned)d);
+    shr = (uint32_t)(pshift - 32);
+  };
+  magic(P.hw_out, P.hw_mul, P.hw_shr);
+  magic(P.Wout, P.w_mul, P.w_shr);
   P.out_mode = op.out_f32 ? 1 : 0;
   P.A_total = p->A;
   P.nc = p->nc;
