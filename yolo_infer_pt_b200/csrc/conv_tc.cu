@@ -171,7 +171,13 @@ __device__ __forceinline__ void cp_async_wait_pending(int n) {
 __device__ __forceinline__ int fast_div(int n, uint32_t mul, uint32_t shr, int d) {
   return d == 1 ? n : (int)(__umulhi((uint32_t)n, mul) >> shr);
 }
-__device__ __forceinline__ float silu_f(float x) { return __fdividef(x, 1.f + __expf(-x)); }
+// SiLU(x) = x * sigmoid(x) = h + h * tanh(h), h = x/2: one MUFU op (tanh.approx) instead of two
+// (ex2 + rcp).  The epilogue is MUFU-throughput bound on the small-channel layers.
+__device__ __forceinline__ float silu_f(float x) {
+  float h = 0.5f * x, t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
@@ -230,7 +236,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
     }
     for (int a = 0; a < 2; a++) {
       mbar_init(tmem_full_bar(a), 1u);
-      mbar_init(tmem_empty_bar(a), 128u);
+      mbar_init(tmem_empty_bar(a), P.a_tma ? 256u : 128u);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -247,8 +253,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp < EPI_WARPS) {
+  // With A fed by TMA the im2col warps have nothing to gather: they join the epilogue as a second
+  // group that converts the odd 16-column chunks of the accumulator (same TMEM lane quadrants).
+  if (warp < EPI_WARPS || (P.a_tma && warp < MMA_WARP)) {
     // ============================ epilogue =================================================
+    const int grp = warp >> 2;                  // 0: warps 0-3, 1: warps 4-7
+    const int ngrp = P.a_tma ? 2 : 1;
+    const int etid = tid & 127;                 // row of the tile owned by this thread
+    const int qwarp = warp & 3;                 // TMEM lane quadrant
+    const int cstep = (P.out_mode == 2) ? 16 : 16 * ngrp;   // DFL decode needs all 4 sides in one thread
+    const int cfirst = (P.out_mode == 2) ? (grp ? BN : 0) : 16 * grp;
     int ti = 0;
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ti++) {
       const int m0 = (tile / P.n_tiles) * BM;
@@ -258,9 +272,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       // the previous tile's TMA stores must have finished reading the staging buffer
       if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      for (int i = tid; i < BN; i += 128) bias_s[i] = __ldg(P.bias + n0 + i);
-      asm volatile("bar.sync 1, 128;" ::: "memory");
-      const int m = m0 + tid;
+      for (int i = tid; i < BN; i += 128 * ngrp) bias_s[i] = __ldg(P.bias + n0 + i);
+      if (ngrp == 2) asm volatile("bar.sync 1, 256;" ::: "memory");
+      else asm volatile("bar.sync 1, 128;" ::: "memory");
+      const int m = m0 + etid;
       const bool row_ok = m < P.M;
       int n_img = 0, r = 0;
       if (row_ok) {
@@ -269,9 +284,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
       }
       const size_t drow = (size_t)n_img * P.dst_rows_per_img + P.dst_row_off + r;
       const __nv_bfloat16* resp = P.res ? P.res + (size_t)m * P.res_ld : nullptr;
-      const uint32_t t_row = tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * BN);
+      const uint32_t t_row = tmem_base + ((uint32_t)(qwarp * 32) << 16) + (uint32_t)(acc * BN);
       float dist[4];
-      for (int c0 = 0; c0 < BN; c0 += 16) {
+      for (int c0 = cfirst; c0 < BN; c0 += cstep) {
         uint32_t v[16];
         tmem_ld16(t_row + (uint32_t)c0, v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -286,7 +301,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
         if (P.out_mode == 0) {
           // bf16 tile staged in shared memory in the TMA SWIZZLE_128B layout (16-byte chunk index
           // XOR row%8 inside each 128-byte row), then written with one TMA store per 64 channels
-          const uint32_t srow = c_base + (uint32_t)(c0 >> 6) * C_GROUP_BYTES + (uint32_t)tid * 128u;
+          const uint32_t srow = c_base + (uint32_t)(c0 >> 6) * C_GROUP_BYTES + (uint32_t)etid * 128u;
 #pragma unroll
           for (int h = 0; h < 2; h++) {
             if (nb + 8 * h < P.cout_store) {
@@ -301,7 +316,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
                 }
               }
               const uint32_t chunk = (uint32_t)(((c0 & 63) >> 3) + h);
-              const uint32_t addr = srow + ((chunk ^ (uint32_t)(tid & 7)) << 4);
+              const uint32_t addr = srow + ((chunk ^ (uint32_t)(etid & 7)) << 4);
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
                            "r"(pack_bf16(f[8 * h + 0], f[8 * h + 1])), "r"(pack_bf16(f[8 * h + 2], f[8 * h + 3])),
                            "r"(pack_bf16(f[8 * h + 4], f[8 * h + 5])), "r"(pack_bf16(f[8 * h + 6], f[8 * h + 7]))
@@ -339,7 +354,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
           }
         }
       }
-      if (P.out_mode == 2 && row_ok) {
+      if (P.out_mode == 2 && row_ok && grp == 0) {
         const int y = fast_div(r, P.w_mul, P.w_shr, P.Wout), x = r - y * P.Wout;
         const float ax = (float)x + 0.5f, ay = (float)y + 0.5f, st = P.lvl_stride;
         const float x1 = ax - dist[0], y1 = ay - dist[1], x2 = ax + dist[2], y2 = ay + dist[3];
@@ -354,7 +369,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
       mbar_arrive(tmem_empty_bar(acc));
       if (P.out_mode == 0) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("bar.sync 1, 128;" ::: "memory");
+        if (ngrp == 2) asm volatile("bar.sync 1, 256;" ::: "memory");
+        else asm volatile("bar.sync 1, 128;" ::: "memory");
         if (tid == 0) {
           for (uint32_t g = 0; g < c_groups; g++) {
             const int cg0 = n0 + (int)g * 64;
@@ -372,8 +388,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
     }
     if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   } else if (warp < MMA_WARP) {
-    // ============================ im2col producer (idle when A comes by TMA) ================
-    if (!P.a_tma) {
+    // ============================ im2col producer ==========================================
+    {
       const int ptid = tid - PROD_WARP0 * 32;
       const int g = ptid & 7;       // 16-byte granule (8 channels) inside the 128-byte K row
       const int rbase = ptid >> 3;  // rows rbase + 16*i
@@ -433,11 +449,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
               uint32_t mk = 0;
               if (row_n[i] >= 0) {
                 if (P.ksize == 3) {
+                  // separable: 3 column bits replicated per row of taps, gated by the 3 row bits
+                  uint32_t xm = 0, ym = 0;
 #pragma unroll
-                  for (int t = 0; t < 9; t++) {
-                    int iy = row_y[i] + t / 3, ix = row_x[i] + t % 3;
-                    if ((unsigned)iy < (unsigned)P.Hin && (unsigned)ix < (unsigned)P.Win) mk |= 1u << t;
+                  for (int t = 0; t < 3; t++) {
+                    if ((unsigned)(row_x[i] + t) < (unsigned)P.Win) xm |= 1u << t;
+                    if ((unsigned)(row_y[i] + t) < (unsigned)P.Hin) ym |= 7u << (3 * t);
                   }
+                  mk = (xm * 0x49u) & ym;
                 } else {
                   mk = 1u;
                 }

@@ -10,7 +10,11 @@
 
 namespace yb {
 
-__device__ __forceinline__ float silu_acc(float x) { return __fdividef(x, 1.f + __expf(-x)); }
+__device__ __forceinline__ float silu_acc(float x) {  // h + h*tanh(h), h = x/2 (one MUFU op)
+  float h = 0.5f * x, t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
 
 __device__ __forceinline__ void bf16x8_to_float(const uint4& v, float* f) {
   const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
