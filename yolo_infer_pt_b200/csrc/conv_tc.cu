@@ -103,12 +103,25 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug traps (surfacing as a CUDA error) instead of hanging the GPU.
+// try_wait suspends the thread in hardware for a bounded time, so this loop polls rarely.
+// -DYB_BOUNDED_WAIT turns a protocol bug into a trap (a CUDA error) instead of a hang.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+#ifdef YB_BOUNDED_WAIT
   uint32_t spins = 0;
   while (!mbar_try(bar, parity)) {
     if (++spins > (1u << 27)) __trap();
   }
+#else
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, 0x989680;\n\t"
+      "@p bra.uni WAIT_DONE;\n\t"
+      "bra.uni WAIT_LOOP;\n\t"
+      "WAIT_DONE:\n\t}" ::"r"(bar),
+      "r"(parity)
+      : "memory");
+#endif
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1,
                                             uint32_t bar) {
@@ -265,8 +278,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
     const int cfirst = (P.out_mode == 2) ? (grp ? BN : 0) : 16 * grp;
     int ti = 0;
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ti++) {
-      const int m0 = (tile / P.n_tiles) * BM;
-      const int n0 = (tile % P.n_tiles) * BN;
+      const int mt = P.n_tiles == 1 ? tile : tile / P.n_tiles;
+      const int m0 = mt * BM;
+      const int n0 = (tile - mt * P.n_tiles) * BN;
       const int acc = ti & 1;
       mbar_wait(tmem_full_bar(acc), (uint32_t)(ti >> 1) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -401,9 +415,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
       // thread's fence.proxy.async after it acquires the barrier.
       // Address arithmetic is hoisted: per tile each row keeps the pixel index of its tap (0,0) and
       // a 9-bit in-bounds mask; a k-block then costs one add + one wide multiply per row.
-      int it = 0;
+      int stage = 0;
+      uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-        const int m0 = (tile / P.n_tiles) * BM;
+        const int m0 = (P.n_tiles == 1 ? tile : tile / P.n_tiles) * BM;
         int row_n[8], row_y[8], row_x[8];
 #pragma unroll
         for (int i = 0; i < 8; i++) {
@@ -431,8 +446,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
           tap++;
         }
         for (int kb = 0; kb < num_kb; kb++) {
-          const int s = it % S;
-          const uint32_t ph = (uint32_t)(it / S) & 1u;
+          const int s = stage;
+          const uint32_t ph = phase;
           const bool k_ok = (kb * BK + g * 8) < P.K;
           int seg = 0, c = rem;
           while (seg + 1 < P.nseg && c >= P.src_cp[seg]) {
@@ -483,7 +498,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
             cp_async16(a_s + (uint32_t)(rbase + 16 * i) * 128u, gp, ok ? 16u : 0u);
           }
           asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full_bar(s)) : "memory");
-          it++;
+          if (++stage == S) {
+            stage = 0;
+            phase ^= 1u;
+          }
           rem += BK;
           while (rem >= P.per_tap) {
             rem -= P.per_tap;
@@ -497,15 +515,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
     if (lane == 0) {
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
                              ((uint32_t)(BM >> 4) << 24);
-      int it = 0, ti = 0;
+      int ti = 0, stage = 0;
+      uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ti++) {
         const int acc = ti & 1;
         mbar_wait(tmem_empty_bar(acc), ((uint32_t)(ti >> 1) & 1u) ^ 1u);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < num_kb; kb++, it++) {
-          const int s = it % S;
-          const uint32_t ph = (uint32_t)(it / S) & 1u;
+        for (int kb = 0; kb < num_kb; kb++) {
+          const int s = stage;
+          const uint32_t ph = phase;
           mbar_wait(full_bar(s), ph);
           if (!P.a_tma) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -517,6 +536,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
                       (uint32_t)((kb | k) != 0));
           }
           umma_commit(empty_bar(s));  // frees the smem stage once these MMAs have read it
+          if (++stage == S) {
+            stage = 0;
+            phase ^= 1u;
+          }
         }
         umma_commit(tmem_full_bar(acc));  // accumulator complete -> epilogue
       }
@@ -525,14 +548,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
     // ============================ TMA producer ============================================
     if (lane == 0) {
       const uint32_t tx = b_stage_bytes + (P.a_tma ? (uint32_t)A_STAGE_BYTES : 0u);
-      int it = 0;
+      int stage = 0;
+      uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-        const int m0 = (tile / P.n_tiles) * BM;
-        const int n0 = (tile % P.n_tiles) * BN;
+        const int mt = P.n_tiles == 1 ? tile : tile / P.n_tiles;
+        const int m0 = mt * BM;
+        const int n0 = (tile - mt * P.n_tiles) * BN;
         int seg = 0, kk = 0;
-        for (int kb = 0; kb < num_kb; kb++, it++) {
-          const int s = it % S;
-          const uint32_t ph = (uint32_t)(it / S) & 1u;
+        for (int kb = 0; kb < num_kb; kb++) {
+          const int s = stage;
+          const uint32_t ph = phase;
           mbar_wait(empty_bar(s), ph ^ 1u);
           mbar_expect_tx(full_bar(s), tx);
           tma_load_2d(b_base + (uint32_t)s * b_stage_bytes, &tmap_b, kb * BK, n0, full_bar(s));
@@ -544,6 +569,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
               kk = 0;
               seg++;
             }
+          }
+          if (++stage == S) {
+            stage = 0;
+            phase ^= 1u;
           }
         }
       }

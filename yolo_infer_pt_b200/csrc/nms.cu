@@ -1,12 +1,11 @@
 // non_max_suppression on the device (reference utils/util.py:123-169, torchvision.ops.nms CPU
 // semantics for the greedy step).  No host synchronisation, no data-dependent launch shapes:
 //
-//   1. scan      one coalesced pass over (B, 4+nc, A): every score > conf becomes a 64-bit key
+//   1. append    one coalesced pass over (B, 4+nc, A): every score > conf becomes a 64-bit key
 //                  key = ~orderable(score) << 32 | (anchor * nc + class)
 //                ascending key order == descending score, ties by ascending candidate index
 //                (anchor-major, class-minor: the row-major order of util.py:147's nonzero()).
-//                Keys are appended to a per-image list while it has room; an 11-bit histogram of
-//                the key's top digit is built on the way.
+//                Keys are appended to a per-image list while it has room.
 //   2. select    only for images with more than max_nms candidates (util.py:157's [:max_nms]):
 //                an exact radix select of the max_nms-th smallest key (6 histogram passes over
 //                the scores, gated per image), then a re-compaction of keys <= that threshold.
@@ -71,16 +70,74 @@ __device__ __forceinline__ unsigned long long make_key(float score, unsigned int
 __device__ __forceinline__ int pass_shift(int pass) { return pass < 5 ? 64 - 11 * (pass + 1) : 0; }
 __device__ __forceinline__ int pass_bits(int pass) { return pass < 5 ? 11 : 9; }
 
-// mode 0: scan (count + append + histogram of digit 0)
-// mode 1: histogram of digit `pass` among keys matching the prefix (overflow images only)
-// mode 2: re-compaction of keys <= threshold (overflow images only)
+// Pass over the scores of every image: each score > conf becomes a key appended to the image's
+// list (unordered; the sort orders them).  Reads 4 anchors per thread (float4 when aligned), one
+// atomic per warp iteration.
+__global__ void __launch_bounds__(256) nms_append_kernel(const NmsArgs a, int vec4) {
+  const int b = blockIdx.y;
+  NmsHeader* h = a.hdr + b;
+  const long long total = (long long)a.nc * a.A;
+  const float* sp = a.pred + ((size_t)b * (4 + a.nc) + 4) * a.A;
+  unsigned long long* keys = a.keys + (size_t)b * a.cap;
+  const int lane = threadIdx.x & 31;
+  const long long stride = (long long)gridDim.x * blockDim.x * 4;
+  const long long iters = (total + stride - 1) / stride;
+  long long e = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  int local_count = 0;
+  for (long long it = 0; it < iters; it++, e += stride) {
+    float v[4] = {0.f, 0.f, 0.f, 0.f};
+    int nv = 0;
+    if (e < total) {
+      nv = (int)min((long long)4, total - e);
+      if (vec4 && nv == 4) {
+        float4 q = __ldg(reinterpret_cast<const float4*>(sp + e));
+        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+      } else {
+        for (int j = 0; j < nv; j++) v[j] = __ldg(sp + e + j);
+      }
+    }
+    int cnt = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) cnt += (j < nv && v[j] > a.conf) ? 1 : 0;
+    // warp-wide exclusive prefix of cnt
+    int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    const int wtotal = __shfl_sync(0xffffffffu, incl, 31);
+    if (wtotal == 0) continue;
+    int base = 0;
+    if (lane == 0) base = atomicAdd(&h->sel_count, wtotal);
+    base = __shfl_sync(0xffffffffu, base, 0);
+    int slot = base + incl - cnt;
+    local_count += cnt;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      if (j < nv && v[j] > a.conf) {
+        long long ee = e + j;
+        int c = (int)(ee / a.A);
+        int an = (int)(ee - (long long)c * a.A);
+        if (slot < a.cap) keys[slot] = make_key(v[j], (unsigned int)an * (unsigned int)a.nc + (unsigned int)c);
+        slot++;
+      }
+    }
+  }
+  for (int o = 16; o > 0; o >>= 1) local_count += __shfl_xor_sync(0xffffffffu, local_count, o);
+  if (lane == 0 && local_count) atomicAdd(&h->cand_count, local_count);
+}
+
+// Overflow images only (more than max_nms candidates):
+// mode 1: histogram of digit `pass` among keys matching the radix-select prefix
+// mode 2: re-compaction of keys <= threshold
 template <int MODE>
 __global__ void __launch_bounds__(256) nms_scan_kernel(const NmsArgs a, int pass) {
   __shared__ unsigned int hist_s[HIST_BINS];
   const int b = blockIdx.y;
   NmsHeader* h = a.hdr + b;
-  if (MODE != 0 && !h->overflow) return;
-  if (MODE != 2) {
+  if (!h->overflow) return;
+  if (MODE == 1) {
     for (int i = threadIdx.x; i < HIST_BINS; i += blockDim.x) hist_s[i] = 0;
     __syncthreads();
   }
@@ -90,7 +147,6 @@ __global__ void __launch_bounds__(256) nms_scan_kernel(const NmsArgs a, int pass
   const unsigned long long prefix = h->prefix;
   const int shift = pass_shift(pass), bits = pass_bits(pass);
   const int lane = threadIdx.x & 31;
-  int local_count = 0;
   // all lanes of a warp run the same number of iterations (ballots below)
   const long long stride = (long long)gridDim.x * blockDim.x;
   const long long iters = (total + stride - 1) / stride;
@@ -107,25 +163,9 @@ __global__ void __launch_bounds__(256) nms_scan_kernel(const NmsArgs a, int pass
         cand = true;
       }
     }
-    if (MODE == 0) {
-      if (cand) {
-        local_count++;
-        atomicAdd(&hist_s[(unsigned int)(key >> shift) & ((1u << bits) - 1u)], 1u);
-      }
-      unsigned int m = __ballot_sync(0xffffffffu, cand);
-      if (m) {
-        int leader = __ffs(m) - 1;
-        int base = 0;
-        if (lane == leader) base = atomicAdd(&h->sel_count, __popc(m));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (cand) {
-          int slot = base + __popc(m & ((1u << lane) - 1u));
-          if (slot < a.cap) keys[slot] = key;
-        }
-      }
-    } else if (MODE == 1) {
-      if (cand && (key >> (shift + bits)) == prefix)
-        atomicAdd(&hist_s[(unsigned int)(key >> shift) & ((1u << bits) - 1u)], 1u);
+    if (MODE == 1) {
+      bool match = pass == 0 ? true : ((key >> (shift + bits)) == prefix);
+      if (cand && match) atomicAdd(&hist_s[(unsigned int)(key >> shift) & ((1u << bits) - 1u)], 1u);
     } else {
       bool take = cand && key <= prefix;
       unsigned int m = __ballot_sync(0xffffffffu, take);
@@ -141,12 +181,7 @@ __global__ void __launch_bounds__(256) nms_scan_kernel(const NmsArgs a, int pass
       }
     }
   }
-  if (MODE == 0) {
-    // block-level count
-    for (int o = 16; o > 0; o >>= 1) local_count += __shfl_xor_sync(0xffffffffu, local_count, o);
-    if (lane == 0 && local_count) atomicAdd(&h->cand_count, local_count);
-  }
-  if (MODE != 2) {
+  if (MODE == 1) {
     __syncthreads();
     unsigned int* hg = a.hist + (size_t)b * HIST_BINS;
     for (int i = threadIdx.x; i < HIST_BINS; i += blockDim.x)
@@ -160,8 +195,7 @@ __global__ void __launch_bounds__(1024) nms_pick_kernel(const NmsArgs a, int pas
   const int b = blockIdx.x;
   NmsHeader* h = a.hdr + b;
   unsigned int* hg = a.hist + (size_t)b * HIST_BINS;
-  if (pass == 0) {
-    __syncthreads();
+  if (pass < 0) {  // decision step: does this image exceed max_nms candidates?
     if (threadIdx.x == 0) {
       int total = h->cand_count;
       if (total > a.max_nms) {
@@ -174,7 +208,7 @@ __global__ void __launch_bounds__(1024) nms_pick_kernel(const NmsArgs a, int pas
         h->n_final = total;
       }
     }
-    __syncthreads();
+    return;
   }
   if (!h->overflow) return;
   const int nb = 1 << pass_bits(pass);
@@ -462,19 +496,21 @@ int nms_run(const float* pred, int B, int nc, int A, float conf, double iou, int
   a.out_counts = out_counts;
   YB_CUDA(cudaMemsetAsync(ws, 0, hdr_bytes + (size_t)B * HIST_BINS * 4, st));
   long long total = (long long)nc * A;
-  int gx = (int)std::min<long long>((total + 256 * 8 - 1) / (256 * 8), 1024);
-  dim3 sgrid(gx, B);
-  nms_scan_kernel<0><<<sgrid, 256, 0, st>>>(a, 0);
+  int gx = (int)std::min<long long>((total + 256 * 16 - 1) / (256 * 16), 1024);
+  int vec4 = (A % 4 == 0) && ((reinterpret_cast<uintptr_t>(pred) & 15) == 0);
+  nms_append_kernel<<<dim3(gx, B), 256, 0, st>>>(a, vec4);
   count_launch();
-  nms_pick_kernel<<<B, 1024, 0, st>>>(a, 0);
+  nms_pick_kernel<<<B, 32, 0, st>>>(a, -1);
   count_launch();
-  for (int pass = 1; pass < NUM_PASSES; pass++) {
-    nms_scan_kernel<1><<<sgrid, 256, 0, st>>>(a, pass);
+  // radix select + re-compaction: every block returns at once unless its image overflowed
+  dim3 ogrid(std::min(gx, 48), B);
+  for (int pass = 0; pass < NUM_PASSES; pass++) {
+    nms_scan_kernel<1><<<ogrid, 256, 0, st>>>(a, pass);
     count_launch();
     nms_pick_kernel<<<B, 1024, 0, st>>>(a, pass);
     count_launch();
   }
-  nms_scan_kernel<2><<<sgrid, 256, 0, st>>>(a, 0);
+  nms_scan_kernel<2><<<ogrid, 256, 0, st>>>(a, 0);
   count_launch();
   dim3 tgrid(a.cap / SORT_TILE, B);
   nms_sort_tile_kernel<<<tgrid, 1024, 0, st>>>(a, 0, 0);
