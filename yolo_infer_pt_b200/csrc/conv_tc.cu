@@ -65,6 +65,9 @@ struct ConvParams {
   int BN, stages, a_tma, tmem_cols;
   int n_tiles, total_tiles;
   uint32_t hw_mul, hw_shr, w_mul, w_shr;  // magic numbers: division by hw_out and by Wout
+  // 2-D spatial tiles (8 x 16 output pixels) when Hout % 8 == 0 and Wout % 16 == 0
+  int tile2d, tiles_x, tiles_per_img;
+  uint32_t tpi_mul, tpi_shr, tx_mul, tx_shr;
   // fused head decode (out_mode 2 / 3): dst is the (B, 4+nc, A) fp32 output tensor
   int out_mode;       // 0 bf16 slice, 1 fp32 logits, 2 DFL box decode, 3 class sigmoid
   int A_total, nc;
@@ -131,6 +134,37 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map
       "l"((uint64_t)map), "r"(c0), "r"(c1), "r"(bar)
       : "memory");
 }
+// q = n / d for n < 2^31 with host-computed (mul, shr): mul = ceil(2^(31+ceil_log2 d) / d)
+__device__ __forceinline__ int fast_div(int n, uint32_t mul, uint32_t shr, int d) {
+  return d == 1 ? n : (int)(__umulhi((uint32_t)n, mul) >> shr);
+}
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, int c0, int c1, int c2,
+                                            int c3, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, "
+      "%3, %4, %5}], [%6];" ::"r"(dst),
+      "l"((uint64_t)map), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(bar)
+      : "memory");
+}
+// Tile -> position.  Linear tiles: 128 consecutive rows of the flattened (image, y, x) index.
+// 2-D tiles: an 8 (y) x 16 (x) patch of one image; tile row r = ly * 16 + lx.
+struct TilePos {
+  int m0;            // linear: first row
+  int n, oy0, ox0;   // 2-D: image and patch origin
+};
+__device__ __forceinline__ TilePos tile_pos(const ConvParams& P, int mt) {
+  TilePos t;
+  t.m0 = mt * BM;
+  t.n = t.oy0 = t.ox0 = 0;
+  if (P.tile2d) {
+    t.n = fast_div(mt, P.tpi_mul, P.tpi_shr, P.tiles_per_img);
+    int r = mt - t.n * P.tiles_per_img;
+    int ty = fast_div(r, P.tx_mul, P.tx_shr, P.tiles_x);
+    t.oy0 = ty * 8;
+    t.ox0 = (r - ty * P.tiles_x) * 16;
+  }
+  return t;
+}
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
   // K-major, SWIZZLE_128B canonical layout: 8-row x 128B atoms, SBO = 1024 B, LBO = 1 (unused),
   // descriptor version 1 (sm_100), layout type 2.
@@ -179,10 +213,6 @@ __device__ __forceinline__ void cp_async_wait_pending(int n) {
     case 5: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
     default: asm volatile("cp.async.wait_group 6;" ::: "memory"); break;
   }
-}
-// q = n / d for n < 2^31 with host-computed (mul, shr): mul = ceil(2^(31+ceil_log2 d) / d)
-__device__ __forceinline__ int fast_div(int n, uint32_t mul, uint32_t shr, int d) {
-  return d == 1 ? n : (int)(__umulhi((uint32_t)n, mul) >> shr);
 }
 // SiLU(x) = x * sigmoid(x) = h + h * tanh(h), h = x/2: one MUFU op (tanh.approx) instead of two
 // (ex2 + rcp).  The epilogue is MUFU-throughput bound on the small-channel layers.
@@ -279,7 +309,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
     int ti = 0;
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ti++) {
       const int mt = P.n_tiles == 1 ? tile : tile / P.n_tiles;
-      const int m0 = mt * BM;
+      const TilePos tp = tile_pos(P, mt);
+      const int m0 = tp.m0;
       const int n0 = (tile - mt * P.n_tiles) * BN;
       const int acc = ti & 1;
       mbar_wait(tmem_full_bar(acc), (uint32_t)(ti >> 1) & 1u);
@@ -289,10 +320,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
       for (int i = tid; i < BN; i += 128 * ngrp) bias_s[i] = __ldg(P.bias + n0 + i);
       if (ngrp == 2) asm volatile("bar.sync 1, 256;" ::: "memory");
       else asm volatile("bar.sync 1, 128;" ::: "memory");
-      const int m = m0 + etid;
-      const bool row_ok = m < P.M;
+      int m = m0 + etid;
+      bool row_ok = m < P.M;
       int n_img = 0, r = 0;
-      if (row_ok) {
+      if (P.tile2d) {
+        n_img = tp.n;
+        r = (tp.oy0 + (etid >> 4)) * P.Wout + tp.ox0 + (etid & 15);
+        m = n_img * P.hw_out + r;
+        row_ok = true;
+      } else if (row_ok) {
         n_img = fast_div(m, P.hw_mul, P.hw_shr, P.hw_out);
         r = m - n_img * P.hw_out;
       }
@@ -389,11 +425,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
           for (uint32_t g = 0; g < c_groups; g++) {
             const int cg0 = n0 + (int)g * 64;
             if (cg0 < P.cout_store) {
-              asm volatile(
-                  "cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
-                      (uint64_t)&tmap_c),
-                  "r"(cg0), "r"(m0), "r"(c_base + g * C_GROUP_BYTES)
-                  : "memory");
+              if (P.tile2d) {
+                asm volatile(
+                    "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];" ::"l"(
+                        (uint64_t)&tmap_c),
+                    "r"(cg0), "r"(tp.ox0), "r"(tp.oy0), "r"(tp.n), "r"(c_base + g * C_GROUP_BYTES)
+                    : "memory");
+              } else {
+                asm volatile(
+                    "cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
+                        (uint64_t)&tmap_c),
+                    "r"(cg0), "r"(m0), "r"(c_base + g * C_GROUP_BYTES)
+                    : "memory");
+              }
             }
           }
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -418,22 +462,34 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-        const int m0 = (P.n_tiles == 1 ? tile : tile / P.n_tiles) * BM;
+        const TilePos tp = tile_pos(P, P.n_tiles == 1 ? tile : tile / P.n_tiles);
+        // input coordinates of tap (0,0) for this thread's 8 rows (rows rbase + 16*i of the tile).
+        // In a 2-D tile those are the 8 image rows of one column: ox is shared, oy = oy0 + i.
         int row_n[8], row_y[8], row_x[8];
+        if (P.tile2d) {
+          const int x0 = (tp.ox0 + rbase) * P.stride - P.pad;
 #pragma unroll
-        for (int i = 0; i < 8; i++) {
-          int m = m0 + rbase + 16 * i;
-          if (m < P.M) {
-            int n = fast_div(m, P.hw_mul, P.hw_shr, P.hw_out);
-            int r = m - n * P.hw_out;
-            int oy = fast_div(r, P.w_mul, P.w_shr, P.Wout);
-            row_n[i] = n;
-            row_y[i] = oy * P.stride - P.pad;
-            row_x[i] = (r - oy * P.Wout) * P.stride - P.pad;
-          } else {
-            row_n[i] = -1;
-            row_y[i] = 0;
-            row_x[i] = 0;
+          for (int i = 0; i < 8; i++) {
+            row_n[i] = tp.n;
+            row_y[i] = (tp.oy0 + i) * P.stride - P.pad;
+            row_x[i] = x0;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 8; i++) {
+            int m = tp.m0 + rbase + 16 * i;
+            if (m < P.M) {
+              int n = fast_div(m, P.hw_mul, P.hw_shr, P.hw_out);
+              int r = m - n * P.hw_out;
+              int oy = fast_div(r, P.w_mul, P.w_shr, P.Wout);
+              row_n[i] = n;
+              row_y[i] = oy * P.stride - P.pad;
+              row_x[i] = (r - oy * P.Wout) * P.stride - P.pad;
+            } else {
+              row_n[i] = -1;
+              row_y[i] = 0;
+              row_x[i] = 0;
+            }
           }
         }
         int pix[8];
@@ -459,19 +515,30 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
           if (seg != cur_seg) {  // new tile, or the K walk crossed into the next source of a concat
             cur_seg = seg;
             const int Hs = P.Hin >> up;
+            uint32_t xm = 0;
+            if (P.ksize == 3) {
+#pragma unroll
+              for (int t = 0; t < 3; t++)
+                if ((unsigned)(row_x[0] + t) < (unsigned)P.Win) xm |= 1u << t;
+              xm *= 0x49u;  // the 3 column bits replicated for each of the 3 tap rows
+            }
 #pragma unroll
             for (int i = 0; i < 8; i++) {
               uint32_t mk = 0;
               if (row_n[i] >= 0) {
                 if (P.ksize == 3) {
-                  // separable: 3 column bits replicated per row of taps, gated by the 3 row bits
-                  uint32_t xm = 0, ym = 0;
+                  if (!P.tile2d) {
+                    xm = 0;
 #pragma unroll
-                  for (int t = 0; t < 3; t++) {
-                    if ((unsigned)(row_x[i] + t) < (unsigned)P.Win) xm |= 1u << t;
-                    if ((unsigned)(row_y[i] + t) < (unsigned)P.Hin) ym |= 7u << (3 * t);
+                    for (int t = 0; t < 3; t++)
+                      if ((unsigned)(row_x[i] + t) < (unsigned)P.Win) xm |= 1u << t;
+                    xm *= 0x49u;
                   }
-                  mk = (xm * 0x49u) & ym;
+                  uint32_t ym = 0;
+#pragma unroll
+                  for (int t = 0; t < 3; t++)
+                    if ((unsigned)(row_y[i] + t) < (unsigned)P.Hin) ym |= 7u << (3 * t);
+                  mk = xm & ym;
                 } else {
                   mk = 1u;
                 }
@@ -494,8 +561,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
 #pragma unroll
           for (int i = 0; i < 8; i++) {
             const bool ok = k_ok && ((okmask[i] >> tbit) & 1u);
-            const __nv_bfloat16* gp = ok ? sp + (long long)(pix[i] + delta) * ld : P.src[0];
-            cp_async16(a_s + (uint32_t)(rbase + 16 * i) * 128u, gp, ok ? 16u : 0u);
+            const int idx = ok ? pix[i] + delta : 0;   // a valid address even when zero-filling
+            cp_async16(a_s + (uint32_t)(rbase + 16 * i) * 128u, sp + (long long)idx * ld, ok ? 16u : 0u);
           }
           asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full_bar(s)) : "memory");
           if (++stage == S) {
@@ -552,7 +619,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
         const int mt = P.n_tiles == 1 ? tile : tile / P.n_tiles;
-        const int m0 = mt * BM;
+        const TilePos tp = tile_pos(P, mt);
         const int n0 = (tile - mt * P.n_tiles) * BN;
         int seg = 0, kk = 0;
         for (int kb = 0; kb < num_kb; kb++) {
@@ -564,7 +631,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
           if (P.a_tma) {
             const CUtensorMap* ma =
                 seg == 0 ? &tmap_a0 : seg == 1 ? &tmap_a1 : seg == 2 ? &tmap_a2 : &tmap_a3;
-            tma_load_2d(a_base + (uint32_t)s * A_STAGE_BYTES, ma, kk * BK, m0, full_bar(s));
+            if (P.tile2d)
+              tma_load_4d(a_base + (uint32_t)s * A_STAGE_BYTES, ma, kk * BK, tp.ox0, tp.oy0, tp.n, full_bar(s));
+            else
+              tma_load_2d(a_base + (uint32_t)s * A_STAGE_BYTES, ma, kk * BK, tp.m0, full_bar(s));
             if (++kk == P.seg_kb[seg]) {
               kk = 0;
               seg++;
@@ -674,6 +744,31 @@ static int make_tmap_2d(CUtensorMap* map, const void* base, uint64_t inner, uint
   return YB_OK;
 }
 
+// 4-D map over an NHWC slice {C, W, H, N} with an 8 (y) x 16 (x) x 64-channel box: smem rows come
+// out as r = ly * 16 + lx, 128 bytes each, SWIZZLE_128B — the same image as a 128-row 2-D box.
+static int make_tmap_nhwc(CUtensorMap* map, const void* base, uint64_t C, uint64_t W, uint64_t H, uint64_t N,
+                          uint64_t ld_elems) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled driver entry point not available");
+    return YB_ERR_CUDA;
+  }
+  cuuint64_t dims[4] = {C, W, H, N};
+  cuuint64_t strides[3] = {ld_elems * 2, W * ld_elems * 2, H * W * ld_elems * 2};
+  cuuint32_t box[4] = {64, 16, 8, 1};
+  cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (4-D NHWC) failed with %d (C=%llu W=%llu H=%llu N=%llu ld=%llu)", (int)r,
+              (unsigned long long)C, (unsigned long long)W, (unsigned long long)H, (unsigned long long)N,
+              (unsigned long long)ld_elems);
+    return YB_ERR_CUDA;
+  }
+  return YB_OK;
+}
+
 static size_t conv_smem_bytes(int stages, int BN) {
   return 1024 + (size_t)stages * (A_STAGE_BYTES + (size_t)BN * 128) + (size_t)((BN + 63) / 64) * C_GROUP_BYTES +
          (2 * MAX_STAGES + 4) * 8 + 16 + 256 * 4 + 64;
@@ -711,12 +806,17 @@ int conv_tc_prepare(yb_plan* p, Op& op) {
                         (uint64_t)op.K_pad * 2, BK, (uint32_t)op.BN);
   if (rc) return rc;
   for (int i = 0; i < 4; i++) op.tmap_a[i] = op.tmap_b;
+  op.tile2d = (op.Hout % 8 == 0 && op.Wout % 16 == 0 && !op.out_f32 && getenv("YB_NO_TILE2D") == nullptr) ? 1 : 0;
   if (op.a_tma) {
     for (int i = 0; i < op.nseg; i++) {
       const Buf& b = p->bufs[op.src[i].buf];
       const uint8_t* base = buf_ptr(p, op.src[i].buf) + (size_t)op.src[i].c_off * 2;
-      rc = make_tmap_2d(&op.tmap_a[i], base, (uint64_t)cpad8(op.src[i].C),
-                        (uint64_t)p->B * b.rows_per_img, (uint64_t)b.C * 2, BK, BM);
+      if (op.tile2d)
+        rc = make_tmap_nhwc(&op.tmap_a[i], base, (uint64_t)cpad8(op.src[i].C), (uint64_t)b.W, (uint64_t)b.H,
+                            (uint64_t)p->B, (uint64_t)b.C);
+      else
+        rc = make_tmap_2d(&op.tmap_a[i], base, (uint64_t)cpad8(op.src[i].C),
+                          (uint64_t)p->B * b.rows_per_img, (uint64_t)b.C * 2, BK, BM);
       if (rc) return rc;
     }
   }
@@ -724,8 +824,12 @@ int conv_tc_prepare(yb_plan* p, Op& op) {
   if (!op.out_f32) {
     const Buf& db = p->bufs[op.dst.buf];
     const uint8_t* dbase = buf_ptr(p, op.dst.buf) + (size_t)op.dst.c_off * 2;
-    rc = make_tmap_2d(&op.tmap_c, dbase, (uint64_t)cpad8(op.dst.C), (uint64_t)p->B * db.rows_per_img,
-                      (uint64_t)db.C * 2, 64, BM);
+    if (op.tile2d)
+      rc = make_tmap_nhwc(&op.tmap_c, dbase, (uint64_t)cpad8(op.dst.C), (uint64_t)db.W, (uint64_t)db.H,
+                          (uint64_t)p->B, (uint64_t)db.C);
+    else
+      rc = make_tmap_2d(&op.tmap_c, dbase, (uint64_t)cpad8(op.dst.C), (uint64_t)p->B * db.rows_per_img,
+                        (uint64_t)db.C * 2, 64, BM);
     if (rc) return rc;
   }
   static bool attr_set = false;
@@ -803,6 +907,13 @@ static void fill_params(const yb_plan* p, const Op& op, ConvParams& P) {
   };
   magic(P.hw_out, P.hw_mul, P.hw_shr);
   magic(P.Wout, P.w_mul, P.w_shr);
+  P.tile2d = op.tile2d;
+  if (op.tile2d) {
+    P.tiles_x = op.Wout / 16;
+    P.tiles_per_img = P.tiles_x * (op.Hout / 8);
+    magic(P.tiles_per_img, P.tpi_mul, P.tpi_shr);
+    magic(P.tiles_x, P.tx_mul, P.tx_shr);
+  }
   P.out_mode = op.out_f32 ? 1 : 0;
   P.A_total = p->A;
   P.nc = p->nc;

@@ -73,6 +73,7 @@ struct Op {
   int seg_kpad[4] = {0, 0, 0, 0};  // per-segment padded K (a_tma mode)
   int N_pad = 0, BN = 0;   // padded Cout, N tile
   int stages = 0;
+  int tile2d = 0;          // 8 x 16 spatial output tiles (else 128 consecutive flattened rows)
   int occ = 1;             // resident CTAs per SM of the persistent GEMM kernel
   int head_part = 0;       // 1: box tail (fusable DFL decode), 2: cls tail (fusable sigmoid)
   size_t smem_bytes = 0;
