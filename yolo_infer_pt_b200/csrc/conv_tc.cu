@@ -67,7 +67,9 @@ struct ConvParams {
   uint32_t hw_mul, hw_shr, w_mul, w_shr;  // magic numbers: division by hw_out and by Wout
   // 2-D spatial tiles (8 x 16 output pixels) when Hout % 8 == 0 and Wout % 16 == 0
   int tile2d, tiles_x, tiles_per_img;
+  int dbg;            // bring-up experiments (YB_DBG): 1 skip gathers, 2 skip output store, 4 skip epilogue math
   uint32_t tpi_mul, tpi_shr, tx_mul, tx_shr;
+  uint32_t pt_mul, pt_shr;   // division by per_tap
   // fused head decode (out_mode 2 / 3): dst is the (B, 4+nc, A) fp32 output tensor
   int out_mode;       // 0 bf16 slice, 1 fp32 logits, 2 DFL box decode, 3 class sigmoid
   int A_total, nc;
@@ -274,7 +276,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
 
   if (tid == 0) {
     for (int s = 0; s < S; s++) {
-      mbar_init(full_bar(s), P.a_tma ? 1u : 129u);
+      mbar_init(full_bar(s), P.a_tma ? 1u : ((P.dbg & 8) ? 128u : 129u));
       mbar_init(empty_bar(s), 1u);
     }
     for (int a = 0; a < 2; a++) {
@@ -342,6 +344,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         const int nb = n0 + c0;
         if (nb >= P.cout_store || (!row_ok && P.out_mode != 0)) continue;
+        if (P.dbg & 4) continue;
         float f[16];
 #pragma unroll
         for (int j = 0; j < 16; j++) {
@@ -417,7 +420,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
       // accumulator stage drained: hand it back to the MMA warp
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(tmem_empty_bar(acc));
-      if (P.out_mode == 0) {
+      if (P.out_mode == 0 && !(P.dbg & 2)) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         if (ngrp == 2) asm volatile("bar.sync 1, 256;" ::: "memory");
         else asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -462,50 +465,113 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-        const TilePos tp = tile_pos(P, P.n_tiles == 1 ? tile : tile / P.n_tiles);
-        // input coordinates of tap (0,0) for this thread's 8 rows (rows rbase + 16*i of the tile).
-        // In a 2-D tile those are the 8 image rows of one column: ox is shared, oy = oy0 + i.
-        int row_n[8], row_y[8], row_x[8];
-        if (P.tile2d) {
-          const int x0 = (tp.ox0 + rbase) * P.stride - P.pad;
-#pragma unroll
-          for (int i = 0; i < 8; i++) {
-            row_n[i] = tp.n;
-            row_y[i] = (tp.oy0 + i) * P.stride - P.pad;
-            row_x[i] = x0;
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 8; i++) {
-            int m = tp.m0 + rbase + 16 * i;
-            if (m < P.M) {
-              int n = fast_div(m, P.hw_mul, P.hw_shr, P.hw_out);
-              int r = m - n * P.hw_out;
-              int oy = fast_div(r, P.w_mul, P.w_shr, P.Wout);
-              row_n[i] = n;
-              row_y[i] = oy * P.stride - P.pad;
-              row_x[i] = (r - oy * P.Wout) * P.stride - P.pad;
-            } else {
-              row_n[i] = -1;
-              row_y[i] = 0;
-              row_x[i] = 0;
+        if (P.dbg & 16) {
+          for (int kb = 0; kb < num_kb; kb++) {
+            mbar_wait(empty_bar(stage), phase ^ 1u);
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full_bar(stage)) : "memory");
+            if (++stage == S) {
+              stage = 0;
+              phase ^= 1u;
             }
+          }
+          continue;
+        }
+        const TilePos tp = tile_pos(P, P.n_tiles == 1 ? tile : tile / P.n_tiles);
+        if (P.tile2d) {
+          // ---- fast path: 8 x 16 spatial tile.  This thread's 8 rows are the 8 image rows of one
+          // tile column (ly = i, lx = rbase), so x validity is shared and y validity per tap row is
+          // a byte over i: only the first / last row of the patch can fall outside the image.
+          const int x0 = (tp.ox0 + rbase) * P.stride - P.pad;
+          const int y0 = tp.oy0 * P.stride - P.pad;
+          uint32_t xbits = 1u, ybits[3] = {0xFFu, 0xFFu, 0xFFu};
+          if (P.ksize == 3) {
+            xbits = 0;
+#pragma unroll
+            for (int t = 0; t < 3; t++) {
+              if ((unsigned)(x0 + t) < (unsigned)P.Win) xbits |= 1u << t;
+              if (y0 + t < 0) ybits[t] &= ~1u;
+              if (y0 + t + 7 * P.stride >= P.Hin) ybits[t] &= ~0x80u;
+            }
+          }
+          int pix[8];
+          int cur_seg = -1;
+          for (int kb = 0; kb < num_kb; kb++) {
+            const int s = stage;
+            const uint32_t ph = phase;
+            const int k0 = kb * BK + g * 8;
+            int tap = fast_div(k0, P.pt_mul, P.pt_shr, P.per_tap);
+            int c = k0 - tap * P.per_tap;
+            int seg = 0;
+            while (seg + 1 < P.nseg && c >= P.src_cp[seg]) {
+              c -= P.src_cp[seg];
+              seg++;
+            }
+            const int up = P.src_up[seg];
+            const int Ws = P.Win >> up;
+            if (seg != cur_seg) {
+              cur_seg = seg;
+              const int Hs = P.Hin >> up;
+#pragma unroll
+              for (int i = 0; i < 8; i++)
+                pix[i] = (tp.n * Hs + ((y0 + i * P.stride) >> up)) * Ws + (x0 >> up);
+            }
+            int delta = 0;
+            uint32_t ok8 = (k0 < P.K) ? 0xFFu : 0u;
+            if (P.ksize == 3) {
+              const int dy = (tap * 11) >> 5;  // tap / 3 for tap < 16
+              const int dx = tap - dy * 3;
+              delta = dy * Ws + dx;
+              ok8 = (k0 < P.K && ((xbits >> dx) & 1u)) ? (dy == 0 ? ybits[0] : dy == 1 ? ybits[1] : ybits[2]) : 0u;
+            }
+            const __nv_bfloat16* sp = P.src[seg] + c;
+            const int ld = P.src_ld[seg];
+            const __nv_bfloat16* gp[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) gp[i] = sp + (long long)(pix[i] + delta) * ld;
+            mbar_wait(empty_bar(s), ph ^ 1u);
+            const uint32_t a_s = a_base + (uint32_t)s * A_STAGE_BYTES + sw_off + (uint32_t)rbase * 128u;
+            if (!(P.dbg & 1)) {
+#pragma unroll
+              for (int i = 0; i < 8; i++)  // masked taps are zero-filled; their source is never read
+                cp_async16(a_s + (uint32_t)i * 2048u, gp[i], ((ok8 >> i) & 1u) ? 16u : 0u);
+            }
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full_bar(s)) : "memory");
+            if (++stage == S) {
+              stage = 0;
+              phase ^= 1u;
+            }
+          }
+          continue;
+        }
+        // ---- general path: 128 consecutive rows of the flattened (image, y, x) index
+        int row_n[8], row_y[8], row_x[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          int m = tp.m0 + rbase + 16 * i;
+          if (m < P.M) {
+            int n = fast_div(m, P.hw_mul, P.hw_shr, P.hw_out);
+            int r = m - n * P.hw_out;
+            int oy = fast_div(r, P.w_mul, P.w_shr, P.Wout);
+            row_n[i] = n;
+            row_y[i] = oy * P.stride - P.pad;
+            row_x[i] = (r - oy * P.Wout) * P.stride - P.pad;
+          } else {
+            row_n[i] = -1;
+            row_y[i] = 0;
+            row_x[i] = 0;
           }
         }
         int pix[8];
         uint32_t okmask[8];
         int cur_seg = -1;
-        int tap = 0;
-        int rem = g * 8;  // position inside the tap's [seg0 | seg1 | ...] channel run
-        while (rem >= P.per_tap) {
-          rem -= P.per_tap;
-          tap++;
-        }
         for (int kb = 0; kb < num_kb; kb++) {
           const int s = stage;
           const uint32_t ph = phase;
-          const bool k_ok = (kb * BK + g * 8) < P.K;
-          int seg = 0, c = rem;
+          const int k0 = kb * BK + g * 8;
+          const bool k_ok = k0 < P.K;
+          int tap = fast_div(k0, P.pt_mul, P.pt_shr, P.per_tap);
+          int c = k0 - tap * P.per_tap;
+          int seg = 0;
           while (seg + 1 < P.nseg && c >= P.src_cp[seg]) {
             c -= P.src_cp[seg];
             seg++;
@@ -515,30 +581,18 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
           if (seg != cur_seg) {  // new tile, or the K walk crossed into the next source of a concat
             cur_seg = seg;
             const int Hs = P.Hin >> up;
-            uint32_t xm = 0;
-            if (P.ksize == 3) {
-#pragma unroll
-              for (int t = 0; t < 3; t++)
-                if ((unsigned)(row_x[0] + t) < (unsigned)P.Win) xm |= 1u << t;
-              xm *= 0x49u;  // the 3 column bits replicated for each of the 3 tap rows
-            }
 #pragma unroll
             for (int i = 0; i < 8; i++) {
               uint32_t mk = 0;
               if (row_n[i] >= 0) {
                 if (P.ksize == 3) {
-                  if (!P.tile2d) {
-                    xm = 0;
+                  uint32_t xm = 0, ym = 0;
 #pragma unroll
-                    for (int t = 0; t < 3; t++)
-                      if ((unsigned)(row_x[i] + t) < (unsigned)P.Win) xm |= 1u << t;
-                    xm *= 0x49u;
-                  }
-                  uint32_t ym = 0;
-#pragma unroll
-                  for (int t = 0; t < 3; t++)
+                  for (int t = 0; t < 3; t++) {
+                    if ((unsigned)(row_x[i] + t) < (unsigned)P.Win) xm |= 1u << t;
                     if ((unsigned)(row_y[i] + t) < (unsigned)P.Hin) ym |= 7u << (3 * t);
-                  mk = xm & ym;
+                  }
+                  mk = (xm * 0x49u) & ym;
                 } else {
                   mk = 1u;
                 }
@@ -550,7 +604,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
           }
           int delta = 0, tbit = 0;
           if (P.ksize == 3) {
-            int dy = tap / 3;
+            int dy = (tap * 11) >> 5;
             delta = dy * Ws + (tap - dy * 3);
             tbit = tap;
           }
@@ -561,18 +615,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
 #pragma unroll
           for (int i = 0; i < 8; i++) {
             const bool ok = k_ok && ((okmask[i] >> tbit) & 1u);
-            const int idx = ok ? pix[i] + delta : 0;   // a valid address even when zero-filling
-            cp_async16(a_s + (uint32_t)(rbase + 16 * i) * 128u, sp + (long long)idx * ld, ok ? 16u : 0u);
+            const int idx = ok ? pix[i] + delta : 0;
+            if (!(P.dbg & 1))
+              cp_async16(a_s + (uint32_t)(rbase + 16 * i) * 128u, sp + (long long)idx * ld, ok ? 16u : 0u);
           }
           asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full_bar(s)) : "memory");
           if (++stage == S) {
             stage = 0;
             phase ^= 1u;
-          }
-          rem += BK;
-          while (rem >= P.per_tap) {
-            rem -= P.per_tap;
-            tap++;
           }
         }
       }
@@ -625,6 +675,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
         for (int kb = 0; kb < num_kb; kb++) {
           const int s = stage;
           const uint32_t ph = phase;
+          if ((P.dbg & 8) && !P.a_tma) continue;
           mbar_wait(empty_bar(s), ph ^ 1u);
           mbar_expect_tx(full_bar(s), tx);
           tma_load_2d(b_base + (uint32_t)s * b_stage_bytes, &tmap_b, kb * BK, n0, full_bar(s));
@@ -907,6 +958,9 @@ static void fill_params(const yb_plan* p, const Op& op, ConvParams& P) {
   };
   magic(P.hw_out, P.hw_mul, P.hw_shr);
   magic(P.Wout, P.w_mul, P.w_shr);
+  magic(P.per_tap, P.pt_mul, P.pt_shr);
+  static const int dbg = [] { const char* e = getenv("YB_DBG"); return e ? atoi(e) : 0; }();
+  P.dbg = dbg;
   P.tile2d = op.tile2d;
   if (op.tile2d) {
     P.tiles_x = op.Wout / 16;
