@@ -67,7 +67,6 @@ struct ConvParams {
   uint32_t hw_mul, hw_shr, w_mul, w_shr;  // magic numbers: division by hw_out and by Wout
   // 2-D spatial tiles (8 x 16 output pixels) when Hout % 8 == 0 and Wout % 16 == 0
   int tile2d, tiles_x, tiles_per_img;
-  int dbg;            // bring-up experiments (YB_DBG): 1 skip gathers, 2 skip output store, 4 skip epilogue math
   uint32_t tpi_mul, tpi_shr, tx_mul, tx_shr;
   uint32_t pt_mul, pt_shr;   // division by per_tap
   // fused head decode (out_mode 2 / 3): dst is the (B, 4+nc, A) fp32 output tensor
@@ -276,7 +275,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
 
   if (tid == 0) {
     for (int s = 0; s < S; s++) {
-      mbar_init(full_bar(s), P.a_tma ? 1u : ((P.dbg & 8) ? 128u : 129u));
+      mbar_init(full_bar(s), P.a_tma ? 1u : 129u);
       mbar_init(empty_bar(s), 1u);
     }
     for (int a = 0; a < 2; a++) {
@@ -344,7 +343,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         const int nb = n0 + c0;
         if (nb >= P.cout_store || (!row_ok && P.out_mode != 0)) continue;
-        if (P.dbg & 4) continue;
         float f[16];
 #pragma unroll
         for (int j = 0; j < 16; j++) {
@@ -420,7 +418,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
       // accumulator stage drained: hand it back to the MMA warp
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(tmem_empty_bar(acc));
-      if (P.out_mode == 0 && !(P.dbg & 2)) {
+      if (P.out_mode == 0) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         if (ngrp == 2) asm volatile("bar.sync 1, 256;" ::: "memory");
         else asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -464,18 +462,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
       // a 9-bit in-bounds mask; a k-block then costs one add + one wide multiply per row.
       int stage = 0;
       uint32_t phase = 0;
+      const int ksize = P.ksize, Win = P.Win, Hin = P.Hin, K = P.K, per_tap = P.per_tap, nseg = P.nseg;
       for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-        if (P.dbg & 16) {
-          for (int kb = 0; kb < num_kb; kb++) {
-            mbar_wait(empty_bar(stage), phase ^ 1u);
-            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full_bar(stage)) : "memory");
-            if (++stage == S) {
-              stage = 0;
-              phase ^= 1u;
-            }
-          }
-          continue;
-        }
         const TilePos tp = tile_pos(P, P.n_tiles == 1 ? tile : tile / P.n_tiles);
         if (P.tile2d) {
           // ---- fast path: 8 x 16 spatial tile.  This thread's 8 rows are the 8 image rows of one
@@ -484,57 +472,58 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
           const int x0 = (tp.ox0 + rbase) * P.stride - P.pad;
           const int y0 = tp.oy0 * P.stride - P.pad;
           uint32_t xbits = 1u, ybits[3] = {0xFFu, 0xFFu, 0xFFu};
-          if (P.ksize == 3) {
+          if (ksize == 3) {
             xbits = 0;
 #pragma unroll
             for (int t = 0; t < 3; t++) {
-              if ((unsigned)(x0 + t) < (unsigned)P.Win) xbits |= 1u << t;
+              if ((unsigned)(x0 + t) < (unsigned)Win) xbits |= 1u << t;
               if (y0 + t < 0) ybits[t] &= ~1u;
-              if (y0 + t + 7 * P.stride >= P.Hin) ybits[t] &= ~0x80u;
+              if (y0 + t + 7 * P.stride >= Hin) ybits[t] &= ~0x80u;
             }
           }
-          int pix[8];
-          int cur_seg = -1;
+          // byte offset of tap (0,0) of each row inside its image (32-bit), image base 64-bit
+          uint32_t offb[8];
+          const char* img_base = nullptr;
+          uint32_t ld2 = 0;
+          int Ws = 0, cur_seg = -1;
           for (int kb = 0; kb < num_kb; kb++) {
             const int s = stage;
             const uint32_t ph = phase;
             const int k0 = kb * BK + g * 8;
-            int tap = fast_div(k0, P.pt_mul, P.pt_shr, P.per_tap);
-            int c = k0 - tap * P.per_tap;
+            int tap = fast_div(k0, P.pt_mul, P.pt_shr, per_tap);
+            int c = k0 - tap * per_tap;
             int seg = 0;
-            while (seg + 1 < P.nseg && c >= P.src_cp[seg]) {
-              c -= P.src_cp[seg];
-              seg++;
+            if (nseg > 1) {
+              while (seg + 1 < nseg && c >= P.src_cp[seg]) {
+                c -= P.src_cp[seg];
+                seg++;
+              }
             }
-            const int up = P.src_up[seg];
-            const int Ws = P.Win >> up;
-            if (seg != cur_seg) {
+            if (seg != cur_seg) {  // first k-block of the tile, or the K walk entered the next concat source
               cur_seg = seg;
-              const int Hs = P.Hin >> up;
+              const int up = P.src_up[seg];
+              Ws = Win >> up;
+              ld2 = (uint32_t)P.src_ld[seg] * 2u;
+              img_base = reinterpret_cast<const char*>(P.src[seg]) +
+                         (size_t)tp.n * (size_t)((Hin >> up) * Ws) * ld2;
 #pragma unroll
               for (int i = 0; i < 8; i++)
-                pix[i] = (tp.n * Hs + ((y0 + i * P.stride) >> up)) * Ws + (x0 >> up);
+                offb[i] = (uint32_t)(((y0 + i * P.stride) >> up) * Ws + (x0 >> up)) * ld2;
             }
-            int delta = 0;
-            uint32_t ok8 = (k0 < P.K) ? 0xFFu : 0u;
-            if (P.ksize == 3) {
+            uint32_t deltab = (uint32_t)c * 2u;
+            uint32_t ok8 = (k0 < K) ? 0xFFu : 0u;
+            if (ksize == 3) {
               const int dy = (tap * 11) >> 5;  // tap / 3 for tap < 16
               const int dx = tap - dy * 3;
-              delta = dy * Ws + dx;
-              ok8 = (k0 < P.K && ((xbits >> dx) & 1u)) ? (dy == 0 ? ybits[0] : dy == 1 ? ybits[1] : ybits[2]) : 0u;
+              deltab += (uint32_t)(dy * Ws + dx) * ld2;
+              ok8 = (k0 < K && ((xbits >> dx) & 1u)) ? (dy == 0 ? ybits[0] : dy == 1 ? ybits[1] : ybits[2]) : 0u;
             }
-            const __nv_bfloat16* sp = P.src[seg] + c;
-            const int ld = P.src_ld[seg];
-            const __nv_bfloat16* gp[8];
-#pragma unroll
-            for (int i = 0; i < 8; i++) gp[i] = sp + (long long)(pix[i] + delta) * ld;
             mbar_wait(empty_bar(s), ph ^ 1u);
             const uint32_t a_s = a_base + (uint32_t)s * A_STAGE_BYTES + sw_off + (uint32_t)rbase * 128u;
-            if (!(P.dbg & 1)) {
 #pragma unroll
-              for (int i = 0; i < 8; i++)  // masked taps are zero-filled; their source is never read
-                cp_async16(a_s + (uint32_t)i * 2048u, gp[i], ((ok8 >> i) & 1u) ? 16u : 0u);
-            }
+            for (int i = 0; i < 8; i++)  // masked taps are zero-filled; their source is never read
+              cp_async16(a_s + (uint32_t)i * 2048u, img_base + (uint32_t)(offb[i] + deltab),
+                         ((ok8 >> i) & 1u) ? 16u : 0u);
             asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full_bar(s)) : "memory");
             if (++stage == S) {
               stage = 0;
@@ -616,8 +605,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
           for (int i = 0; i < 8; i++) {
             const bool ok = k_ok && ((okmask[i] >> tbit) & 1u);
             const int idx = ok ? pix[i] + delta : 0;
-            if (!(P.dbg & 1))
-              cp_async16(a_s + (uint32_t)(rbase + 16 * i) * 128u, sp + (long long)idx * ld, ok ? 16u : 0u);
+            cp_async16(a_s + (uint32_t)(rbase + 16 * i) * 128u, sp + (long long)idx * ld, ok ? 16u : 0u);
           }
           asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full_bar(s)) : "memory");
           if (++stage == S) {
@@ -675,7 +663,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
         for (int kb = 0; kb < num_kb; kb++) {
           const int s = stage;
           const uint32_t ph = phase;
-          if ((P.dbg & 8) && !P.a_tma) continue;
           mbar_wait(empty_bar(s), ph ^ 1u);
           mbar_expect_tx(full_bar(s), tx);
           tma_load_2d(b_base + (uint32_t)s * b_stage_bytes, &tmap_b, kb * BK, n0, full_bar(s));
@@ -959,8 +946,6 @@ static void fill_params(const yb_plan* p, const Op& op, ConvParams& P) {
   magic(P.hw_out, P.hw_mul, P.hw_shr);
   magic(P.Wout, P.w_mul, P.w_shr);
   magic(P.per_tap, P.pt_mul, P.pt_shr);
-  static const int dbg = [] { const char* e = getenv("YB_DBG"); return e ? atoi(e) : 0; }();
-  P.dbg = dbg;
   P.tile2d = op.tile2d;
   if (op.tile2d) {
     P.tiles_x = op.Wout / 16;
