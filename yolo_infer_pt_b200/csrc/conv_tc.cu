@@ -314,13 +314,6 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
       const int m0 = tp.m0;
       const int n0 = (tile - mt * P.n_tiles) * BN;
       const int acc = ti & 1;
-      mbar_wait(tmem_full_bar(acc), (uint32_t)(ti >> 1) & 1u);
-      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      // the previous tile's TMA stores must have finished reading the staging buffer
-      if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      for (int i = tid; i < BN; i += 128 * ngrp) bias_s[i] = __ldg(P.bias + n0 + i);
-      if (ngrp == 2) asm volatile("bar.sync 1, 256;" ::: "memory");
-      else asm volatile("bar.sync 1, 128;" ::: "memory");
       int m = m0 + etid;
       bool row_ok = m < P.M;
       int n_img = 0, r = 0;
@@ -334,15 +327,35 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
         r = m - n_img * P.hw_out;
       }
       const size_t drow = (size_t)n_img * P.dst_rows_per_img + P.dst_row_off + r;
-      const __nv_bfloat16* resp = P.res ? P.res + (size_t)m * P.res_ld : nullptr;
+      const __nv_bfloat16* resp = (P.res && row_ok) ? P.res + (size_t)m * P.res_ld : nullptr;
+      // residual operand: prefetched two chunks ahead so its global-load latency hides behind the
+      // wait for the accumulator and the math of the previous chunks
+      uint4 ra0, ra1, rb0, rb1;
+      ra0 = ra1 = rb0 = rb1 = make_uint4(0u, 0u, 0u, 0u);
+      auto res_fetch = [&](int c0, uint4& r0, uint4& r1) {
+        if (resp && c0 < BN) {
+          const int nb = n0 + c0;
+          if (nb < P.cout_store) r0 = __ldg(reinterpret_cast<const uint4*>(resp + nb));
+          if (nb + 8 < P.cout_store) r1 = __ldg(reinterpret_cast<const uint4*>(resp + nb + 8));
+        }
+      };
+      res_fetch(cfirst, ra0, ra1);
+      res_fetch(cfirst + cstep, rb0, rb1);
+      mbar_wait(tmem_full_bar(acc), (uint32_t)(ti >> 1) & 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      // the previous tile's TMA stores must have finished reading the staging buffer
+      if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      for (int i = tid; i < BN; i += 128 * ngrp) bias_s[i] = __ldg(P.bias + n0 + i);
+      if (ngrp == 2) asm volatile("bar.sync 1, 256;" ::: "memory");
+      else asm volatile("bar.sync 1, 128;" ::: "memory");
       const uint32_t t_row = tmem_base + ((uint32_t)(qwarp * 32) << 16) + (uint32_t)(acc * BN);
       float dist[4];
-      for (int c0 = cfirst; c0 < BN; c0 += cstep) {
+      auto do_chunk = [&](int c0, const uint4& rv0, const uint4& rv1) {
         uint32_t v[16];
         tmem_ld16(t_row + (uint32_t)c0, v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         const int nb = n0 + c0;
-        if (nb >= P.cout_store || (!row_ok && P.out_mode != 0)) continue;
+        if (nb >= P.cout_store || (!row_ok && P.out_mode != 0)) return;
         float f[16];
 #pragma unroll
         for (int j = 0; j < 16; j++) {
@@ -356,8 +369,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
 #pragma unroll
           for (int h = 0; h < 2; h++) {
             if (nb + 8 * h < P.cout_store) {
-              if (resp && row_ok) {
-                uint4 rv = __ldg(reinterpret_cast<const uint4*>(resp + nb + 8 * h));
+              if (resp) {
+                const uint4 rv = h ? rv1 : rv0;
                 const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
@@ -403,6 +416,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
           for (int j = 0; j < 16; j++) {
             if (nb + j < P.nc) ob[(size_t)j * P.A_total] = 1.f / (1.f + __expf(-f[j]));
           }
+        }
+      };
+      for (int c0 = cfirst; c0 < BN; c0 += 2 * cstep) {
+        do_chunk(c0, ra0, ra1);
+        res_fetch(c0 + 2 * cstep, ra0, ra1);
+        if (c0 + cstep < BN) {
+          do_chunk(c0 + cstep, rb0, rb1);
+          res_fetch(c0 + 3 * cstep, rb0, rb1);
         }
       }
       if (P.out_mode == 2 && row_ok && grp == 0) {

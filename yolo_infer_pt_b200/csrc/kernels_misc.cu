@@ -16,6 +16,15 @@ __device__ __forceinline__ float silu_acc(float x) {  // h + h*tanh(h), h = x/2 
   return fmaf(h, t, h);
 }
 
+// Blackwell packed fp32 FMA: two independent fused multiply-adds per instruction (FFMA2).
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a);
+  unsigned long long rb = *reinterpret_cast<unsigned long long*>(&b);
+  unsigned long long rc = *reinterpret_cast<unsigned long long*>(&c), rd;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  return *reinterpret_cast<float2*>(&rd);
+}
+
 __device__ __forceinline__ void bf16x8_to_float(const uint4& v, float* f) {
   const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
 #pragma unroll
@@ -140,24 +149,25 @@ __global__ void __launch_bounds__(256)
         x[(ci * 3 + ky) * 3 + kx] = tile[(ci * STEM_IH + 2 * ly + ky) * STEM_PITCH + EPV - 1 + 2 * lx + kx];
   __nv_bfloat16* op = out + (((size_t)b * Ho + oy) * Wo + ox) * out_ld;
   for (int c0 = 0; c0 < Cp; c0 += 8) {
-    float acc[8];
+    float2 acc2[4];
 #pragma unroll
-    for (int j = 0; j < 8; j++) acc[j] = bs[c0 + j];
+    for (int j = 0; j < 4; j++) acc2[j] = make_float2(bs[c0 + 2 * j], bs[c0 + 2 * j + 1]);
 #pragma unroll
     for (int t = 0; t < 27; t++) {
       const float4 w0 = *reinterpret_cast<const float4*>(ws + t * Cp + c0);
       const float4 w1 = *reinterpret_cast<const float4*>(ws + t * Cp + c0 + 4);
-      acc[0] = fmaf(x[t], w0.x, acc[0]);
-      acc[1] = fmaf(x[t], w0.y, acc[1]);
-      acc[2] = fmaf(x[t], w0.z, acc[2]);
-      acc[3] = fmaf(x[t], w0.w, acc[3]);
-      acc[4] = fmaf(x[t], w1.x, acc[4]);
-      acc[5] = fmaf(x[t], w1.y, acc[5]);
-      acc[6] = fmaf(x[t], w1.z, acc[6]);
-      acc[7] = fmaf(x[t], w1.w, acc[7]);
+      const float2 xx = make_float2(x[t], x[t]);
+      acc2[0] = ffma2(xx, make_float2(w0.x, w0.y), acc2[0]);
+      acc2[1] = ffma2(xx, make_float2(w0.z, w0.w), acc2[1]);
+      acc2[2] = ffma2(xx, make_float2(w1.x, w1.y), acc2[2]);
+      acc2[3] = ffma2(xx, make_float2(w1.z, w1.w), acc2[3]);
     }
+    float acc[8];
 #pragma unroll
-    for (int j = 0; j < 8; j++) acc[j] = silu_acc(acc[j]);
+    for (int j = 0; j < 4; j++) {
+      acc[2 * j] = silu_acc(acc2[j].x);
+      acc[2 * j + 1] = silu_acc(acc2[j].y);
+    }
     *reinterpret_cast<uint4*>(op + c0) = float_to_bf16x8(acc);
   }
 }
@@ -222,34 +232,42 @@ __global__ void __launch_bounds__(256)
   const int b = (int)(t / ((long long)xq * H));
   const int c = cg * 8;
   const int sc = (c / gsz) * gstride + goff + (c % gsz);
-  float acc[DW_PX][8];
+  float2 acc[DW_PX][4];
   const float* bias = wgt + 9 * Cp;
 #pragma unroll
   for (int p = 0; p < DW_PX; p++)
 #pragma unroll
-    for (int j = 0; j < 8; j++) acc[p][j] = bias[c + j];
+    for (int j = 0; j < 4; j++) acc[p][j] = make_float2(bias[c + 2 * j], bias[c + 2 * j + 1]);
 #pragma unroll
   for (int ky = 0; ky < 3; ky++) {
     const int iy = y - 1 + ky;
     if ((unsigned)iy >= (unsigned)H) continue;
-    float w[3][8];
+    float2 w[3][4];
 #pragma unroll
-    for (int kx = 0; kx < 3; kx++)
-#pragma unroll
-      for (int j = 0; j < 8; j++) w[kx][j] = wgt[(ky * 3 + kx) * Cp + c + j];
+    for (int kx = 0; kx < 3; kx++) {
+      const float4 w0 = __ldg(reinterpret_cast<const float4*>(wgt + (ky * 3 + kx) * Cp + c));
+      const float4 w1 = __ldg(reinterpret_cast<const float4*>(wgt + (ky * 3 + kx) * Cp + c + 4));
+      w[kx][0] = make_float2(w0.x, w0.y);
+      w[kx][1] = make_float2(w0.z, w0.w);
+      w[kx][2] = make_float2(w1.x, w1.y);
+      w[kx][3] = make_float2(w1.z, w1.w);
+    }
     const __nv_bfloat16* rowp = src + ((size_t)(b * H + iy) * W) * src_ld + sc;
 #pragma unroll
     for (int col = 0; col < DW_PX + 2; col++) {
       const int ix = x0 - 1 + col;
       if ((unsigned)ix >= (unsigned)W) continue;
-      float f[8];
-      bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(rowp + (size_t)ix * src_ld)), f);
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(rowp + (size_t)ix * src_ld));
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&v);
+      float2 f[4];
+#pragma unroll
+      for (int j = 0; j < 4; j++) f[j] = __bfloat1622float2(h2[j]);
 #pragma unroll
       for (int kx = 0; kx < 3; kx++) {
         const int p = col - kx;  // output pixel this column feeds through tap kx
         if (p >= 0 && p < DW_PX) {
 #pragma unroll
-          for (int j = 0; j < 8; j++) acc[p][j] = fmaf(f[j], w[kx][j], acc[p][j]);
+          for (int j = 0; j < 4; j++) acc[p][j] = ffma2(f[j], w[kx][j], acc[p][j]);
         }
       }
     }
@@ -258,18 +276,20 @@ __global__ void __launch_bounds__(256)
   for (int p = 0; p < DW_PX; p++) {
     const int x = x0 + p;
     if (x >= W) break;
-    if (act) {
+    float o[8];
 #pragma unroll
-      for (int j = 0; j < 8; j++) acc[p][j] = silu_acc(acc[p][j]);
+    for (int j = 0; j < 4; j++) {
+      o[2 * j] = act ? silu_acc(acc[p][j].x) : acc[p][j].x;
+      o[2 * j + 1] = act ? silu_acc(acc[p][j].y) : acc[p][j].y;
     }
     __nv_bfloat16* dp = dst + ((size_t)(b * H + y) * W + x) * dst_ld + c;
     if (add) {
       float f[8];
       bf16x8_to_float(*reinterpret_cast<const uint4*>(dp), f);
 #pragma unroll
-      for (int j = 0; j < 8; j++) acc[p][j] += f[j];
+      for (int j = 0; j < 8; j++) o[j] += f[j];
     }
-    *reinterpret_cast<uint4*>(dp) = float_to_bf16x8(acc[p]);
+    *reinterpret_cast<uint4*>(dp) = float_to_bf16x8(o);
   }
 }
 
@@ -400,7 +420,7 @@ __global__ void __launch_bounds__(ATT_Q)
   const int qi = qt * ATT_Q + tid;
   const bool q_ok = qi < N;
   const __nv_bfloat16* base = qkv + (size_t)b * N * qkv_ld + h * 128;
-  float q[32];
+  float2 q2[16];
   {
     const __nv_bfloat16* qp = base + (size_t)(q_ok ? qi : 0) * qkv_ld;
 #pragma unroll
@@ -408,12 +428,12 @@ __global__ void __launch_bounds__(ATT_Q)
       float f[8];
       bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(qp + 8 * j)), f);
 #pragma unroll
-      for (int t = 0; t < 8; t++) q[8 * j + t] = f[t] * scale_log2e;
+      for (int t = 0; t < 4; t++) q2[4 * j + t] = make_float2(f[2 * t] * scale_log2e, f[2 * t + 1] * scale_log2e);
     }
   }
-  float acc[64];
+  float2 acc2[32];
 #pragma unroll
-  for (int d = 0; d < 64; d++) acc[d] = 0.f;
+  for (int d = 0; d < 32; d++) acc2[d] = make_float2(0.f, 0.f);
   float mrun = -INFINITY, lrun = 0.f;
 
   for (int k0 = 0; k0 < N; k0 += ATT_KT) {
@@ -440,47 +460,52 @@ __global__ void __launch_bounds__(ATT_Q)
       float cmax = -INFINITY;
 #pragma unroll
       for (int u = 0; u < 8; u++) {
-        float a = 0.f;
+        float2 a2 = make_float2(0.f, 0.f);
 #pragma unroll
-        for (int d4 = 0; d4 < 8; d4++) {
-          float4 kk = *reinterpret_cast<const float4*>(&Ks[c0 + u][4 * d4]);
-          a = fmaf(q[4 * d4], kk.x, a);
-          a = fmaf(q[4 * d4 + 1], kk.y, a);
-          a = fmaf(q[4 * d4 + 2], kk.z, a);
-          a = fmaf(q[4 * d4 + 3], kk.w, a);
+        for (int d4 = 0; d4 < 8; d4++) {  // packed FFMA2: two channels per instruction
+          const float4 kk = *reinterpret_cast<const float4*>(&Ks[c0 + u][4 * d4]);
+          a2 = ffma2(q2[2 * d4], make_float2(kk.x, kk.y), a2);
+          a2 = ffma2(q2[2 * d4 + 1], make_float2(kk.z, kk.w), a2);
         }
+        const float a = a2.x + a2.y;
         s[u] = (c0 + u < kmax) ? a : -INFINITY;
         cmax = fmaxf(cmax, s[u]);
       }
-      float mnew = fmaxf(mrun, cmax);
-      float corr = exp2f(mrun - mnew);
+      const float mnew = fmaxf(mrun, cmax);
+      const float corr = exp2f(mrun - mnew);
       lrun *= corr;
+      const float2 corr2 = make_float2(corr, corr);
 #pragma unroll
-      for (int d = 0; d < 64; d++) acc[d] *= corr;
+      for (int d = 0; d < 32; d++) {
+        acc2[d].x *= corr2.x;
+        acc2[d].y *= corr2.y;
+      }
       mrun = mnew;
 #pragma unroll
       for (int u = 0; u < 8; u++) {
-        float pj = exp2f(s[u] - mnew);
+        const float pj = exp2f(s[u] - mnew);
         lrun += pj;
+        const float2 pp = make_float2(pj, pj);
 #pragma unroll
         for (int d4 = 0; d4 < 16; d4++) {
-          float4 vv = *reinterpret_cast<const float4*>(&Vs[c0 + u][4 * d4]);
-          acc[4 * d4] = fmaf(pj, vv.x, acc[4 * d4]);
-          acc[4 * d4 + 1] = fmaf(pj, vv.y, acc[4 * d4 + 1]);
-          acc[4 * d4 + 2] = fmaf(pj, vv.z, acc[4 * d4 + 2]);
-          acc[4 * d4 + 3] = fmaf(pj, vv.w, acc[4 * d4 + 3]);
+          const float4 vv = *reinterpret_cast<const float4*>(&Vs[c0 + u][4 * d4]);
+          acc2[2 * d4] = ffma2(pp, make_float2(vv.x, vv.y), acc2[2 * d4]);
+          acc2[2 * d4 + 1] = ffma2(pp, make_float2(vv.z, vv.w), acc2[2 * d4 + 1]);
         }
       }
     }
   }
   if (q_ok) {
-    float inv = 1.f / lrun;
+    const float inv = 1.f / lrun;
     __nv_bfloat16* op = out + ((size_t)b * N + qi) * out_ld + h * 64;
 #pragma unroll
     for (int j = 0; j < 8; j++) {
       float f[8];
 #pragma unroll
-      for (int t = 0; t < 8; t++) f[t] = acc[8 * j + t] * inv;
+      for (int t = 0; t < 4; t++) {
+        f[2 * t] = acc2[4 * j + t].x * inv;
+        f[2 * t + 1] = acc2[4 * j + t].y * inv;
+      }
       *reinterpret_cast<uint4*>(op + 8 * j) = float_to_bf16x8(f);
     }
   }
