@@ -12,7 +12,7 @@ for s in $SRCS; do
   obj=build/$s.o
   if [ ! -f "$obj" ] || [ "$src" -nt "$obj" ] || [ yolo_infer_pt_b200/csrc/yb_internal.h -nt "$obj" ] || [ include/yolob200.h -nt "$obj" ]; then
     "$NVCC" -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 \
-      -Xcompiler -fPIC -Xptxas -v -c "$src" -o "$obj" 2> "build/$s.ptxas.log" || { cat "build/$s.ptxas.log"; exit 1; }
+      -Xcompiler -fPIC -Xptxas -v ${NVCC_EXTRA:-} -c "$src" -o "$obj" 2> "build/$s.ptxas.log" || { cat "build/$s.ptxas.log"; exit 1; }
   fi
   OBJS="$OBJS $obj"
 done

@@ -18,8 +18,8 @@
 //       straight into the channel slice of the consumer's buffer.
 //
 // The kernel is persistent: grid = SMs x resident CTAs, each CTA walks tiles t = blockIdx.x + i*grid.
-// Warp roles (320 threads): warps 0-3 epilogue (TMEM lane = output row), warps 4-7 im2col
-// producers, warp 8 TMEM allocator + MMA issuer, warp 9 TMA producer.  Two accumulator stages in
+// Warp roles (352 threads): warps 0-3 epilogue (TMEM lane = output row), warps 4-7 im2col
+// producers, warp 8 TMEM allocator + MMA issuer, warp 9 TMA producer, warp 10 proxy-fence relay.  Two accumulator stages in
 // TMEM (2 x BN columns) let the epilogue of tile i overlap the main loop of tile i+1; the smem
 // stage ring runs continuously across tiles.
 // Epilogue modes: bf16 NHWC slice (+residual) | fp32 head logits | fused DFL box decode
@@ -153,11 +153,12 @@ struct TilePos {
   int m0;            // linear: first row
   int n, oy0, ox0;   // 2-D: image and patch origin
 };
+template <bool T2D>
 __device__ __forceinline__ TilePos tile_pos(const ConvParams& P, int mt) {
   TilePos t;
   t.m0 = mt * BM;
   t.n = t.oy0 = t.ox0 = 0;
-  if (P.tile2d) {
+  if (T2D) {
     t.n = fast_div(mt, P.tpi_mul, P.tpi_shr, P.tiles_per_img);
     int r = mt - t.n * P.tiles_per_img;
     int ty = fast_div(r, P.tx_mul, P.tx_shr, P.tiles_x);
@@ -185,6 +186,15 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t da, uint64_t
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
       "l"(da), "l"(db), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
@@ -231,12 +241,18 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 // ------------------------------------------------------------------------------------------
 // The kernel
 // ------------------------------------------------------------------------------------------
-static constexpr int NUM_THREADS = 320;
+static constexpr int NUM_THREADS = 352;
 static constexpr int EPI_WARPS = 4;      // warps 0-3
 static constexpr int PROD_WARP0 = 4;     // warps 4-7
 static constexpr int MMA_WARP = 8;
 static constexpr int TMA_WARP = 9;
+static constexpr int RELAY_WARP = 10;    // proxy-fence relay between the im2col warps and the MMA warp
 
+// Specialised at compile time on the A-operand path (TMA tiles vs im2col gather), the tile shape
+// (8x16 spatial patch vs 128 flattened rows) and the epilogue family (bf16 slice vs head modes):
+// every instantiation carries only the code of its own roles, which keeps it inside the
+// instruction cache (11 warps run disjoint code).
+template <bool A_TMA, bool T2D, bool HEAD>
 __global__ void __launch_bounds__(NUM_THREADS, 2)
     conv_gemm_tcgen05_kernel(const ConvParams P, const __grid_constant__ CUtensorMap tmap_b,
                              const __grid_constant__ CUtensorMap tmap_a0,
@@ -258,15 +274,16 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
   const uint32_t c_groups = (uint32_t)(BN + 63) / 64;
   const uint32_t c_base = b_base + (uint32_t)S * b_stage_bytes;
   uint8_t* tail = smem + (size_t)S * (A_STAGE_BYTES + b_stage_bytes) + (size_t)c_groups * C_GROUP_BYTES;
-  // barriers: full[MAX_STAGES], empty[MAX_STAGES], tmem_full[2], tmem_empty[2]
+  // barriers: full[MAX_STAGES], empty[MAX_STAGES], tmem_full[2], tmem_empty[2], gathered[MAX_STAGES]
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + (2 * MAX_STAGES + 4) * 8);
-  float* bias_s = reinterpret_cast<float*>(tail + (2 * MAX_STAGES + 4) * 8 + 16);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + (3 * MAX_STAGES + 4) * 8);
+  float* bias_s = reinterpret_cast<float*>(tail + (3 * MAX_STAGES + 4) * 8 + 16);
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (MAX_STAGES + s); };
   auto tmem_full_bar = [&](int a) { return bar0 + 8u * (2 * MAX_STAGES + a); };
   auto tmem_empty_bar = [&](int a) { return bar0 + 8u * (2 * MAX_STAGES + 2 + a); };
+  auto gathered_bar = [&](int s) { return bar0 + 8u * (2 * MAX_STAGES + 4 + s); };
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -275,12 +292,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
 
   if (tid == 0) {
     for (int s = 0; s < S; s++) {
-      mbar_init(full_bar(s), P.a_tma ? 1u : 129u);
+      mbar_init(full_bar(s), A_TMA ? 1u : 2u);   // TMA expect_tx (+ the relay warp on im2col layers)
       mbar_init(empty_bar(s), 1u);
+      mbar_init(gathered_bar(s), 128u);            // one cp.async-completion arrive per im2col thread
     }
     for (int a = 0; a < 2; a++) {
       mbar_init(tmem_full_bar(a), 1u);
-      mbar_init(tmem_empty_bar(a), P.a_tma ? 256u : 128u);
+      mbar_init(tmem_empty_bar(a), A_TMA ? 256u : 128u);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -299,25 +317,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
 
   // With A fed by TMA the im2col warps have nothing to gather: they join the epilogue as a second
   // group that converts the odd 16-column chunks of the accumulator (same TMEM lane quadrants).
-  if (warp < EPI_WARPS || (P.a_tma && warp < MMA_WARP)) {
+  if (warp < EPI_WARPS || (A_TMA && warp < MMA_WARP)) {
     // ============================ epilogue =================================================
     const int grp = warp >> 2;                  // 0: warps 0-3, 1: warps 4-7
-    const int ngrp = P.a_tma ? 2 : 1;
+    const int ngrp = A_TMA ? 2 : 1;
     const int etid = tid & 127;                 // row of the tile owned by this thread
     const int qwarp = warp & 3;                 // TMEM lane quadrant
-    const int cstep = (P.out_mode == 2) ? 16 : 16 * ngrp;   // DFL decode needs all 4 sides in one thread
-    const int cfirst = (P.out_mode == 2) ? (grp ? BN : 0) : 16 * grp;
+    const int cstep = (HEAD && P.out_mode == 2) ? 16 : 16 * ngrp;   // DFL decode needs all 4 sides in one thread
+    const int cfirst = (HEAD && P.out_mode == 2) ? (grp ? BN : 0) : 16 * grp;
     int ti = 0;
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ti++) {
       const int mt = P.n_tiles == 1 ? tile : tile / P.n_tiles;
-      const TilePos tp = tile_pos(P, mt);
+      const TilePos tp = tile_pos<T2D>(P, mt);
       const int m0 = tp.m0;
       const int n0 = (tile - mt * P.n_tiles) * BN;
       const int acc = ti & 1;
       int m = m0 + etid;
       bool row_ok = m < P.M;
       int n_img = 0, r = 0;
-      if (P.tile2d) {
+      if (T2D) {
         n_img = tp.n;
         r = (tp.oy0 + (etid >> 4)) * P.Wout + tp.ox0 + (etid & 15);
         m = n_img * P.hw_out + r;
@@ -327,7 +345,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
         r = m - n_img * P.hw_out;
       }
       const size_t drow = (size_t)n_img * P.dst_rows_per_img + P.dst_row_off + r;
-      const __nv_bfloat16* resp = (P.res && row_ok) ? P.res + (size_t)m * P.res_ld : nullptr;
+      const __nv_bfloat16* resp = (!HEAD && P.res && row_ok) ? P.res + (size_t)m * P.res_ld : nullptr;
       // residual operand: prefetched two chunks ahead so its global-load latency hides behind the
       // wait for the accumulator and the math of the previous chunks
       uint4 ra0, ra1, rb0, rb1;
@@ -355,14 +373,14 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
         tmem_ld16(t_row + (uint32_t)c0, v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         const int nb = n0 + c0;
-        if (nb >= P.cout_store || (!row_ok && P.out_mode != 0)) return;
+        if (nb >= P.cout_store || (!row_ok && HEAD)) return;
         float f[16];
 #pragma unroll
         for (int j = 0; j < 16; j++) {
           float x = __uint_as_float(v[j]) + bias_s[c0 + j];
           f[j] = P.act ? silu_f(x) : x;
         }
-        if (P.out_mode == 0) {
+        if (!HEAD) {
           // bf16 tile staged in shared memory in the TMA SWIZZLE_128B layout (16-byte chunk index
           // XOR row%8 inside each 128-byte row), then written with one TMA store per 64 channels
           const uint32_t srow = c_base + (uint32_t)(c0 >> 6) * C_GROUP_BYTES + (uint32_t)etid * 128u;
@@ -426,7 +444,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
           res_fetch(c0 + 3 * cstep, rb0, rb1);
         }
       }
-      if (P.out_mode == 2 && row_ok && grp == 0) {
+      if (HEAD && P.out_mode == 2 && row_ok && grp == 0) {
         const int y = fast_div(r, P.w_mul, P.w_shr, P.Wout), x = r - y * P.Wout;
         const float ax = (float)x + 0.5f, ay = (float)y + 0.5f, st = P.lvl_stride;
         const float x1 = ax - dist[0], y1 = ay - dist[1], x2 = ax + dist[2], y2 = ay + dist[3];
@@ -439,7 +457,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
       // accumulator stage drained: hand it back to the MMA warp
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(tmem_empty_bar(acc));
-      if (P.out_mode == 0) {
+      if (!HEAD) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         if (ngrp == 2) asm volatile("bar.sync 1, 256;" ::: "memory");
         else asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -447,7 +465,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
           for (uint32_t g = 0; g < c_groups; g++) {
             const int cg0 = n0 + (int)g * 64;
             if (cg0 < P.cout_store) {
-              if (P.tile2d) {
+              if (T2D) {
                 asm volatile(
                     "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];" ::"l"(
                         (uint64_t)&tmap_c),
@@ -485,8 +503,8 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
       uint32_t phase = 0;
       const int ksize = P.ksize, Win = P.Win, Hin = P.Hin, K = P.K, per_tap = P.per_tap, nseg = P.nseg;
       for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-        const TilePos tp = tile_pos(P, P.n_tiles == 1 ? tile : tile / P.n_tiles);
-        if (P.tile2d) {
+        const TilePos tp = tile_pos<T2D>(P, P.n_tiles == 1 ? tile : tile / P.n_tiles);
+        if (T2D) {
           // ---- fast path: 8 x 16 spatial tile.  This thread's 8 rows are the 8 image rows of one
           // tile column (ly = i, lx = rbase), so x validity is shared and y validity per tap row is
           // a byte over i: only the first / last row of the patch can fall outside the image.
@@ -545,7 +563,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
             for (int i = 0; i < 8; i++)  // masked taps are zero-filled; their source is never read
               cp_async16(a_s + (uint32_t)i * 2048u, img_base + (uint32_t)(offb[i] + deltab),
                          ((ok8 >> i) & 1u) ? 16u : 0u);
-            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full_bar(s)) : "memory");
+            asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(gathered_bar(s)) : "memory");
             if (++stage == S) {
               stage = 0;
               phase ^= 1u;
@@ -628,7 +646,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
             const int idx = ok ? pix[i] + delta : 0;
             cp_async16(a_s + (uint32_t)(rbase + 16 * i) * 128u, sp + (long long)idx * ld, ok ? 16u : 0u);
           }
-          asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(full_bar(s)) : "memory");
+          asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(gathered_bar(s)) : "memory");
           if (++stage == S) {
             stage = 0;
             phase ^= 1u;
@@ -638,47 +656,66 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
     }
   } else if (warp == MMA_WARP) {
     // ============================ MMA issuer ==============================================
-    if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
-                             ((uint32_t)(BM >> 4) << 24);
-      int ti = 0, stage = 0;
-      uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ti++) {
-        const int acc = ti & 1;
-        mbar_wait(tmem_empty_bar(acc), ((uint32_t)(ti >> 1) & 1u) ^ 1u);
+    // The whole warp walks the loop converged; one elected lane issues the tcgen05 instructions.
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                           ((uint32_t)(BM >> 4) << 24);
+    const uint64_t desc_hi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61) |
+                             ((uint64_t)1 << 16);
+    int ti = 0, stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ti++) {
+      const int acc = ti & 1;
+      mbar_wait(tmem_empty_bar(acc), ((uint32_t)(ti >> 1) & 1u) ^ 1u);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+      for (int kb = 0; kb < num_kb; kb++) {
+        mbar_wait(full_bar(stage), phase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-        for (int kb = 0; kb < num_kb; kb++) {
-          const int s = stage;
-          const uint32_t ph = phase;
-          mbar_wait(full_bar(s), ph);
-          if (!P.a_tma) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t a_s = a_base + (uint32_t)s * A_STAGE_BYTES;
-          const uint32_t b_s = b_base + (uint32_t)s * b_stage_bytes;
+        if (elect_one()) {
+          const uint64_t da = desc_hi | (uint64_t)(((a_base + (uint32_t)stage * A_STAGE_BYTES) >> 4) & 0x3FFF);
+          const uint64_t db = desc_hi | (uint64_t)(((b_base + (uint32_t)stage * b_stage_bytes) >> 4) & 0x3FFF);
 #pragma unroll
-          for (int k = 0; k < BK / 16; k++) {
-            umma_bf16(d_tmem, umma_desc_sw128(a_s + k * 32), umma_desc_sw128(b_s + k * 32), idesc,
-                      (uint32_t)((kb | k) != 0));
-          }
-          umma_commit(empty_bar(s));  // frees the smem stage once these MMAs have read it
+          for (int k = 0; k < BK / 16; k++)  // +32 bytes (2 x 16 B units) per K=16 step inside the swizzle atom
+            umma_bf16(d_tmem, da + 2u * k, db + 2u * k, idesc, (uint32_t)((kb | k) != 0));
+          umma_commit(empty_bar(stage));  // frees the smem stage once these MMAs have read it
+          if (kb == num_kb - 1) umma_commit(tmem_full_bar(acc));  // accumulator complete -> epilogue
+        }
+        __syncwarp();
+        if (++stage == S) {
+          stage = 0;
+          phase ^= 1u;
+        }
+      }
+    }
+  } else if (warp == RELAY_WARP) {
+    // ============================ proxy-fence relay ========================================
+    // im2col data is written by cp.async (generic proxy) but read by the tensor core through the
+    // async proxy.  This thread acquires a gathered stage, issues the proxy fence and forwards the
+    // arrival to the MMA warp, keeping the (expensive) fence off the MMA issue path.
+    if (!A_TMA && lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+        for (int kb = 0; kb < num_kb; kb++) {
+          mbar_wait(gathered_bar(stage), phase);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbar_arrive(full_bar(stage));
           if (++stage == S) {
             stage = 0;
             phase ^= 1u;
           }
         }
-        umma_commit(tmem_full_bar(acc));  // accumulator complete -> epilogue
       }
     }
   } else {
     // ============================ TMA producer ============================================
     if (lane == 0) {
-      const uint32_t tx = b_stage_bytes + (P.a_tma ? (uint32_t)A_STAGE_BYTES : 0u);
+      const uint32_t tx = b_stage_bytes + (A_TMA ? (uint32_t)A_STAGE_BYTES : 0u);
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
         const int mt = P.n_tiles == 1 ? tile : tile / P.n_tiles;
-        const TilePos tp = tile_pos(P, mt);
+        const TilePos tp = tile_pos<T2D>(P, mt);
         const int n0 = (tile - mt * P.n_tiles) * BN;
         int seg = 0, kk = 0;
         for (int kb = 0; kb < num_kb; kb++) {
@@ -687,10 +724,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
           mbar_wait(empty_bar(s), ph ^ 1u);
           mbar_expect_tx(full_bar(s), tx);
           tma_load_2d(b_base + (uint32_t)s * b_stage_bytes, &tmap_b, kb * BK, n0, full_bar(s));
-          if (P.a_tma) {
+          if (A_TMA) {
             const CUtensorMap* ma =
                 seg == 0 ? &tmap_a0 : seg == 1 ? &tmap_a1 : seg == 2 ? &tmap_a2 : &tmap_a3;
-            if (P.tile2d)
+            if (T2D)
               tma_load_4d(a_base + (uint32_t)s * A_STAGE_BYTES, ma, kk * BK, tp.ox0, tp.oy0, tp.n, full_bar(s));
             else
               tma_load_2d(a_base + (uint32_t)s * A_STAGE_BYTES, ma, kk * BK, tp.m0, full_bar(s));
@@ -830,7 +867,7 @@ static int make_tmap_nhwc(CUtensorMap* map, const void* base, uint64_t C, uint64
 
 static size_t conv_smem_bytes(int stages, int BN) {
   return 1024 + (size_t)stages * (A_STAGE_BYTES + (size_t)BN * 128) + (size_t)((BN + 63) / 64) * C_GROUP_BYTES +
-         (2 * MAX_STAGES + 4) * 8 + 16 + 256 * 4 + 64;
+         (3 * MAX_STAGES + 4) * 8 + 16 + 256 * 4 + 64;
 }
 
 static int tmem_cols_for(int BN) {
@@ -893,8 +930,13 @@ int conv_tc_prepare(yb_plan* p, Op& op) {
   }
   static bool attr_set = false;
   if (!attr_set) {
-    YB_CUDA(cudaFuncSetAttribute(conv_gemm_tcgen05_kernel,
-                                 cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    const int smem_max = 227 * 1024;
+    YB_CUDA(cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+    YB_CUDA(cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+    YB_CUDA(cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+    YB_CUDA(cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+    YB_CUDA(cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+    YB_CUDA(cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
     attr_set = true;
   }
   return YB_OK;
@@ -991,9 +1033,21 @@ int launch_conv_tc(const yb_plan* p, const Op& op, cudaStream_t st, float* fused
     P.lvl_stride = p->lvl_stride[lvl];
   }
   int grid = std::min(P.total_tiles, p->num_sms * op.occ);
-  conv_gemm_tcgen05_kernel<<<grid, NUM_THREADS, op.smem_bytes, st>>>(P, op.tmap_b, op.tmap_a[0],
-                                                                    op.tmap_a[1], op.tmap_a[2], op.tmap_a[3],
-                                                                    op.tmap_c);
+#define YB_LAUNCH(ATMA, T2D, HEAD)                                                                       \
+  conv_gemm_tcgen05_kernel<ATMA, T2D, HEAD><<<grid, NUM_THREADS, op.smem_bytes, st>>>(                   \
+      P, op.tmap_b, op.tmap_a[0], op.tmap_a[1], op.tmap_a[2], op.tmap_a[3], op.tmap_c)
+  const bool head = P.out_mode != 0;
+  if (head) {
+    if (P.a_tma) YB_LAUNCH(true, false, true);
+    else YB_LAUNCH(false, false, true);
+  } else if (P.a_tma) {
+    if (P.tile2d) YB_LAUNCH(true, true, false);
+    else YB_LAUNCH(true, false, false);
+  } else {
+    if (P.tile2d) YB_LAUNCH(false, true, false);
+    else YB_LAUNCH(false, false, false);
+  }
+#undef YB_LAUNCH
   count_launch();
   YB_CUDA(cudaGetLastError());
   return YB_OK;
