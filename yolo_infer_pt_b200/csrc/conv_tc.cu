@@ -436,13 +436,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
           }
         }
       };
-      for (int c0 = cfirst; c0 < BN; c0 += 2 * cstep) {
+      for (int c0 = cfirst; c0 < BN; c0 += cstep) {  // one inlined copy of the chunk body (code size)
         do_chunk(c0, ra0, ra1);
-        res_fetch(c0 + 2 * cstep, ra0, ra1);
-        if (c0 + cstep < BN) {
-          do_chunk(c0 + cstep, rb0, rb1);
-          res_fetch(c0 + 3 * cstep, rb0, rb1);
-        }
+        ra0 = rb0;
+        ra1 = rb1;
+        res_fetch(c0 + 2 * cstep, rb0, rb1);
       }
       if (HEAD && P.out_mode == 2 && row_ok && grp == 0) {
         const int y = fast_div(r, P.w_mul, P.w_shr, P.Wout), x = r - y * P.Wout;
