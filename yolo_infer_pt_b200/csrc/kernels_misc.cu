@@ -62,40 +62,48 @@ __device__ __forceinline__ float load_px<__nv_bfloat16>(const __nv_bfloat16* p) 
 template <>
 __device__ __forceinline__ float load_px<uint8_t>(const uint8_t* p) { return (float)__ldg(p); }
 
-static constexpr int STEM_TW = 32, STEM_TH = 8;              // output tile per CTA (256 threads)
+static constexpr int STEM_TW = 64, STEM_TH = 8;              // output tile per CTA (256 threads x 2 pixels)
 static constexpr int STEM_IH = 2 * STEM_TH + 1;
-static constexpr int STEM_PITCH = 2 * STEM_TW + 32 + 1;      // widest aligned window (uint8: 96) + 1
+static constexpr int STEM_HP = STEM_TW + 16 + 4;             // half-row pitch (even or odd columns), floats
 
+// unpack one 16-byte vector of pixels into its even-column and odd-column halves
 template <typename T>
-__device__ __forceinline__ void unpack16(const uint4& v, float* f, float scale);
+__device__ __forceinline__ void unpack_eo(const uint4& v, float* ev, float* od, float scale);
 template <>
-__device__ __forceinline__ void unpack16<float>(const uint4& v, float* f, float scale) {
-  f[0] = __uint_as_float(v.x) * scale;
-  f[1] = __uint_as_float(v.y) * scale;
-  f[2] = __uint_as_float(v.z) * scale;
-  f[3] = __uint_as_float(v.w) * scale;
+__device__ __forceinline__ void unpack_eo<float>(const uint4& v, float* ev, float* od, float scale) {
+  ev[0] = __uint_as_float(v.x) * scale;
+  od[0] = __uint_as_float(v.y) * scale;
+  ev[1] = __uint_as_float(v.z) * scale;
+  od[1] = __uint_as_float(v.w) * scale;
 }
 template <>
-__device__ __forceinline__ void unpack16<__half>(const uint4& v, float* f, float scale) {
+__device__ __forceinline__ void unpack_eo<__half>(const uint4& v, float* ev, float* od, float scale) {
   const __half2* h = reinterpret_cast<const __half2*>(&v);
 #pragma unroll
   for (int j = 0; j < 4; j++) {
     float2 t = __half22float2(h[j]);
-    f[2 * j] = t.x * scale;
-    f[2 * j + 1] = t.y * scale;
+    ev[j] = t.x * scale;
+    od[j] = t.y * scale;
   }
 }
 template <>
-__device__ __forceinline__ void unpack16<__nv_bfloat16>(const uint4& v, float* f, float scale) {
-  bf16x8_to_float(v, f);
+__device__ __forceinline__ void unpack_eo<__nv_bfloat16>(const uint4& v, float* ev, float* od, float scale) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
 #pragma unroll
-  for (int j = 0; j < 8; j++) f[j] *= scale;
+  for (int j = 0; j < 4; j++) {
+    float2 t = __bfloat1622float2(h[j]);
+    ev[j] = t.x * scale;
+    od[j] = t.y * scale;
+  }
 }
 template <>
-__device__ __forceinline__ void unpack16<uint8_t>(const uint4& v, float* f, float scale) {
+__device__ __forceinline__ void unpack_eo<uint8_t>(const uint4& v, float* ev, float* od, float scale) {
   const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-  for (int j = 0; j < 16; j++) f[j] = (float)((w[j >> 2] >> (8 * (j & 3))) & 0xFFu) * scale;
+  for (int j = 0; j < 8; j++) {
+    ev[j] = (float)((w[j >> 1] >> (16 * (j & 1))) & 0xFFu) * scale;
+    od[j] = (float)((w[j >> 1] >> (16 * (j & 1) + 8)) & 0xFFu) * scale;
+  }
 }
 
 template <typename T>
@@ -104,8 +112,12 @@ __global__ void __launch_bounds__(256)
                      const float* __restrict__ wgt, int B, int H, int W, int Ho, int Wo, int Cp,
                      int out_ld, float in_scale) {
   constexpr int EPV = 16 / (int)sizeof(T);  // elements per 16-byte vector (W % 32 == 0 keeps rows aligned)
-  extern __shared__ float ws[];  // [27][Cp] weights, [Cp] bias, then the input tile [3][IH][PITCH]
-  float* tile = ws + 28 * Cp;
+  constexpr int HV = EPV / 2;               // even (or odd) columns per vector
+  // shared: [27][Cp] weights, [Cp] bias, then the input patch split into even and odd columns
+  // [3][IH][HP] each: with stride 2 a warp's taps become unit-stride, conflict-free reads
+  extern __shared__ float ws[];
+  float* te = ws + 28 * Cp;
+  float* to = te + 3 * STEM_IH * STEM_HP;
   const int tiles_x = (Wo + STEM_TW - 1) / STEM_TW, tiles_y = (Ho + STEM_TH - 1) / STEM_TH;
   int bid = blockIdx.x;
   const int tx = bid % tiles_x;
@@ -113,62 +125,99 @@ __global__ void __launch_bounds__(256)
   const int ty = bid % tiles_y;
   const int b = bid / tiles_y;
   for (int i = threadIdx.x; i < 28 * Cp; i += blockDim.x) ws[i] = wgt[i];
-  // aligned window of the input rows: starts at gxa <= 2*tx*TW - 1, a multiple of EPV
+  // aligned window of the input rows: starts at gxa = 2*tx*TW - EPV (a multiple of EPV)
   const int gy0 = 2 * ty * STEM_TH - 1;
   const int gxa = 2 * tx * STEM_TW - EPV;
-  const int nvec = (2 * STEM_TW + 1 + EPV + EPV - 1) / EPV;  // covers [gxa, gxa + EPV + 2*TW + 1)
-  for (int i = threadIdx.x; i < 3 * STEM_IH * nvec; i += blockDim.x) {
-    const int vx = i % nvec;
-    const int iy = (i / nvec) % STEM_IH;
-    const int ci = i / (nvec * STEM_IH);
+  constexpr int NVEC = (2 * STEM_TW + 1 + EPV + EPV - 1) / EPV;  // covers [gxa, gxa + EPV + 2*TW + 1)
+  for (int i = threadIdx.x; i < 3 * STEM_IH * NVEC; i += blockDim.x) {
+    const int vx = i % NVEC;
+    const int row = i / NVEC;  // ci * IH + iy
+    const int iy = row % STEM_IH, ci = row / STEM_IH;
     const int gy = gy0 + iy, gx = gxa + vx * EPV;
-    float f[EPV];
+    float ev[HV], od[HV];
     if ((unsigned)gy < (unsigned)H && gx >= 0 && gx < W) {
       uint4 v = __ldg(reinterpret_cast<const uint4*>(in + (((size_t)b * 3 + ci) * H + gy) * W + gx));
-      unpack16<T>(v, f, in_scale);
+      unpack_eo<T>(v, ev, od, in_scale);
     } else {
 #pragma unroll
-      for (int j = 0; j < EPV; j++) f[j] = 0.f;
+      for (int j = 0; j < HV; j++) ev[j] = od[j] = 0.f;
     }
-    float* tp = tile + (ci * STEM_IH + iy) * STEM_PITCH + vx * EPV;
+    float* pe = te + row * STEM_HP + vx * HV;
+    float* po = to + row * STEM_HP + vx * HV;
+    if (HV % 4 == 0) {
 #pragma unroll
-    for (int j = 0; j < EPV; j++) tp[j] = f[j];
+      for (int j = 0; j < HV; j += 4) {
+        *reinterpret_cast<float4*>(pe + j) = make_float4(ev[j], ev[j + 1], ev[j + 2], ev[j + 3]);
+        *reinterpret_cast<float4*>(po + j) = make_float4(od[j], od[j + 1], od[j + 2], od[j + 3]);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < HV; j++) {
+        pe[j] = ev[j];
+        po[j] = od[j];
+      }
+    }
   }
   __syncthreads();
   const float* bs = ws + 27 * Cp;
-  const int lx = threadIdx.x % STEM_TW, ly = threadIdx.x / STEM_TW;
+  // one thread = output pixels lx and lx + 32 of a tile row: every weight read from shared memory
+  // (a broadcast) feeds two packed FFMA2s, and lanes read consecutive even / odd columns
+  const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;
   const int ox = tx * STEM_TW + lx, oy = ty * STEM_TH + ly;
   if (ox >= Wo || oy >= Ho) return;
-  float x[27];
+  float x0[27], x1[27];
 #pragma unroll
   for (int ci = 0; ci < 3; ci++)
 #pragma unroll
-    for (int ky = 0; ky < 3; ky++)
-#pragma unroll
-      for (int kx = 0; kx < 3; kx++)
-        x[(ci * 3 + ky) * 3 + kx] = tile[(ci * STEM_IH + 2 * ly + ky) * STEM_PITCH + EPV - 1 + 2 * lx + kx];
+    for (int ky = 0; ky < 3; ky++) {
+      // input column 2*ox + kx - 1: local index EPV + 2*lx + kx - 1 -> odd[e-1], even[e], odd[e], e = HV + lx
+      const float* re = te + (ci * STEM_IH + 2 * ly + ky) * STEM_HP + HV + lx;
+      const float* ro = to + (ci * STEM_IH + 2 * ly + ky) * STEM_HP + HV + lx;
+      const int t = (ci * 3 + ky) * 3;
+      x0[t] = ro[-1];
+      x0[t + 1] = re[0];
+      x0[t + 2] = ro[0];
+      x1[t] = ro[31];
+      x1[t + 1] = re[32];
+      x1[t + 2] = ro[32];
+    }
   __nv_bfloat16* op = out + (((size_t)b * Ho + oy) * Wo + ox) * out_ld;
+  const bool two = ox + 32 < Wo;
   for (int c0 = 0; c0 < Cp; c0 += 8) {
-    float2 acc2[4];
+    float2 a0[4], a1[4];
 #pragma unroll
-    for (int j = 0; j < 4; j++) acc2[j] = make_float2(bs[c0 + 2 * j], bs[c0 + 2 * j + 1]);
+    for (int j = 0; j < 4; j++) a0[j] = a1[j] = make_float2(bs[c0 + 2 * j], bs[c0 + 2 * j + 1]);
 #pragma unroll
     for (int t = 0; t < 27; t++) {
       const float4 w0 = *reinterpret_cast<const float4*>(ws + t * Cp + c0);
       const float4 w1 = *reinterpret_cast<const float4*>(ws + t * Cp + c0 + 4);
-      const float2 xx = make_float2(x[t], x[t]);
-      acc2[0] = ffma2(xx, make_float2(w0.x, w0.y), acc2[0]);
-      acc2[1] = ffma2(xx, make_float2(w0.z, w0.w), acc2[1]);
-      acc2[2] = ffma2(xx, make_float2(w1.x, w1.y), acc2[2]);
-      acc2[3] = ffma2(xx, make_float2(w1.z, w1.w), acc2[3]);
+      const float2 wa = make_float2(w0.x, w0.y), wb = make_float2(w0.z, w0.w);
+      const float2 wc = make_float2(w1.x, w1.y), wd = make_float2(w1.z, w1.w);
+      const float2 p0 = make_float2(x0[t], x0[t]), p1 = make_float2(x1[t], x1[t]);
+      a0[0] = ffma2(p0, wa, a0[0]);
+      a0[1] = ffma2(p0, wb, a0[1]);
+      a0[2] = ffma2(p0, wc, a0[2]);
+      a0[3] = ffma2(p0, wd, a0[3]);
+      a1[0] = ffma2(p1, wa, a1[0]);
+      a1[1] = ffma2(p1, wb, a1[1]);
+      a1[2] = ffma2(p1, wc, a1[2]);
+      a1[3] = ffma2(p1, wd, a1[3]);
     }
-    float acc[8];
+    float o[8];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-      acc[2 * j] = silu_acc(acc2[j].x);
-      acc[2 * j + 1] = silu_acc(acc2[j].y);
+      o[2 * j] = silu_acc(a0[j].x);
+      o[2 * j + 1] = silu_acc(a0[j].y);
     }
-    *reinterpret_cast<uint4*>(op + c0) = float_to_bf16x8(acc);
+    *reinterpret_cast<uint4*>(op + c0) = float_to_bf16x8(o);
+    if (two) {
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        o[2 * j] = silu_acc(a1[j].x);
+        o[2 * j + 1] = silu_acc(a1[j].y);
+      }
+      *reinterpret_cast<uint4*>(op + (size_t)32 * out_ld + c0) = float_to_bf16x8(o);
+    }
   }
 }
 
@@ -180,7 +229,7 @@ int launch_stem(const yb_plan* p, const Op& op, const void* in, int in_dtype, cu
   int Cp = cpad8(op.dst.C);
   int threads = 256;
   unsigned blocks = (unsigned)(p->B * ((op.Hout + STEM_TH - 1) / STEM_TH) * ((op.Wout + STEM_TW - 1) / STEM_TW));
-  size_t smem = ((size_t)28 * Cp + 3 * STEM_IH * STEM_PITCH) * 4;
+  size_t smem = ((size_t)28 * Cp + 2 * 3 * STEM_IH * STEM_HP) * 4;
   switch (in_dtype) {
     case YB_F32:
       stem_conv_kernel<float><<<blocks, threads, smem, st>>>((const float*)in, out, w, p->B, p->H, p->W,
