@@ -308,16 +308,25 @@ struct BoxF {
 };
 
 // torchvision CPU nms_kernel_impl, operation by operation (std::max(a,b) = a < b ? b : a).
-__device__ __forceinline__ bool suppresses(const BoxF& i, const BoxF& j, double thr) {
+// Two exits ahead of the IEEE division leave the decision unchanged: boxes that do not intersect
+// have inter == 0 (never > thr for thr >= 0; NaN compares false), and a 2-ulp fast quotient that is
+// more than 1e-4 (relative) away from the threshold decides the same way as the rounded one.
+__device__ __forceinline__ bool suppresses(const BoxF& i, const BoxF& j, double thr, float thr_lo, float thr_hi) {
   float xx1 = (i.x1 < j.x1) ? j.x1 : i.x1;
   float yy1 = (i.y1 < j.y1) ? j.y1 : i.y1;
   float xx2 = (j.x2 < i.x2) ? j.x2 : i.x2;
   float yy2 = (j.y2 < i.y2) ? j.y2 : i.y2;
   float dw = __fsub_rn(xx2, xx1), dh = __fsub_rn(yy2, yy1);
+  if (thr_lo >= 0.f && (!(dw > 0.f) || !(dh > 0.f))) return false;
   float w = (0.f < dw) ? dw : 0.f;
   float h = (0.f < dh) ? dh : 0.f;
   float inter = __fmul_rn(w, h);
   float uni = __fsub_rn(__fadd_rn(i.area, j.area), inter);
+  if (uni > 1e-30f && uni < 1e30f && inter < 1e30f) {
+    float q = __fdividef(inter, uni);
+    if (q > thr_hi) return true;
+    if (q < thr_lo) return false;
+  }
   float ovr = __fdiv_rn(inter, uni);
   return (double)ovr > thr;
 }
@@ -365,6 +374,10 @@ __global__ void __launch_bounds__(G_CHUNK) nms_greedy_kernel(const NmsArgs a) {
   const int n = min(a.hdr[b].n_final, a.cap);
   const unsigned long long* keys = a.keys + (size_t)b * a.cap;
   const double thr = a.iou;
+  // brackets of the threshold for the fast quotient (only used when 0 <= thr < 1e30)
+  const bool thr_ok = thr >= 0.0 && thr < 1e30;
+  const float thr_lo = thr_ok ? (float)thr * 0.9999f - 1e-30f : -1.f;
+  const float thr_hi = thr_ok ? (float)thr * 1.0001f + 1e-30f : 3.0e38f;
   if (tid == 0) s_K = 0;
   __syncthreads();
   for (int base = 0; base < n; base += G_CHUNK) {
@@ -377,7 +390,7 @@ __global__ void __launch_bounds__(G_CHUNK) nms_greedy_kernel(const NmsArgs a) {
     if (alive) {
       load_candidate(a, b, keys[ci], me, nullptr);
       for (int k = 0; k < K; k++) {
-        if (suppresses(kept[k], me, thr)) {
+        if (suppresses(kept[k], me, thr, thr_lo, thr_hi)) {
           alive = false;
           break;
         }
@@ -406,7 +419,7 @@ __global__ void __launch_bounds__(G_CHUNK) nms_greedy_kernel(const NmsArgs a) {
       int i = task / (G_CHUNK / 32), wcol = task - i * (G_CHUNK / 32);
       int j = wcol * 32 + lane;
       bool sup = false;
-      if (j > i && j < m) sup = suppresses(live[i], live[j], thr);
+      if (j > i && j < m) sup = suppresses(live[i], live[j], thr, thr_lo, thr_hi);
       unsigned int bits = __ballot_sync(0xffffffffu, sup);
       if (lane == 0) mask[i][wcol] = bits;
     }
