@@ -287,10 +287,24 @@ __global__ void __launch_bounds__(256)
   for (int p = 0; p < DW_PX; p++)
 #pragma unroll
     for (int j = 0; j < 4; j++) acc[p][j] = make_float2(bias[c + 2 * j], bias[c + 2 * j + 1]);
+  // All 18 tap loads are predicated (no branches), so they issue back to back and the thread waits
+  // once for the whole 3 x 6 window instead of once per tap.
+  uint4 v[3][DW_PX + 2];
 #pragma unroll
   for (int ky = 0; ky < 3; ky++) {
     const int iy = y - 1 + ky;
-    if ((unsigned)iy >= (unsigned)H) continue;
+    const bool row_ok = (unsigned)iy < (unsigned)H;
+    const __nv_bfloat16* rowp = src + ((size_t)(b * H + (row_ok ? iy : y)) * W) * src_ld + sc;
+#pragma unroll
+    for (int col = 0; col < DW_PX + 2; col++) {
+      const int ix = x0 - 1 + col;
+      v[ky][col] = make_uint4(0u, 0u, 0u, 0u);
+      if (row_ok && (unsigned)ix < (unsigned)W)
+        v[ky][col] = __ldg(reinterpret_cast<const uint4*>(rowp + (size_t)ix * src_ld));
+    }
+  }
+#pragma unroll
+  for (int ky = 0; ky < 3; ky++) {
     float2 w[3][4];
 #pragma unroll
     for (int kx = 0; kx < 3; kx++) {
@@ -301,13 +315,9 @@ __global__ void __launch_bounds__(256)
       w[kx][2] = make_float2(w1.x, w1.y);
       w[kx][3] = make_float2(w1.z, w1.w);
     }
-    const __nv_bfloat16* rowp = src + ((size_t)(b * H + iy) * W) * src_ld + sc;
 #pragma unroll
     for (int col = 0; col < DW_PX + 2; col++) {
-      const int ix = x0 - 1 + col;
-      if ((unsigned)ix >= (unsigned)W) continue;
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(rowp + (size_t)ix * src_ld));
-      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&v);
+      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&v[ky][col]);
       float2 f[4];
 #pragma unroll
       for (int j = 0; j < 4; j++) f[j] = __bfloat1622float2(h2[j]);
@@ -450,113 +460,159 @@ int launch_pool(const yb_plan* p, const Op& op, cudaStream_t st) {
 // C2PSA attention core (nets/nn.py:112-122): per (image, head)
 //     out[:, i] = sum_j softmax_j( (q_i . k_j) * dk^-1/2 ) v_j
 // qkv rows are tokens; channels of head h are [q(32) | k(32) | v(64)] at h*128 (the reference's
-// view(b, heads, 2*dk+dh, N) split).  One thread owns one query: q and the 64-wide accumulator
-// stay in registers, K/V tiles are staged once per CTA in shared memory as fp32 and read as
-// broadcasts; softmax is computed online in base 2.
+// view(b, heads, 2*dk+dh, N) split).  Flash-style tensor-core kernel: a CTA owns 128 queries of one
+// (image, head), each warp a 16-query strip.  K/V chunks of 128 keys are staged in shared memory as
+// bf16 (rows padded so fragment reads are conflict-free); S = Q K^T and O += P V run as
+// mma.sync.m16n8k16 bf16 with fp32 accumulators, the S accumulator layout doubling as the A
+// fragment of the second MMA; softmax is computed online in base 2 on the fp32 S registers.
+// (N = 400 keys of 96 channels is far too small a problem for a tcgen05/TMEM pipeline to pay.)
 // ---------------------------------------------------------------------------------------------
-static constexpr int ATT_Q = 128;  // queries per CTA
-static constexpr int ATT_KT = 64;  // keys per shared-memory tile
+static constexpr int ATT_Q = 128;   // queries per CTA (8 warps x 16)
+static constexpr int ATT_KC = 128;  // keys per shared-memory chunk
+static constexpr int ATT_KP = 40;   // K row pitch, bf16 (80 B)
+static constexpr int ATT_VP = 72;   // V row pitch, bf16 (144 B)
 
-__global__ void __launch_bounds__(ATT_Q)
+__device__ __forceinline__ void mma_bf16_16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+      "{%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack2_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(256)
     attention_kernel(const __nv_bfloat16* __restrict__ qkv, int qkv_ld, __nv_bfloat16* __restrict__ out,
                      int out_ld, int N, int heads, float scale_log2e) {
-  __shared__ __align__(16) float Ks[ATT_KT][32];
-  __shared__ __align__(16) float Vs[ATT_KT][64];
-  const int qt = blockIdx.x;
-  const int h = blockIdx.y;
-  const int b = blockIdx.z;
-  const int tid = threadIdx.x;
-  const int qi = qt * ATT_Q + tid;
-  const bool q_ok = qi < N;
+  __shared__ __align__(16) __nv_bfloat16 Ks[ATT_KC * ATT_KP];
+  __shared__ __align__(16) __nv_bfloat16 Vs[ATT_KC * ATT_VP];
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int q0 = blockIdx.x * ATT_Q + warp * 16;
   const __nv_bfloat16* base = qkv + (size_t)b * N * qkv_ld + h * 128;
-  float2 q2[16];
+  // Q fragments (A operand, 16 queries x 32 channels = 2 k-steps), rows clamped into the image
+  uint32_t qa[2][4];
   {
-    const __nv_bfloat16* qp = base + (size_t)(q_ok ? qi : 0) * qkv_ld;
+    const __nv_bfloat16* r0 = base + (size_t)min(q0 + g, N - 1) * qkv_ld;
+    const __nv_bfloat16* r1 = base + (size_t)min(q0 + g + 8, N - 1) * qkv_ld;
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-      float f[8];
-      bf16x8_to_float(__ldg(reinterpret_cast<const uint4*>(qp + 8 * j)), f);
-#pragma unroll
-      for (int t = 0; t < 4; t++) q2[4 * j + t] = make_float2(f[2 * t] * scale_log2e, f[2 * t + 1] * scale_log2e);
+    for (int ks = 0; ks < 2; ks++) {
+      qa[ks][0] = __ldg(reinterpret_cast<const uint32_t*>(r0 + ks * 16 + 2 * t));
+      qa[ks][1] = __ldg(reinterpret_cast<const uint32_t*>(r1 + ks * 16 + 2 * t));
+      qa[ks][2] = __ldg(reinterpret_cast<const uint32_t*>(r0 + ks * 16 + 8 + 2 * t));
+      qa[ks][3] = __ldg(reinterpret_cast<const uint32_t*>(r1 + ks * 16 + 8 + 2 * t));
     }
   }
-  float2 acc2[32];
+  float o[8][4];
 #pragma unroll
-  for (int d = 0; d < 32; d++) acc2[d] = make_float2(0.f, 0.f);
-  float mrun = -INFINITY, lrun = 0.f;
+  for (int i = 0; i < 8; i++) o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+  float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+  const uint32_t ks_s = (uint32_t)__cvta_generic_to_shared(Ks);
+  const uint32_t vs_s = (uint32_t)__cvta_generic_to_shared(Vs);
 
-  for (int k0 = 0; k0 < N; k0 += ATT_KT) {
+  for (int k0 = 0; k0 < N; k0 += ATT_KC) {
     __syncthreads();
-    // stage K (64 x 32) and V (64 x 64): 12 granules of 8 channels per key
-    for (int i = tid; i < ATT_KT * 12; i += ATT_Q) {
-      int key = i / 12, gr = i - key * 12;
-      float f[8];
-      if (k0 + key < N) {
-        bf16x8_to_float(
-            __ldg(reinterpret_cast<const uint4*>(base + (size_t)(k0 + key) * qkv_ld + 32 + gr * 8)), f);
-      } else {
-#pragma unroll
-        for (int t = 0; t < 8; t++) f[t] = 0.f;
-      }
-      float* dp = gr < 4 ? &Ks[key][gr * 8] : &Vs[key][(gr - 4) * 8];
-      *reinterpret_cast<float4*>(dp) = make_float4(f[0], f[1], f[2], f[3]);
-      *reinterpret_cast<float4*>(dp + 4) = make_float4(f[4], f[5], f[6], f[7]);
+    // stage K (KC x 32) and V (KC x 64): 12 granules of 8 channels per key, zero-filled past N
+    for (int i = tid; i < ATT_KC * 12; i += 256) {
+      const int key = i / 12, gr = i - key * 12;
+      const bool ok = k0 + key < N;
+      const __nv_bfloat16* sp = base + (size_t)(ok ? k0 + key : 0) * qkv_ld + 32 + gr * 8;
+      const uint32_t dp = gr < 4 ? ks_s + (uint32_t)(key * ATT_KP + gr * 8) * 2u
+                                 : vs_s + (uint32_t)(key * ATT_VP + (gr - 4) * 8) * 2u;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dp), "l"(sp), "r"(ok ? 16u : 0u)
+                   : "memory");
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
-    const int kmax = min(ATT_KT, N - k0);
-    for (int c0 = 0; c0 < kmax; c0 += 8) {
-      float s[8];
-      float cmax = -INFINITY;
+    const int kmax = min(ATT_KC, N - k0);
+    for (int kb = 0; kb < kmax; kb += 64) {
+      float s[8][4];
 #pragma unroll
-      for (int u = 0; u < 8; u++) {
-        float2 a2 = make_float2(0.f, 0.f);
+      for (int nt = 0; nt < 8; nt++) {
+        s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+        const __nv_bfloat16* kr = Ks + (kb + nt * 8 + g) * ATT_KP + 2 * t;
 #pragma unroll
-        for (int d4 = 0; d4 < 8; d4++) {  // packed FFMA2: two channels per instruction
-          const float4 kk = *reinterpret_cast<const float4*>(&Ks[c0 + u][4 * d4]);
-          a2 = ffma2(q2[2 * d4], make_float2(kk.x, kk.y), a2);
-          a2 = ffma2(q2[2 * d4 + 1], make_float2(kk.z, kk.w), a2);
+        for (int ks = 0; ks < 2; ks++)
+          mma_bf16_16816(s[nt], qa[ks], *reinterpret_cast<const uint32_t*>(kr + ks * 16),
+                         *reinterpret_cast<const uint32_t*>(kr + ks * 16 + 8));
+      }
+      float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+      for (int nt = 0; nt < 8; nt++) {
+        const int key = kb + nt * 8 + 2 * t;
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+          const float v = (key + (e & 1) < kmax) ? s[nt][e] * scale_log2e : -INFINITY;
+          s[nt][e] = v;
+          if (e < 2) mx0 = fmaxf(mx0, v);
+          else mx1 = fmaxf(mx1, v);
         }
-        const float a = a2.x + a2.y;
-        s[u] = (c0 + u < kmax) ? a : -INFINITY;
-        cmax = fmaxf(cmax, s[u]);
       }
-      const float mnew = fmaxf(mrun, cmax);
-      const float corr = exp2f(mrun - mnew);
-      lrun *= corr;
-      const float2 corr2 = make_float2(corr, corr);
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+      mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+      mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+      const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);  // finite: every sub-block holds a valid key
+      const float c0 = exp2f(m0 - mn0), c1 = exp2f(m1 - mn1);
+      m0 = mn0;
+      m1 = mn1;
+      l0 *= c0;
+      l1 *= c1;
 #pragma unroll
-      for (int d = 0; d < 32; d++) {
-        acc2[d].x *= corr2.x;
-        acc2[d].y *= corr2.y;
+      for (int i = 0; i < 8; i++) {
+        o[i][0] *= c0;
+        o[i][1] *= c0;
+        o[i][2] *= c1;
+        o[i][3] *= c1;
       }
-      mrun = mnew;
+      uint32_t pa[4][4];
 #pragma unroll
-      for (int u = 0; u < 8; u++) {
-        const float pj = exp2f(s[u] - mnew);
-        lrun += pj;
-        const float2 pp = make_float2(pj, pj);
+      for (int nt = 0; nt < 8; nt++) {
+        const float p0 = exp2f(s[nt][0] - mn0), p1 = exp2f(s[nt][1] - mn0);
+        const float p2 = exp2f(s[nt][2] - mn1), p3 = exp2f(s[nt][3] - mn1);
+        l0 += p0 + p1;
+        l1 += p2 + p3;
+        pa[nt >> 1][(nt & 1) * 2] = pack2_bf16(p0, p1);
+        pa[nt >> 1][(nt & 1) * 2 + 1] = pack2_bf16(p2, p3);
+      }
 #pragma unroll
-        for (int d4 = 0; d4 < 16; d4++) {
-          const float4 vv = *reinterpret_cast<const float4*>(&Vs[c0 + u][4 * d4]);
-          acc2[2 * d4] = ffma2(pp, make_float2(vv.x, vv.y), acc2[2 * d4]);
-          acc2[2 * d4 + 1] = ffma2(pp, make_float2(vv.z, vv.w), acc2[2 * d4 + 1]);
+      for (int j = 0; j < 4; j++) {
+        // V fragments (B operand, k = key, n = channel) through ldmatrix.trans on [key][channel] rows
+        const uint32_t vrow = vs_s + (uint32_t)((kb + j * 16 + (lane & 7) + ((lane >> 3) & 1) * 8) * ATT_VP +
+                                                (lane >> 4) * 8) * 2u;
+#pragma unroll
+        for (int dp = 0; dp < 4; dp++) {
+          uint32_t r0, r1, r2, r3;
+          asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                       : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
+                       : "r"(vrow + (uint32_t)dp * 32u));
+          mma_bf16_16816(o[2 * dp], pa[j], r0, r1);
+          mma_bf16_16816(o[2 * dp + 1], pa[j], r2, r3);
         }
       }
     }
   }
-  if (q_ok) {
-    const float inv = 1.f / lrun;
-    __nv_bfloat16* op = out + ((size_t)b * N + qi) * out_ld + h * 64;
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+  l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+  l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+  const float i0 = 1.f / l0, i1 = 1.f / l1;
+  __nv_bfloat16* ob = out + (size_t)b * N * out_ld + h * 64 + 2 * t;
+  if (q0 + g < N) {
+    __nv_bfloat16* op = ob + (size_t)(q0 + g) * out_ld;
 #pragma unroll
-    for (int j = 0; j < 8; j++) {
-      float f[8];
+    for (int nt = 0; nt < 8; nt++)
+      *reinterpret_cast<uint32_t*>(op + nt * 8) = pack2_bf16(o[nt][0] * i0, o[nt][1] * i0);
+  }
+  if (q0 + g + 8 < N) {
+    __nv_bfloat16* op = ob + (size_t)(q0 + g + 8) * out_ld;
 #pragma unroll
-      for (int t = 0; t < 4; t++) {
-        f[2 * t] = acc2[4 * j + t].x * inv;
-        f[2 * t + 1] = acc2[4 * j + t].y * inv;
-      }
-      *reinterpret_cast<uint4*>(op + 8 * j) = float_to_bf16x8(f);
-    }
+    for (int nt = 0; nt < 8; nt++)
+      *reinterpret_cast<uint32_t*>(op + nt * 8) = pack2_bf16(o[nt][2] * i1, o[nt][3] * i1);
   }
 }
 
@@ -566,10 +622,14 @@ int launch_attn(const yb_plan* p, const Op& op, cudaStream_t st) {
   const __nv_bfloat16* qkv =
       reinterpret_cast<const __nv_bfloat16*>(buf_ptr(p, op.src[0].buf)) + op.src[0].c_off;
   __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(buf_ptr(p, op.dst.buf)) + op.dst.c_off;
+  if (op.dk != 32 || op.dh != 64) {
+    set_error("attention kernel is specialised for dim_key 32 / dim_head 64 (got %d / %d)", op.dk, op.dh);
+    return YB_ERR_UNSUPPORTED;
+  }
   int N = op.Hin * op.Win;
   dim3 grid((N + ATT_Q - 1) / ATT_Q, op.heads, p->B);
-  attention_kernel<<<grid, ATT_Q, 0, st>>>(qkv, sb.C, out, db.C, N, op.heads,
-                                           op.scale * 1.4426950408889634f);
+  attention_kernel<<<grid, 256, 0, st>>>(qkv, sb.C, out, db.C, N, op.heads,
+                                         op.scale * 1.4426950408889634f);
   count_launch();
   YB_CUDA(cudaGetLastError());
   return YB_OK;
