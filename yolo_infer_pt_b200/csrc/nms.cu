@@ -6,16 +6,19 @@
 //                ascending key order == descending score, ties by ascending candidate index
 //                (anchor-major, class-minor: the row-major order of util.py:147's nonzero()).
 //                Keys are appended to a per-image list while it has room.
-//   2. select    only for images with more than max_nms candidates (util.py:157's [:max_nms]):
-//                an exact radix select of the max_nms-th smallest key (6 histogram passes over
-//                the scores, gated per image), then a re-compaction of keys <= that threshold.
-//   3. sort      per-image bitonic sort of <= max_nms keys (shared-memory tiles of 4096 keys,
-//                global compare-exchange steps above that).
-//   4. greedy    one CTA per image walks the sorted candidates in chunks of 256: each candidate
-//                is tested against the boxes kept so far (<= max_det of them), survivors are
-//                resolved inside the chunk with a ballot-built IoU bitmask and a serial scan.
-//                Greedy NMS only ever needs the first max_det kept boxes (util.py:163), so the
-//                walk stops there and the n x n mask of torchvision's CUDA kernel is never built.
+//   2. walk      one CTA (1024 threads) per image consumes the candidates lazily, in descending
+//                score order, one *band* at a time: a 2048-bin histogram of the score bits picks a
+//                key range holding <= 4096 candidates, the band is compacted into shared memory,
+//                bitonic-sorted there and handed to the greedy step; the next band is fetched only
+//                if fewer than max_det boxes are kept so far.  Greedy NMS only ever needs the first
+//                max_det kept boxes (util.py:163) and only the max_nms best candidates
+//                (util.py:157), so a full sort of the list and the n x n mask of torchvision's CUDA
+//                kernel are never built.  A histogram bin with more than 4096 candidates (massive
+//                score ties) is split exactly by re-histogramming the lower key bits.  Images with
+//                more candidates than the key list holds are banded straight from the scores.
+//      greedy    256 candidates at a time: each is tested against the boxes kept so far (4 threads
+//                per candidate), survivors are resolved inside the chunk with a ballot-built IoU
+//                bitmask and a serial scan.
 //
 // IoU arithmetic replicates torchvision's CPU kernel operation by operation in fp32 with
 // round-to-nearest intrinsics (no FMA contraction), on the class-offset boxes of util.py:160-161,
@@ -29,18 +32,11 @@ namespace yb {
 
 static constexpr int HIST_BINS = 2048;
 static constexpr int SORT_TILE = 4096;
-static constexpr int NUM_PASSES = 6;  // 11,11,11,11,11,9 bits
 
 struct NmsHeader {  // per image, zeroed at the start of every call
   int cand_count;   // candidates found by the scan
   int sel_count;    // keys appended by the scan (may exceed capacity; clamp on read)
-  int sel2_count;   // keys appended by the re-compaction
-  int overflow;     // cand_count > max_nms
-  int need;         // remaining rank inside the current prefix
-  int n_final;      // keys to sort / walk
-  int pad[2];
-  unsigned long long prefix;  // radix-select prefix; after the last pass: the threshold key
-  unsigned long long pad2;
+  int pad[6];
 };
 
 struct NmsArgs {
@@ -51,7 +47,6 @@ struct NmsArgs {
   int max_det, max_nms, cap;
   float max_wh;
   NmsHeader* hdr;
-  unsigned int* hist;        // [B][HIST_BINS]
   unsigned long long* keys;  // [B][cap]
   float* out;
   int* out_counts;
@@ -67,8 +62,6 @@ __device__ __forceinline__ float from_orderable(unsigned int u) {
 __device__ __forceinline__ unsigned long long make_key(float score, unsigned int idx) {
   return ((unsigned long long)(~orderable(score)) << 32) | idx;
 }
-__device__ __forceinline__ int pass_shift(int pass) { return pass < 5 ? 64 - 11 * (pass + 1) : 0; }
-__device__ __forceinline__ int pass_bits(int pass) { return pass < 5 ? 11 : 9; }
 
 // Pass over the scores of every image: each score > conf becomes a key appended to the image's
 // list (unordered; the sort orders them).  Reads 4 anchors per thread (float4 when aligned), one
@@ -128,178 +121,6 @@ __global__ void __launch_bounds__(256) nms_append_kernel(const NmsArgs a, int ve
   if (lane == 0 && local_count) atomicAdd(&h->cand_count, local_count);
 }
 
-// Overflow images only (more than max_nms candidates):
-// mode 1: histogram of digit `pass` among keys matching the radix-select prefix
-// mode 2: re-compaction of keys <= threshold
-template <int MODE>
-__global__ void __launch_bounds__(256) nms_scan_kernel(const NmsArgs a, int pass) {
-  __shared__ unsigned int hist_s[HIST_BINS];
-  const int b = blockIdx.y;
-  NmsHeader* h = a.hdr + b;
-  if (!h->overflow) return;
-  if (MODE == 1) {
-    for (int i = threadIdx.x; i < HIST_BINS; i += blockDim.x) hist_s[i] = 0;
-    __syncthreads();
-  }
-  const long long total = (long long)a.nc * a.A;
-  const float* sp = a.pred + ((size_t)b * (4 + a.nc) + 4) * a.A;
-  unsigned long long* keys = a.keys + (size_t)b * a.cap;
-  const unsigned long long prefix = h->prefix;
-  const int shift = pass_shift(pass), bits = pass_bits(pass);
-  const int lane = threadIdx.x & 31;
-  // all lanes of a warp run the same number of iterations (ballots below)
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  const long long iters = (total + stride - 1) / stride;
-  long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  for (long long it = 0; it < iters; it++, e += stride) {
-    bool cand = false;
-    unsigned long long key = 0;
-    if (e < total) {
-      float s = __ldg(sp + e);
-      if (s > a.conf) {
-        int c = (int)(e / a.A);
-        int an = (int)(e - (long long)c * a.A);
-        key = make_key(s, (unsigned int)an * (unsigned int)a.nc + (unsigned int)c);
-        cand = true;
-      }
-    }
-    if (MODE == 1) {
-      bool match = pass == 0 ? true : ((key >> (shift + bits)) == prefix);
-      if (cand && match) atomicAdd(&hist_s[(unsigned int)(key >> shift) & ((1u << bits) - 1u)], 1u);
-    } else {
-      bool take = cand && key <= prefix;
-      unsigned int m = __ballot_sync(0xffffffffu, take);
-      if (m) {
-        int leader = __ffs(m) - 1;
-        int base = 0;
-        if (lane == leader) base = atomicAdd(&h->sel2_count, __popc(m));
-        base = __shfl_sync(0xffffffffu, base, leader);
-        if (take) {
-          int slot = base + __popc(m & ((1u << lane) - 1u));
-          if (slot < a.cap) keys[slot] = key;
-        }
-      }
-    }
-  }
-  if (MODE == 1) {
-    __syncthreads();
-    unsigned int* hg = a.hist + (size_t)b * HIST_BINS;
-    for (int i = threadIdx.x; i < HIST_BINS; i += blockDim.x)
-      if (hist_s[i]) atomicAdd(&hg[i], hist_s[i]);
-  }
-}
-
-// One block per image: consume the histogram of digit `pass`, extend the prefix.
-__global__ void __launch_bounds__(1024) nms_pick_kernel(const NmsArgs a, int pass) {
-  __shared__ unsigned int cum[HIST_BINS];
-  const int b = blockIdx.x;
-  NmsHeader* h = a.hdr + b;
-  unsigned int* hg = a.hist + (size_t)b * HIST_BINS;
-  if (pass < 0) {  // decision step: does this image exceed max_nms candidates?
-    if (threadIdx.x == 0) {
-      int total = h->cand_count;
-      if (total > a.max_nms) {
-        h->overflow = 1;
-        h->need = a.max_nms;
-        h->prefix = 0ull;
-        h->n_final = a.max_nms;
-      } else {
-        h->overflow = 0;
-        h->n_final = total;
-      }
-    }
-    return;
-  }
-  if (!h->overflow) return;
-  const int nb = 1 << pass_bits(pass);
-  for (int i = threadIdx.x; i < HIST_BINS; i += blockDim.x) cum[i] = i < nb ? hg[i] : 0u;
-  __syncthreads();
-  // inclusive scan over 2048 bins (Hillis-Steele in shared memory, 11 rounds)
-  for (int off = 1; off < HIST_BINS; off <<= 1) {
-    unsigned int v0 = 0, v1 = 0;
-    int i0 = threadIdx.x, i1 = threadIdx.x + 1024;
-    if (i0 >= off) v0 = cum[i0 - off];
-    if (i1 >= off) v1 = cum[i1 - off];
-    __syncthreads();
-    cum[i0] += v0;
-    cum[i1] += v1;
-    __syncthreads();
-  }
-  const unsigned int need = (unsigned int)h->need;
-  __syncthreads();
-  for (int i = threadIdx.x; i < nb; i += blockDim.x) {
-    unsigned int before = i ? cum[i - 1] : 0u;
-    if (before < need && cum[i] >= need) {  // exactly one bin satisfies this
-      h->prefix = (h->prefix << pass_bits(pass)) | (unsigned long long)i;
-      h->need = (int)(need - before);
-    }
-  }
-  for (int i = threadIdx.x; i < HIST_BINS; i += blockDim.x) hg[i] = 0u;
-}
-
-// ---------------------------------------------------------------------------------------------
-// Bitonic sort of each image's key list (ascending).  Lists are padded with all-ones sentinels
-// up to P = max(SORT_TILE, next_pow2(n)); tiles beyond P are skipped.
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ int padded_len(int n) {
-  int p = SORT_TILE;
-  while (p < n) p <<= 1;
-  return p;
-}
-
-// phase 0: load (+pad), full sort of each tile;  phase 1: finish stage k (j = SORT_TILE/2 .. 1)
-__global__ void __launch_bounds__(1024) nms_sort_tile_kernel(const NmsArgs a, int phase, int k) {
-  __shared__ unsigned long long s[SORT_TILE];
-  const int b = blockIdx.y;
-  const int n = min(a.hdr[b].n_final, a.cap);
-  if (n <= 1 && phase == 0) return;
-  const int P = padded_len(n);
-  const int t0 = blockIdx.x * SORT_TILE;
-  if (t0 >= P) return;
-  if (phase == 1 && k > P) return;
-  unsigned long long* keys = a.keys + (size_t)b * a.cap + t0;
-  for (int i = threadIdx.x; i < SORT_TILE; i += blockDim.x)
-    s[i] = (phase == 0 && t0 + i >= n) ? ~0ull : keys[i];
-  __syncthreads();
-  const int kk_begin = phase == 0 ? 2 : k;
-  const int kk_end = phase == 0 ? SORT_TILE : k;
-  for (int kk = kk_begin; kk <= kk_end; kk <<= 1) {
-    for (int j = min(kk >> 1, SORT_TILE >> 1); j > 0; j >>= 1) {
-      for (int t = threadIdx.x; t < SORT_TILE / 2; t += blockDim.x) {
-        int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // lower index of the pair
-        int l = i | j;
-        bool asc = (((t0 + i) & kk) == 0);
-        unsigned long long x = s[i], y = s[l];
-        if ((x > y) == asc) {
-          s[i] = y;
-          s[l] = x;
-        }
-      }
-      __syncthreads();
-    }
-  }
-  for (int i = threadIdx.x; i < SORT_TILE; i += blockDim.x) keys[i] = s[i];
-}
-
-// one global compare-exchange step (k, j) with j >= SORT_TILE
-__global__ void __launch_bounds__(256) nms_sort_global_kernel(const NmsArgs a, int k, int j) {
-  const int b = blockIdx.y;
-  const int n = min(a.hdr[b].n_final, a.cap);
-  const int P = padded_len(n);
-  if (k > P) return;
-  int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= P / 2) return;
-  int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-  int l = i | j;
-  unsigned long long* keys = a.keys + (size_t)b * a.cap;
-  bool asc = ((i & k) == 0);
-  unsigned long long x = keys[i], y = keys[l];
-  if ((x > y) == asc) {
-    keys[i] = y;
-    keys[l] = x;
-  }
-}
-
 // ---------------------------------------------------------------------------------------------
 // Greedy walk.
 // ---------------------------------------------------------------------------------------------
@@ -333,6 +154,7 @@ __device__ __forceinline__ bool suppresses(const BoxF& i, const BoxF& j, double 
 
 static constexpr int G_CHUNK = 256;
 static constexpr int G_MAXDET = 1024;  // shared-memory capacity for kept boxes
+static constexpr int FIRST_BAND = 1024;  // preferred size of the first band (most images finish inside it)
 
 __device__ __forceinline__ void load_candidate(const NmsArgs& a, int b, unsigned long long key, BoxF& off,
                                                float* raw6) {
@@ -361,94 +183,321 @@ __device__ __forceinline__ void load_candidate(const NmsArgs& a, int b, unsigned
   }
 }
 
-__global__ void __launch_bounds__(G_CHUNK) nms_greedy_kernel(const NmsArgs a) {
-  __shared__ BoxF kept[G_MAXDET];
-  __shared__ int kept_pos[G_MAXDET];            // position in the sorted list
-  __shared__ BoxF live[G_CHUNK];
-  __shared__ int live_pos[G_CHUNK];
-  __shared__ unsigned int mask[G_CHUNK][G_CHUNK / 32];
-  __shared__ int warp_cnt[G_CHUNK / 32];
-  __shared__ int s_K, s_m;
+// Histogram bins over the high key word (= bit-inverted orderable score): bin 0 starts at score 1.0
+// and every bin spans 2^16 consecutive fp32 values, so [conf = 0.001, 1] covers ~1277 bins; anything
+// outside is clamped, which keeps bins monotone in the key order (all that correctness needs).
+static constexpr long long KH_ONE = 0x407FFFFFll;  // high key word of score 1.0f
+__device__ __forceinline__ int bin_of(unsigned long long key) {
+  long long d = ((long long)(unsigned int)(key >> 32) - KH_ONE) >> 16;
+  return (int)(d < 0 ? 0 : (d > HIST_BINS - 1 ? HIST_BINS - 1 : d));
+}
+// smallest key of bin b (b in [0, HIST_BINS]); ~0 is never a real key
+__device__ __forceinline__ unsigned long long edge_key(int b) {
+  if (b <= 0) return 0ull;
+  if (b >= HIST_BINS) return ~0ull;
+  return (unsigned long long)(KH_ONE + ((long long)b << 16)) << 32;
+}
+
+struct ImgSmem {
+  unsigned long long tile[SORT_TILE];
+  unsigned int hist[HIST_BINS];
+  unsigned int hist2[HIST_BINS];
+  BoxF kept[G_MAXDET];
+  unsigned long long kept_key[G_MAXDET];
+  BoxF live[G_CHUNK];      // candidates of the chunk, then (compacted in place) its survivors
+  unsigned long long live_key[G_CHUNK];
+  unsigned int mask[G_CHUNK][G_CHUNK / 32];
+  int dead[G_CHUNK];
+  int warp_cnt[G_CHUNK / 32];
+  int K, m, cnt, walk_end;
+  unsigned int walk_cum;
+};
+
+// The image's candidates: the appended key list when it is complete, else the raw scores.
+struct Src {
+  const unsigned long long* keys;
+  int n;
+  const float* sp;
+  long long total;
+  int A, nc;
+  float conf;
+  bool complete;
+};
+// Calls f(valid, key) with a uniform trip count over the CTA (f may use warp collectives).
+template <int IMG_T, typename F>
+__device__ __forceinline__ void scan_src(const Src& s, F f) {
+  if (s.complete) {
+    const int iters = (s.n + IMG_T - 1) / IMG_T;
+    int i = threadIdx.x;
+    for (int it = 0; it < iters; it++, i += IMG_T) {
+      const bool v = i < s.n;
+      f(v, v ? s.keys[i] : ~0ull);
+    }
+  } else {
+    const long long iters = (s.total + IMG_T - 1) / IMG_T;
+    long long e = threadIdx.x;
+    for (long long it = 0; it < iters; it++, e += IMG_T) {
+      bool v = false;
+      unsigned long long key = ~0ull;
+      if (e < s.total) {
+        const float sc = __ldg(s.sp + e);
+        if (sc > s.conf) {
+          const int c = (int)(e / s.A);
+          const int an = (int)(e - (long long)c * s.A);
+          key = make_key(sc, (unsigned int)an * (unsigned int)s.nc + (unsigned int)c);
+          v = true;
+        }
+      }
+      f(v, key);
+    }
+  }
+}
+
+// Warp 0: longest run of bins [start, end) with sum <= limit.  Results in sm.walk_end / sm.walk_cum.
+__device__ __forceinline__ void walk_bins(ImgSmem& sm, const unsigned int* h, int start, int nb, unsigned int limit) {
+  if (threadIdx.x >= 32) return;
+  const int lane = threadIdx.x;
+  unsigned int cum = 0;
+  int end = start;
+  for (int b0 = start; b0 < nb; b0 += 32) {
+    unsigned int incl = (b0 + lane < nb) ? h[b0 + lane] : 0u;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    const bool ok = (b0 + lane < nb) && (cum + incl <= limit);
+    const int nok = __popc(__ballot_sync(0xffffffffu, ok));  // ok is a prefix of the lanes (incl is monotone)
+    if (nok > 0) cum += __shfl_sync(0xffffffffu, incl, nok - 1);
+    end = b0 + nok;
+    if (nok < 32) break;
+  }
+  if (lane == 0) {
+    sm.walk_end = end;
+    sm.walk_cum = cum;
+  }
+}
+
+// IMG_T threads per image: 1024 for small batches (latency), 512 (two CTAs per SM) for large ones.
+template <int IMG_T>
+__global__ void __launch_bounds__(IMG_T) nms_image_kernel(const NmsArgs a) {
+  extern __shared__ __align__(16) uint8_t nms_smem_raw[];
+  ImgSmem& sm = *reinterpret_cast<ImgSmem*>(nms_smem_raw);
   const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int n = min(a.hdr[b].n_final, a.cap);
-  const unsigned long long* keys = a.keys + (size_t)b * a.cap;
+  const NmsHeader h = a.hdr[b];
+  Src src;
+  src.complete = h.sel_count <= a.cap;
+  src.keys = a.keys + (size_t)b * a.cap;
+  src.n = min(h.sel_count, a.cap);
+  src.sp = a.pred + ((size_t)b * (4 + a.nc) + 4) * a.A;
+  src.total = (long long)a.nc * a.A;
+  src.A = a.A;
+  src.nc = a.nc;
+  src.conf = a.conf;
   const double thr = a.iou;
   // brackets of the threshold for the fast quotient (only used when 0 <= thr < 1e30)
   const bool thr_ok = thr >= 0.0 && thr < 1e30;
   const float thr_lo = thr_ok ? (float)thr * 0.9999f - 1e-30f : -1.f;
   const float thr_hi = thr_ok ? (float)thr * 1.0001f + 1e-30f : 3.0e38f;
-  if (tid == 0) s_K = 0;
+
+  for (int i = tid; i < HIST_BINS; i += IMG_T) sm.hist[i] = 0u;
+  if (tid == 0) sm.K = 0;
   __syncthreads();
-  for (int base = 0; base < n; base += G_CHUNK) {
-    const int K = s_K;
-    if (K >= a.max_det) break;
-    const int ci = base + tid;
-    bool alive = ci < n;
-    BoxF me;
-    me.x1 = me.y1 = me.x2 = me.y2 = me.area = 0.f;
-    if (alive) {
-      load_candidate(a, b, keys[ci], me, nullptr);
-      for (int k = 0; k < K; k++) {
-        if (suppresses(kept[k], me, thr, thr_lo, thr_hi)) {
-          alive = false;
+  if (h.cand_count > 0) {
+    scan_src<IMG_T>(src, [&](bool v, unsigned long long k) {
+      if (v) atomicAdd(&sm.hist[bin_of(k)], 1u);
+    });
+  }
+  __syncthreads();
+
+  int cur_bin = 0;
+  int consumed = 0;                 // candidates handed to the greedy step so far (sorted positions)
+  unsigned long long lo_done = 0;   // every key below this has been consumed
+  bool first = true;
+  while (h.cand_count > 0 && cur_bin < HIST_BINS && consumed < a.max_nms && sm.K < a.max_det) {
+    // ---- choose the band [lo_done, band_hi)
+    walk_bins(sm, sm.hist, cur_bin, HIST_BINS, first ? FIRST_BAND : SORT_TILE);
+    __syncthreads();
+    int b_end = sm.walk_end;
+    unsigned int cnt = sm.walk_cum;
+    unsigned long long band_hi;
+    int next_bin;
+    if (b_end == HIST_BINS && cnt == 0) break;  // nothing left
+    if (b_end > cur_bin && cnt > 0) {
+      band_hi = edge_key(b_end);
+      next_bin = b_end;
+    } else {
+      // skip the empty bins walked over; the bin at b_end alone exceeds the limit
+      const int fat = b_end;
+      const unsigned int fat_cnt = sm.hist[fat];
+      if (fat_cnt <= (unsigned int)SORT_TILE) {
+        band_hi = edge_key(fat + 1);
+        cnt = fat_cnt;
+        next_bin = fat + 1;
+      } else {
+        // exact split of a bin with more than SORT_TILE keys: re-histogram the lower key bits
+        unsigned long long lo = lo_done > edge_key(fat) ? lo_done : edge_key(fat);
+        unsigned long long hi = edge_key(fat + 1);
+        for (;;) {
+          const unsigned long long span = hi - lo;
+          const int need_bits = 64 - __clzll((long long)(span - 1));
+          const int shift = need_bits > 11 ? need_bits - 11 : 0;
+          __syncthreads();
+          for (int i = tid; i < HIST_BINS; i += IMG_T) sm.hist2[i] = 0u;
+          __syncthreads();
+          scan_src<IMG_T>(src, [&](bool v, unsigned long long k) {
+            if (v && k >= lo && k < hi) atomicAdd(&sm.hist2[(unsigned int)((k - lo) >> shift)], 1u);
+          });
+          __syncthreads();
+          walk_bins(sm, sm.hist2, 0, HIST_BINS, SORT_TILE);
+          __syncthreads();
+          const int e = sm.walk_end;
+          if (e == 0) {  // the first sub-bin alone is still too fat: descend into it
+            hi = lo + (1ull << shift);
+            continue;
+          }
+          cnt = sm.walk_cum;
+          band_hi = (((span - 1) >> shift) < (unsigned long long)e) ? hi : lo + ((unsigned long long)e << shift);
           break;
         }
+        __syncthreads();
+        if (tid == 0) sm.hist[fat] -= cnt;  // the rest of the bin stays for the next round
+        next_bin = fat;
       }
     }
-    // ordered compaction of the survivors
-    unsigned int bal = __ballot_sync(0xffffffffu, alive);
-    if (lane == 0) warp_cnt[warp] = __popc(bal);
+    // ---- compact the band into the tile, pad, sort ascending (= descending score)
+    if (tid == 0) sm.cnt = 0;
     __syncthreads();
-    int before = 0;
-    for (int wi = 0; wi < warp; wi++) before += warp_cnt[wi];
-    if (alive) {
-      int pos = before + __popc(bal & ((1u << lane) - 1u));
-      live[pos] = me;
-      live_pos[pos] = ci;
-    }
-    if (tid == 0) {
-      int m = 0;
-      for (int wi = 0; wi < G_CHUNK / 32; wi++) m += warp_cnt[wi];
-      s_m = m;
-    }
-    __syncthreads();
-    const int m = s_m;
-    // suppression bitmask inside the chunk: mask[i][w] bit l <=> live[i] suppresses live[32w+l], 32w+l > i
-    for (int task = warp; task < m * (G_CHUNK / 32); task += G_CHUNK / 32) {
-      int i = task / (G_CHUNK / 32), wcol = task - i * (G_CHUNK / 32);
-      int j = wcol * 32 + lane;
-      bool sup = false;
-      if (j > i && j < m) sup = suppresses(live[i], live[j], thr, thr_lo, thr_hi);
-      unsigned int bits = __ballot_sync(0xffffffffu, sup);
-      if (lane == 0) mask[i][wcol] = bits;
-    }
-    __syncthreads();
-    if (warp == 0) {
-      unsigned int remv = 0;  // lane w (< 8) holds removed-bits word w
-      int Kc = K;
-      for (int i = 0; i < m; i++) {
-        unsigned int word = __shfl_sync(0xffffffffu, remv, i >> 5);
-        if (!((word >> (i & 31)) & 1u)) {
-          if (lane == 0) {
-            kept[Kc] = live[i];
-            kept_pos[Kc] = live_pos[i];
+    {
+      const unsigned long long lo = lo_done;
+      scan_src<IMG_T>(src, [&](bool v, unsigned long long k) {
+        const bool take = v && k >= lo && k < band_hi;
+        const unsigned int m = __ballot_sync(0xffffffffu, take);
+        if (m) {
+          const int leader = __ffs(m) - 1;
+          int base = 0;
+          if (lane == leader) base = atomicAdd(&sm.cnt, __popc(m));
+          base = __shfl_sync(0xffffffffu, base, leader);
+          if (take) {
+            const int slot = base + __popc(m & ((1u << lane) - 1u));
+            if (slot < SORT_TILE) sm.tile[slot] = k;
           }
-          Kc++;
-          if (Kc >= a.max_det) break;
-          if (lane < G_CHUNK / 32) remv |= mask[i][lane];
+        }
+      });
+    }
+    __syncthreads();
+    const int n_band = min(sm.cnt, SORT_TILE);
+    int P = 32;
+    while (P < n_band) P <<= 1;
+    for (int i = n_band + tid; i < P; i += IMG_T) sm.tile[i] = ~0ull;
+    __syncthreads();
+    for (int kk = 2; kk <= P; kk <<= 1) {
+      for (int j = kk >> 1; j > 0; j >>= 1) {
+        for (int t = tid; t < P / 2; t += IMG_T) {
+          const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // lower index of the pair
+          const int l = i | j;
+          const bool asc = ((i & kk) == 0);
+          const unsigned long long x = sm.tile[i], y = sm.tile[l];
+          if ((x > y) == asc) {
+            sm.tile[i] = y;
+            sm.tile[l] = x;
+          }
+        }
+        __syncthreads();
+      }
+    }
+    // ---- greedy step over the sorted band, 256 candidates at a time
+    const int n_use = min(n_band, a.max_nms - consumed);  // util.py:157: only the max_nms best
+    for (int base = 0; base < n_use; base += G_CHUNK) {
+      const int K = sm.K;
+      if (K >= a.max_det) break;
+      const int j = tid & (G_CHUNK - 1), part = tid >> 8;
+      const int ci = base + j;
+      if (tid < G_CHUNK) {
+        sm.dead[j] = ci < n_use ? 0 : 1;
+        if (ci < n_use) load_candidate(a, b, sm.tile[ci], sm.live[j], nullptr);
+      }
+      __syncthreads();
+      if (ci < n_use) {
+        const BoxF me = sm.live[j];
+        for (int k = part; k < K; k += IMG_T / G_CHUNK) {
+          if (suppresses(sm.kept[k], me, thr, thr_lo, thr_hi)) {
+            sm.dead[j] = 1;
+            break;
+          }
         }
       }
-      if (lane == 0) s_K = Kc;
+      __syncthreads();
+      // ordered compaction of the survivors (threads 0..255, in place: pos <= j)
+      bool alive = false;
+      BoxF me;
+      unsigned int bal = 0;
+      if (tid < G_CHUNK) {
+        alive = !sm.dead[j];
+        me = sm.live[j];
+        bal = __ballot_sync(0xffffffffu, alive);
+        if (lane == 0) sm.warp_cnt[warp] = __popc(bal);
+      }
+      __syncthreads();
+      if (tid < G_CHUNK) {
+        int before = 0;
+        for (int wi = 0; wi < warp; wi++) before += sm.warp_cnt[wi];
+        if (alive) {
+          const int pos = before + __popc(bal & ((1u << lane) - 1u));
+          sm.live[pos] = me;
+          sm.live_key[pos] = sm.tile[ci];
+        }
+        if (tid == 0) {
+          int m = 0;
+          for (int wi = 0; wi < G_CHUNK / 32; wi++) m += sm.warp_cnt[wi];
+          sm.m = m;
+        }
+      }
+      __syncthreads();
+      const int m = sm.m;
+      // suppression bitmask inside the chunk: mask[i][w] bit l <=> live[i] suppresses live[32w+l], 32w+l > i
+      for (int task = warp; task < m * (G_CHUNK / 32); task += IMG_T / 32) {
+        const int i = task / (G_CHUNK / 32), wcol = task - i * (G_CHUNK / 32);
+        const int jj = wcol * 32 + lane;
+        bool sup = false;
+        if (jj > i && jj < m) sup = suppresses(sm.live[i], sm.live[jj], thr, thr_lo, thr_hi);
+        const unsigned int bits = __ballot_sync(0xffffffffu, sup);
+        if (lane == 0) sm.mask[i][wcol] = bits;
+      }
+      __syncthreads();
+      if (warp == 0) {
+        unsigned int remv = 0;  // lane w (< 8) holds removed-bits word w
+        int Kc = K;
+        for (int i = 0; i < m; i++) {
+          const unsigned int word = __shfl_sync(0xffffffffu, remv, i >> 5);
+          if (!((word >> (i & 31)) & 1u)) {
+            if (lane == 0) {
+              sm.kept[Kc] = sm.live[i];
+              sm.kept_key[Kc] = sm.live_key[i];
+            }
+            Kc++;
+            if (Kc >= a.max_det) break;
+            if (lane < G_CHUNK / 32) remv |= sm.mask[i][lane];
+          }
+        }
+        if (lane == 0) sm.K = Kc;
+      }
+      __syncthreads();
     }
+    consumed += n_band;
+    lo_done = band_hi;
+    cur_bin = next_bin;
+    first = false;
     __syncthreads();
   }
-  const int K = s_K;
+  __syncthreads();
+  const int K = sm.K;
   if (tid == 0) a.out_counts[b] = K;
-  for (int k = tid; k < K; k += blockDim.x) {
+  for (int k = tid; k < K; k += IMG_T) {
     BoxF tmp;
     float r[6];
-    load_candidate(a, b, keys[kept_pos[k]], tmp, r);
+    load_candidate(a, b, sm.kept_key[k], tmp, r);
     float* op = a.out + ((size_t)b * a.max_det + k) * 6;
 #pragma unroll
     for (int q = 0; q < 6; q++) op[q] = r[q];
@@ -466,9 +515,8 @@ size_t nms_workspace_bytes(int B, int nc, int A, int max_nms) {
   (void)nc;
   (void)A;
   size_t hdr = ((size_t)B * sizeof(NmsHeader) + 255) / 256 * 256;
-  size_t hist = (size_t)B * HIST_BINS * 4;
   size_t keys = (size_t)B * cap_for(max_nms) * 8;
-  return hdr + hist + keys;
+  return hdr + keys;
 }
 
 int nms_run(const float* pred, int B, int nc, int A, float conf, double iou, int max_det, int max_nms,
@@ -503,41 +551,25 @@ int nms_run(const float* pred, int B, int nc, int A, float conf, double iou, int
   a.max_wh = max_wh;
   size_t hdr_bytes = ((size_t)B * sizeof(NmsHeader) + 255) / 256 * 256;
   a.hdr = reinterpret_cast<NmsHeader*>(ws);
-  a.hist = reinterpret_cast<unsigned int*>((uint8_t*)ws + hdr_bytes);
-  a.keys = reinterpret_cast<unsigned long long*>((uint8_t*)ws + hdr_bytes + (size_t)B * HIST_BINS * 4);
+  a.keys = reinterpret_cast<unsigned long long*>((uint8_t*)ws + hdr_bytes);
   a.out = out;
   a.out_counts = out_counts;
-  YB_CUDA(cudaMemsetAsync(ws, 0, hdr_bytes + (size_t)B * HIST_BINS * 4, st));
+  static bool attr_set = false;
+  if (!attr_set) {
+    YB_CUDA(cudaFuncSetAttribute(nms_image_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)sizeof(ImgSmem)));
+    YB_CUDA(cudaFuncSetAttribute(nms_image_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)sizeof(ImgSmem)));
+    attr_set = true;
+  }
+  YB_CUDA(cudaMemsetAsync(ws, 0, hdr_bytes, st));
   long long total = (long long)nc * A;
   int gx = (int)std::min<long long>((total + 256 * 16 - 1) / (256 * 16), 1024);
   int vec4 = (A % 4 == 0) && ((reinterpret_cast<uintptr_t>(pred) & 15) == 0);
   nms_append_kernel<<<dim3(gx, B), 256, 0, st>>>(a, vec4);
   count_launch();
-  nms_pick_kernel<<<B, 32, 0, st>>>(a, -1);
-  count_launch();
-  // radix select + re-compaction: every block returns at once unless its image overflowed
-  dim3 ogrid(std::min(gx, 48), B);
-  for (int pass = 0; pass < NUM_PASSES; pass++) {
-    nms_scan_kernel<1><<<ogrid, 256, 0, st>>>(a, pass);
-    count_launch();
-    nms_pick_kernel<<<B, 1024, 0, st>>>(a, pass);
-    count_launch();
-  }
-  nms_scan_kernel<2><<<ogrid, 256, 0, st>>>(a, 0);
-  count_launch();
-  dim3 tgrid(a.cap / SORT_TILE, B);
-  nms_sort_tile_kernel<<<tgrid, 1024, 0, st>>>(a, 0, 0);
-  count_launch();
-  for (int k = 2 * SORT_TILE; k <= a.cap; k <<= 1) {
-    for (int j = k >> 1; j >= SORT_TILE; j >>= 1) {
-      dim3 ggrid(a.cap / 2 / 256, B);
-      nms_sort_global_kernel<<<ggrid, 256, 0, st>>>(a, k, j);
-      count_launch();
-    }
-    nms_sort_tile_kernel<<<tgrid, 1024, 0, st>>>(a, 1, k);
-    count_launch();
-  }
-  nms_greedy_kernel<<<B, G_CHUNK, 0, st>>>(a);
+  if (B <= 160) nms_image_kernel<1024><<<B, 1024, sizeof(ImgSmem), st>>>(a);
+  else nms_image_kernel<512><<<B, 512, sizeof(ImgSmem), st>>>(a);
   count_launch();
   YB_CUDA(cudaGetLastError());
   return YB_OK;
