@@ -52,6 +52,68 @@ def test_nms_ties_break_by_candidate_index():
         assert np.array_equal(a, b)
 
 
+def _clustered(rng, B, nc, A, img, centres):
+    pred = np.zeros((B, 4 + nc, A), dtype=np.float32)
+    c = rng.uniform(60, img - 60, size=(B, centres, 2)).astype(np.float32)
+    pick = rng.integers(0, centres, size=(B, A))
+    for b in range(B):
+        pred[b, 0] = c[b, pick[b], 0] + rng.normal(0, 6, A)
+        pred[b, 1] = c[b, pick[b], 1] + rng.normal(0, 6, A)
+    pred[:, 2] = rng.uniform(90, 110, size=(B, A))
+    pred[:, 3] = rng.uniform(90, 110, size=(B, A))
+    return pred
+
+
+def test_nms_fat_histogram_bins_and_many_bands():
+    """Candidates share two score values (score bins with far more than 4096 keys: the band select has
+    to split them exactly on the index bits) and the boxes are clustered, so most are suppressed and
+    the lazy walk runs through many bands.  Image 0 fits the key list, image 1 (> 32768 candidates)
+    is banded from the raw scores and hits the max_nms = 30000 cut (util.py:157)."""
+    rng = np.random.default_rng(50)
+    B, nc, A = 2, 80, 8400
+    pred = _clustered(rng, B, nc, A, 640, 12)
+    for b, ncls in enumerate((3, 6)):          # few classes -> far fewer than max_det survivors
+        on = rng.random((ncls, A)) < 0.8
+        pred[b, 4:4 + ncls] = np.where(on, rng.choice(np.float32([0.5, 0.25]), size=(ncls, A)), 0)
+    out = _run(pred, 0.001, 0.65)
+    ref = nms_oracle.non_max_suppression(pred, 0.001, 0.65)
+    for b in range(B):
+        assert len(ref[b]) < 300
+        assert np.array_equal(out[b], ref[b]), f"image {b}"
+
+
+def test_nms_many_bands_distinct_scores():
+    """Clustered boxes with distinct scores: fewer than max_det survive, every candidate is consumed."""
+    rng = np.random.default_rng(51)
+    B, nc, A = 2, 80, 8400
+    pred = _clustered(rng, B, nc, A, 640, 6)
+    n = 3 * A
+    ladder = (rng.permutation(n).astype(np.float32) + 1) / np.float32(n + 2)      # tie-free
+    on = rng.random(n) < 0.8
+    pred[:, 4:7] = np.where(on, ladder, 0).reshape(3, A).astype(np.float32)
+    out = _run(pred, 0.001, 0.65)
+    ref = nms_oracle.non_max_suppression(pred, 0.001, 0.65)
+    for b in range(B):
+        assert len(ref[b]) < 300
+        assert np.array_equal(out[b], ref[b]), f"image {b}"
+
+
+def test_nms_scores_outside_unit_interval():
+    """Negative threshold, scores on both sides of [0, 1] (clamped histogram bins at both ends)."""
+    rng = np.random.default_rng(52)
+    pred = synth.synth_predictions(1, 80, 2100, img=320, mode="sparse", seed=53)
+    n = 80 * 2100
+    vals = np.concatenate([np.linspace(-0.9, 3.0, n // 2, dtype=np.float32),
+                           -np.geomspace(1e-30, 0.5, n - n // 2).astype(np.float32)])
+    vals = np.unique(vals)
+    sc = np.full(n, -5.0, dtype=np.float32)
+    sc[:len(vals)] = vals
+    pred[0, 4:] = rng.permutation(sc).reshape(80, 2100)
+    out = _run(pred, -1.0, 0.65)
+    ref = nms_oracle.non_max_suppression(pred, -1.0, 0.65)
+    assert np.array_equal(out[0], ref[0])
+
+
 def test_nms_edge_cases():
     # threshold compared in double: fl32(1/3) > 1/3 suppresses (SURVEY §8 a16)
     pred = np.zeros((1, 5, 2), dtype=np.float32)
