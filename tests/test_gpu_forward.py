@@ -213,13 +213,17 @@ def test_batch_independence():
         assert torch.equal(e1.forward(x[i:i + 1].contiguous())[0], y3[i])
 
 
-@pytest.mark.parametrize("size,hw", [("n", 64), ("n", 160), ("t", 64), ("x", 64), ("s", 96)])
-def test_every_op_teacher_forced(size, hw, monkeypatch):
+@pytest.mark.parametrize("size,hw,patch_min_hw", [("n", 64, None), ("n", 160, None), ("t", 64, None), ("x", 64, None),
+                                                   ("s", 96, None), ("n", 160, "1"), ("s", 96, "1"), ("x", 64, "1"),
+                                                   ("m", 64, "1"), ("n", 320, None)])
+def test_every_op_teacher_forced(size, hw, patch_min_hw, monkeypatch):
     """Per-op parity with identical inputs: before each op the GPU buffers are overwritten with the CPU
     replay's (bf16-exact) state, the op runs alone through both conv implementations, and its output
     slice is compared with the replay's.  No error can accumulate, so the tolerance is a couple of
     bf16 ulps: a wrong tap order, slice offset, swizzle, K layout, N tile or residual shows at once."""
     monkeypatch.setenv("YB_NO_REUSE", "1")
+    if patch_min_hw:  # halo-patch 3x3 path on every map size (tiles hanging over the image edge included)
+        monkeypatch.setenv("YB_PATCH_MIN_HW", patch_min_hw)
     model = _model(size, "calibrated")
     x = synth.synth_images(2, hw, hw, seed=1)
     eng = Engine(*model._arch, 2, hw, hw, "cuda:0")
@@ -252,8 +256,8 @@ def test_every_op_teacher_forced(size, hw, monkeypatch):
                 err = (got - want).abs().max().item() / scale
                 worst = max(worst, err)
                 if err > 0.01:
-                    report.append(f"{op['name']} impl={impl} k{op['k']} s{op['stride']} tma{op['a_tma']} "
+                    report.append(f"{op['name']} impl={impl} k{op['k']} s{op['stride']} tma{op['a_tma']} patch{op.get('patch', 0)} "
                                   f"K{op['K_pad']} N{op['N_pad']}/BN{op['BN']}: max err {err:.4f} of max |x|")
             eng.set_conv_impl(0)
-    print(f"{size}@{hw}: worst per-op error {worst:.5f} of the layer's max |activation|")
+    print(f"{size}@{hw} patch_min_hw={patch_min_hw}: worst per-op error {worst:.5f} of the layer's max |activation|")
     assert not report, "\n".join(report)

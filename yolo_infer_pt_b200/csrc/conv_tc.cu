@@ -38,8 +38,13 @@ namespace yb {
 static constexpr int BM = 128;
 static constexpr int BK = 64;
 static constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
-static constexpr int MAX_STAGES = 8;
+static constexpr int MAX_STAGES = 12;
 static constexpr int C_GROUP_BYTES = BM * 128;    // 128 rows x 64 bf16 output staging sub-tile
+static constexpr int MAX_PATCH_STAGES = 4;
+static constexpr int NUM_BARS = 3 * MAX_STAGES + 4 + 2 * MAX_PATCH_STAGES;
+static constexpr int PT_H = 16, PT_W = 8;          // PATCH mode output tile (pixels)
+static constexpr int PP_H = PT_H + 2, PP_W = PT_W + 2;  // its input halo patch
+enum { MODE_GATHER = 0, MODE_ATMA = 1, MODE_PATCH = 2 };
 
 struct ConvParams {
   const __nv_bfloat16* src[4];
@@ -69,6 +74,14 @@ struct ConvParams {
   int tile2d, tiles_x, tiles_per_img;
   uint32_t tpi_mul, tpi_shr, tx_mul, tx_shr;
   uint32_t pt_mul, pt_shr;   // division by per_tap
+  // 3x3 / stride-1 convs fed from TMA halo patches (mode PATCH): an 18 x 10 pixel patch of `cblk`
+  // channels per 16 x 8 output tile; each tap is a shifted UMMA descriptor into the patch
+  int patch, cblk, ncb, a_layout;
+  int patch_tx_bytes, patch_stage_bytes, patch_stages;
+  int a_region_bytes;   // shared memory of the A ring (stages x 16 KB, or the patch ring)
+  int b_resident;       // weights stay in shared memory for the whole kernel: slot kb, loaded during the first tile
+  int b_slots;          // weight slots in shared memory (num_kb when resident, else stages)
+  int c_bufs;           // output staging buffers (2: the epilogue never waits for the previous tile's TMA store)
   // fused head decode (out_mode 2 / 3): dst is the (B, 4+nc, A) fp32 output tensor
   int out_mode;       // 0 bf16 slice, 1 fp32 logits, 2 DFL box decode, 3 class sigmoid
   int A_total, nc;
@@ -153,7 +166,7 @@ struct TilePos {
   int m0;            // linear: first row
   int n, oy0, ox0;   // 2-D: image and patch origin
 };
-template <bool T2D>
+template <bool T2D, int TW>
 __device__ __forceinline__ TilePos tile_pos(const ConvParams& P, int mt) {
   TilePos t;
   t.m0 = mt * BM;
@@ -162,8 +175,8 @@ __device__ __forceinline__ TilePos tile_pos(const ConvParams& P, int mt) {
     t.n = fast_div(mt, P.tpi_mul, P.tpi_shr, P.tiles_per_img);
     int r = mt - t.n * P.tiles_per_img;
     int ty = fast_div(r, P.tx_mul, P.tx_shr, P.tiles_x);
-    t.oy0 = ty * 8;
-    t.ox0 = (r - ty * P.tiles_x) * 16;
+    t.oy0 = ty * (BM / TW);
+    t.ox0 = (r - ty * P.tiles_x) * TW;
   }
   return t;
 }
@@ -238,6 +251,40 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   return *reinterpret_cast<uint32_t*>(&h);
 }
 
+// All MMAs of one halo patch (one channel block, 9 taps) against weights resident in shared memory,
+// fully unrolled: tap offsets and K steps are compile-time constants, so the single issuing thread
+// spends two integer adds per tcgen05.mma instead of divisions and descriptor assembly (with
+// N <= 64 an MMA retires in ~48 cycles; a longer issue sequence is the bottleneck).
+// a_lo / b_lo: low descriptor words (address >> 4) of the patch and of weight slot `kb0`; bstep =
+// slot stride >> 4; first: the accumulator is overwritten by the first MMA.
+template <int CBLK>
+__device__ __forceinline__ void issue_patch_steady(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                                   uint32_t b_hi, uint32_t bstep, uint32_t idesc, bool first) {
+  constexpr int ROWB = CBLK * 2;
+  constexpr int NMMA = CBLK == 8 ? 5 : 9 * CBLK / 16;
+#pragma unroll
+  for (int i = 0; i < NMMA; i++) {
+    uint32_t a_off, lbo = 1;
+    int kslot, k;
+    if (CBLK == 8) {
+      const int t0 = 2 * i, t1 = i < 4 ? 2 * i + 1 : 2 * i;
+      const int o0 = ((t0 / 3) * PP_W + t0 % 3) * 16, o1 = ((t1 / 3) * PP_W + t1 % 3) * 16;
+      a_off = o0;
+      lbo = i < 4 ? (uint32_t)((o1 - o0) >> 4) : 1u;
+      kslot = i / 4;
+      k = i % 4;
+    } else {
+      const int kg = i * 16, tap = kg / CBLK, cin = kg % CBLK;
+      a_off = ((tap / 3) * PP_W + tap % 3) * ROWB + cin * 2;
+      kslot = kg / 64;
+      k = (kg % 64) / 16;
+    }
+    const uint64_t da = ((uint64_t)a_hi << 32) | (uint64_t)((a_lo + (a_off >> 4)) & 0x3FFFu) | ((uint64_t)lbo << 16);
+    const uint64_t db = ((uint64_t)b_hi << 32) | (uint64_t)((b_lo + (uint32_t)kslot * bstep + 2u * k) & 0x3FFFu) | (1ull << 16);
+    umma_bf16(d_tmem, da, db, idesc, (uint32_t)(!(first && i == 0)));
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // The kernel
 // ------------------------------------------------------------------------------------------
@@ -252,7 +299,7 @@ static constexpr int RELAY_WARP = 10;    // proxy-fence relay between the im2col
 // (8x16 spatial patch vs 128 flattened rows) and the epilogue family (bf16 slice vs head modes):
 // every instantiation carries only the code of its own roles, which keeps it inside the
 // instruction cache (11 warps run disjoint code).
-template <bool A_TMA, bool T2D, bool HEAD>
+template <int MODE, bool T2D, bool HEAD>
 __global__ void __launch_bounds__(NUM_THREADS, 2)
     conv_gemm_tcgen05_kernel(const ConvParams P, const __grid_constant__ CUtensorMap tmap_b,
                              const __grid_constant__ CUtensorMap tmap_a0,
@@ -260,6 +307,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
                              const __grid_constant__ CUtensorMap tmap_a2,
                              const __grid_constant__ CUtensorMap tmap_a3,
                              const __grid_constant__ CUtensorMap tmap_c) {
+  constexpr bool A_TMA = MODE != MODE_GATHER;       // no im2col producer warps: they join the epilogue
+  constexpr bool PATCH = MODE == MODE_PATCH;
+  constexpr int TW = PATCH ? PT_W : 16;            // 2-D tile width (rows of the tile: r = ly * TW + lx)
+  constexpr int TWS = PATCH ? 3 : 4;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024 B alignment
@@ -269,21 +320,26 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
   const int BN = P.BN;
   const uint32_t b_stage_bytes = (uint32_t)BN * 128u;
   const uint32_t a_base = base;
-  const uint32_t b_base = base + (uint32_t)S * A_STAGE_BYTES;
+  const uint32_t b_base = base + (uint32_t)P.a_region_bytes;
   // output staging for the TMA store: one 128 x 64 bf16 swizzled sub-tile (16 KB) per 64 channels
   const uint32_t c_groups = (uint32_t)(BN + 63) / 64;
-  const uint32_t c_base = b_base + (uint32_t)S * b_stage_bytes;
-  uint8_t* tail = smem + (size_t)S * (A_STAGE_BYTES + b_stage_bytes) + (size_t)c_groups * C_GROUP_BYTES;
-  // barriers: full[MAX_STAGES], empty[MAX_STAGES], tmem_full[2], tmem_empty[2], gathered[MAX_STAGES]
+  const uint32_t c_base = b_base + (uint32_t)P.b_slots * b_stage_bytes;
+  uint8_t* tail = smem + (size_t)P.a_region_bytes + (size_t)P.b_slots * b_stage_bytes +
+                  (size_t)c_groups * C_GROUP_BYTES * (size_t)P.c_bufs;
+  const bool RES = P.b_resident != 0;
+  // barriers: full[MAX_STAGES], empty[MAX_STAGES], tmem_full[2], tmem_empty[2], gathered[MAX_STAGES],
+  //           patch_full[MAX_PATCH_STAGES], patch_empty[MAX_PATCH_STAGES]
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + (3 * MAX_STAGES + 4) * 8);
-  float* bias_s = reinterpret_cast<float*>(tail + (3 * MAX_STAGES + 4) * 8 + 16);
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tail + NUM_BARS * 8);
+  float* bias_s = reinterpret_cast<float*>(tail + NUM_BARS * 8 + 16);
   const uint32_t bar0 = smem_u32(bars);
   auto full_bar = [&](int s) { return bar0 + 8u * s; };
   auto empty_bar = [&](int s) { return bar0 + 8u * (MAX_STAGES + s); };
   auto tmem_full_bar = [&](int a) { return bar0 + 8u * (2 * MAX_STAGES + a); };
   auto tmem_empty_bar = [&](int a) { return bar0 + 8u * (2 * MAX_STAGES + 2 + a); };
   auto gathered_bar = [&](int s) { return bar0 + 8u * (2 * MAX_STAGES + 4 + s); };
+  auto patch_full_bar = [&](int s) { return bar0 + 8u * (3 * MAX_STAGES + 4 + s); };
+  auto patch_empty_bar = [&](int s) { return bar0 + 8u * (3 * MAX_STAGES + 4 + MAX_PATCH_STAGES + s); };
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5;
@@ -292,15 +348,25 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
 
   if (tid == 0) {
     for (int s = 0; s < S; s++) {
-      mbar_init(full_bar(s), A_TMA ? 1u : 2u);   // TMA expect_tx (+ the relay warp on im2col layers)
+      mbar_init(full_bar(s), MODE == MODE_GATHER ? 2u : 1u);   // TMA expect_tx (+ the relay warp on im2col layers)
       mbar_init(empty_bar(s), 1u);
       mbar_init(gathered_bar(s), 128u);            // one cp.async-completion arrive per im2col thread
+    }
+    for (int s = 0; s < MAX_PATCH_STAGES; s++) {
+      mbar_init(patch_full_bar(s), 1u);
+      mbar_init(patch_empty_bar(s), 1u);
     }
     for (int a = 0; a < 2; a++) {
       mbar_init(tmem_full_bar(a), 1u);
       mbar_init(tmem_empty_bar(a), A_TMA ? 256u : 128u);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (PATCH && P.cblk == 8 && tid < P.patch_stages) {
+    // 8-channel patches pair two taps per K=16 MMA; the unpaired ninth tap reads 16 bytes past the
+    // patch (against zero weights), which must therefore hold finite data
+    *reinterpret_cast<uint4*>(smem + (size_t)tid * P.patch_stage_bytes + P.patch_tx_bytes) = make_uint4(0u, 0u, 0u, 0u);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
   if (warp == MMA_WARP) {
@@ -326,9 +392,19 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
     const int cstep = (HEAD && P.out_mode == 2) ? 16 : 16 * ngrp;   // DFL decode needs all 4 sides in one thread
     const int cfirst = (HEAD && P.out_mode == 2) ? (grp ? BN : 0) : 16 * grp;
     int ti = 0;
+    // One N tile: the bias vector is loaded once.  With two staging buffers the tile loop then needs
+    // a single CTA-level barrier per tile (before the TMA store), and never waits on the previous
+    // tile's store: that one is drained (wait_group.read) a full tile later.
+    const bool bias_once = P.n_tiles == 1;
+    const bool fast_flow = bias_once && (HEAD || P.c_bufs == 2);
+    if (bias_once) {
+      for (int i = tid; i < BN; i += 128 * ngrp) bias_s[i] = __ldg(P.bias + i);
+      if (ngrp == 2) asm volatile("bar.sync 1, 256;" ::: "memory");
+      else asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ti++) {
       const int mt = P.n_tiles == 1 ? tile : tile / P.n_tiles;
-      const TilePos tp = tile_pos<T2D>(P, mt);
+      const TilePos tp = tile_pos<T2D, TW>(P, mt);
       const int m0 = tp.m0;
       const int n0 = (tile - mt * P.n_tiles) * BN;
       const int acc = ti & 1;
@@ -337,9 +413,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
       int n_img = 0, r = 0;
       if (T2D) {
         n_img = tp.n;
-        r = (tp.oy0 + (etid >> 4)) * P.Wout + tp.ox0 + (etid & 15);
+        const int oy = tp.oy0 + (etid >> TWS), ox = tp.ox0 + (etid & (TW - 1));
+        r = oy * P.Wout + ox;
         m = n_img * P.hw_out + r;
-        row_ok = true;
+        row_ok = !PATCH || (oy < P.Hout && ox < P.Wout);   // PATCH tiles may hang over the image edge
       } else if (row_ok) {
         n_img = fast_div(m, P.hw_mul, P.hw_shr, P.hw_out);
         r = m - n_img * P.hw_out;
@@ -361,11 +438,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
       res_fetch(cfirst + cstep, rb0, rb1);
       mbar_wait(tmem_full_bar(acc), (uint32_t)(ti >> 1) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      // the previous tile's TMA stores must have finished reading the staging buffer
-      if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-      for (int i = tid; i < BN; i += 128 * ngrp) bias_s[i] = __ldg(P.bias + n0 + i);
-      if (ngrp == 2) asm volatile("bar.sync 1, 256;" ::: "memory");
-      else asm volatile("bar.sync 1, 128;" ::: "memory");
+      if (!fast_flow) {
+        // the previous tile's TMA stores must have finished reading the staging buffer
+        if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        if (!bias_once)
+          for (int i = tid; i < BN; i += 128 * ngrp) bias_s[i] = __ldg(P.bias + n0 + i);
+        if (ngrp == 2) asm volatile("bar.sync 1, 256;" ::: "memory");
+        else asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+      const uint32_t c_buf = c_base + ((fast_flow && (ti & 1)) ? c_groups * C_GROUP_BYTES : 0u);
       const uint32_t t_row = tmem_base + ((uint32_t)(qwarp * 32) << 16) + (uint32_t)(acc * BN);
       float dist[4];
       auto do_chunk = [&](int c0, const uint4& rv0, const uint4& rv1) {
@@ -383,7 +464,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
         if (!HEAD) {
           // bf16 tile staged in shared memory in the TMA SWIZZLE_128B layout (16-byte chunk index
           // XOR row%8 inside each 128-byte row), then written with one TMA store per 64 channels
-          const uint32_t srow = c_base + (uint32_t)(c0 >> 6) * C_GROUP_BYTES + (uint32_t)etid * 128u;
+          const uint32_t srow = c_buf + (uint32_t)(c0 >> 6) * C_GROUP_BYTES + (uint32_t)etid * 128u;
 #pragma unroll
           for (int h = 0; h < 2; h++) {
             if (nb + 8 * h < P.cout_store) {
@@ -457,6 +538,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
       mbar_arrive(tmem_empty_bar(acc));
       if (!HEAD) {
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        // fast flow: the store of tile t-1 (other buffer) has had this whole tile to finish reading;
+        // after the barrier below every thread may overwrite that buffer for tile t+1
+        if (fast_flow && tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         if (ngrp == 2) asm volatile("bar.sync 1, 256;" ::: "memory");
         else asm volatile("bar.sync 1, 128;" ::: "memory");
         if (tid == 0) {
@@ -467,13 +551,13 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
                 asm volatile(
                     "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];" ::"l"(
                         (uint64_t)&tmap_c),
-                    "r"(cg0), "r"(tp.ox0), "r"(tp.oy0), "r"(tp.n), "r"(c_base + g * C_GROUP_BYTES)
+                    "r"(cg0), "r"(tp.ox0), "r"(tp.oy0), "r"(tp.n), "r"(c_buf + g * C_GROUP_BYTES)
                     : "memory");
               } else {
                 asm volatile(
                     "cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
                         (uint64_t)&tmap_c),
-                    "r"(cg0), "r"(m0), "r"(c_base + g * C_GROUP_BYTES)
+                    "r"(cg0), "r"(m0), "r"(c_buf + g * C_GROUP_BYTES)
                     : "memory");
               }
             }
@@ -501,7 +585,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
       uint32_t phase = 0;
       const int ksize = P.ksize, Win = P.Win, Hin = P.Hin, K = P.K, per_tap = P.per_tap, nseg = P.nseg;
       for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-        const TilePos tp = tile_pos<T2D>(P, P.n_tiles == 1 ? tile : tile / P.n_tiles);
+        const TilePos tp = tile_pos<T2D, TW>(P, P.n_tiles == 1 ? tile : tile / P.n_tiles);
         if (T2D) {
           // ---- fast path: 8 x 16 spatial tile.  This thread's 8 rows are the 8 image rows of one
           // tile column (ly = i, lx = rbase), so x validity is shared and y validity per tap row is
@@ -654,43 +738,150 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
     }
   } else if (warp == MMA_WARP) {
     // ============================ MMA issuer ==============================================
-    // The whole warp walks the loop converged; one elected lane issues the tcgen05 instructions.
+    // One thread runs the whole issue loop (tcgen05.mma / commit are single-thread instructions):
+    // with N <= 64 an MMA retires in ~48 cycles, so every instruction on this thread's path counts.
+    if (lane == 0) {
     const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
                            ((uint32_t)(BM >> 4) << 24);
     const uint64_t desc_hi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61) |
                              ((uint64_t)1 << 16);
-    int ti = 0, stage = 0;
-    uint32_t phase = 0;
+    int ti = 0, stage = 0, pstage = 0;
+    uint32_t phase = 0, pphase = 0;
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ti++) {
       const int acc = ti & 1;
       mbar_wait(tmem_empty_bar(acc), ((uint32_t)(ti >> 1) & 1u) ^ 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+      if (PATCH) {
+        // k-blocks in consumption order: (channel block, tap) for >= 64 channels, else the packed
+        // (tap, channel) order.  Every K=16 step reads the patch through a descriptor shifted by the
+        // tap's pixel offset: the swizzle is a function of the shared-memory address bits, so any
+        // 16-byte-aligned start inside the TMA-written patch is a valid operand origin.
+        const int cblk = P.cblk;
+        const uint32_t row_bytes = (uint32_t)cblk * 2u;
+        const uint64_t adesc_hi = ((uint64_t)((PP_W * row_bytes) >> 4) << 32) | ((uint64_t)1 << 46) |
+                                  ((uint64_t)P.a_layout << 61);
+        if (RES && ti > 0) {
+          // steady state with resident weights: nothing to wait for but the patches
+          for (int cb = 0; cb < P.ncb; cb++) {
+            mbar_wait(patch_full_bar(pstage), pphase);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            {
+              const uint32_t a_lo = (a_base + (uint32_t)pstage * (uint32_t)P.patch_stage_bytes) >> 4;
+              const uint32_t a_hi = (uint32_t)(adesc_hi >> 32), b_hi = (uint32_t)(desc_hi >> 32);
+              const uint32_t bstep = b_stage_bytes >> 4;
+              const uint32_t b_lo = (b_base >> 4) + (uint32_t)(cb * 9) * bstep;
+              const bool first = cb == 0;
+              if (cblk == 64) issue_patch_steady<64>(d_tmem, a_lo, a_hi, b_lo, b_hi, bstep, idesc, first);
+              else if (cblk == 32) issue_patch_steady<32>(d_tmem, a_lo, a_hi, b_lo, b_hi, bstep, idesc, first);
+              else if (cblk == 16) issue_patch_steady<16>(d_tmem, a_lo, a_hi, b_lo, b_hi, bstep, idesc, first);
+              else issue_patch_steady<8>(d_tmem, a_lo, a_hi, b_lo, b_hi, bstep, idesc, first);
+              umma_commit(patch_empty_bar(pstage));
+              if (cb == P.ncb - 1) umma_commit(tmem_full_bar(acc));
+            }
+              if (++pstage == P.patch_stages) {
+              pstage = 0;
+              pphase ^= 1u;
+            }
+          }
+          continue;
+        }
+        for (int kb = 0; kb < num_kb; kb++) {
+          const bool first_of_patch = cblk >= 64 ? (kb % 9 == 0) : (kb == 0);
+          const bool last_of_patch = cblk >= 64 ? (kb % 9 == 8) : (kb == num_kb - 1);
+          if (first_of_patch) mbar_wait(patch_full_bar(pstage), pphase);
+          if (!RES || ti == 0) mbar_wait(full_bar(stage), phase);   // resident weights: stage == kb, loaded once
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          {
+            const uint32_t pa = a_base + (uint32_t)pstage * (uint32_t)P.patch_stage_bytes;
+            const uint64_t db = desc_hi | (uint64_t)(((b_base + (uint32_t)stage * b_stage_bytes) >> 4) & 0x3FFF);
+#pragma unroll
+            for (int k = 0; k < BK / 16; k++) {
+              uint32_t a_addr;
+              uint64_t lbo = 1;
+              if (cblk >= 64) {
+                const int tap = kb % 9, dy = (tap * 11) >> 5, dx = tap - dy * 3;
+                a_addr = pa + (uint32_t)(dy * PP_W + dx) * row_bytes + 32u * k;
+              } else if (cblk >= 16) {
+                const int kg = kb * BK + k * 16;
+                const int tap = kg / cblk;
+                if (tap >= 9) break;
+                const int dy = (tap * 11) >> 5, dx = tap - dy * 3;
+                a_addr = pa + (uint32_t)(dy * PP_W + dx) * row_bytes + (uint32_t)(kg - tap * cblk) * 2u;
+              } else {
+                // 8 channels: one MMA covers taps (2j, 2j+1); LBO = distance between their pixels
+                const int j = kb * 4 + k;
+                if (j >= 5) break;
+                const int t0 = 2 * j, t1 = j < 4 ? 2 * j + 1 : 2 * j;
+                const int dy0 = (t0 * 11) >> 5, dy1 = (t1 * 11) >> 5;
+                const uint32_t o0 = (uint32_t)(dy0 * PP_W + (t0 - dy0 * 3)) * 16u;
+                const uint32_t o1 = (uint32_t)(dy1 * PP_W + (t1 - dy1 * 3)) * 16u;
+                a_addr = pa + o0;
+                lbo = j < 4 ? (uint64_t)((o1 - o0) >> 4) : 1;
+              }
+              const uint64_t da = adesc_hi | (lbo << 16) | (uint64_t)((a_addr >> 4) & 0x3FFF);
+              umma_bf16(d_tmem, da, db + 2u * k, idesc, (uint32_t)((kb | k) != 0));
+            }
+            umma_commit(empty_bar(stage));
+            if (last_of_patch) umma_commit(patch_empty_bar(pstage));
+            if (kb == num_kb - 1) umma_commit(tmem_full_bar(acc));
+          }
+          if (last_of_patch && ++pstage == P.patch_stages) {
+            pstage = 0;
+            pphase ^= 1u;
+          }
+          if (++stage == S) {
+            stage = 0;
+            phase ^= 1u;
+          }
+        }
+        continue;
+      }
       for (int kb = 0; kb < num_kb; kb++) {
         mbar_wait(full_bar(stage), phase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (elect_one()) {
+        {
           const uint64_t da = desc_hi | (uint64_t)(((a_base + (uint32_t)stage * A_STAGE_BYTES) >> 4) & 0x3FFF);
-          const uint64_t db = desc_hi | (uint64_t)(((b_base + (uint32_t)stage * b_stage_bytes) >> 4) & 0x3FFF);
+          const uint64_t db = desc_hi | (uint64_t)(((b_base + (uint32_t)(RES ? kb : stage) * b_stage_bytes) >> 4) & 0x3FFF);
 #pragma unroll
           for (int k = 0; k < BK / 16; k++)  // +32 bytes (2 x 16 B units) per K=16 step inside the swizzle atom
             umma_bf16(d_tmem, da + 2u * k, db + 2u * k, idesc, (uint32_t)((kb | k) != 0));
           umma_commit(empty_bar(stage));  // frees the smem stage once these MMAs have read it
           if (kb == num_kb - 1) umma_commit(tmem_full_bar(acc));  // accumulator complete -> epilogue
         }
-        __syncwarp();
         if (++stage == S) {
           stage = 0;
           phase ^= 1u;
         }
       }
     }
+    }
   } else if (warp == RELAY_WARP) {
     // ============================ proxy-fence relay ========================================
     // im2col data is written by cp.async (generic proxy) but read by the tensor core through the
     // async proxy.  This thread acquires a gathered stage, issues the proxy fence and forwards the
     // arrival to the MMA warp, keeping the (expensive) fence off the MMA issue path.
-    if (!A_TMA && lane == 0) {
+    if (PATCH && lane == 0) {
+      // ---- halo-patch producer: one 4-D TMA box {cblk, 10, 18, 1} per (tile, channel block);
+      // coordinates start one pixel above / left of the tile, out-of-image pixels are zero-filled
+      // by the TMA unit (= the convolution's padding)
+      int pstage = 0;
+      uint32_t pphase = 0;
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+        const TilePos tp = tile_pos<T2D, TW>(P, P.n_tiles == 1 ? tile : tile / P.n_tiles);
+        for (int cb = 0; cb < P.ncb; cb++) {
+          mbar_wait(patch_empty_bar(pstage), pphase ^ 1u);
+          mbar_expect_tx(patch_full_bar(pstage), (uint32_t)P.patch_tx_bytes);
+          tma_load_4d(a_base + (uint32_t)pstage * (uint32_t)P.patch_stage_bytes, &tmap_a0, cb * 64, tp.ox0 - 1,
+                      tp.oy0 - 1, tp.n, patch_full_bar(pstage));
+          if (++pstage == P.patch_stages) {
+            pstage = 0;
+            pphase ^= 1u;
+          }
+        }
+      }
+    }
+    if (MODE == MODE_GATHER && lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
@@ -708,21 +899,29 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
   } else {
     // ============================ TMA producer ============================================
     if (lane == 0) {
-      const uint32_t tx = b_stage_bytes + (A_TMA ? (uint32_t)A_STAGE_BYTES : 0u);
+      const uint32_t a_tx = MODE == MODE_ATMA ? (uint32_t)A_STAGE_BYTES : 0u;
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+        // resident weights are fetched during the CTA's first tile only
+        const bool load_b = !RES || tile == (int)blockIdx.x;
+        if (PATCH && !load_b) break;   // nothing left to load: the MMA warp no longer waits on these barriers
+        const uint32_t tx = a_tx + (load_b ? b_stage_bytes : 0u);
         const int mt = P.n_tiles == 1 ? tile : tile / P.n_tiles;
-        const TilePos tp = tile_pos<T2D>(P, mt);
+        const TilePos tp = tile_pos<T2D, TW>(P, mt);
         const int n0 = (tile - mt * P.n_tiles) * BN;
         int seg = 0, kk = 0;
         for (int kb = 0; kb < num_kb; kb++) {
           const int s = stage;
           const uint32_t ph = phase;
           mbar_wait(empty_bar(s), ph ^ 1u);
-          mbar_expect_tx(full_bar(s), tx);
-          tma_load_2d(b_base + (uint32_t)s * b_stage_bytes, &tmap_b, kb * BK, n0, full_bar(s));
-          if (A_TMA) {
+          if (tx) mbar_expect_tx(full_bar(s), tx);
+          else mbar_arrive(full_bar(s));   // im2col layer with resident weights: only the gather feeds this stage
+          // PATCH with >= 64 channels consumes k-blocks channel-block-major; they are packed tap-major
+          const int kb_w = (PATCH && P.cblk >= 64) ? (kb % 9) * P.ncb + kb / 9 : kb;
+          if (load_b)
+            tma_load_2d(b_base + (uint32_t)(RES ? kb : s) * b_stage_bytes, &tmap_b, kb_w * BK, n0, full_bar(s));
+          if (MODE == MODE_ATMA) {
             const CUtensorMap* ma =
                 seg == 0 ? &tmap_a0 : seg == 1 ? &tmap_a1 : seg == 2 ? &tmap_a2 : &tmap_a3;
             if (T2D)
@@ -841,7 +1040,7 @@ static int make_tmap_2d(CUtensorMap* map, const void* base, uint64_t inner, uint
 // 4-D map over an NHWC slice {C, W, H, N} with an 8 (y) x 16 (x) x 64-channel box: smem rows come
 // out as r = ly * 16 + lx, 128 bytes each, SWIZZLE_128B — the same image as a 128-row 2-D box.
 static int make_tmap_nhwc(CUtensorMap* map, const void* base, uint64_t C, uint64_t W, uint64_t H, uint64_t N,
-                          uint64_t ld_elems) {
+                          uint64_t ld_elems, uint32_t box_c = 64, uint32_t box_w = 16, uint32_t box_h = 8) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled driver entry point not available");
@@ -849,10 +1048,14 @@ static int make_tmap_nhwc(CUtensorMap* map, const void* base, uint64_t C, uint64
   }
   cuuint64_t dims[4] = {C, W, H, N};
   cuuint64_t strides[3] = {ld_elems * 2, W * ld_elems * 2, H * W * ld_elems * 2};
-  cuuint32_t box[4] = {64, 16, 8, 1};
+  cuuint32_t box[4] = {box_c, box_w, box_h, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
+  // rows of box_c channels: the swizzle span equals the row size (16-byte rows are not swizzled)
+  const CUtensorMapSwizzle sw = box_c >= 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                : box_c == 32 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                : box_c == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled (4-D NHWC) failed with %d (C=%llu W=%llu H=%llu N=%llu ld=%llu)", (int)r,
@@ -863,9 +1066,22 @@ static int make_tmap_nhwc(CUtensorMap* map, const void* base, uint64_t C, uint64
   return YB_OK;
 }
 
-static size_t conv_smem_bytes(int stages, int BN) {
-  return 1024 + (size_t)stages * (A_STAGE_BYTES + (size_t)BN * 128) + (size_t)((BN + 63) / 64) * C_GROUP_BYTES +
-         (3 * MAX_STAGES + 4) * 8 + 16 + 256 * 4 + 64;
+// a_region: bytes of the A ring when it is not `stages` x 16 KB (PATCH mode), else 0;
+// b_slots: weight slots (num_kb when the weights are resident), 0 = one per stage
+static size_t conv_smem_bytes(int stages, int BN, size_t a_region = 0, int b_slots = 0, int c_bufs = 1) {
+  return 1024 + (a_region ? a_region : (size_t)stages * A_STAGE_BYTES) + (size_t)(b_slots ? b_slots : stages) * BN * 128 +
+         (size_t)((BN + 63) / 64) * C_GROUP_BYTES * c_bufs + NUM_BARS * 8 + 16 + 256 * 4 + 64;
+}
+
+static bool patch_eligible(const yb_plan* p, const Op& op) {
+  if (getenv("YB_NO_PATCH")) return false;
+  if (op.k != 3 || op.stride != 1 || op.nseg != 1 || op.src[0].up || op.out_f32) return false;
+  const int C = op.src[0].C;
+  if (!(C == 8 || C == 16 || C == 32 || (C % 64 == 0 && C > 0))) return false;
+  int min_hw = 40;  // below this the 16 x 8 tiles hang too far over the image edge
+  if (const char* e = getenv("YB_PATCH_MIN_HW")) min_hw = atoi(e);
+  (void)p;
+  return op.Hout >= min_hw && op.Wout >= min_hw;
 }
 
 static int tmem_cols_for(int BN) {
@@ -885,12 +1101,65 @@ int conv_tc_prepare(yb_plan* p, Op& op) {
   if (const char* e = getenv("YB_OCC")) occ = std::max(1, std::min(occ, atoi(e)));
   if (!op.a_tma)
     if (const char* e = getenv("YB_OCC_GATHER")) occ = std::max(1, std::min(occ, atoi(e)));
-  size_t budget = SMEM_MAX / occ;
-  int st = MAX_STAGES;
-  while (st > 2 && conv_smem_bytes(st, op.BN) > budget) st--;
-  if (const char* e = getenv("YB_STAGES")) st = std::max(1, std::min(st, atoi(e)));
+  op.patch = patch_eligible(p, op) ? 1 : 0;
+  const int num_kb = op.K_pad / BK;
+  const size_t w_bytes = (size_t)num_kb * op.BN * 128;
+  // Weights resident in shared memory (loaded once per CTA instead of once per tile) whenever the
+  // whole [BN x K_pad] matrix fits next to a useful A ring: L2 -> SM bandwidth (~43 B/clk/SM) is the
+  // scarce resource of the small-channel layers, and the weight tile is 30-60 % of their traffic.
+  const bool res_ok = op.N_pad == op.BN && num_kb <= MAX_STAGES && getenv("YB_NO_RESIDENT") == nullptr;
+  const bool cb2_ok = op.N_pad == op.BN && op.BN <= 128 && !op.out_f32 && getenv("YB_ONE_CBUF") == nullptr;
+  // shared-memory plan: (occupancy, resident weights, staging buffers, minimum A stages) -> stages
+  auto plan_smem = [&](int occ_try, bool resident, int cb, int min_st, int& st_out, int& pst_out) -> bool {
+    const size_t bud = SMEM_MAX / occ_try;
+    if (op.patch) {
+      const int C = op.src[0].C, cblk = std::min(C, 64);
+      op.patch_stage_bytes = round_up(PP_H * PP_W * cblk * 2 + 16, 1024);
+      for (int pst = MAX_PATCH_STAGES; pst >= 2; pst--) {
+        const size_t a_region = (size_t)pst * op.patch_stage_bytes;
+        if (resident) {
+          if (conv_smem_bytes(num_kb, op.BN, a_region, num_kb, cb) <= bud) { st_out = num_kb; pst_out = pst; return true; }
+        } else {
+          for (int st = std::min(MAX_STAGES, 8); st >= min_st; st--)
+            if (conv_smem_bytes(st, op.BN, a_region, 0, cb) <= bud) { st_out = st; pst_out = pst; return true; }
+        }
+      }
+      return false;
+    }
+    for (int st = std::min(MAX_STAGES, 8); st >= min_st; st--)
+      if (conv_smem_bytes(st, op.BN, 0, resident ? num_kb : 0, cb) <= bud) { st_out = st; pst_out = 0; return true; }
+    return false;
+  };
+  int st = 2, pst = 0, cb = 1;
+  bool found = false;
+  op.b_resident = 0;
+  struct Try { int occ; bool res; int cb; int min_st; };
+  const Try tries[] = {
+      {occ, true, 2, 4}, {occ, true, 1, 4}, {occ, false, 2, 5}, {1, true, 2, 4}, {occ, false, 1, 4},
+      {occ, true, 1, 3}, {occ, false, 1, 2}};
+  for (const Try& t : tries) {
+    if (t.res && !res_ok) continue;
+    if (t.cb == 2 && !cb2_ok) continue;
+    if (t.occ != occ && !(op.patch && occ > 1 && w_bytes >= 24 * 1024 && getenv("YB_NO_RESIDENT_OCC1") == nullptr)) continue;
+    if (plan_smem(t.occ, t.res, t.cb, t.min_st, st, pst)) {
+      op.b_resident = t.res ? 1 : 0;
+      cb = t.cb;
+      occ = t.occ;
+      found = true;
+      break;
+    }
+  }
+  if (!found && op.patch) {  // patches + streamed weights do not fit: fall back to the gather path
+    op.patch = 0;
+    plan_smem(occ, false, 1, 2, st, pst);
+  }
+  op.c_bufs = cb;
+  if (const char* e = getenv("YB_STAGES"))
+    if (!op.b_resident && !op.patch) st = std::max(1, std::min(st, atoi(e)));
   op.stages = st;
-  op.smem_bytes = std::max(conv_smem_bytes(st, op.BN), SMEM_MAX / (occ + 1) + 1024);
+  op.patch_stages = pst;
+  const size_t a_region = op.patch ? (size_t)pst * op.patch_stage_bytes : 0;
+  op.smem_bytes = std::max(conv_smem_bytes(st, op.BN, a_region, op.b_resident ? num_kb : 0, cb), SMEM_MAX / (occ + 1) + 1024);
   if (op.smem_bytes > SMEM_MAX) {
     set_error("conv %s: tile needs %zu bytes of shared memory", op.name.c_str(), op.smem_bytes);
     return YB_ERR_UNSUPPORTED;
@@ -901,6 +1170,14 @@ int conv_tc_prepare(yb_plan* p, Op& op) {
   if (rc) return rc;
   for (int i = 0; i < 4; i++) op.tmap_a[i] = op.tmap_b;
   op.tile2d = (op.Hout % 8 == 0 && op.Wout % 16 == 0 && !op.out_f32 && getenv("YB_NO_TILE2D") == nullptr) ? 1 : 0;
+  if (op.patch) {
+    op.tile2d = 1;
+    const Buf& b = p->bufs[op.src[0].buf];
+    const uint8_t* base = buf_ptr(p, op.src[0].buf) + (size_t)op.src[0].c_off * 2;
+    rc = make_tmap_nhwc(&op.tmap_a[0], base, (uint64_t)op.src[0].C, (uint64_t)b.W, (uint64_t)b.H, (uint64_t)p->B,
+                        (uint64_t)b.C, (uint32_t)std::min(op.src[0].C, 64), PP_W, PP_H);
+    if (rc) return rc;
+  }
   if (op.a_tma) {
     for (int i = 0; i < op.nseg; i++) {
       const Buf& b = p->bufs[op.src[i].buf];
@@ -918,7 +1195,10 @@ int conv_tc_prepare(yb_plan* p, Op& op) {
   if (!op.out_f32) {
     const Buf& db = p->bufs[op.dst.buf];
     const uint8_t* dbase = buf_ptr(p, op.dst.buf) + (size_t)op.dst.c_off * 2;
-    if (op.tile2d)
+    if (op.patch)
+      rc = make_tmap_nhwc(&op.tmap_c, dbase, (uint64_t)cpad8(op.dst.C), (uint64_t)db.W, (uint64_t)db.H,
+                          (uint64_t)p->B, (uint64_t)db.C, 64, PT_W, PT_H);
+    else if (op.tile2d)
       rc = make_tmap_nhwc(&op.tmap_c, dbase, (uint64_t)cpad8(op.dst.C), (uint64_t)db.W, (uint64_t)db.H,
                           (uint64_t)p->B, (uint64_t)db.C);
     else
@@ -929,12 +1209,13 @@ int conv_tc_prepare(yb_plan* p, Op& op) {
   static bool attr_set = false;
   if (!attr_set) {
     const int smem_max = 227 * 1024;
-    YB_CUDA(cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-    YB_CUDA(cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-    YB_CUDA(cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<true, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-    YB_CUDA(cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<true, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-    YB_CUDA(cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<false, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-    YB_CUDA(cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<false, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+    YB_CUDA(cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<MODE_ATMA, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+    YB_CUDA(cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<MODE_GATHER, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+    YB_CUDA(cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<MODE_ATMA, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+    YB_CUDA(cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<MODE_ATMA, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+    YB_CUDA(cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<MODE_GATHER, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+    YB_CUDA(cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<MODE_GATHER, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+    YB_CUDA(cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<MODE_PATCH, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
     attr_set = true;
   }
   return YB_OK;
@@ -1008,7 +1289,26 @@ static void fill_params(const yb_plan* p, const Op& op, ConvParams& P) {
   magic(P.Wout, P.w_mul, P.w_shr);
   magic(P.per_tap, P.pt_mul, P.pt_shr);
   P.tile2d = op.tile2d;
-  if (op.tile2d) {
+  P.a_region_bytes = op.stages * A_STAGE_BYTES;
+  P.b_resident = op.b_resident;
+  P.b_slots = op.b_resident ? P.num_kb : op.stages;
+  P.c_bufs = op.c_bufs;
+  if (op.patch) {
+    const int C = op.src[0].C;
+    P.patch = 1;
+    P.cblk = std::min(C, 64);
+    P.ncb = (C + 63) / 64;
+    P.a_layout = P.cblk == 64 ? 2 : P.cblk == 32 ? 4 : P.cblk == 16 ? 6 : 0;
+    P.patch_tx_bytes = PP_H * PP_W * P.cblk * 2;
+    P.patch_stage_bytes = op.patch_stage_bytes;
+    P.patch_stages = op.patch_stages;
+    P.a_region_bytes = op.patch_stages * op.patch_stage_bytes;
+    P.tiles_x = (op.Wout + PT_W - 1) / PT_W;
+    P.tiles_per_img = P.tiles_x * ((op.Hout + PT_H - 1) / PT_H);
+    P.total_tiles = p->B * P.tiles_per_img * P.n_tiles;
+    magic(P.tiles_per_img, P.tpi_mul, P.tpi_shr);
+    magic(P.tiles_x, P.tx_mul, P.tx_shr);
+  } else if (op.tile2d) {
     P.tiles_x = op.Wout / 16;
     P.tiles_per_img = P.tiles_x * (op.Hout / 8);
     magic(P.tiles_per_img, P.tpi_mul, P.tpi_shr);
@@ -1036,14 +1336,16 @@ int launch_conv_tc(const yb_plan* p, const Op& op, cudaStream_t st, float* fused
       P, op.tmap_b, op.tmap_a[0], op.tmap_a[1], op.tmap_a[2], op.tmap_a[3], op.tmap_c)
   const bool head = P.out_mode != 0;
   if (head) {
-    if (P.a_tma) YB_LAUNCH(true, false, true);
-    else YB_LAUNCH(false, false, true);
+    if (P.a_tma) YB_LAUNCH(MODE_ATMA, false, true);
+    else YB_LAUNCH(MODE_GATHER, false, true);
+  } else if (P.patch) {
+    YB_LAUNCH(MODE_PATCH, true, false);
   } else if (P.a_tma) {
-    if (P.tile2d) YB_LAUNCH(true, true, false);
-    else YB_LAUNCH(true, false, false);
+    if (P.tile2d) YB_LAUNCH(MODE_ATMA, true, false);
+    else YB_LAUNCH(MODE_ATMA, false, false);
   } else {
-    if (P.tile2d) YB_LAUNCH(false, true, false);
-    else YB_LAUNCH(false, false, false);
+    if (P.tile2d) YB_LAUNCH(MODE_GATHER, true, false);
+    else YB_LAUNCH(MODE_GATHER, false, false);
   }
 #undef YB_LAUNCH
   count_launch();

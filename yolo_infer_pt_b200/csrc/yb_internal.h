@@ -74,6 +74,10 @@ struct Op {
   int N_pad = 0, BN = 0;   // padded Cout, N tile
   int stages = 0;
   int tile2d = 0;          // 8 x 16 spatial output tiles (else 128 consecutive flattened rows)
+  int patch = 0;           // 3x3/s1: A operand read from TMA halo patches through shifted descriptors
+  int patch_stage_bytes = 0, patch_stages = 0;
+  int b_resident = 0;      // weight matrix stays in shared memory across the CTA's tiles
+  int c_bufs = 1;          // output staging buffers
   int occ = 1;             // resident CTAs per SM of the persistent GEMM kernel
   int head_part = 0;       // 1: box tail (fusable DFL decode), 2: cls tail (fusable sigmoid)
   size_t smem_bytes = 0;
