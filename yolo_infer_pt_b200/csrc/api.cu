@@ -20,6 +20,11 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) v = getenv("YB_NO_PDL") ? 0 : 1;
+  return v != 0;
+}
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 size_t nms_workspace_bytes(int B, int nc, int A, int max_nms);

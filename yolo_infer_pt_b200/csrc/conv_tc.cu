@@ -380,6 +380,10 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
+  // prologue done (barriers, TMEM): let the next kernel start its own, then wait for the producer of
+  // our inputs before the first global-memory access
+  pdl_prologue_done();
+  pdl_wait();
 
   // With A fed by TMA the im2col warps have nothing to gather: they join the epilogue as a second
   // group that converts the odd 16-column chunks of the accumulator (same TMEM lane quadrants).
@@ -1332,8 +1336,8 @@ int launch_conv_tc(const yb_plan* p, const Op& op, cudaStream_t st, float* fused
   }
   int grid = std::min(P.total_tiles, p->num_sms * op.occ);
 #define YB_LAUNCH(ATMA, T2D, HEAD)                                                                       \
-  conv_gemm_tcgen05_kernel<ATMA, T2D, HEAD><<<grid, NUM_THREADS, op.smem_bytes, st>>>(                   \
-      P, op.tmap_b, op.tmap_a[0], op.tmap_a[1], op.tmap_a[2], op.tmap_a[3], op.tmap_c)
+  YB_CUDA(launch_pdl(conv_gemm_tcgen05_kernel<ATMA, T2D, HEAD>, dim3(grid), dim3(NUM_THREADS), op.smem_bytes, st, \
+                     P, op.tmap_b, op.tmap_a[0], op.tmap_a[1], op.tmap_a[2], op.tmap_a[3], op.tmap_c))
   const bool head = P.out_mode != 0;
   if (head) {
     if (P.a_tma) YB_LAUNCH(MODE_ATMA, false, true);

@@ -116,6 +116,8 @@ __global__ void __launch_bounds__(256)
   // shared: [27][Cp] weights, [Cp] bias, then the input patch split into even and odd columns
   // [3][IH][HP] each: with stride 2 a warp's taps become unit-stride, conflict-free reads
   extern __shared__ float ws[];
+  pdl_prologue_done();
+  pdl_wait();
   float* te = ws + 28 * Cp;
   float* to = te + 3 * STEM_IH * STEM_HP;
   const int tiles_x = (Wo + STEM_TW - 1) / STEM_TW, tiles_y = (Ho + STEM_TH - 1) / STEM_TH;
@@ -232,21 +234,20 @@ int launch_stem(const yb_plan* p, const Op& op, const void* in, int in_dtype, cu
   size_t smem = ((size_t)28 * Cp + 2 * 3 * STEM_IH * STEM_HP) * 4;
   switch (in_dtype) {
     case YB_F32:
-      stem_conv_kernel<float><<<blocks, threads, smem, st>>>((const float*)in, out, w, p->B, p->H, p->W,
-                                                            op.Hout, op.Wout, Cp, db.C, 1.f);
+      YB_CUDA(launch_pdl(stem_conv_kernel<float>, dim3(blocks), dim3(threads), smem, st, (const float*)in, out, w,
+                         p->B, p->H, p->W, op.Hout, op.Wout, Cp, db.C, 1.f));
       break;
     case YB_F16:
-      stem_conv_kernel<__half><<<blocks, threads, smem, st>>>((const __half*)in, out, w, p->B, p->H,
-                                                             p->W, op.Hout, op.Wout, Cp, db.C, 1.f);
+      YB_CUDA(launch_pdl(stem_conv_kernel<__half>, dim3(blocks), dim3(threads), smem, st, (const __half*)in, out, w,
+                         p->B, p->H, p->W, op.Hout, op.Wout, Cp, db.C, 1.f));
       break;
     case YB_BF16:
-      stem_conv_kernel<__nv_bfloat16><<<blocks, threads, smem, st>>>(
-          (const __nv_bfloat16*)in, out, w, p->B, p->H, p->W, op.Hout, op.Wout, Cp, db.C, 1.f);
+      YB_CUDA(launch_pdl(stem_conv_kernel<__nv_bfloat16>, dim3(blocks), dim3(threads), smem, st,
+                         (const __nv_bfloat16*)in, out, w, p->B, p->H, p->W, op.Hout, op.Wout, Cp, db.C, 1.f));
       break;
     case YB_U8:
-      stem_conv_kernel<uint8_t><<<blocks, threads, smem, st>>>((const uint8_t*)in, out, w, p->B, p->H,
-                                                              p->W, op.Hout, op.Wout, Cp, db.C,
-                                                              1.f / 255.f);
+      YB_CUDA(launch_pdl(stem_conv_kernel<uint8_t>, dim3(blocks), dim3(threads), smem, st, (const uint8_t*)in, out, w,
+                         p->B, p->H, p->W, op.Hout, op.Wout, Cp, db.C, 1.f / 255.f));
       break;
     default:
       set_error("unsupported input dtype %d", in_dtype);
@@ -269,6 +270,8 @@ __global__ void __launch_bounds__(256)
     dwconv3x3_kernel(const __nv_bfloat16* __restrict__ src, int src_ld, __nv_bfloat16* dst, int dst_ld,
                      const float* __restrict__ wgt, int Cp, int B, int H, int W, int C, int gsz,
                      int gstride, int goff, int act, int add) {
+  pdl_prologue_done();
+  pdl_wait();
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int cgs = C >> 3;
   const int xq = (W + DW_PX - 1) / DW_PX;
@@ -364,9 +367,8 @@ int launch_dw(const yb_plan* p, const Op& op, cudaStream_t st) {
   long long total = (long long)p->B * op.Hout * ((op.Wout + DW_PX - 1) / DW_PX) * (C >> 3);
   int threads = 256;
   unsigned blocks = (unsigned)((total + threads - 1) / threads);
-  dwconv3x3_kernel<<<blocks, threads, 0, st>>>(src, sb.C, dst, db.C, w, cpad8(C), p->B, op.Hout, op.Wout,
-                                               C, op.dw_gsz, op.dw_gstride, op.dw_goff, op.act,
-                                               op.dw_add);
+  YB_CUDA(launch_pdl(dwconv3x3_kernel, dim3(blocks), dim3(threads), 0, st, src, sb.C, dst, db.C, w, cpad8(C), p->B,
+                     op.Hout, op.Wout, C, op.dw_gsz, op.dw_gstride, op.dw_goff, op.act, op.dw_add));
   count_launch();
   YB_CUDA(cudaGetLastError());
   return YB_OK;
@@ -391,6 +393,8 @@ __global__ void __launch_bounds__(256)
     sppf_pool_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* dst, int ld, int H, int W,
                      int Chalf) {
   extern __shared__ uint4 pl[];  // cur[HW], tmp[HW]
+  pdl_prologue_done();
+  pdl_wait();
   const int HW = H * W;
   uint4* cur = pl;
   uint4* tmp = pl + HW;
@@ -449,8 +453,7 @@ int launch_pool(const yb_plan* p, const Op& op, cudaStream_t st) {
   }
   // src (slice 0) and dst (slices 1..3) live in the same concat buffer
   unsigned blocks = (unsigned)(p->B * (Chalf >> 3));
-  sppf_pool_kernel<<<blocks, 256, smem, st>>>(src, dst, sb.C, op.Hin, op.Win,
-                                              Chalf);
+  YB_CUDA(launch_pdl(sppf_pool_kernel, dim3(blocks), dim3(256), smem, st, src, dst, sb.C, op.Hin, op.Win, Chalf));
   count_launch();
   YB_CUDA(cudaGetLastError());
   return YB_OK;
@@ -489,6 +492,8 @@ __global__ void __launch_bounds__(256)
                      int out_ld, int N, int heads, float scale_log2e) {
   __shared__ __align__(16) __nv_bfloat16 Ks[ATT_KC * ATT_KP];
   __shared__ __align__(16) __nv_bfloat16 Vs[ATT_KC * ATT_VP];
+  pdl_prologue_done();
+  pdl_wait();
   const int h = blockIdx.y, b = blockIdx.z;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
@@ -628,8 +633,8 @@ int launch_attn(const yb_plan* p, const Op& op, cudaStream_t st) {
   }
   int N = op.Hin * op.Win;
   dim3 grid((N + ATT_Q - 1) / ATT_Q, op.heads, p->B);
-  attention_kernel<<<grid, 256, 0, st>>>(qkv, sb.C, out, db.C, N, op.heads,
-                                         op.scale * 1.4426950408889634f);
+  YB_CUDA(launch_pdl(attention_kernel, grid, dim3(256), 0, st, qkv, sb.C, out, db.C, N, op.heads,
+                     op.scale * 1.4426950408889634f));
   count_launch();
   YB_CUDA(cudaGetLastError());
   return YB_OK;
@@ -652,6 +657,8 @@ static constexpr int DEC_T = 64;
 __global__ void __launch_bounds__(256)
     head_decode_kernel(const float* __restrict__ logits, float* __restrict__ out, const DecodeParams D) {
   extern __shared__ float tile[];  // [DEC_T][ldp]
+  pdl_prologue_done();
+  pdl_wait();
   const int no = 64 + D.nc;
   const int ldp = no | 1;  // odd row pitch: conflict-free column access
   float* dist = tile + DEC_T * ldp;  // [DEC_T][4]
@@ -726,7 +733,7 @@ int launch_decode(const yb_plan* p, const float* logits, float* out, cudaStream_
   }
   long long rows = (long long)p->B * p->A;
   unsigned blocks = (unsigned)((rows + DEC_T - 1) / DEC_T);
-  head_decode_kernel<<<blocks, 256, smem, st>>>(logits, out, D);
+  YB_CUDA(launch_pdl(head_decode_kernel, dim3(blocks), dim3(256), smem, st, logits, out, D));
   count_launch();
   YB_CUDA(cudaGetLastError());
   return YB_OK;

@@ -67,6 +67,8 @@ __device__ __forceinline__ unsigned long long make_key(float score, unsigned int
 // list (unordered; the sort orders them).  Reads 4 anchors per thread (float4 when aligned), one
 // atomic per warp iteration.
 __global__ void __launch_bounds__(256) nms_append_kernel(const NmsArgs a, int vec4) {
+  pdl_prologue_done();
+  pdl_wait();
   const int b = blockIdx.y;
   NmsHeader* h = a.hdr + b;
   const long long total = (long long)a.nc * a.A;
@@ -283,6 +285,8 @@ template <int IMG_T>
 __global__ void __launch_bounds__(IMG_T) nms_image_kernel(const NmsArgs a) {
   extern __shared__ __align__(16) uint8_t nms_smem_raw[];
   ImgSmem& sm = *reinterpret_cast<ImgSmem*>(nms_smem_raw);
+  pdl_prologue_done();
+  pdl_wait();
   const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const NmsHeader h = a.hdr[b];
@@ -566,10 +570,10 @@ int nms_run(const float* pred, int B, int nc, int A, float conf, double iou, int
   long long total = (long long)nc * A;
   int gx = (int)std::min<long long>((total + 256 * 16 - 1) / (256 * 16), 1024);
   int vec4 = (A % 4 == 0) && ((reinterpret_cast<uintptr_t>(pred) & 15) == 0);
-  nms_append_kernel<<<dim3(gx, B), 256, 0, st>>>(a, vec4);
+  YB_CUDA(launch_pdl(nms_append_kernel, dim3(gx, B), dim3(256), 0, st, a, vec4));
   count_launch();
-  if (B <= 160) nms_image_kernel<1024><<<B, 1024, sizeof(ImgSmem), st>>>(a);
-  else nms_image_kernel<512><<<B, 512, sizeof(ImgSmem), st>>>(a);
+  if (B <= 160) YB_CUDA(launch_pdl(nms_image_kernel<1024>, dim3(B), dim3(1024), sizeof(ImgSmem), st, a));
+  else YB_CUDA(launch_pdl(nms_image_kernel<512>, dim3(B), dim3(512), sizeof(ImgSmem), st, a));
   count_launch();
   YB_CUDA(cudaGetLastError());
   return YB_OK;

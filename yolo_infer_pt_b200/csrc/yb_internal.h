@@ -24,6 +24,34 @@ void count_launch();
     }                                                                                  \
   } while (0)
 
+// Programmatic dependent launch: every kernel of the forward / NMS chain is launched with the
+// programmatic-stream-serialization attribute, triggers its dependents at once and executes
+// griddepcontrol.wait before its first global-memory access.  A dependent grid therefore starts as
+// soon as all CTAs of its predecessor are running (or done) and overlaps its prologue (barrier
+// init, TMEM allocation, descriptor prefetch) with the predecessor's tail; data is only touched
+// after the predecessor has completed and flushed.  Every CTA of every kernel executes the wait, so
+// completion of kernel N implies completion of kernel N-1 (buffer-reuse hazards stay ordered).
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ void pdl_prologue_done() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+#endif
+
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 static inline int cpad8(int c) { return round_up(c, 8); }
 
