@@ -82,6 +82,7 @@ struct ConvParams {
   int b_resident;       // weights stay in shared memory for the whole kernel: slot kb, loaded during the first tile
   int b_slots;          // weight slots in shared memory (num_kb when resident, else stages)
   int c_bufs;           // output staging buffers (2: the epilogue never waits for the previous tile's TMA store)
+  int alt_epilogue;     // the two epilogue warp groups take alternate tiles (when the kernel has two)
   // fused head decode (out_mode 2 / 3): dst is the (B, 4+nc, A) fp32 output tensor
   int out_mode;       // 0 bf16 slice, 1 fp32 logits, 2 DFL box decode, 3 class sigmoid
   int A_total, nc;
@@ -300,7 +301,7 @@ static constexpr int RELAY_WARP = 10;    // proxy-fence relay between the im2col
 // every instantiation carries only the code of its own roles, which keeps it inside the
 // instruction cache (11 warps run disjoint code).
 template <int MODE, bool T2D, bool HEAD>
-__global__ void __launch_bounds__(NUM_THREADS, 2)
+__global__ void __launch_bounds__(NUM_THREADS, MODE == MODE_PATCH ? 3 : 2)
     conv_gemm_tcgen05_kernel(const ConvParams P, const __grid_constant__ CUtensorMap tmap_b,
                              const __grid_constant__ CUtensorMap tmap_a0,
                              const __grid_constant__ CUtensorMap tmap_a1,
@@ -327,6 +328,11 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
   uint8_t* tail = smem + (size_t)P.a_region_bytes + (size_t)P.b_slots * b_stage_bytes +
                   (size_t)c_groups * C_GROUP_BYTES * (size_t)P.c_bufs;
   const bool RES = P.b_resident != 0;
+  // Two epilogue warp groups exist when no im2col producers are needed.  With one N tile and two
+  // staging buffers they take alternate tiles (group g drains TMEM stage g into staging buffer g, its
+  // own named barrier and TMA stores), so two epilogue chains are in flight; otherwise they split
+  // the columns of every tile.
+  const bool alt_epi = A_TMA && P.n_tiles == 1 && (HEAD || P.c_bufs == 2) && P.alt_epilogue;
   // barriers: full[MAX_STAGES], empty[MAX_STAGES], tmem_full[2], tmem_empty[2], gathered[MAX_STAGES],
   //           patch_full[MAX_PATCH_STAGES], patch_empty[MAX_PATCH_STAGES]
   uint64_t* bars = reinterpret_cast<uint64_t*>(tail);
@@ -358,7 +364,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
     }
     for (int a = 0; a < 2; a++) {
       mbar_init(tmem_full_bar(a), 1u);
-      mbar_init(tmem_empty_bar(a), A_TMA ? 256u : 128u);
+      mbar_init(tmem_empty_bar(a), (A_TMA && !alt_epi) ? 256u : 128u);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -393,20 +399,32 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
     const int ngrp = A_TMA ? 2 : 1;
     const int etid = tid & 127;                 // row of the tile owned by this thread
     const int qwarp = warp & 3;                 // TMEM lane quadrant
-    const int cstep = (HEAD && P.out_mode == 2) ? 16 : 16 * ngrp;   // DFL decode needs all 4 sides in one thread
-    const int cfirst = (HEAD && P.out_mode == 2) ? (grp ? BN : 0) : 16 * grp;
+    const int cstep = (alt_epi || (HEAD && P.out_mode == 2)) ? 16 : 16 * ngrp;   // DFL decode needs all 4 sides in one thread
+    const int cfirst = alt_epi ? 0 : (HEAD && P.out_mode == 2) ? (grp ? BN : 0) : 16 * grp;
+    const bool leader = alt_epi ? etid == 0 : tid == 0;
+    auto epi_sync = [&]() {
+      if (alt_epi) {
+        if (grp) asm volatile("bar.sync 2, 128;" ::: "memory");
+        else asm volatile("bar.sync 1, 128;" ::: "memory");
+      } else if (ngrp == 2) {
+        asm volatile("bar.sync 1, 256;" ::: "memory");
+      } else {
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+      }
+    };
     int ti = 0;
     // One N tile: the bias vector is loaded once.  With two staging buffers the tile loop then needs
     // a single CTA-level barrier per tile (before the TMA store), and never waits on the previous
     // tile's store: that one is drained (wait_group.read) a full tile later.
     const bool bias_once = P.n_tiles == 1;
-    const bool fast_flow = bias_once && (HEAD || P.c_bufs == 2);
+    const bool fast_flow = !alt_epi && bias_once && (HEAD || P.c_bufs == 2);
     if (bias_once) {
       for (int i = tid; i < BN; i += 128 * ngrp) bias_s[i] = __ldg(P.bias + i);
       if (ngrp == 2) asm volatile("bar.sync 1, 256;" ::: "memory");
       else asm volatile("bar.sync 1, 128;" ::: "memory");
     }
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ti++) {
+      if (alt_epi && (ti & 1) != grp) continue;
       const int mt = P.n_tiles == 1 ? tile : tile / P.n_tiles;
       const TilePos tp = tile_pos<T2D, TW>(P, mt);
       const int m0 = tp.m0;
@@ -442,15 +460,15 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
       res_fetch(cfirst + cstep, rb0, rb1);
       mbar_wait(tmem_full_bar(acc), (uint32_t)(ti >> 1) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (!fast_flow) {
-        // the previous tile's TMA stores must have finished reading the staging buffer
-        if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+      if (!fast_flow && !(alt_epi && HEAD)) {
+        // the previous tile's TMA stores (this group's, when the groups alternate: issued a whole
+        // tile ago) must have finished reading the staging buffer
+        if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         if (!bias_once)
           for (int i = tid; i < BN; i += 128 * ngrp) bias_s[i] = __ldg(P.bias + n0 + i);
-        if (ngrp == 2) asm volatile("bar.sync 1, 256;" ::: "memory");
-        else asm volatile("bar.sync 1, 128;" ::: "memory");
+        epi_sync();
       }
-      const uint32_t c_buf = c_base + ((fast_flow && (ti & 1)) ? c_groups * C_GROUP_BYTES : 0u);
+      const uint32_t c_buf = c_base + (((fast_flow && (ti & 1)) || (alt_epi && grp)) ? c_groups * C_GROUP_BYTES : 0u);
       const uint32_t t_row = tmem_base + ((uint32_t)(qwarp * 32) << 16) + (uint32_t)(acc * BN);
       float dist[4];
       auto do_chunk = [&](int c0, const uint4& rv0, const uint4& rv1) {
@@ -527,7 +545,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
         ra1 = rb1;
         res_fetch(c0 + 2 * cstep, rb0, rb1);
       }
-      if (HEAD && P.out_mode == 2 && row_ok && grp == 0) {
+      if (HEAD && P.out_mode == 2 && row_ok && (alt_epi || grp == 0)) {
         const int y = fast_div(r, P.w_mul, P.w_shr, P.Wout), x = r - y * P.Wout;
         const float ax = (float)x + 0.5f, ay = (float)y + 0.5f, st = P.lvl_stride;
         const float x1 = ax - dist[0], y1 = ay - dist[1], x2 = ax + dist[2], y2 = ay + dist[3];
@@ -544,10 +562,9 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         // fast flow: the store of tile t-1 (other buffer) has had this whole tile to finish reading;
         // after the barrier below every thread may overwrite that buffer for tile t+1
-        if (fast_flow && tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-        if (ngrp == 2) asm volatile("bar.sync 1, 256;" ::: "memory");
-        else asm volatile("bar.sync 1, 128;" ::: "memory");
-        if (tid == 0) {
+        if (fast_flow && leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        epi_sync();
+        if (leader) {
           for (uint32_t g = 0; g < c_groups; g++) {
             const int cg0 = n0 + (int)g * 64;
             if (cg0 < P.cout_store) {
@@ -570,7 +587,7 @@ __global__ void __launch_bounds__(NUM_THREADS, 2)
         }
       }
     }
-    if (tid == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+    if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   } else if (warp < MMA_WARP) {
     // ============================ im2col producer ==========================================
     {
@@ -1101,7 +1118,9 @@ int conv_tc_prepare(yb_plan* p, Op& op) {
   // capped at 2.  The shared-memory request is sized so that exactly `occ` CTAs fit, which keeps
   // tcgen05.alloc from ever waiting on a co-resident persistent CTA.
   const size_t SMEM_MAX = 227 * 1024;
-  int occ = std::min(2, 512 / tmem_cols_for(op.BN));
+  // patch layers with tiny N tiles are bound by per-tile latency chains: a third resident CTA hides them
+  const bool tiny_patch = patch_eligible(p, op) && op.BN <= 32 && op.Hout >= 80 && getenv("YB_NO_OCC3") == nullptr;
+  int occ = std::min(tiny_patch ? 3 : 2, 512 / tmem_cols_for(op.BN));
   if (const char* e = getenv("YB_OCC")) occ = std::max(1, std::min(occ, atoi(e)));
   if (!op.a_tma)
     if (const char* e = getenv("YB_OCC_GATHER")) occ = std::max(1, std::min(occ, atoi(e)));
@@ -1297,6 +1316,8 @@ static void fill_params(const yb_plan* p, const Op& op, ConvParams& P) {
   P.b_resident = op.b_resident;
   P.b_slots = op.b_resident ? P.num_kb : op.stages;
   P.c_bufs = op.c_bufs;
+  // measured: alternate tiles win except on patch layers with >= 32 output channels
+  P.alt_epilogue = (getenv("YB_NO_ALT_EPI") || (op.patch && op.BN >= 32)) ? 0 : 1;
   if (op.patch) {
     const int C = op.src[0].C;
     P.patch = 1;
