@@ -42,6 +42,18 @@ __device__ __forceinline__ uint4 float_to_bf16x8(const float* f) {
   return o;
 }
 
+__device__ __forceinline__ void mma_bf16_16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+      "{%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack2_bf16(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+
 // ---------------------------------------------------------------------------------------------
 // Stem: net.p1.0 = Conv(3 -> w1, k3, s2, p1) + SiLU (nets/nn.py:161).  Reads the caller's NCHW
 // image (fp32 / fp16 / bf16 / uint8), writes NHWC bf16.  K = 27 is far below the tensor-core
@@ -223,36 +235,257 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-int launch_stem(const yb_plan* p, const Op& op, const void* in, int in_dtype, cudaStream_t st) {
+// ---------------------------------------------------------------------------------------------
+// Stem on the tensor cores (default).  The 3x3x3 receptive field is a K = 27 (padded to 32) GEMM row:
+// a CTA stages the input patch of an 8 x 64 output tile in shared memory as bf16 (uint8 pixels are
+// exact in bf16; the 1/255 scale is folded into the weights), every warp owns one tile row and builds
+// its mma.sync.m16n8k16 A fragments straight from the patch (one 16-bit shared load per element,
+// addresses = pixel base + a per-thread tap offset), the weights live in registers as B fragments.
+// Against the direct version this trades 27 x Cp FMAs per pixel for 16 loads + 2 x Cp/8 MMAs per
+// 16 pixels; the output tile goes through a per-warp staging buffer so that global stores are 16 B
+// per lane and contiguous.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ void unpack_bf16(const uint4& v, __nv_bfloat16* o);
+template <>
+__device__ __forceinline__ void unpack_bf16<float>(const uint4& v, __nv_bfloat16* o) {
+  o[0] = __float2bfloat16(__uint_as_float(v.x));
+  o[1] = __float2bfloat16(__uint_as_float(v.y));
+  o[2] = __float2bfloat16(__uint_as_float(v.z));
+  o[3] = __float2bfloat16(__uint_as_float(v.w));
+}
+template <>
+__device__ __forceinline__ void unpack_bf16<__half>(const uint4& v, __nv_bfloat16* o) {
+  const __half* h = reinterpret_cast<const __half*>(&v);
+#pragma unroll
+  for (int j = 0; j < 8; j++) o[j] = __float2bfloat16(__half2float(h[j]));
+}
+template <>
+__device__ __forceinline__ void unpack_bf16<__nv_bfloat16>(const uint4& v, __nv_bfloat16* o) {
+  *reinterpret_cast<uint4*>(o) = v;
+}
+template <>
+__device__ __forceinline__ void unpack_bf16<uint8_t>(const uint4& v, __nv_bfloat16* o) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int j = 0; j < 16; j++) o[j] = __float2bfloat16((float)((w[j >> 2] >> (8 * (j & 3))) & 0xFFu));
+}
+
+template <typename T>
+__device__ __forceinline__ float vec_elem(const uint4& v, int j);   // element j of a 16-byte vector as fp32
+template <>
+__device__ __forceinline__ float vec_elem<float>(const uint4& v, int j) {
+  return __uint_as_float(j == 0 ? v.x : j == 1 ? v.y : j == 2 ? v.z : v.w);
+}
+template <>
+__device__ __forceinline__ float vec_elem<__half>(const uint4& v, int j) {
+  const uint32_t w = (j >> 1) == 0 ? v.x : (j >> 1) == 1 ? v.y : (j >> 1) == 2 ? v.z : v.w;
+  return __half2float(__ushort_as_half((unsigned short)((w >> (16 * (j & 1))) & 0xFFFFu)));
+}
+template <>
+__device__ __forceinline__ float vec_elem<__nv_bfloat16>(const uint4& v, int j) {
+  const uint32_t w = (j >> 1) == 0 ? v.x : (j >> 1) == 1 ? v.y : (j >> 1) == 2 ? v.z : v.w;
+  return __uint_as_float((j & 1) ? (w & 0xFFFF0000u) : (w << 16));
+}
+template <>
+__device__ __forceinline__ float vec_elem<uint8_t>(const uint4& v, int j) {
+  const uint32_t w = (j >> 2) == 0 ? v.x : (j >> 2) == 1 ? v.y : (j >> 2) == 2 ? v.z : v.w;
+  return (float)((w >> (8 * (j & 3))) & 0xFFu);
+}
+
+// NT: n-tiles (8 channels each) per pass over the tile; wider stems take several passes.
+// SPLIT: the input is not exactly representable in bf16 (fp32 / fp16 images): input and weights are
+// staged as hi + lo bf16 pairs and multiplied as hi*W_hi + hi*W_lo + lo*W_hi, which matches an fp32
+// convolution to ~2^-16 relative.  uint8 / bf16 images are exact in bf16 and use bf16 weights like
+// every other layer of the network.
+template <typename T, int NT, bool SPLIT>
+__global__ void __launch_bounds__(256)
+    stem_mma_kernel(const T* __restrict__ in, __nv_bfloat16* __restrict__ out, const float* __restrict__ wgt,
+                    int B, int H, int W, int Ho, int Wo, int Cp, int out_ld, float in_scale) {
+  constexpr int EPV = 16 / (int)sizeof(T);
+  constexpr int NVEC = (2 * STEM_TW + 1 + EPV + EPV - 1) / EPV;
+  constexpr int PITCH = NVEC * EPV + 8;   // bf16 elements per patch row
+  constexpr int PSZ = 3 * STEM_IH * PITCH;
+  extern __shared__ __align__(16) uint8_t stem_smem[];
+  __nv_bfloat16* patch = reinterpret_cast<__nv_bfloat16*>(stem_smem);          // [hi|lo][3][IH][PITCH]
+  __nv_bfloat16* stage = patch + (SPLIT ? 2 : 1) * PSZ;                         // [8 warps][16 px][NT*8]
+  pdl_prologue_done();
+  pdl_wait();
+  const int tiles_x = (Wo + STEM_TW - 1) / STEM_TW, tiles_y = (Ho + STEM_TH - 1) / STEM_TH;
+  int bid = blockIdx.x;
+  const int tx = bid % tiles_x;
+  bid /= tiles_x;
+  const int ty = bid % tiles_y;
+  const int b = bid / tiles_y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  // ---- per-thread tap offsets of its 8 K columns (k = 2t, 2t+1, 2t+8, 2t+9 of each k-step)
+  int koff[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    const int k = (j >> 2) * 16 + ((j >> 1) & 1) * 8 + 2 * t + (j & 1);
+    const int ci = k / 9, r9 = k - ci * 9, ky = r9 / 3, kx = r9 - ky * 3;
+    koff[j] = k < 27 ? (ci * STEM_IH + ky) * PITCH + kx : -1;
+  }
+  // ---- stage the input patch as bf16 (hi, and lo = x - hi when SPLIT)
+  const int gy0 = 2 * ty * STEM_TH - 1;
+  const int gxa = 2 * tx * STEM_TW - EPV;
+  for (int i = tid; i < 3 * STEM_IH * NVEC; i += 256) {
+    const int vx = i % NVEC;
+    const int row = i / NVEC;  // ci * IH + iy
+    const int iy = row % STEM_IH, ci = row / STEM_IH;
+    const int gy = gy0 + iy, gx = gxa + vx * EPV;
+    __align__(16) __nv_bfloat16 o[EPV], ol[EPV];
+    if ((unsigned)gy < (unsigned)H && gx >= 0 && gx < W) {
+      const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + (((size_t)b * 3 + ci) * H + gy) * W + gx));
+      if (SPLIT) {
+#pragma unroll
+        for (int j = 0; j < EPV; j++) {
+          const float x = vec_elem<T>(v, j);
+          o[j] = __float2bfloat16(x);
+          ol[j] = __float2bfloat16(x - __bfloat162float(o[j]));
+        }
+      } else {
+        unpack_bf16<T>(v, o);
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < EPV; j++) o[j] = ol[j] = __float2bfloat16(0.f);
+    }
+    __nv_bfloat16* dp = patch + row * PITCH + vx * EPV;
+    if (EPV >= 8) {
+#pragma unroll
+      for (int j = 0; j < EPV; j += 8) {
+        *reinterpret_cast<uint4*>(dp + j) = *reinterpret_cast<const uint4*>(o + j);
+        if (SPLIT) *reinterpret_cast<uint4*>(dp + PSZ + j) = *reinterpret_cast<const uint4*>(ol + j);
+      }
+    } else {
+      *reinterpret_cast<uint2*>(dp) = *reinterpret_cast<const uint2*>(o);
+      if (SPLIT) *reinterpret_cast<uint2*>(dp + PSZ) = *reinterpret_cast<const uint2*>(ol);
+    }
+  }
+  __syncthreads();
+  const int oy = ty * STEM_TH + warp;
+  if (oy >= Ho) return;
+  const float* bias = wgt + 27 * Cp;
+  const unsigned short* pu = reinterpret_cast<const unsigned short*>(patch);
+  __nv_bfloat16* wstage = stage + warp * 16 * NT * 8;
+#pragma unroll 1
+  for (int c0 = 0; c0 < Cp; c0 += NT * 8) {
+    // weights of this channel group -> B fragments (n = g per n-tile), scale folded, hi + lo split
+    uint32_t bhi[NT][2][2], blo[NT][2][2];
+    float bia[NT][2];
+#pragma unroll
+    for (int nt = 0; nt < NT; nt++) {
+      const int n = c0 + nt * 8 + g;
+#pragma unroll
+      for (int ks = 0; ks < 2; ks++)
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const int k0 = ks * 16 + h * 8 + 2 * t;
+          const float w0 = (k0 < 27 && n < Cp) ? __ldg(wgt + k0 * Cp + n) * in_scale : 0.f;
+          const float w1 = (k0 + 1 < 27 && n < Cp) ? __ldg(wgt + (k0 + 1) * Cp + n) * in_scale : 0.f;
+          const __nv_bfloat16 h0 = __float2bfloat16(w0), h1 = __float2bfloat16(w1);
+          bhi[nt][ks][h] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+          blo[nt][ks][h] = pack2_bf16(w0 - __bfloat162float(h0), w1 - __bfloat162float(h1));
+        }
+      const int cb = c0 + nt * 8 + 2 * t;
+      bia[nt][0] = cb < Cp ? __ldg(bias + cb) : 0.f;
+      bia[nt][1] = cb + 1 < Cp ? __ldg(bias + cb + 1) : 0.f;
+    }
+#pragma unroll 1
+    for (int mi = 0; mi < STEM_TW / 16; mi++) {
+      // input column of tap kx for output column lx: EPV + 2*lx + kx - 1
+      const int base0 = (2 * warp) * PITCH + EPV - 1 + 2 * (mi * 16 + g);
+      const int base1 = base0 + 16;
+      uint32_t afr[SPLIT ? 2 : 1][2][4];
+#pragma unroll
+      for (int part = 0; part < (SPLIT ? 2 : 1); part++)
+#pragma unroll
+        for (int ks = 0; ks < 2; ks++)
+#pragma unroll
+          for (int h = 0; h < 2; h++) {
+            const int o0 = koff[ks * 4 + h * 2], o1 = koff[ks * 4 + h * 2 + 1];
+            const unsigned short* pp = pu + part * PSZ;
+            const uint32_t a00 = o0 >= 0 ? pp[base0 + o0] : 0u, a01 = o1 >= 0 ? pp[base0 + o1] : 0u;
+            const uint32_t a10 = o0 >= 0 ? pp[base1 + o0] : 0u, a11 = o1 >= 0 ? pp[base1 + o1] : 0u;
+            afr[part][ks][h * 2] = a00 | (a01 << 16);       // row g
+            afr[part][ks][h * 2 + 1] = a10 | (a11 << 16);   // row g + 8
+          }
+      float d[NT][4];
+#pragma unroll
+      for (int nt = 0; nt < NT; nt++) {
+        d[nt][0] = d[nt][2] = bia[nt][0];
+        d[nt][1] = d[nt][3] = bia[nt][1];
+#pragma unroll
+        for (int ks = 0; ks < 2; ks++) {
+          if (SPLIT) {
+            mma_bf16_16816(d[nt], afr[0][ks], blo[nt][ks][0], blo[nt][ks][1]);
+            mma_bf16_16816(d[nt], afr[SPLIT ? 1 : 0][ks], bhi[nt][ks][0], bhi[nt][ks][1]);
+          }
+          mma_bf16_16816(d[nt], afr[0][ks], bhi[nt][ks][0], bhi[nt][ks][1]);
+        }
+      }
+      // SiLU -> bf16 -> per-warp staging [16 px][NT*8] -> 16-byte contiguous global stores
+      __syncwarp();
+#pragma unroll
+      for (int nt = 0; nt < NT; nt++) {
+        *reinterpret_cast<uint32_t*>(wstage + g * NT * 8 + nt * 8 + 2 * t) = pack2_bf16(silu_acc(d[nt][0]), silu_acc(d[nt][1]));
+        *reinterpret_cast<uint32_t*>(wstage + (g + 8) * NT * 8 + nt * 8 + 2 * t) = pack2_bf16(silu_acc(d[nt][2]), silu_acc(d[nt][3]));
+      }
+      __syncwarp();
+      const int ox0 = tx * STEM_TW + mi * 16;
+      for (int c = lane; c < 16 * NT; c += 32) {   // 16-byte chunks of the 16 x (NT*8) tile
+        const int px = c / NT, cg = c - px * NT;
+        if (ox0 + px < Wo && c0 + cg * 8 < Cp)
+          *reinterpret_cast<uint4*>(out + (((size_t)b * Ho + oy) * Wo + ox0 + px) * out_ld + c0 + cg * 8) =
+              *reinterpret_cast<const uint4*>(wstage + px * NT * 8 + cg * 8);
+      }
+    }
+  }
+}
+
+template <typename T, bool SPLIT>
+static int launch_stem_t(const yb_plan* p, const Op& op, const void* in, float scale, cudaStream_t st) {
   const ConvW& cw = p->convs[op.conv_index];
   const float* w = reinterpret_cast<const float*>(p->d_weights + cw.info.blob_offset);
   const Buf& db = p->bufs[op.dst.buf];
   __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(buf_ptr(p, op.dst.buf)) + op.dst.c_off;
-  int Cp = cpad8(op.dst.C);
-  int threads = 256;
-  unsigned blocks = (unsigned)(p->B * ((op.Hout + STEM_TH - 1) / STEM_TH) * ((op.Wout + STEM_TW - 1) / STEM_TW));
-  size_t smem = ((size_t)28 * Cp + 2 * 3 * STEM_IH * STEM_HP) * 4;
+  const int Cp = cpad8(op.dst.C);
+  const unsigned blocks = (unsigned)(p->B * ((op.Hout + STEM_TH - 1) / STEM_TH) * ((op.Wout + STEM_TW - 1) / STEM_TW));
+  if (getenv("YB_STEM_DIRECT")) {  // CUDA-core version (cross-check)
+    const size_t smem = ((size_t)28 * Cp + 2 * 3 * STEM_IH * STEM_HP) * 4;
+    YB_CUDA(launch_pdl(stem_conv_kernel<T>, dim3(blocks), dim3(256), smem, st, (const T*)in, out, w, p->B, p->H, p->W,
+                       op.Hout, op.Wout, Cp, db.C, scale));
+    return YB_OK;
+  }
+  constexpr int EPV = 16 / (int)sizeof(T);
+  constexpr int NVEC = (2 * STEM_TW + 1 + EPV + EPV - 1) / EPV;
+  constexpr int PITCH = NVEC * EPV + 8;
+  const int nt = (Cp / 8) % 3 == 0 ? 3 : ((Cp / 8) % 4 == 0 ? 4 : 2);   // n-tiles per pass
+  const size_t smem = ((size_t)(SPLIT ? 2 : 1) * 3 * STEM_IH * PITCH + (size_t)8 * 16 * nt * 8) * 2;
+#define YB_STEM_MMA(NT)                                                                                         \
+  YB_CUDA(launch_pdl(stem_mma_kernel<T, NT, SPLIT>, dim3(blocks), dim3(256), smem, st, (const T*)in, out, w, p->B, \
+                     p->H, p->W, op.Hout, op.Wout, Cp, db.C, scale))
+  if (nt == 3) YB_STEM_MMA(3);
+  else if (nt == 4) YB_STEM_MMA(4);
+  else YB_STEM_MMA(2);
+#undef YB_STEM_MMA
+  return YB_OK;
+}
+
+int launch_stem(const yb_plan* p, const Op& op, const void* in, int in_dtype, cudaStream_t st) {
+  int rc;
   switch (in_dtype) {
-    case YB_F32:
-      YB_CUDA(launch_pdl(stem_conv_kernel<float>, dim3(blocks), dim3(threads), smem, st, (const float*)in, out, w,
-                         p->B, p->H, p->W, op.Hout, op.Wout, Cp, db.C, 1.f));
-      break;
-    case YB_F16:
-      YB_CUDA(launch_pdl(stem_conv_kernel<__half>, dim3(blocks), dim3(threads), smem, st, (const __half*)in, out, w,
-                         p->B, p->H, p->W, op.Hout, op.Wout, Cp, db.C, 1.f));
-      break;
-    case YB_BF16:
-      YB_CUDA(launch_pdl(stem_conv_kernel<__nv_bfloat16>, dim3(blocks), dim3(threads), smem, st,
-                         (const __nv_bfloat16*)in, out, w, p->B, p->H, p->W, op.Hout, op.Wout, Cp, db.C, 1.f));
-      break;
-    case YB_U8:
-      YB_CUDA(launch_pdl(stem_conv_kernel<uint8_t>, dim3(blocks), dim3(threads), smem, st, (const uint8_t*)in, out, w,
-                         p->B, p->H, p->W, op.Hout, op.Wout, Cp, db.C, 1.f / 255.f));
-      break;
+    case YB_F32: rc = launch_stem_t<float, true>(p, op, in, 1.f, st); break;
+    case YB_F16: rc = launch_stem_t<__half, true>(p, op, in, 1.f, st); break;
+    case YB_BF16: rc = launch_stem_t<__nv_bfloat16, false>(p, op, in, 1.f, st); break;
+    case YB_U8: rc = launch_stem_t<uint8_t, false>(p, op, in, 1.f / 255.f, st); break;
     default:
       set_error("unsupported input dtype %d", in_dtype);
       return YB_ERR_ARG;
   }
+  if (rc) return rc;
   count_launch();
   YB_CUDA(cudaGetLastError());
   return YB_OK;
@@ -474,18 +707,6 @@ static constexpr int ATT_Q = 128;   // queries per CTA (8 warps x 16)
 static constexpr int ATT_KC = 128;  // keys per shared-memory chunk
 static constexpr int ATT_KP = 40;   // K row pitch, bf16 (80 B)
 static constexpr int ATT_VP = 72;   // V row pitch, bf16 (144 B)
-
-__device__ __forceinline__ void mma_bf16_16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
-      "{%0,%1,%2,%3};"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ uint32_t pack2_bf16(float a, float b) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
 
 __global__ void __launch_bounds__(256)
     attention_kernel(const __nv_bfloat16* __restrict__ qkv, int qkv_ld, __nv_bfloat16* __restrict__ out,
