@@ -237,6 +237,8 @@ def test_every_op_teacher_forced(size, hw, patch_min_hw, monkeypatch):
             if op["kind"] == 5:
                 break
             touched = {s["buf"] for s in op["src"]} | {op["dst"]["buf"]} | ({op["res"]["buf"]} if op["has_res"] else set())
+            if op.get("dw_fused"):   # the kernel recomputes the depthwise conv in front of it from that op's input
+                touched |= {s["buf"] for s in desc["ops"][i - 1]["src"]}
             before = {b: rep.buffer_bytes(b) for b in touched if b >= 0}
             rep.step(op, x)
             want = rep.final_slice(op) if op["kind"] != 3 else None
@@ -256,7 +258,7 @@ def test_every_op_teacher_forced(size, hw, patch_min_hw, monkeypatch):
                 err = (got - want).abs().max().item() / scale
                 worst = max(worst, err)
                 if err > 0.01:
-                    report.append(f"{op['name']} impl={impl} k{op['k']} s{op['stride']} tma{op['a_tma']} patch{op.get('patch', 0)} "
+                    report.append(f"{op['name']} impl={impl} k{op['k']} s{op['stride']} tma{op['a_tma']} patch{op.get('patch', 0)} dwf{op.get('dw_fused', 0)} "
                                   f"K{op['K_pad']} N{op['N_pad']}/BN{op['BN']}: max err {err:.4f} of max |x|")
             eng.set_conv_impl(0)
     print(f"{size}@{hw} patch_min_hw={patch_min_hw}: worst per-op error {worst:.5f} of the layer's max |activation|")

@@ -44,7 +44,7 @@ static constexpr int MAX_PATCH_STAGES = 4;
 static constexpr int NUM_BARS = 3 * MAX_STAGES + 4 + 2 * MAX_PATCH_STAGES;
 static constexpr int PT_H = 16, PT_W = 8;          // PATCH mode output tile (pixels)
 static constexpr int PP_H = PT_H + 2, PP_W = PT_W + 2;  // its input halo patch
-enum { MODE_GATHER = 0, MODE_ATMA = 1, MODE_PATCH = 2 };
+enum { MODE_GATHER = 0, MODE_ATMA = 1, MODE_PATCH = 2, MODE_DW = 3 };
 
 struct ConvParams {
   const __nv_bfloat16* src[4];
@@ -83,6 +83,13 @@ struct ConvParams {
   int b_slots;          // weight slots in shared memory (num_kb when resident, else stages)
   int c_bufs;           // output staging buffers (2: the epilogue never waits for the previous tile's TMA store)
   int alt_epilogue;     // the two epilogue warp groups take alternate tiles (when the kernel has two)
+  // MODE_DW: a depthwise 3x3 (+bias, SiLU) fused in front of this 1x1 conv.  Its input comes in as
+  // TMA halo patches (unswizzled), warps 4-7 compute the depthwise output of the tile straight into
+  // the swizzled A stage; the intermediate tensor never exists in global memory.
+  int dw;
+  const float* dw_w;    // [9][dw_cp] fp32 taps + [dw_cp] bias
+  int dw_C, dw_cp, dw_act;
+  int dw_patch_bytes;   // shared memory of the patch ring (the A ring follows it)
   // fused head decode (out_mode 2 / 3): dst is the (B, 4+nc, A) fp32 output tensor
   int out_mode;       // 0 bf16 slice, 1 fp32 logits, 2 DFL box decode, 3 class sigmoid
   int A_total, nc;
@@ -308,10 +315,12 @@ __global__ void __launch_bounds__(NUM_THREADS, MODE == MODE_PATCH ? 3 : 2)
                              const __grid_constant__ CUtensorMap tmap_a2,
                              const __grid_constant__ CUtensorMap tmap_a3,
                              const __grid_constant__ CUtensorMap tmap_c) {
-  constexpr bool A_TMA = MODE != MODE_GATHER;       // no im2col producer warps: they join the epilogue
+  constexpr bool DW = MODE == MODE_DW;
+  constexpr bool A_TMA = MODE == MODE_ATMA || MODE == MODE_PATCH;   // no producer warps: they join the epilogue
   constexpr bool PATCH = MODE == MODE_PATCH;
-  constexpr int TW = PATCH ? PT_W : 16;            // 2-D tile width (rows of the tile: r = ly * TW + lx)
-  constexpr int TWS = PATCH ? 3 : 4;
+  constexpr bool PGEO = PATCH || DW;               // 16 x 8 pixel tiles
+  constexpr int TW = PGEO ? PT_W : 16;             // 2-D tile width (rows of the tile: r = ly * TW + lx)
+  constexpr int TWS = PGEO ? 3 : 4;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024 B alignment
@@ -328,6 +337,7 @@ __global__ void __launch_bounds__(NUM_THREADS, MODE == MODE_PATCH ? 3 : 2)
   uint8_t* tail = smem + (size_t)P.a_region_bytes + (size_t)P.b_slots * b_stage_bytes +
                   (size_t)c_groups * C_GROUP_BYTES * (size_t)P.c_bufs;
   const bool RES = P.b_resident != 0;
+  const uint32_t ring_base = a_base + (DW ? (uint32_t)P.dw_patch_bytes : 0u);   // A stage ring
   // Two epilogue warp groups exist when no im2col producers are needed.  With one N tile and two
   // staging buffers they take alternate tiles (group g drains TMEM stage g into staging buffer g, its
   // own named barrier and TMA stores), so two epilogue chains are in flight; otherwise they split
@@ -354,13 +364,14 @@ __global__ void __launch_bounds__(NUM_THREADS, MODE == MODE_PATCH ? 3 : 2)
 
   if (tid == 0) {
     for (int s = 0; s < S; s++) {
-      mbar_init(full_bar(s), MODE == MODE_GATHER ? 2u : 1u);   // TMA expect_tx (+ the relay warp on im2col layers)
+      // TMA expect_tx (+ the relay warp on im2col layers, + the 128 depthwise threads in MODE_DW)
+      mbar_init(full_bar(s), MODE == MODE_GATHER ? 2u : DW ? 129u : 1u);
       mbar_init(empty_bar(s), 1u);
       mbar_init(gathered_bar(s), 128u);            // one cp.async-completion arrive per im2col thread
     }
     for (int s = 0; s < MAX_PATCH_STAGES; s++) {
       mbar_init(patch_full_bar(s), 1u);
-      mbar_init(patch_empty_bar(s), 1u);
+      mbar_init(patch_empty_bar(s), DW ? 128u : 1u);
     }
     for (int a = 0; a < 2; a++) {
       mbar_init(tmem_full_bar(a), 1u);
@@ -438,7 +449,7 @@ __global__ void __launch_bounds__(NUM_THREADS, MODE == MODE_PATCH ? 3 : 2)
         const int oy = tp.oy0 + (etid >> TWS), ox = tp.ox0 + (etid & (TW - 1));
         r = oy * P.Wout + ox;
         m = n_img * P.hw_out + r;
-        row_ok = !PATCH || (oy < P.Hout && ox < P.Wout);   // PATCH tiles may hang over the image edge
+        row_ok = !PGEO || (oy < P.Hout && ox < P.Wout);   // 16 x 8 tiles may hang over the image edge
       } else if (row_ok) {
         n_img = fast_div(m, P.hw_mul, P.hw_shr, P.hw_out);
         r = m - n_img * P.hw_out;
@@ -589,6 +600,92 @@ __global__ void __launch_bounds__(NUM_THREADS, MODE == MODE_PATCH ? 3 : 2)
     }
     if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   } else if (warp < MMA_WARP) {
+    if (DW) {
+      // ============================ depthwise producer =======================================
+      // thread = 2 channels (cpair) x 4 pixel columns (xh) x 8 tile rows (rg).  Patch rows stream
+      // through registers once; a row feeds the three output rows it overlaps (ky = 0, 1, 2), whose
+      // accumulators rotate through three slots.  Lanes of a warp are consecutive channel pairs, so
+      // every shared-memory access of a warp is one 128-byte row.
+      const int ptid = tid - PROD_WARP0 * 32;
+      const int cpair = ptid & 31, q = ptid >> 5, xh = q & 1, rg = q >> 1;
+      const int CW = P.ncb * 64;
+      float* dww = bias_s + 256;   // [10][CW]: 9 taps + bias, zero beyond the real channels
+      for (int i = ptid; i < 10 * CW; i += 128) {
+        const int tap = i / CW, c = i - tap * CW;
+        dww[i] = c < P.dw_C ? __ldg(P.dw_w + tap * P.dw_cp + c) : 0.f;
+      }
+      asm volatile("bar.sync 3, 128;" ::: "memory");
+      int stage = 0, pstage = 0;
+      uint32_t phase = 0, pphase = 0;
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+        for (int cb = 0; cb < P.ncb; cb++) {
+          float2 w[9];
+#pragma unroll
+          for (int t9 = 0; t9 < 9; t9++) w[t9] = *reinterpret_cast<const float2*>(dww + t9 * CW + cb * 64 + 2 * cpair);
+          const float2 bias2 = *reinterpret_cast<const float2*>(dww + 9 * CW + cb * 64 + 2 * cpair);
+          mbar_wait(patch_full_bar(pstage), pphase);
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t pbase = a_base + (uint32_t)pstage * (uint32_t)P.patch_stage_bytes +
+                                 (uint32_t)((8 * rg) * PP_W + 4 * xh) * 128u + (uint32_t)cpair * 4u;
+          const uint32_t sbase = ring_base + (uint32_t)stage * A_STAGE_BYTES + (uint32_t)(cpair & 3) * 4u;
+          float2 acc[3][4];
+#pragma unroll
+          for (int pr = 0; pr < 10; pr++) {
+            float2 f[6];
+#pragma unroll
+            for (int i = 0; i < 6; i++) {
+              uint32_t v;
+              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(pbase + (uint32_t)(pr * PP_W + i) * 128u));
+              f[i] = make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xFFFF0000u));
+            }
+#pragma unroll
+            for (int ky = 0; ky < 3; ky++) {
+              const int r = pr - ky;          // output row (0..7 of this thread's group) fed through tap row ky
+              if (r < 0 || r >= 8) continue;
+              const int slot = r % 3;
+#pragma unroll
+              for (int px = 0; px < 4; px++) {
+                if (ky == 0) acc[slot][px] = bias2;
+#pragma unroll
+                for (int kx = 0; kx < 3; kx++) {
+                  // packed fp32 FMA on the channel pair
+                  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&f[px + kx]);
+                  unsigned long long rb = *reinterpret_cast<unsigned long long*>(&w[ky * 3 + kx]);
+                  unsigned long long rc = *reinterpret_cast<unsigned long long*>(&acc[slot][px]), rd;
+                  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+                  acc[slot][px] = *reinterpret_cast<float2*>(&rd);
+                }
+              }
+              if (ky == 2) {   // row r complete: activation, bf16, swizzled K-major A stage
+#pragma unroll
+                for (int px = 0; px < 4; px++) {
+                  float2 o = acc[slot][px];
+                  if (P.dw_act) {
+                    o.x = silu_f(o.x);
+                    o.y = silu_f(o.y);
+                  }
+                  const uint32_t m = (uint32_t)((8 * rg + r) * PT_W + 4 * xh + px);
+                  const uint32_t addr = sbase + m * 128u + ((((uint32_t)cpair >> 2) ^ (m & 7u)) << 4);
+                  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(pack_bf16(o.x, o.y)) : "memory");
+                }
+              }
+            }
+          }
+          // generic-proxy writes -> visible to the tensor core's async-proxy reads
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbar_arrive(full_bar(stage));
+          mbar_arrive(patch_empty_bar(pstage));
+          if (++stage == S) {
+            stage = 0;
+            phase ^= 1u;
+          }
+          if (++pstage == P.patch_stages) {
+            pstage = 0;
+            pphase ^= 1u;
+          }
+        }
+      }
+    } else
     // ============================ im2col producer ==========================================
     {
       const int ptid = tid - PROD_WARP0 * 32;
@@ -862,7 +959,7 @@ __global__ void __launch_bounds__(NUM_THREADS, MODE == MODE_PATCH ? 3 : 2)
         mbar_wait(full_bar(stage), phase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         {
-          const uint64_t da = desc_hi | (uint64_t)(((a_base + (uint32_t)stage * A_STAGE_BYTES) >> 4) & 0x3FFF);
+          const uint64_t da = desc_hi | (uint64_t)(((ring_base + (uint32_t)stage * A_STAGE_BYTES) >> 4) & 0x3FFF);
           const uint64_t db = desc_hi | (uint64_t)(((b_base + (uint32_t)(RES ? kb : stage) * b_stage_bytes) >> 4) & 0x3FFF);
 #pragma unroll
           for (int k = 0; k < BK / 16; k++)  // +32 bytes (2 x 16 B units) per K=16 step inside the swizzle atom
@@ -882,7 +979,7 @@ __global__ void __launch_bounds__(NUM_THREADS, MODE == MODE_PATCH ? 3 : 2)
     // im2col data is written by cp.async (generic proxy) but read by the tensor core through the
     // async proxy.  This thread acquires a gathered stage, issues the proxy fence and forwards the
     // arrival to the MMA warp, keeping the (expensive) fence off the MMA issue path.
-    if (PATCH && lane == 0) {
+    if (PGEO && lane == 0) {
       // ---- halo-patch producer: one 4-D TMA box {cblk, 10, 18, 1} per (tile, channel block);
       // coordinates start one pixel above / left of the tile, out-of-image pixels are zero-filled
       // by the TMA unit (= the convolution's padding)
@@ -1061,7 +1158,8 @@ static int make_tmap_2d(CUtensorMap* map, const void* base, uint64_t inner, uint
 // 4-D map over an NHWC slice {C, W, H, N} with an 8 (y) x 16 (x) x 64-channel box: smem rows come
 // out as r = ly * 16 + lx, 128 bytes each, SWIZZLE_128B — the same image as a 128-row 2-D box.
 static int make_tmap_nhwc(CUtensorMap* map, const void* base, uint64_t C, uint64_t W, uint64_t H, uint64_t N,
-                          uint64_t ld_elems, uint32_t box_c = 64, uint32_t box_w = 16, uint32_t box_h = 8) {
+                          uint64_t ld_elems, uint32_t box_c = 64, uint32_t box_w = 16, uint32_t box_h = 8,
+                          bool no_swizzle = false) {
   PFN_encodeTiled enc = get_encode();
   if (!enc) {
     set_error("cuTensorMapEncodeTiled driver entry point not available");
@@ -1072,7 +1170,7 @@ static int make_tmap_nhwc(CUtensorMap* map, const void* base, uint64_t C, uint64
   cuuint32_t box[4] = {box_c, box_w, box_h, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
   // rows of box_c channels: the swizzle span equals the row size (16-byte rows are not swizzled)
-  const CUtensorMapSwizzle sw = box_c >= 64 ? CU_TENSOR_MAP_SWIZZLE_128B
+  const CUtensorMapSwizzle sw = no_swizzle ? CU_TENSOR_MAP_SWIZZLE_NONE : box_c >= 64 ? CU_TENSOR_MAP_SWIZZLE_128B
                                 : box_c == 32 ? CU_TENSOR_MAP_SWIZZLE_64B
                                 : box_c == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
@@ -1135,6 +1233,16 @@ int conv_tc_prepare(yb_plan* p, Op& op) {
   // shared-memory plan: (occupancy, resident weights, staging buffers, minimum A stages) -> stages
   auto plan_smem = [&](int occ_try, bool resident, int cb, int min_st, int& st_out, int& pst_out) -> bool {
     const size_t bud = SMEM_MAX / occ_try;
+    if (op.dw_fused) {
+      // patch ring (2 stages) + depthwise weights sit next to the usual A ring
+      op.patch_stage_bytes = round_up(PP_H * PP_W * 128, 1024);
+      for (int pst = 3; pst >= 2; pst--) {
+        const size_t extra = (size_t)pst * op.patch_stage_bytes + (size_t)10 * num_kb * 64 * 4;
+        for (int st = std::min(MAX_STAGES, 4); st >= std::min(min_st, 3); st--)
+          if (conv_smem_bytes(st, op.BN, 0, resident ? num_kb : 0, cb) + extra <= bud) { st_out = st; pst_out = pst; return true; }
+      }
+      return false;
+    }
     if (op.patch) {
       const int C = op.src[0].C, cblk = std::min(C, 64);
       op.patch_stage_bytes = round_up(PP_H * PP_W * cblk * 2 + 16, 1024);
@@ -1163,13 +1271,31 @@ int conv_tc_prepare(yb_plan* p, Op& op) {
   for (const Try& t : tries) {
     if (t.res && !res_ok) continue;
     if (t.cb == 2 && !cb2_ok) continue;
-    if (t.occ != occ && !(op.patch && occ > 1 && w_bytes >= 24 * 1024 && getenv("YB_NO_RESIDENT_OCC1") == nullptr)) continue;
+    if (t.occ != occ && !op.dw_fused &&
+        !(op.patch && occ > 1 && w_bytes >= 24 * 1024 && getenv("YB_NO_RESIDENT_OCC1") == nullptr))
+      continue;
     if (plan_smem(t.occ, t.res, t.cb, t.min_st, st, pst)) {
       op.b_resident = t.res ? 1 : 0;
       cb = t.cb;
       occ = t.occ;
       found = true;
       break;
+    }
+  }
+  if (!found && op.dw_fused) {   // last resort for the fused depthwise path: one CTA per SM
+    for (int cbt = 2; cbt >= 1 && !found; cbt--)
+      for (int res = 1; res >= 0 && !found; res--) {
+        if ((res && !res_ok) || (cbt == 2 && !cb2_ok)) continue;
+        if (plan_smem(1, res != 0, cbt, 3, st, pst)) {
+          op.b_resident = res;
+          cb = cbt;
+          occ = 1;
+          found = true;
+        }
+      }
+    if (!found) {
+      set_error("conv %s: fused depthwise tile does not fit shared memory", op.name.c_str());
+      return YB_ERR_UNSUPPORTED;
     }
   }
   if (!found && op.patch) {  // patches + streamed weights do not fit: fall back to the gather path
@@ -1182,7 +1308,9 @@ int conv_tc_prepare(yb_plan* p, Op& op) {
   op.stages = st;
   op.patch_stages = pst;
   const size_t a_region = op.patch ? (size_t)pst * op.patch_stage_bytes : 0;
-  op.smem_bytes = std::max(conv_smem_bytes(st, op.BN, a_region, op.b_resident ? num_kb : 0, cb), SMEM_MAX / (occ + 1) + 1024);
+  const size_t dw_extra = op.dw_fused ? (size_t)pst * op.patch_stage_bytes + (size_t)10 * num_kb * 64 * 4 : 0;
+  op.smem_bytes = std::max(conv_smem_bytes(st, op.BN, a_region, op.b_resident ? num_kb : 0, cb) + dw_extra,
+                           SMEM_MAX / (occ + 1) + 1024);
   if (op.smem_bytes > SMEM_MAX) {
     set_error("conv %s: tile needs %zu bytes of shared memory", op.name.c_str(), op.smem_bytes);
     return YB_ERR_UNSUPPORTED;
@@ -1193,7 +1321,16 @@ int conv_tc_prepare(yb_plan* p, Op& op) {
   if (rc) return rc;
   for (int i = 0; i < 4; i++) op.tmap_a[i] = op.tmap_b;
   op.tile2d = (op.Hout % 8 == 0 && op.Wout % 16 == 0 && !op.out_f32 && getenv("YB_NO_TILE2D") == nullptr) ? 1 : 0;
-  if (op.patch) {
+  if (op.dw_fused) {
+    // the A operand is computed in-kernel from halo patches of the depthwise conv's own input
+    const Op& dwop = p->ops[op.dw_op];
+    op.tile2d = 1;
+    const Buf& b = p->bufs[dwop.src[0].buf];
+    const uint8_t* base = buf_ptr(p, dwop.src[0].buf) + (size_t)dwop.src[0].c_off * 2;
+    rc = make_tmap_nhwc(&op.tmap_a[0], base, (uint64_t)dwop.src[0].C, (uint64_t)b.W, (uint64_t)b.H, (uint64_t)p->B,
+                        (uint64_t)b.C, 64, PP_W, PP_H, true);
+    if (rc) return rc;
+  } else if (op.patch) {
     op.tile2d = 1;
     const Buf& b = p->bufs[op.src[0].buf];
     const uint8_t* base = buf_ptr(p, op.src[0].buf) + (size_t)op.src[0].c_off * 2;
@@ -1201,7 +1338,7 @@ int conv_tc_prepare(yb_plan* p, Op& op) {
                         (uint64_t)b.C, (uint32_t)std::min(op.src[0].C, 64), PP_W, PP_H);
     if (rc) return rc;
   }
-  if (op.a_tma) {
+  if (op.a_tma && !op.dw_fused) {
     for (int i = 0; i < op.nseg; i++) {
       const Buf& b = p->bufs[op.src[i].buf];
       const uint8_t* base = buf_ptr(p, op.src[i].buf) + (size_t)op.src[i].c_off * 2;
@@ -1218,7 +1355,7 @@ int conv_tc_prepare(yb_plan* p, Op& op) {
   if (!op.out_f32) {
     const Buf& db = p->bufs[op.dst.buf];
     const uint8_t* dbase = buf_ptr(p, op.dst.buf) + (size_t)op.dst.c_off * 2;
-    if (op.patch)
+    if (op.patch || op.dw_fused)
       rc = make_tmap_nhwc(&op.tmap_c, dbase, (uint64_t)cpad8(op.dst.C), (uint64_t)db.W, (uint64_t)db.H,
                           (uint64_t)p->B, (uint64_t)db.C, 64, PT_W, PT_H);
     else if (op.tile2d)
@@ -1239,6 +1376,7 @@ int conv_tc_prepare(yb_plan* p, Op& op) {
     YB_CUDA(cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<MODE_GATHER, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
     YB_CUDA(cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<MODE_GATHER, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
     YB_CUDA(cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<MODE_PATCH, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+    YB_CUDA(cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<MODE_DW, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
     attr_set = true;
   }
   return YB_OK;
@@ -1333,6 +1471,25 @@ static void fill_params(const yb_plan* p, const Op& op, ConvParams& P) {
     P.total_tiles = p->B * P.tiles_per_img * P.n_tiles;
     magic(P.tiles_per_img, P.tpi_mul, P.tpi_shr);
     magic(P.tiles_x, P.tx_mul, P.tx_shr);
+  } else if (op.dw_fused) {
+    const Op& dwop = p->ops[op.dw_op];
+    const ConvW& dcw = p->convs[dwop.conv_index];
+    P.dw = 1;
+    P.dw_w = reinterpret_cast<const float*>(p->d_weights + dcw.info.blob_offset);
+    P.dw_C = dwop.dst.C;
+    P.dw_cp = cpad8(dwop.dst.C);
+    P.dw_act = dwop.act;
+    P.ncb = P.num_kb;
+    P.patch_tx_bytes = PP_H * PP_W * 128;
+    P.patch_stage_bytes = op.patch_stage_bytes;
+    P.patch_stages = op.patch_stages;
+    P.dw_patch_bytes = op.patch_stages * op.patch_stage_bytes;
+    P.a_region_bytes = P.dw_patch_bytes + op.stages * A_STAGE_BYTES;
+    P.tiles_x = (op.Wout + PT_W - 1) / PT_W;
+    P.tiles_per_img = P.tiles_x * ((op.Hout + PT_H - 1) / PT_H);
+    P.total_tiles = p->B * P.tiles_per_img * P.n_tiles;
+    magic(P.tiles_per_img, P.tpi_mul, P.tpi_shr);
+    magic(P.tiles_x, P.tx_mul, P.tx_shr);
   } else if (op.tile2d) {
     P.tiles_x = op.Wout / 16;
     P.tiles_per_img = P.tiles_x * (op.Hout / 8);
@@ -1363,6 +1520,8 @@ int launch_conv_tc(const yb_plan* p, const Op& op, cudaStream_t st, float* fused
   if (head) {
     if (P.a_tma) YB_LAUNCH(MODE_ATMA, false, true);
     else YB_LAUNCH(MODE_GATHER, false, true);
+  } else if (P.dw) {
+    YB_LAUNCH(MODE_DW, true, false);
   } else if (P.patch) {
     YB_LAUNCH(MODE_PATCH, true, false);
   } else if (P.a_tma) {

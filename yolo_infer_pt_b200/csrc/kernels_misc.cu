@@ -1,6 +1,7 @@
 // Memory-bound kernels of the YOLOv11 forward: stem conv, depthwise 3x3, SPPF pooling, the C2PSA
 // attention core and the DFL box decode.  All activations are NHWC bf16; arithmetic is fp32.
 #include <math.h>
+#include <algorithm>
 #include <stdio.h>
 #include <string.h>
 
@@ -499,22 +500,22 @@ int launch_stem(const yb_plan* p, const Op& op, const void* in, int in_dtype, cu
 // ---------------------------------------------------------------------------------------------
 static constexpr int DW_PX = 4;  // output pixels along x per thread: 18 tap loads for 4 outputs
 
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
     dwconv3x3_kernel(const __nv_bfloat16* __restrict__ src, int src_ld, __nv_bfloat16* dst, int dst_ld,
                      const float* __restrict__ wgt, int Cp, int B, int H, int W, int C, int gsz,
                      int gstride, int goff, int act, int add) {
   pdl_prologue_done();
   pdl_wait();
-  long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  // grid = (ceil(xq * cgs / 256), H, B): one 32-bit division per thread instead of 64-bit index math
   const int cgs = C >> 3;
   const int xq = (W + DW_PX - 1) / DW_PX;
-  long long total = (long long)B * H * xq * cgs;
-  if (idx >= total) return;
-  const int cg = (int)(idx % cgs);
-  long long t = idx / cgs;
-  const int x0 = (int)(t % xq) * DW_PX;
-  const int y = (int)((t / xq) % H);
-  const int b = (int)(t / ((long long)xq * H));
+  const int tix = (int)(blockIdx.x * blockDim.x + threadIdx.x);
+  if (tix >= xq * cgs) return;
+  const int xqi = tix / cgs;
+  const int cg = tix - xqi * cgs;
+  const int x0 = xqi * DW_PX;
+  const int y = (int)blockIdx.y;
+  const int b = (int)blockIdx.z;
   const int c = cg * 8;
   const int sc = (c / gsz) * gstride + goff + (c % gsz);
   float2 acc[DW_PX][4];
@@ -597,10 +598,11 @@ int launch_dw(const yb_plan* p, const Op& op, cudaStream_t st) {
       reinterpret_cast<const __nv_bfloat16*>(buf_ptr(p, op.src[0].buf)) + op.src[0].c_off;
   __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(buf_ptr(p, op.dst.buf)) + op.dst.c_off;
   int C = op.dst.C;
-  long long total = (long long)p->B * op.Hout * ((op.Wout + DW_PX - 1) / DW_PX) * (C >> 3);
-  int threads = 256;
-  unsigned blocks = (unsigned)((total + threads - 1) / threads);
-  YB_CUDA(launch_pdl(dwconv3x3_kernel, dim3(blocks), dim3(threads), 0, st, src, sb.C, dst, db.C, w, cpad8(C), p->B,
+  const int per_row = ((op.Wout + DW_PX - 1) / DW_PX) * (C >> 3);
+  int threads = std::min(256, round_up(per_row, 32));
+  if (per_row > 256) threads = round_up((per_row + (per_row + 255) / 256 - 1) / ((per_row + 255) / 256), 32);
+  dim3 blocks((unsigned)((per_row + threads - 1) / threads), (unsigned)op.Hout, (unsigned)p->B);
+  YB_CUDA(launch_pdl(dwconv3x3_kernel, blocks, dim3(threads), 0, st, src, sb.C, dst, db.C, w, cpad8(C), p->B,
                      op.Hout, op.Wout, C, op.dw_gsz, op.dw_gstride, op.dw_goff, op.act, op.dw_add));
   count_launch();
   YB_CUDA(cudaGetLastError());

@@ -413,6 +413,23 @@ int build_plan(yb_plan* p) {
     p->ops.push_back(op);
   }
 
+  // ---- depthwise 3x3 -> 1x1 fusion (head cls branches, nn.py:248-251): the depthwise output is
+  // produced tile by tile inside the 1x1 conv's kernel when that conv is its only consumer.
+  if (!getenv("YB_NO_DWFUSE")) {
+    for (size_t i = 0; i + 1 < p->ops.size(); i++) {
+      Op& d = p->ops[i];
+      Op& c = p->ops[i + 1];
+      if (d.kind != OP_DW || c.kind != OP_CONV) continue;
+      if (d.dw_add || d.dw_goff || d.dw_gsz != d.dst.C || d.src[0].up) continue;
+      if (c.k != 1 || c.stride != 1 || c.nseg != 1 || !c.a_tma || c.out_f32 || c.has_res) continue;
+      if (c.src[0].buf != d.dst.buf || c.src[0].c_off != d.dst.c_off || c.src[0].C != d.dst.C) continue;
+      if (p->bufs[d.dst.buf].last_use != (int)i + 1) continue;
+      if (c.N_pad != c.BN || c.K_pad / 64 > 4 || c.Hout < 20) continue;
+      c.dw_fused = 1;
+      c.dw_op = (int)i;
+      d.fused_away = 1;
+    }
+  }
   if (getenv("YB_NO_FUSE_DECODE")) p->fuse_decode = 0;
   // ---- weight blob layout ----
   size_t off = 0;

@@ -106,6 +106,9 @@ struct Op {
   int patch_stage_bytes = 0, patch_stages = 0;
   int b_resident = 0;      // weight matrix stays in shared memory across the CTA's tiles
   int c_bufs = 1;          // output staging buffers
+  int dw_fused = 0;        // OP_CONV: the depthwise conv `dw_op` in front of this 1x1 is computed by its producer warps
+  int dw_op = -1;
+  int fused_away = 0;      // OP_DW: computed inside the consumer's kernel, not launched in a forward
   int occ = 1;             // resident CTAs per SM of the persistent GEMM kernel
   int head_part = 0;       // 1: box tail (fusable DFL decode), 2: cls tail (fusable sigmoid)
   size_t smem_bytes = 0;
