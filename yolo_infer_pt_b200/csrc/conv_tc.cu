@@ -302,13 +302,16 @@ static constexpr int PROD_WARP0 = 4;     // warps 4-7
 static constexpr int MMA_WARP = 8;
 static constexpr int TMA_WARP = 9;
 static constexpr int RELAY_WARP = 10;    // proxy-fence relay between the im2col warps and the MMA warp
+static constexpr int DW_WARP0 = 11;      // MODE_DW: warps 11-18 compute the depthwise conv (both epilogue groups stay)
+static constexpr int DW_THREADS = 256;
+static constexpr int NUM_THREADS_DW = (DW_WARP0 + DW_THREADS / 32) * 32;
 
 // Specialised at compile time on the A-operand path (TMA tiles vs im2col gather), the tile shape
 // (8x16 spatial patch vs 128 flattened rows) and the epilogue family (bf16 slice vs head modes):
 // every instantiation carries only the code of its own roles, which keeps it inside the
 // instruction cache (11 warps run disjoint code).
 template <int MODE, bool T2D, bool HEAD>
-__global__ void __launch_bounds__(NUM_THREADS, MODE == MODE_PATCH ? 3 : 2)
+__global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS, MODE == MODE_PATCH ? 3 : MODE == MODE_DW ? 1 : 2)
     conv_gemm_tcgen05_kernel(const ConvParams P, const __grid_constant__ CUtensorMap tmap_b,
                              const __grid_constant__ CUtensorMap tmap_a0,
                              const __grid_constant__ CUtensorMap tmap_a1,
@@ -316,7 +319,7 @@ __global__ void __launch_bounds__(NUM_THREADS, MODE == MODE_PATCH ? 3 : 2)
                              const __grid_constant__ CUtensorMap tmap_a3,
                              const __grid_constant__ CUtensorMap tmap_c) {
   constexpr bool DW = MODE == MODE_DW;
-  constexpr bool A_TMA = MODE == MODE_ATMA || MODE == MODE_PATCH;   // no producer warps: they join the epilogue
+  constexpr bool A_TMA = MODE != MODE_GATHER;   // warps 4-7 are not im2col producers: they join the epilogue
   constexpr bool PATCH = MODE == MODE_PATCH;
   constexpr bool PGEO = PATCH || DW;               // 16 x 8 pixel tiles
   constexpr int TW = PGEO ? PT_W : 16;             // 2-D tile width (rows of the tile: r = ly * TW + lx)
@@ -365,13 +368,13 @@ __global__ void __launch_bounds__(NUM_THREADS, MODE == MODE_PATCH ? 3 : 2)
   if (tid == 0) {
     for (int s = 0; s < S; s++) {
       // TMA expect_tx (+ the relay warp on im2col layers, + the 128 depthwise threads in MODE_DW)
-      mbar_init(full_bar(s), MODE == MODE_GATHER ? 2u : DW ? 129u : 1u);
+      mbar_init(full_bar(s), MODE == MODE_GATHER ? 2u : DW ? (uint32_t)DW_THREADS + 1u : 1u);
       mbar_init(empty_bar(s), 1u);
       mbar_init(gathered_bar(s), 128u);            // one cp.async-completion arrive per im2col thread
     }
     for (int s = 0; s < MAX_PATCH_STAGES; s++) {
       mbar_init(patch_full_bar(s), 1u);
-      mbar_init(patch_empty_bar(s), DW ? 128u : 1u);
+      mbar_init(patch_empty_bar(s), DW ? (uint32_t)DW_THREADS : 1u);
     }
     for (int a = 0; a < 2; a++) {
       mbar_init(tmem_full_bar(a), 1u);
@@ -600,92 +603,6 @@ __global__ void __launch_bounds__(NUM_THREADS, MODE == MODE_PATCH ? 3 : 2)
     }
     if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   } else if (warp < MMA_WARP) {
-    if (DW) {
-      // ============================ depthwise producer =======================================
-      // thread = 2 channels (cpair) x 4 pixel columns (xh) x 8 tile rows (rg).  Patch rows stream
-      // through registers once; a row feeds the three output rows it overlaps (ky = 0, 1, 2), whose
-      // accumulators rotate through three slots.  Lanes of a warp are consecutive channel pairs, so
-      // every shared-memory access of a warp is one 128-byte row.
-      const int ptid = tid - PROD_WARP0 * 32;
-      const int cpair = ptid & 31, q = ptid >> 5, xh = q & 1, rg = q >> 1;
-      const int CW = P.ncb * 64;
-      float* dww = bias_s + 256;   // [10][CW]: 9 taps + bias, zero beyond the real channels
-      for (int i = ptid; i < 10 * CW; i += 128) {
-        const int tap = i / CW, c = i - tap * CW;
-        dww[i] = c < P.dw_C ? __ldg(P.dw_w + tap * P.dw_cp + c) : 0.f;
-      }
-      asm volatile("bar.sync 3, 128;" ::: "memory");
-      int stage = 0, pstage = 0;
-      uint32_t phase = 0, pphase = 0;
-      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-        for (int cb = 0; cb < P.ncb; cb++) {
-          float2 w[9];
-#pragma unroll
-          for (int t9 = 0; t9 < 9; t9++) w[t9] = *reinterpret_cast<const float2*>(dww + t9 * CW + cb * 64 + 2 * cpair);
-          const float2 bias2 = *reinterpret_cast<const float2*>(dww + 9 * CW + cb * 64 + 2 * cpair);
-          mbar_wait(patch_full_bar(pstage), pphase);
-          mbar_wait(empty_bar(stage), phase ^ 1u);
-          const uint32_t pbase = a_base + (uint32_t)pstage * (uint32_t)P.patch_stage_bytes +
-                                 (uint32_t)((8 * rg) * PP_W + 4 * xh) * 128u + (uint32_t)cpair * 4u;
-          const uint32_t sbase = ring_base + (uint32_t)stage * A_STAGE_BYTES + (uint32_t)(cpair & 3) * 4u;
-          float2 acc[3][4];
-#pragma unroll
-          for (int pr = 0; pr < 10; pr++) {
-            float2 f[6];
-#pragma unroll
-            for (int i = 0; i < 6; i++) {
-              uint32_t v;
-              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(pbase + (uint32_t)(pr * PP_W + i) * 128u));
-              f[i] = make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xFFFF0000u));
-            }
-#pragma unroll
-            for (int ky = 0; ky < 3; ky++) {
-              const int r = pr - ky;          // output row (0..7 of this thread's group) fed through tap row ky
-              if (r < 0 || r >= 8) continue;
-              const int slot = r % 3;
-#pragma unroll
-              for (int px = 0; px < 4; px++) {
-                if (ky == 0) acc[slot][px] = bias2;
-#pragma unroll
-                for (int kx = 0; kx < 3; kx++) {
-                  // packed fp32 FMA on the channel pair
-                  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&f[px + kx]);
-                  unsigned long long rb = *reinterpret_cast<unsigned long long*>(&w[ky * 3 + kx]);
-                  unsigned long long rc = *reinterpret_cast<unsigned long long*>(&acc[slot][px]), rd;
-                  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
-                  acc[slot][px] = *reinterpret_cast<float2*>(&rd);
-                }
-              }
-              if (ky == 2) {   // row r complete: activation, bf16, swizzled K-major A stage
-#pragma unroll
-                for (int px = 0; px < 4; px++) {
-                  float2 o = acc[slot][px];
-                  if (P.dw_act) {
-                    o.x = silu_f(o.x);
-                    o.y = silu_f(o.y);
-                  }
-                  const uint32_t m = (uint32_t)((8 * rg + r) * PT_W + 4 * xh + px);
-                  const uint32_t addr = sbase + m * 128u + ((((uint32_t)cpair >> 2) ^ (m & 7u)) << 4);
-                  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(pack_bf16(o.x, o.y)) : "memory");
-                }
-              }
-            }
-          }
-          // generic-proxy writes -> visible to the tensor core's async-proxy reads
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          mbar_arrive(full_bar(stage));
-          mbar_arrive(patch_empty_bar(pstage));
-          if (++stage == S) {
-            stage = 0;
-            phase ^= 1u;
-          }
-          if (++pstage == P.patch_stages) {
-            pstage = 0;
-            pphase ^= 1u;
-          }
-        }
-      }
-    } else
     // ============================ im2col producer ==========================================
     {
       const int ptid = tid - PROD_WARP0 * 32;
@@ -974,6 +891,92 @@ __global__ void __launch_bounds__(NUM_THREADS, MODE == MODE_PATCH ? 3 : 2)
       }
     }
     }
+  } else if (DW && warp >= DW_WARP0) {
+      // ============================ depthwise producer =======================================
+      // thread = 2 channels (cpair) x 4 pixel columns (xh) x 4 tile rows (rq).  Patch rows stream
+      // through registers once; a row feeds the three output rows it overlaps (ky = 0, 1, 2), whose
+      // accumulators rotate through three slots.  Lanes of a warp are consecutive channel pairs, so
+      // every shared-memory access of a warp is one 128-byte row.
+      const int ptid = tid - DW_WARP0 * 32;
+      const int cpair = ptid & 31, q = ptid >> 5, xh = q & 1, rq = q >> 1;
+      constexpr int RPT = PT_H / (DW_THREADS / 64);   // tile rows per thread: 64 threads (32 pairs x 2 halves) per row group
+      const int CW = P.ncb * 64;
+      float* dww = bias_s + 256;   // [10][CW]: 9 taps + bias, zero beyond the real channels
+      for (int i = ptid; i < 10 * CW; i += DW_THREADS) {
+        const int tap = i / CW, c = i - tap * CW;
+        dww[i] = c < P.dw_C ? __ldg(P.dw_w + tap * P.dw_cp + c) : 0.f;
+      }
+      asm volatile("bar.sync 3, %0;" ::"n"(DW_THREADS) : "memory");
+      int stage = 0, pstage = 0;
+      uint32_t phase = 0, pphase = 0;
+      for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+        for (int cb = 0; cb < P.ncb; cb++) {
+          float2 w[9];
+#pragma unroll
+          for (int t9 = 0; t9 < 9; t9++) w[t9] = *reinterpret_cast<const float2*>(dww + t9 * CW + cb * 64 + 2 * cpair);
+          const float2 bias2 = *reinterpret_cast<const float2*>(dww + 9 * CW + cb * 64 + 2 * cpair);
+          mbar_wait(patch_full_bar(pstage), pphase);
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t pbase = a_base + (uint32_t)pstage * (uint32_t)P.patch_stage_bytes +
+                                 (uint32_t)((RPT * rq) * PP_W + 4 * xh) * 128u + (uint32_t)cpair * 4u;
+          const uint32_t sbase = ring_base + (uint32_t)stage * A_STAGE_BYTES + (uint32_t)(cpair & 3) * 4u;
+          float2 acc[3][4];
+#pragma unroll
+          for (int pr = 0; pr < RPT + 2; pr++) {
+            float2 f[6];
+#pragma unroll
+            for (int i = 0; i < 6; i++) {
+              uint32_t v;
+              asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(pbase + (uint32_t)(pr * PP_W + i) * 128u));
+              f[i] = make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xFFFF0000u));
+            }
+#pragma unroll
+            for (int ky = 0; ky < 3; ky++) {
+              const int r = pr - ky;          // output row (of this thread's RPT rows) fed through tap row ky
+              if (r < 0 || r >= RPT) continue;
+              const int slot = r % 3;
+#pragma unroll
+              for (int px = 0; px < 4; px++) {
+                if (ky == 0) acc[slot][px] = bias2;
+#pragma unroll
+                for (int kx = 0; kx < 3; kx++) {
+                  // packed fp32 FMA on the channel pair
+                  unsigned long long ra = *reinterpret_cast<unsigned long long*>(&f[px + kx]);
+                  unsigned long long rb = *reinterpret_cast<unsigned long long*>(&w[ky * 3 + kx]);
+                  unsigned long long rc = *reinterpret_cast<unsigned long long*>(&acc[slot][px]), rd;
+                  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+                  acc[slot][px] = *reinterpret_cast<float2*>(&rd);
+                }
+              }
+              if (ky == 2) {   // row r complete: activation, bf16, swizzled K-major A stage
+#pragma unroll
+                for (int px = 0; px < 4; px++) {
+                  float2 o = acc[slot][px];
+                  if (P.dw_act) {
+                    o.x = silu_f(o.x);
+                    o.y = silu_f(o.y);
+                  }
+                  const uint32_t m = (uint32_t)((RPT * rq + r) * PT_W + 4 * xh + px);
+                  const uint32_t addr = sbase + m * 128u + ((((uint32_t)cpair >> 2) ^ (m & 7u)) << 4);
+                  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(pack_bf16(o.x, o.y)) : "memory");
+                }
+              }
+            }
+          }
+          // generic-proxy writes -> visible to the tensor core's async-proxy reads
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          mbar_arrive(full_bar(stage));
+          mbar_arrive(patch_empty_bar(pstage));
+          if (++stage == S) {
+            stage = 0;
+            phase ^= 1u;
+          }
+          if (++pstage == P.patch_stages) {
+            pstage = 0;
+            pphase ^= 1u;
+          }
+        }
+      }
   } else if (warp == RELAY_WARP) {
     // ============================ proxy-fence relay ========================================
     // im2col data is written by cp.async (generic proxy) but read by the tensor core through the
@@ -1219,6 +1222,7 @@ int conv_tc_prepare(yb_plan* p, Op& op) {
   // patch layers with tiny N tiles are bound by per-tile latency chains: a third resident CTA hides them
   const bool tiny_patch = patch_eligible(p, op) && op.BN <= 32 && op.Hout >= 80 && getenv("YB_NO_OCC3") == nullptr;
   int occ = std::min(tiny_patch ? 3 : 2, 512 / tmem_cols_for(op.BN));
+  if (op.dw_fused) occ = 1;   // 19-warp CTA (8 depthwise warps): one per SM
   if (const char* e = getenv("YB_OCC")) occ = std::max(1, std::min(occ, atoi(e)));
   if (!op.a_tma)
     if (const char* e = getenv("YB_OCC_GATHER")) occ = std::max(1, std::min(occ, atoi(e)));
@@ -1514,7 +1518,8 @@ int launch_conv_tc(const yb_plan* p, const Op& op, cudaStream_t st, float* fused
   }
   int grid = std::min(P.total_tiles, p->num_sms * op.occ);
 #define YB_LAUNCH(ATMA, T2D, HEAD)                                                                       \
-  YB_CUDA(launch_pdl(conv_gemm_tcgen05_kernel<ATMA, T2D, HEAD>, dim3(grid), dim3(NUM_THREADS), op.smem_bytes, st, \
+  YB_CUDA(launch_pdl(conv_gemm_tcgen05_kernel<ATMA, T2D, HEAD>, dim3(grid),                                \
+                     dim3(ATMA == MODE_DW ? NUM_THREADS_DW : NUM_THREADS), op.smem_bytes, st,              \
                      P, op.tmap_b, op.tmap_a[0], op.tmap_a[1], op.tmap_a[2], op.tmap_a[3], op.tmap_c))
   const bool head = P.out_mode != 0;
   if (head) {
