@@ -280,8 +280,23 @@ def run_ours(args, rank, world, local_rank):
         achieved = conv_flops / (conv_ms / 1e3) / 1e12
         peak, unit = peaks["tf_sustained"], "TFLOP/s"
     n_conv = sum(1 for op in desc["ops"] if op["kind"] == 1)
+    # per-layer roofline: every conv launch against max(flops / tensor peak, bytes / HBM peak)
+    t_layers = sum(max(w[0] / (peaks["tf_sustained"] * 1e12), w[1] / (peaks["hbm"] * 1e9)) for w in work) * 1e3
+    # DRAM bytes of the same launches from the committed ncu capture of this workload (profiles/)
+    traffic, traffic_src = None, None
+    try:
+        import glob
+        for tp in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")), reverse=True):
+            tj = json.load(open(tp))
+            if tj.get("model") == args.model and tj.get("batch") == B and tj.get("size") == S:
+                traffic, traffic_src = round(tj["dram_bytes_per_step"] / 1e9, 3), os.path.relpath(tp, ROOT)
+                break
+    except Exception:
+        pass
     roofline = {"bound": bound, "achieved": round(achieved, 2), "peak": peak, "unit": unit,
-                "frac": round(achieved / peak, 4), "traffic": None, "kernel": "conv_gemm_tcgen05_kernel",
+                "frac": round(achieved / peak, 4), "traffic": traffic, "traffic_unit": "GB per step (all launches of the kernel)",
+                "traffic_source": traffic_src, "kernel": "conv_gemm_tcgen05_kernel",
+                "per_layer_roofline_ms": round(t_layers, 4), "frac_of_per_layer_roofline": round(t_layers / conv_ms, 4),
                 "launches_per_step": n_conv, "kernel_ms_per_step": round(conv_ms, 4),
                 "kernel_share_of_step": round(conv_ms / (ms_prof / args.steps), 4),
                 "profiled_ms_per_step": round(ms_prof / args.steps, 4),
