@@ -154,6 +154,16 @@ int yb_nms(const float* pred, int batch, int num_classes, int num_anchors, float
            size_t workspace_bytes, void* cuda_stream);
 
 /* ---- misc ---- */
+/* ---- pre-processing (the step in front of YOLO.forward) ------------------------
+ * Replaces Dataset.load_image's cv2.resize(INTER_LINEAR) (utils/dataset.py:95-103), resize()'s
+ * letterbox with a constant-0 border (utils/dataset.py:292-313) and the HWC->CHW / BGR->RGB shuffle
+ * (utils/dataset.py:86-88) for a whole batch in one kernel, bit-exact with OpenCV's 8-bit bilinear.
+ * desc : device array [batch][3] of int64 = (device pointer of an HWC uint8 BGR image, height, width)
+ * out  : device (batch, 3, input_size, input_size) uint8 RGB, the tensor yb_forward takes as YB_U8
+ * meta : optional device [batch][3] double = (ratio, pad_w, pad_h) as resize() returns them        */
+int yb_letterbox(const long long* desc, int batch, int input_size, uint8_t* out_nchw_rgb, double* meta,
+                 void* cuda_stream);
+
 const char* yb_last_error(void);
 unsigned long long yb_launch_count(void); /* kernels launched by this library so far (process-wide) */
 int yb_version(void);

@@ -116,3 +116,31 @@ def test_nms_threshold_is_compared_in_double():
     pred[0, :, 1] = [2.0, 0.5, 2.0, 1.0, 0.8]   # [1,0,3,1]
     assert len(nms_oracle.non_max_suppression(pred, 0.1, 1.0 / 3.0)[0]) == 1
     assert len(nms_oracle.non_max_suppression(pred, 0.1, float(np.float32(1.0 / 3.0)))[0]) == 2
+
+
+# ---- pre-processing oracle: cv2 INTER_LINEAR + letterbox restatement ------------------
+def test_letterbox_oracle_matches_reference_fixtures(golden_dir):
+    """tests/golden/letterbox_cases.npz was recorded from the reference's own utils/dataset.py functions."""
+    from oracle import letterbox_oracle as lo
+    g = np.load(os.path.join(golden_dir, "letterbox_cases.npz"))
+    S = int(g["input_size"])
+    for i in range(int(g["n"])):
+        out, meta = lo.letterbox(g[f"img{i}"], S)
+        assert np.array_equal(out, g[f"out{i}"]), f"case {i}"
+        assert np.allclose(np.array(meta), g[f"meta{i}"], rtol=0, atol=1e-12)
+
+
+def test_letterbox_oracle_resize_matches_cv2():
+    """The bilinear resampler against the third-party dependency itself (skipped where cv2 is absent)."""
+    cv2 = pytest.importorskip("cv2")
+    from oracle import letterbox_oracle as lo
+    rng = np.random.default_rng(0)
+    cases = [(375, 500, 480, 640), (100, 37, 640, 236), (3, 5, 640, 384), (720, 1280, 360, 640), (1, 1, 5, 7), (2, 9, 3, 640)]
+    for _ in range(12):
+        h, w = int(rng.integers(1, 700)), int(rng.integers(1, 700))
+        r = 640 / max(h, w)
+        cases.append((h, w, max(1, int(h * r)), max(1, int(w * r))))
+    for h, w, dh, dw in cases:
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        ref = cv2.resize(img, dsize=(dw, dh), interpolation=cv2.INTER_LINEAR)
+        assert np.array_equal(lo.resize_linear_u8(img, dw, dh), ref), (h, w, dh, dw)

@@ -31,6 +31,8 @@ size_t nms_workspace_bytes(int B, int nc, int A, int max_nms);
 int nms_run(const float* pred, int B, int nc, int A, float conf, double iou, int max_det, int max_nms,
             float max_wh, float* out, int* out_counts, void* ws, size_t ws_bytes, cudaStream_t st);
 
+int letterbox_run(const long long* desc, int B, int S, uint8_t* out, double* meta, cudaStream_t st);
+
 static int check_device(int device) {
   int n = 0;
   cudaError_t e = cudaGetDeviceCount(&n);
@@ -498,6 +500,11 @@ int yb_nms(const float* pred, int batch, int num_classes, int num_anchors, float
   }
   return nms_run(pred, batch, num_classes, num_anchors, conf, iou, max_det, max_nms, max_wh, out,
                  out_counts, workspace, workspace_bytes, (cudaStream_t)cuda_stream);
+}
+
+int yb_letterbox(const long long* desc, int batch, int input_size, uint8_t* out_nchw_rgb, double* meta,
+                 void* cuda_stream) {
+  return letterbox_run(desc, batch, input_size, out_nchw_rgb, meta, (cudaStream_t)cuda_stream);
 }
 
 const char* yb_last_error(void) { return g_err; }
