@@ -254,6 +254,7 @@ def run_ours(args, rank, world, local_rank):
     assert run_e2e(args.steps) == B * args.steps
     torch.cuda.current_stream(dev).wait_stream(streamer.compute_stream)
     torch.cuda.current_stream(dev).wait_stream(streamer.copy_stream)
+    torch.cuda.current_stream(dev).wait_stream(streamer.d2h_stream)
     ee1.record(torch.cuda.current_stream(dev))
     torch.cuda.synchronize(dev)
     ms_e = ee0.elapsed_time(ee1)

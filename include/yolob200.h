@@ -152,6 +152,14 @@ size_t yb_nms_workspace_bytes(int batch, int num_classes, int num_anchors, int m
 int yb_nms(const float* pred, int batch, int num_classes, int num_anchors, float conf, double iou,
            int max_det, int max_nms, float max_wh, float* out, int* out_counts, void* workspace,
            size_t workspace_bytes, void* cuda_stream);
+/* Same call without the memset node in front of the first kernel, for a workspace whose headers are
+ * known to be zero: one that yb_nms_workspace_init cleared, or that the previous yb_nms / yb_nms_clean
+ * call used with the same (batch, max_nms) - the per-image kernel re-zeroes its header on exit.  Keeps the
+ * forward -> NMS kernel chain free of non-kernel nodes (programmatic dependent launch, batch-1 latency). */
+int yb_nms_workspace_init(void* workspace, size_t workspace_bytes, void* cuda_stream);
+int yb_nms_clean(const float* pred, int batch, int num_classes, int num_anchors, float conf, double iou,
+                 int max_det, int max_nms, float max_wh, float* out, int* out_counts, void* workspace,
+                 size_t workspace_bytes, void* cuda_stream);
 
 /* ---- misc ---- */
 /* ---- pre-processing (the step in front of YOLO.forward) ------------------------

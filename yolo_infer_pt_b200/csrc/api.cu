@@ -29,7 +29,7 @@ void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 size_t nms_workspace_bytes(int B, int nc, int A, int max_nms);
 int nms_run(const float* pred, int B, int nc, int A, float conf, double iou, int max_det, int max_nms,
-            float max_wh, float* out, int* out_counts, void* ws, size_t ws_bytes, cudaStream_t st);
+            float max_wh, float* out, int* out_counts, void* ws, size_t ws_bytes, cudaStream_t st, int ws_clean);
 
 int letterbox_run(const long long* desc, int B, int S, uint8_t* out, double* meta, cudaStream_t st);
 
@@ -499,7 +499,27 @@ int yb_nms(const float* pred, int batch, int num_classes, int num_anchors, float
     return YB_ERR_ARG;
   }
   return nms_run(pred, batch, num_classes, num_anchors, conf, iou, max_det, max_nms, max_wh, out,
-                 out_counts, workspace, workspace_bytes, (cudaStream_t)cuda_stream);
+                 out_counts, workspace, workspace_bytes, (cudaStream_t)cuda_stream, 0);
+}
+
+int yb_nms_workspace_init(void* workspace, size_t workspace_bytes, void* cuda_stream) {
+  if (!workspace) {
+    set_error("yb_nms_workspace_init: null workspace");
+    return YB_ERR_ARG;
+  }
+  YB_CUDA(cudaMemsetAsync(workspace, 0, workspace_bytes, (cudaStream_t)cuda_stream));
+  return YB_OK;
+}
+
+int yb_nms_clean(const float* pred, int batch, int num_classes, int num_anchors, float conf, double iou,
+                 int max_det, int max_nms, float max_wh, float* out, int* out_counts, void* workspace,
+                 size_t workspace_bytes, void* cuda_stream) {
+  if (!pred || !out || !out_counts) {
+    set_error("yb_nms: null argument");
+    return YB_ERR_ARG;
+  }
+  return nms_run(pred, batch, num_classes, num_anchors, conf, iou, max_det, max_nms, max_wh, out,
+                 out_counts, workspace, workspace_bytes, (cudaStream_t)cuda_stream, 1);
 }
 
 int yb_letterbox(const long long* desc, int batch, int input_size, uint8_t* out_nchw_rgb, double* meta,

@@ -497,7 +497,12 @@ __global__ void __launch_bounds__(IMG_T) nms_image_kernel(const NmsArgs a) {
   }
   __syncthreads();
   const int K = sm.K;
-  if (tid == 0) a.out_counts[b] = K;
+  if (tid == 0) {
+    a.out_counts[b] = K;
+    // leave the header zeroed for the next call on this workspace (yb_nms then needs no memset)
+    a.hdr[b].cand_count = 0;
+    a.hdr[b].sel_count = 0;
+  }
   for (int k = tid; k < K; k += IMG_T) {
     BoxF tmp;
     float r[6];
@@ -506,6 +511,9 @@ __global__ void __launch_bounds__(IMG_T) nms_image_kernel(const NmsArgs a) {
 #pragma unroll
     for (int q = 0; q < 6; q++) op[q] = r[q];
   }
+  // rows past the last detection are zero (the caller does not have to clear the buffer)
+  float* tail = a.out + ((size_t)b * a.max_det + K) * 6;
+  for (int i = tid; i < (a.max_det - K) * 6; i += IMG_T) tail[i] = 0.f;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -524,7 +532,7 @@ size_t nms_workspace_bytes(int B, int nc, int A, int max_nms) {
 }
 
 int nms_run(const float* pred, int B, int nc, int A, float conf, double iou, int max_det, int max_nms,
-            float max_wh, float* out, int* out_counts, void* ws, size_t ws_bytes, cudaStream_t st) {
+            float max_wh, float* out, int* out_counts, void* ws, size_t ws_bytes, cudaStream_t st, int ws_clean) {
   if (B <= 0 || nc <= 0 || A <= 0 || max_det <= 0 || max_nms <= 0) {
     set_error("yb_nms: bad sizes B=%d nc=%d A=%d max_det=%d max_nms=%d", B, nc, A, max_det, max_nms);
     return YB_ERR_ARG;
@@ -566,7 +574,9 @@ int nms_run(const float* pred, int B, int nc, int A, float conf, double iou, int
                                  (int)sizeof(ImgSmem)));
     attr_set = true;
   }
-  YB_CUDA(cudaMemsetAsync(ws, 0, hdr_bytes, st));
+  // the per-image kernel leaves the headers zeroed; a workspace last used by yb_nms / yb_nms_workspace_init
+  // with the same batch needs no memset node in front of the append kernel
+  if (!ws_clean) YB_CUDA(cudaMemsetAsync(ws, 0, hdr_bytes, st));
   long long total = (long long)nc * A;
   int gx = (int)std::min<long long>((total + 256 * 16 - 1) / (256 * 16), 1024);
   int vec4 = (A % 4 == 0) && ((reinterpret_cast<uintptr_t>(pred) & 15) == 0);

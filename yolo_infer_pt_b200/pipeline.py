@@ -18,6 +18,7 @@ class StreamingDetector:
         self.conf, self.iou = conf, iou
         self.copy_stream = torch.cuda.Stream(self.device)
         self.compute_stream = torch.cuda.Stream(self.device)
+        self.d2h_stream = torch.cuda.Stream(self.device)
         self.inputs = [torch.empty(batch_shape, dtype=dtype, device=self.device) for _ in range(2)]
         self.copied = [torch.cuda.Event() for _ in range(2)]
         self.consumed = [torch.cuda.Event() for _ in range(2)]
@@ -41,11 +42,18 @@ class StreamingDetector:
             y = self.model(self.inputs[slot])
             det, counts = util.nms_padded(y, self.conf, self.iou)
             self.consumed[slot].record(self.compute_stream)
-            det_h, cnt_h = self.det_host[slot], self.cnt_host[slot]
+            computed = torch.cuda.Event()
+            computed.record(self.compute_stream)
+        # detections go back on their own stream: the next batch's kernels do not queue behind the copy
+        det_h, cnt_h = self.det_host[slot], self.cnt_host[slot]
+        with torch.cuda.stream(self.d2h_stream):
+            self.d2h_stream.wait_event(computed)
+            det.record_stream(self.d2h_stream)
+            counts.record_stream(self.d2h_stream)
             det_h.copy_(det, non_blocking=True)
             cnt_h.copy_(counts, non_blocking=True)
             done = torch.cuda.Event()
-            done.record(self.compute_stream)
+            done.record(self.d2h_stream)
         return det_h, cnt_h, done
 
     def run(self, host_batches):

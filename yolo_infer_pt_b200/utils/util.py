@@ -77,16 +77,17 @@ def nms_padded(outputs, confidence_threshold=0.001, iou_threshold=0.65, max_det=
     ws = _workspaces.get(key)
     if ws is None:
         nbytes = L.yb_nms_workspace_bytes(B, nc, A, max_nms)
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        ws = torch.zeros(nbytes, dtype=torch.uint8, device=dev)   # zero headers once; the kernel keeps them zero
         _workspaces.clear()
         _workspaces[key] = ws
-    det = torch.zeros(B, max_det, 6, dtype=torch.float32, device=dev)
-    counts = torch.zeros(B, dtype=torch.int32, device=dev)
+    # the kernel writes every row (zeros past the last detection) and every count: no fill kernels
+    det = torch.empty(B, max_det, 6, dtype=torch.float32, device=dev)
+    counts = torch.empty(B, dtype=torch.int32, device=dev)
     conf32 = float(numpy.float32(confidence_threshold))  # torch compares an fp32 tensor in fp32
     stream = torch.cuda.current_stream(dev).cuda_stream
-    _lib.check(L.yb_nms(pred.data_ptr(), B, nc, A, conf32, float(iou_threshold), max_det, max_nms,
-                        float(max_wh), det.data_ptr(), counts.data_ptr(), ws.data_ptr(), ws.numel(),
-                        ctypes.c_void_p(stream)), "yb_nms")
+    _lib.check(L.yb_nms_clean(pred.data_ptr(), B, nc, A, conf32, float(iou_threshold), max_det, max_nms,
+                              float(max_wh), det.data_ptr(), counts.data_ptr(), ws.data_ptr(), ws.numel(),
+                              ctypes.c_void_p(stream)), "yb_nms")
     return det, counts
 
 
