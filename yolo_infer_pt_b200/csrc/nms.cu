@@ -24,6 +24,8 @@
 // round-to-nearest intrinsics (no FMA contraction), on the class-offset boxes of util.py:160-161,
 // and compares (double)iou > iou_threshold.
 #include <stdio.h>
+#include <stdlib.h>
+#include <algorithm>
 #include <string.h>
 
 #include "yb_internal.h"
@@ -45,6 +47,7 @@ struct NmsArgs {
   float conf;
   double iou;
   int max_det, max_nms, cap;
+  int first_band, next_band;   // candidates per band (<= SORT_TILE)
   float max_wh;
   NmsHeader* hdr;
   unsigned long long* keys;  // [B][cap]
@@ -154,12 +157,21 @@ __device__ __forceinline__ bool suppresses(const BoxF& i, const BoxF& j, double 
   return (double)ovr > thr;
 }
 
-static constexpr int G_CHUNK = 256;
+#ifndef YB_G_CHUNK
+#define YB_G_CHUNK 128
+#endif
+static constexpr int G_CHUNK = YB_G_CHUNK;   // candidates per greedy step
 static constexpr int G_MAXDET = 1024;  // shared-memory capacity for kept boxes
 static constexpr int FIRST_BAND = 1024;  // preferred size of the first band (most images finish inside it)
+static constexpr int BAND_PRE = 1024;    // candidates of a band whose boxes are gathered in one go (one latency per band)
+static constexpr int NEXT_BAND = 1024;   // and of the following ones: sorting 4 x 1024 keys costs less than 1 x 4096
 
-__device__ __forceinline__ void load_candidate(const NmsArgs& a, int b, unsigned long long key, BoxF& off,
-                                               float* raw6) {
+// Returns the candidate's class code: its class when every raw coordinate lies inside
+// (-max_wh/2, max_wh/2) - then boxes of different classes cannot intersect after the per-class offset of
+// util.py:160, so only same-class pairs need an IoU - and -1 otherwise (NaN / huge boxes: tested against
+// everything, exactly as the reference's single nms over offset boxes would).
+__device__ __forceinline__ int load_candidate(const NmsArgs& a, int b, unsigned long long key, BoxF& off,
+                                              float* raw6) {
   unsigned int idx = (unsigned int)(key & 0xFFFFFFFFull);
   int an = (int)(idx / (unsigned int)a.nc);
   int c = (int)(idx - (unsigned int)an * (unsigned int)a.nc);
@@ -183,6 +195,9 @@ __device__ __forceinline__ void load_candidate(const NmsArgs& a, int b, unsigned
     raw6[4] = from_orderable(~(unsigned int)(key >> 32));
     raw6[5] = fc;
   }
+  const float lim = 0.5f * a.max_wh;
+  const bool normal = fabsf(x1) < lim && fabsf(y1) < lim && fabsf(x2) < lim && fabsf(y2) < lim;
+  return normal ? c : -1;
 }
 
 // Histogram bins over the high key word (= bit-inverted orderable score): bin 0 starts at score 1.0
@@ -206,13 +221,21 @@ struct ImgSmem {
   unsigned int hist2[HIST_BINS];
   BoxF kept[G_MAXDET];
   unsigned long long kept_key[G_MAXDET];
+  short kept_code[G_MAXDET];                 // class code of the kept box (-1: abnormal, tested against everything)
+  BoxF band_box[BAND_PRE];                   // boxes of the band's first candidates, gathered once after the sort
+  short band_code[BAND_PRE];
   BoxF live[G_CHUNK];      // candidates of the chunk, then (compacted in place) its survivors
   unsigned long long live_key[G_CHUNK];
-  unsigned int mask[G_CHUNK][G_CHUNK / 32];
+  int live_code[G_CHUNK];
+  unsigned int maskT[G_CHUNK][G_CHUNK / 32]; // bit i of row j: live[i] (i < j) suppresses live[j]
+  unsigned int decided[G_CHUNK / 32], keptbits[G_CHUNK / 32];
   int dead[G_CHUNK];
   int warp_cnt[G_CHUNK / 32];
   int K, m, cnt, walk_end;
   unsigned int walk_cum;
+  unsigned int scan_tot[32];
+  int st_bands, st_chunks, st_surv, st_tests;   // -DYB_NMS_STATS: work counters, copied to the header pad
+  int st_cyc[8];                                // cycles: 0 hist, 1 select+compact, 2 sort, 3 load+A, 4 compaction, 5 B, 6 C, 7 D
 };
 
 // The image's candidates: the appended key list when it is complete, else the raw scores.
@@ -229,11 +252,16 @@ struct Src {
 template <int IMG_T, typename F>
 __device__ __forceinline__ void scan_src(const Src& s, F f) {
   if (s.complete) {
+    // four independent loads in flight per thread: the list lives in L2 / HBM, its latency is the cost
     const int iters = (s.n + IMG_T - 1) / IMG_T;
     int i = threadIdx.x;
-    for (int it = 0; it < iters; it++, i += IMG_T) {
-      const bool v = i < s.n;
-      f(v, v ? s.keys[i] : ~0ull);
+    for (int it = 0; it < iters; it += 4, i += 4 * IMG_T) {
+      unsigned long long k[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++) k[u] = (i + u * IMG_T < s.n) ? s.keys[i + u * IMG_T] : ~0ull;
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        if (it + u < iters) f(i + u * IMG_T < s.n, k[u]);
     }
   } else {
     const long long iters = (s.total + IMG_T - 1) / IMG_T;
@@ -255,31 +283,65 @@ __device__ __forceinline__ void scan_src(const Src& s, F f) {
   }
 }
 
-// Warp 0: longest run of bins [start, end) with sum <= limit.  Results in sm.walk_end / sm.walk_cum.
+// Longest run of bins [start, end) with sum <= limit (trailing empty bins included), by the whole CTA:
+// per-thread partial sums, a two-level scan, then every thread tests its own bins.  Results in
+// sm.walk_end / sm.walk_cum.  Must be called by all threads; ends with a barrier.
+template <int IMG_T>
 __device__ __forceinline__ void walk_bins(ImgSmem& sm, const unsigned int* h, int start, int nb, unsigned int limit) {
-  if (threadIdx.x >= 32) return;
-  const int lane = threadIdx.x;
-  unsigned int cum = 0;
-  int end = start;
-  for (int b0 = start; b0 < nb; b0 += 32) {
-    unsigned int incl = (b0 + lane < nb) ? h[b0 + lane] : 0u;
+  constexpr int BPT = HIST_BINS / IMG_T;   // consecutive bins per thread
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  unsigned int v[BPT], tot = 0;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
-      if (lane >= o) incl += t;
-    }
-    const bool ok = (b0 + lane < nb) && (cum + incl <= limit);
-    const int nok = __popc(__ballot_sync(0xffffffffu, ok));  // ok is a prefix of the lanes (incl is monotone)
-    if (nok > 0) cum += __shfl_sync(0xffffffffu, incl, nok - 1);
-    end = b0 + nok;
-    if (nok < 32) break;
+  for (int q = 0; q < BPT; q++) {
+    const int i = tid * BPT + q;
+    v[q] = (i >= start && i < nb) ? h[i] : 0u;
+    tot += v[q];
   }
-  if (lane == 0) {
-    sm.walk_end = end;
-    sm.walk_cum = cum;
+  unsigned int incl = tot;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const unsigned int t = __shfl_up_sync(0xffffffffu, incl, o);
+    if (lane >= o) incl += t;
   }
+  if (lane == 31) sm.scan_tot[warp] = incl;
+  if (tid == 0) {
+    sm.walk_end = start;
+    sm.walk_cum = 0u;
+  }
+  __syncthreads();
+  unsigned int base = incl - tot;
+  for (int w = 0; w < warp; w++) base += sm.scan_tot[w];
+  // cum is monotone over bins: the run ends after the last bin whose inclusive sum still fits
+  unsigned int cum = base;
+#pragma unroll
+  for (int q = 0; q < BPT; q++) {
+    const int i = tid * BPT + q;
+    cum += v[q];
+    if (i >= start && i < nb && cum <= limit) atomicMax(&sm.walk_end, i + 1);
+  }
+  __syncthreads();
+  cum = base;
+#pragma unroll
+  for (int q = 0; q < BPT; q++) {
+    const int i = tid * BPT + q;
+    cum += v[q];
+    if (i + 1 == sm.walk_end && i >= start) sm.walk_cum = cum;
+  }
+  __syncthreads();
 }
 
+#ifdef YB_NMS_STATS
+#define YB_T(slot)                                      \
+  do {                                                  \
+    if (tid == 0) {                                     \
+      const long long _n = clock64();                   \
+      sm.st_cyc[slot] += (int)(_n - st_last);           \
+      st_last = _n;                                     \
+    }                                                   \
+  } while (0)
+#else
+#define YB_T(slot) do { } while (0)
+#endif
 // IMG_T threads per image: 1024 for small batches (latency), 512 (two CTAs per SM) for large ones.
 template <int IMG_T>
 __global__ void __launch_bounds__(IMG_T) nms_image_kernel(const NmsArgs a) {
@@ -307,6 +369,15 @@ __global__ void __launch_bounds__(IMG_T) nms_image_kernel(const NmsArgs a) {
 
   for (int i = tid; i < HIST_BINS; i += IMG_T) sm.hist[i] = 0u;
   if (tid == 0) sm.K = 0;
+#ifdef YB_NMS_STATS
+  long long st_last = clock64();
+  if (tid == 0) {
+    sm.st_bands = sm.st_chunks = sm.st_surv = sm.st_tests = 0;
+    for (int i = 0; i < 8; i++) sm.st_cyc[i] = 0;
+  }
+#endif
+  // class-restricted pair tests need "no intersection => not suppressed" (thr >= 0) and a sane offset
+  const bool by_class = thr_ok && a.max_wh > 0.f && a.nc <= 0x7FFF;
   __syncthreads();
   if (h.cand_count > 0) {
     scan_src<IMG_T>(src, [&](bool v, unsigned long long k) {
@@ -315,14 +386,14 @@ __global__ void __launch_bounds__(IMG_T) nms_image_kernel(const NmsArgs a) {
   }
   __syncthreads();
 
+  YB_T(0);
   int cur_bin = 0;
   int consumed = 0;                 // candidates handed to the greedy step so far (sorted positions)
   unsigned long long lo_done = 0;   // every key below this has been consumed
   bool first = true;
   while (h.cand_count > 0 && cur_bin < HIST_BINS && consumed < a.max_nms && sm.K < a.max_det) {
     // ---- choose the band [lo_done, band_hi)
-    walk_bins(sm, sm.hist, cur_bin, HIST_BINS, first ? FIRST_BAND : SORT_TILE);
-    __syncthreads();
+    walk_bins<IMG_T>(sm, sm.hist, cur_bin, HIST_BINS, first ? a.first_band : a.next_band);
     int b_end = sm.walk_end;
     unsigned int cnt = sm.walk_cum;
     unsigned long long band_hi;
@@ -354,8 +425,7 @@ __global__ void __launch_bounds__(IMG_T) nms_image_kernel(const NmsArgs a) {
             if (v && k >= lo && k < hi) atomicAdd(&sm.hist2[(unsigned int)((k - lo) >> shift)], 1u);
           });
           __syncthreads();
-          walk_bins(sm, sm.hist2, 0, HIST_BINS, SORT_TILE);
-          __syncthreads();
+          walk_bins<IMG_T>(sm, sm.hist2, 0, HIST_BINS, SORT_TILE);
           const int e = sm.walk_end;
           if (e == 0) {  // the first sub-bin alone is still too fat: descend into it
             hi = lo + (1ull << shift);
@@ -370,6 +440,7 @@ __global__ void __launch_bounds__(IMG_T) nms_image_kernel(const NmsArgs a) {
         next_bin = fat;
       }
     }
+    YB_T(1);
     // ---- compact the band into the tile, pad, sort ascending (= descending score)
     if (tid == 0) sm.cnt = 0;
     __syncthreads();
@@ -391,13 +462,18 @@ __global__ void __launch_bounds__(IMG_T) nms_image_kernel(const NmsArgs a) {
       });
     }
     __syncthreads();
+    YB_T(2);
     const int n_band = min(sm.cnt, SORT_TILE);
     int P = 32;
     while (P < n_band) P <<= 1;
     for (int i = n_band + tid; i < P; i += IMG_T) sm.tile[i] = ~0ull;
     __syncthreads();
+    // bitonic network; element e lives at thread e % IMG_T.  Stages with partner distance j >= 32 run in
+    // shared memory (one barrier each); the j = 16 .. 1 tail of every kk (and all of kk <= 32) runs in
+    // registers with warp shuffles: one barrier per kk instead of five.
     for (int kk = 2; kk <= P; kk <<= 1) {
-      for (int j = kk >> 1; j > 0; j >>= 1) {
+      int j = kk >> 1;
+      for (; j >= 32; j >>= 1) {
         for (int t = tid; t < P / 2; t += IMG_T) {
           const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // lower index of the pair
           const int l = i | j;
@@ -410,22 +486,67 @@ __global__ void __launch_bounds__(IMG_T) nms_image_kernel(const NmsArgs a) {
         }
         __syncthreads();
       }
+      for (int e = tid; e < P; e += IMG_T) {   // P >= 32 and IMG_T % 32 == 0: whole warps take this branch
+        unsigned long long x = sm.tile[e];
+        const bool asc = ((e & kk) == 0);
+        for (int jj = j; jj > 0; jj >>= 1) {
+          const unsigned long long y = __shfl_xor_sync(0xffffffffu, x, jj);
+          const bool lower = (lane & jj) == 0;
+          const bool take_min = lower == asc;
+          x = take_min ? (x < y ? x : y) : (x < y ? y : x);
+        }
+        sm.tile[e] = x;
+      }
+      __syncthreads();
     }
+    YB_T(3);
+#ifdef YB_NMS_STATS
+    if (tid == 0) sm.st_bands++;
+#endif
     // ---- greedy step over the sorted band, 256 candidates at a time
     const int n_use = min(n_band, a.max_nms - consumed);  // util.py:157: only the max_nms best
+    for (int i = tid; i < min(n_use, BAND_PRE); i += IMG_T) {
+      BoxF bx;
+      const int code = load_candidate(a, b, sm.tile[i], bx, nullptr);
+      sm.band_box[i] = bx;
+      sm.band_code[i] = (short)((by_class && code >= 0) ? code : -1);
+    }
+    __syncthreads();
     for (int base = 0; base < n_use; base += G_CHUNK) {
       const int K = sm.K;
       if (K >= a.max_det) break;
-      const int j = tid & (G_CHUNK - 1), part = tid >> 8;
+      const int j = tid & (G_CHUNK - 1), part = tid / G_CHUNK;
       const int ci = base + j;
+      // -- A: load the chunk's candidates, then test each against the kept boxes it can intersect (same
+      //       class code, or either side abnormal); IMG_T / 256 threads share a candidate's kept list
       if (tid < G_CHUNK) {
+        int code = -1;
+        BoxF cand;
+        cand.x1 = cand.y1 = cand.x2 = cand.y2 = cand.area = 0.f;
+        if (ci < n_use) {
+          if (ci < BAND_PRE) {
+            cand = sm.band_box[ci];
+            code = sm.band_code[ci];
+          } else {
+            code = load_candidate(a, b, sm.tile[ci], cand, nullptr);
+            if (!by_class) code = -1;
+          }
+        }
+        sm.live[j] = cand;
+        sm.live_code[j] = code;
         sm.dead[j] = ci < n_use ? 0 : 1;
-        if (ci < n_use) load_candidate(a, b, sm.tile[ci], sm.live[j], nullptr);
+      }
+      if (tid < G_CHUNK / 32) {
+        sm.decided[tid] = 0u;
+        sm.keptbits[tid] = 0u;
       }
       __syncthreads();
       if (ci < n_use) {
         const BoxF me = sm.live[j];
+        const int code = sm.live_code[j];
         for (int k = part; k < K; k += IMG_T / G_CHUNK) {
+          const int kc = sm.kept_code[k];
+          if (code >= 0 && kc >= 0 && kc != code) continue;
           if (suppresses(sm.kept[k], me, thr, thr_lo, thr_hi)) {
             sm.dead[j] = 1;
             break;
@@ -433,13 +554,15 @@ __global__ void __launch_bounds__(IMG_T) nms_image_kernel(const NmsArgs a) {
         }
       }
       __syncthreads();
-      // ordered compaction of the survivors (threads 0..255, in place: pos <= j)
+      // -- ordered compaction of the survivors (threads 0..255, in place: pos <= j)
       bool alive = false;
       BoxF me;
+      int code = -1;
       unsigned int bal = 0;
       if (tid < G_CHUNK) {
         alive = !sm.dead[j];
         me = sm.live[j];
+        code = sm.live_code[j];
         bal = __ballot_sync(0xffffffffu, alive);
         if (lane == 0) sm.warp_cnt[warp] = __popc(bal);
       }
@@ -451,6 +574,7 @@ __global__ void __launch_bounds__(IMG_T) nms_image_kernel(const NmsArgs a) {
           const int pos = before + __popc(bal & ((1u << lane) - 1u));
           sm.live[pos] = me;
           sm.live_key[pos] = sm.tile[ci];
+          sm.live_code[pos] = code;
         }
         if (tid == 0) {
           int m = 0;
@@ -459,35 +583,75 @@ __global__ void __launch_bounds__(IMG_T) nms_image_kernel(const NmsArgs a) {
         }
       }
       __syncthreads();
+      YB_T(4);
       const int m = sm.m;
-      // suppression bitmask inside the chunk: mask[i][w] bit l <=> live[i] suppresses live[32w+l], 32w+l > i
+#ifdef YB_NMS_STATS
+      if (tid == 0) { sm.st_chunks++; sm.st_surv += m; }
+#endif
+      // -- B: who suppresses whom inside the chunk (transposed: row j holds its potential suppressors i < j)
       for (int task = warp; task < m * (G_CHUNK / 32); task += IMG_T / 32) {
-        const int i = task / (G_CHUNK / 32), wcol = task - i * (G_CHUNK / 32);
-        const int jj = wcol * 32 + lane;
-        bool sup = false;
-        if (jj > i && jj < m) sup = suppresses(sm.live[i], sm.live[jj], thr, thr_lo, thr_hi);
-        const unsigned int bits = __ballot_sync(0xffffffffu, sup);
-        if (lane == 0) sm.mask[i][wcol] = bits;
-      }
-      __syncthreads();
-      if (warp == 0) {
-        unsigned int remv = 0;  // lane w (< 8) holds removed-bits word w
-        int Kc = K;
-        for (int i = 0; i < m; i++) {
-          const unsigned int word = __shfl_sync(0xffffffffu, remv, i >> 5);
-          if (!((word >> (i & 31)) & 1u)) {
-            if (lane == 0) {
-              sm.kept[Kc] = sm.live[i];
-              sm.kept_key[Kc] = sm.live_key[i];
-            }
-            Kc++;
-            if (Kc >= a.max_det) break;
-            if (lane < G_CHUNK / 32) remv |= sm.mask[i][lane];
-          }
+        const int jj = task / (G_CHUNK / 32), wcol = task - jj * (G_CHUNK / 32);
+        if (wcol * 32 >= jj) {   // no i < jj in this word
+          if (lane == 0) sm.maskT[jj][wcol] = 0u;
+          continue;
         }
-        if (lane == 0) sm.K = Kc;
+        const int i = wcol * 32 + lane;
+        bool sup = false;
+        if (i < jj) {
+          const int cj = sm.live_code[jj], cI = sm.live_code[i];
+          if (cj < 0 || cI < 0 || cj == cI) sup = suppresses(sm.live[i], sm.live[jj], thr, thr_lo, thr_hi);
+        }
+        const unsigned int bits = __ballot_sync(0xffffffffu, sup);
+        if (lane == 0) sm.maskT[jj][wcol] = bits;
       }
       __syncthreads();
+      YB_T(5);
+      // -- C: greedy resolution in rounds.  live[j] is dead once a kept earlier box suppresses it, kept once
+      //       all its potential suppressors are decided and none of them is kept.  Chains only form inside a
+      //       class, so a couple of rounds settle the chunk (the fixed point is the serial greedy result).
+      {
+        bool done_j = tid >= m;   // threads beyond the survivors have nothing to decide
+        for (int round = 0; round < G_CHUNK + 1; round++) {
+          bool now = false, keep = false;
+          if (!done_j) {
+            bool pend = false, dead = false;
+            for (int w = 0; w <= (tid >> 5); w++) {
+              const unsigned int sp = sm.maskT[tid][w];
+              if (sp & ~sm.decided[w]) pend = true;
+              if (sp & sm.keptbits[w]) dead = true;
+            }
+            if (dead) now = true;
+            else if (!pend) now = keep = true;
+          }
+          __syncthreads();   // every thread has read this round's snapshot
+          if (now) {
+            if (keep) atomicOr(&sm.keptbits[tid >> 5], 1u << (tid & 31));
+            atomicOr(&sm.decided[tid >> 5], 1u << (tid & 31));
+            done_j = true;
+          }
+          if (__syncthreads_and(done_j)) break;
+        }
+      }
+      YB_T(6);
+      // -- D: append the kept survivors in order (up to max_det)
+      if (tid < m && ((sm.keptbits[tid >> 5] >> (tid & 31)) & 1u)) {
+        int rank = __popc(sm.keptbits[tid >> 5] & ((1u << (tid & 31)) - 1u));
+        for (int w = 0; w < (tid >> 5); w++) rank += __popc(sm.keptbits[w]);
+        const int pos = K + rank;
+        if (pos < a.max_det) {
+          sm.kept[pos] = sm.live[tid];
+          sm.kept_key[pos] = sm.live_key[tid];
+          const int code_k = sm.live_code[tid];
+          sm.kept_code[pos] = (short)(code_k >= 0 ? (code_k & 0x7FFF) : -1);
+        }
+      }
+      if (tid == 0) {
+        int total = 0;
+        for (int w = 0; w < G_CHUNK / 32; w++) total += __popc(sm.keptbits[w]);
+        sm.K = min(K + total, a.max_det);
+      }
+      __syncthreads();
+      YB_T(7);
     }
     consumed += n_band;
     lo_done = band_hi;
@@ -502,6 +666,11 @@ __global__ void __launch_bounds__(IMG_T) nms_image_kernel(const NmsArgs a) {
     // leave the header zeroed for the next call on this workspace (yb_nms then needs no memset)
     a.hdr[b].cand_count = 0;
     a.hdr[b].sel_count = 0;
+#ifdef YB_NMS_STATS
+    for (int i = 0; i < 6; i++) a.hdr[b].pad[i] = sm.st_cyc[i + 2];   // (stats build only: the header is not left zero)
+    a.hdr[b].cand_count = sm.st_cyc[0];
+    a.hdr[b].sel_count = sm.st_cyc[1];
+#endif
   }
   for (int k = tid; k < K; k += IMG_T) {
     BoxF tmp;
@@ -560,6 +729,10 @@ int nms_run(const float* pred, int B, int nc, int A, float conf, double iou, int
   a.max_det = max_det;
   a.max_nms = max_nms;
   a.cap = cap_for(max_nms);
+  a.first_band = FIRST_BAND;
+  a.next_band = NEXT_BAND;
+  if (const char* e = getenv("YB_NMS_FIRST_BAND")) a.first_band = std::max(32, std::min(SORT_TILE, atoi(e)));
+  if (const char* e = getenv("YB_NMS_NEXT_BAND")) a.next_band = std::max(32, std::min(SORT_TILE, atoi(e)));
   a.max_wh = max_wh;
   size_t hdr_bytes = ((size_t)B * sizeof(NmsHeader) + 255) / 256 * 256;
   a.hdr = reinterpret_cast<NmsHeader*>(ws);
