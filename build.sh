@@ -5,7 +5,7 @@ cd "$(dirname "$0")"
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 OUT=yolo_infer_pt_b200/lib
 mkdir -p "$OUT" build
-SRCS="api plan conv_tc kernels_misc nms preprocess"
+SRCS="api plan conv_tc kernels_misc nms preprocess metric"
 OBJS=""
 for s in $SRCS; do
   src=yolo_infer_pt_b200/csrc/$s.cu

@@ -172,6 +172,17 @@ int yb_nms_clean(const float* pred, int batch, int num_classes, int num_anchors,
 int yb_letterbox(const long long* desc, int batch, int input_size, uint8_t* out_nchw_rgb, double* meta,
                  void* cuda_stream);
 
+/* ---- detection consumer (the step behind non_max_suppression) -------------------
+ * Replaces compute_metric (utils/util.py:99-120) for the whole padded batch yb_nms produced: IoU of every
+ * detection with the class-matched labels and the greedy label assignment per IoU threshold, on the
+ * device (the reference round-trips every image through numpy).
+ * det (batch, max_det, 6) + counts (batch): yb_nms's outputs;  targets (batch, max_targets, 5) rows
+ * [class, x1, y1, x2, y2] in pixels + target_counts (batch);  iou_v (n_iou <= 16) thresholds;
+ * correct (batch, max_det, n_iou) uint8: the reference's boolean matrix, zero past counts[b].          */
+int yb_compute_metric(const float* det, const int* counts, const float* targets, const int* target_counts,
+                      int batch, int max_det, int max_targets, const float* iou_v, int n_iou, uint8_t* correct,
+                      void* cuda_stream);
+
 const char* yb_last_error(void);
 unsigned long long yb_launch_count(void); /* kernels launched by this library so far (process-wide) */
 int yb_version(void);

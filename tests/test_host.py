@@ -186,3 +186,42 @@ def test_wh2xy_and_make_anchors():
     pts, st = util.make_anchors(maps, [8, 16])
     assert pts.tolist() == [[0.5, 0.5], [1.5, 0.5], [2.5, 0.5], [0.5, 1.5], [1.5, 1.5], [2.5, 1.5], [0.5, 0.5]]
     assert st.view(-1).tolist() == [8.0] * 6 + [16.0]
+
+
+def test_reference_checkpoint_imports(tmp_path):
+    """a checkpoint written by the reference itself ({'model': module.half()}, what
+    strip_optimizer leaves in weights/best.pt, util.py:332-337) loads (a) through `load_weight` and (b) by
+    plain torch.load with our `nets.nn` standing in for the reference's - `_arch` is inferred from the
+    module tree.  Needs /root/reference (present in the build container only)."""
+    import subprocess, sys, textwrap
+    if not os.path.isdir("/root/reference/nets"):
+        pytest.skip("reference sources not present")
+    ck = str(tmp_path / "best.pt")
+    code = textwrap.dedent(f"""
+        import sys, torch
+        sys.path.insert(0, '/root/reference')
+        from nets import nn
+        torch.manual_seed(3)
+        m = nn.yolo_v11_s(7)
+        for p in m.parameters():
+            p.data.normal_(0, 0.05)
+        torch.save({{'model': m.half()}}, {ck!r})
+        torch.save({{k: v.float() for k, v in m.state_dict().items()}}, {ck!r} + '.sd')
+    """)
+    subprocess.run([sys.executable, "-c", code], check=True)
+    pkg = os.path.join(ROOT, "yolo_infer_pt_b200")
+    code2 = textwrap.dedent(f"""
+        import sys, torch
+        sys.path.insert(0, {pkg!r}); sys.path.insert(0, {ROOT!r})
+        from nets import nn
+        from utils import util
+        sd = torch.load({ck!r} + '.sd')
+        m = util.load_weight(nn.yolo_v11_s(7), {ck!r})
+        assert all(torch.equal(v, sd[k]) for k, v in m.state_dict().items()), 'load_weight'
+        m2 = torch.load({ck!r}, map_location='cpu', weights_only=False)['model'].float().fuse()
+        assert type(m2).__module__ == 'nets.nn' and m2._arch == nn.yolo_v11_s(7)._arch, m2._arch
+        assert len(m2.state_dict()) == len(nn.yolo_v11_s(7).fuse().state_dict())
+        print('ok')
+    """)
+    out = subprocess.run([sys.executable, "-c", code2], check=True, capture_output=True, text=True)
+    assert "ok" in out.stdout

@@ -144,3 +144,12 @@ def test_letterbox_oracle_resize_matches_cv2():
         img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
         ref = cv2.resize(img, dsize=(dw, dh), interpolation=cv2.INTER_LINEAR)
         assert np.array_equal(lo.resize_linear_u8(img, dw, dh), ref), (h, w, dh, dw)
+
+
+# ---- detection-consumer oracle: compute_metric restatement ------------------------------
+def test_metric_oracle_matches_reference_fixtures(golden_dir):
+    """tests/golden/metric_cases.npz was recorded from the reference's own utils.util.compute_metric."""
+    from oracle import metric_oracle as mo
+    g = np.load(os.path.join(golden_dir, "metric_cases.npz"))
+    for i in range(int(g["n"])):
+        assert np.array_equal(mo.compute_metric(g[f"det{i}"], g[f"gt{i}"], g["iou_v"]), g[f"correct{i}"]), f"case {i}"

@@ -31,6 +31,8 @@ size_t nms_workspace_bytes(int B, int nc, int A, int max_nms);
 int nms_run(const float* pred, int B, int nc, int A, float conf, double iou, int max_det, int max_nms,
             float max_wh, float* out, int* out_counts, void* ws, size_t ws_bytes, cudaStream_t st, int ws_clean);
 
+int metric_run(const float* det, const int* counts, const float* tgt, const int* tcounts, int B, int max_det,
+               int max_t, const float* iou_v, int n_iou, uint8_t* correct, cudaStream_t st);
 int letterbox_run(const long long* desc, int B, int S, uint8_t* out, double* meta, cudaStream_t st);
 
 static int check_device(int device) {
@@ -525,6 +527,13 @@ int yb_nms_clean(const float* pred, int batch, int num_classes, int num_anchors,
 int yb_letterbox(const long long* desc, int batch, int input_size, uint8_t* out_nchw_rgb, double* meta,
                  void* cuda_stream) {
   return letterbox_run(desc, batch, input_size, out_nchw_rgb, meta, (cudaStream_t)cuda_stream);
+}
+
+int yb_compute_metric(const float* det, const int* counts, const float* targets, const int* target_counts,
+                      int batch, int max_det, int max_targets, const float* iou_v, int n_iou, uint8_t* correct,
+                      void* cuda_stream) {
+  return metric_run(det, counts, targets, target_counts, batch, max_det, max_targets, iou_v, n_iou, correct,
+                    (cudaStream_t)cuda_stream);
 }
 
 const char* yb_last_error(void) { return g_err; }

@@ -330,6 +330,27 @@ class YOLO(torch.nn.Module):
         state.pop("_yb_tensors", None)
         return state
 
+    def __setstate__(self, state):
+        """Also accepts a module pickled by the reference itself (`torch.load('weights/best.pt')['model']`,
+        main.py:247-249: with `yolo_infer_pt_b200/` on sys.path the pickle's `nets.nn.*` classes resolve
+        to this file): such a state has no `_arch`, so it is read back from the module tree."""
+        self.__dict__.update(state)
+        if "_arch" not in self.__dict__:
+            self.__dict__["_arch"] = self._infer_arch()
+        self.__dict__.pop("_yb_engines", None)
+        self.__dict__.pop("_yb_tensors", None)
+
+    def _infer_arch(self):
+        """(width, depth, csp, num_classes) of the constructor call (nn.py:308-347) from the modules."""
+        net, fpn = self.net, self.fpn
+        width = (net.p1[0].conv.in_channels, net.p1[0].conv.out_channels, net.p2[0].conv.out_channels,
+                 net.p3[0].conv.out_channels, net.p4[0].conv.out_channels, net.p5[0].conv.out_channels)
+        depth = (len(net.p2[1].res_m), len(net.p3[1].res_m), len(net.p4[1].res_m), len(net.p5[1].res_m),
+                 len(net.p5[3].res_m), len(fpn.h1.res_m))
+        is_csp = lambda m: type(m).__name__ == "CSPModule"  # noqa: E731
+        csp = (is_csp(net.p2[1].res_m[0]), is_csp(net.p4[1].res_m[0]))
+        return width, depth, csp, int(self.head.nc)
+
     def __deepcopy__(self, memo):
         import copy
         cls = self.__class__

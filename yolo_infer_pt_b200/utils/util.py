@@ -97,3 +97,55 @@ def non_max_suppression(outputs, confidence_threshold=0.001, iou_threshold=0.65)
     det, counts = nms_padded(outputs, confidence_threshold, iou_threshold)
     counts = counts.cpu().tolist()  # the single host synchronisation of the call
     return [det[i, :k] for i, k in enumerate(counts)]
+
+
+def compute_metric_batch(det, counts, targets, target_counts, iou_v):
+    """Batched, device-resident `compute_metric` (reference util.py:99-120) over the padded output of
+    `nms_padded`: det (B, max_det, 6), counts (B,), targets (B, max_t, 5) rows [class, x1, y1, x2, y2] in
+    pixels, target_counts (B,), iou_v (T,).  Returns correct (B, max_det, T) bool; no host round trip."""
+    if not det.is_cuda:
+        raise RuntimeError("compute_metric runs on the GPU only (no CPU fallback)")
+    _lib = _lib_module()
+    L = _lib.lib()
+    dev = det.device
+    det = det.float().contiguous()
+    counts = counts.to(dev, torch.int32).contiguous()
+    targets = targets.to(dev, torch.float32).contiguous()
+    target_counts = target_counts.to(dev, torch.int32).contiguous()
+    iou_v = iou_v.to(dev, torch.float32).contiguous()
+    B, max_det = det.shape[0], det.shape[1]
+    max_t = targets.shape[1]
+    correct = torch.empty((B, max_det, iou_v.numel()), dtype=torch.uint8, device=dev)
+    tptr = targets.data_ptr() if max_t else det.data_ptr()   # never dereferenced when there are no labels
+    stream = torch.cuda.current_stream(dev).cuda_stream
+    with torch.cuda.device(dev):
+        _lib.check(L.yb_compute_metric(det.data_ptr(), counts.data_ptr(), tptr, target_counts.data_ptr(), B, max_det,
+                                       max_t, iou_v.data_ptr(), iou_v.numel(), correct.data_ptr(),
+                                       ctypes.c_void_p(stream)), "yb_compute_metric")
+    return correct.bool()
+
+
+def compute_metric(output, target, iou_v):
+    """Reference signature (util.py:99): output (N, 6) detections of one image, target (M, 5) labels
+    [class, x1, y1, x2, y2], iou_v (T,) -> correct (N, T) bool on output.device."""
+    n, m = output.shape[0], target.shape[0]
+    dev = output.device
+    cnt = torch.tensor([n], dtype=torch.int32, device=dev)
+    tcnt = torch.tensor([m], dtype=torch.int32, device=dev)
+    det = output[None, :, :6] if n else torch.zeros((1, 1, 6), device=dev)
+    tgt = target[None] if m else torch.zeros((1, 0, 5), device=dev)
+    return compute_metric_batch(det, cnt, tgt, tcnt, iou_v)[0, :n]
+
+
+def load_weight(model, ckpt):
+    """Reference util.py:345-355: copy every tensor of the checkpoint's `model` whose key and shape match
+    into `model` (strict=False).  `ckpt` is a path (or an already loaded dict); its 'model' entry may be a
+    state_dict or a pickled module - the reference's own class works when `yolo_infer_pt_b200/` provides
+    `nets.nn` on sys.path."""
+    dst = model.state_dict()
+    obj = ckpt if isinstance(ckpt, dict) else torch.load(ckpt, map_location="cpu", weights_only=False)
+    src = obj["model"]
+    src = src.float().cpu().state_dict() if isinstance(src, torch.nn.Module) else src
+    keep = {k: v.float() for k, v in src.items() if k in dst and v.shape == dst[k].shape}
+    model.load_state_dict(state_dict=keep, strict=False)
+    return model
