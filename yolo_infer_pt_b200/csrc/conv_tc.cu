@@ -549,7 +549,7 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
                       P.dst_row_off + r;
 #pragma unroll
           for (int j = 0; j < 16; j++) {
-            if (nb + j < P.nc) ob[(size_t)j * P.A_total] = 1.f / (1.f + __expf(-f[j]));
+            if (nb + j < P.nc) ob[(size_t)j * P.A_total] = __fdividef(1.f, 1.f + __expf(-f[j]));  // 2-ulp reciprocal: MUFU.RCP + FMUL
           }
         }
       };
@@ -1242,7 +1242,7 @@ int conv_tc_prepare(yb_plan* p, Op& op) {
       op.patch_stage_bytes = round_up(PP_H * PP_W * 128, 1024);
       for (int pst = 3; pst >= 2; pst--) {
         const size_t extra = (size_t)pst * op.patch_stage_bytes + (size_t)10 * num_kb * 64 * 4;
-        for (int st = std::min(MAX_STAGES, 4); st >= std::min(min_st, 3); st--)
+        for (int st = std::min(MAX_STAGES, 4); st >= std::min(min_st, 3); st--)   // min_st 2 only as the last resort
           if (conv_smem_bytes(st, op.BN, 0, resident ? num_kb : 0, cb) + extra <= bud) { st_out = st; pst_out = pst; return true; }
       }
       return false;
@@ -1290,7 +1290,7 @@ int conv_tc_prepare(yb_plan* p, Op& op) {
     for (int cbt = 2; cbt >= 1 && !found; cbt--)
       for (int res = 1; res >= 0 && !found; res--) {
         if ((res && !res_ok) || (cbt == 2 && !cb2_ok)) continue;
-        if (plan_smem(1, res != 0, cbt, 3, st, pst)) {
+        if (plan_smem(1, res != 0, cbt, cbt == 1 && !res ? 2 : 3, st, pst)) {
           op.b_resident = res;
           cb = cbt;
           occ = 1;

@@ -424,7 +424,9 @@ int build_plan(yb_plan* p) {
       if (c.k != 1 || c.stride != 1 || c.nseg != 1 || !c.a_tma || c.out_f32 || c.has_res) continue;
       if (c.src[0].buf != d.dst.buf || c.src[0].c_off != d.dst.c_off || c.src[0].C != d.dst.C) continue;
       if (p->bufs[d.dst.buf].last_use != (int)i + 1) continue;
-      if (c.N_pad != c.BN || c.K_pad / 64 > 4 || c.Hout < 20) continue;
+      const int max_kb = getenv("YB_DWFUSE_MAX_KB") ? atoi(getenv("YB_DWFUSE_MAX_KB")) : 4;
+      const int max_nt = getenv("YB_DWFUSE_MAX_NT") ? atoi(getenv("YB_DWFUSE_MAX_NT")) : 1;
+      if (c.N_pad / c.BN > max_nt || c.K_pad / 64 > max_kb || c.Hout < 20) continue;
       c.dw_fused = 1;
       c.dw_op = (int)i;
       d.fused_away = 1;
