@@ -166,6 +166,26 @@ def conv_algorithmic_work(desc, batch):
     return work
 
 
+def bind_to_gpu_numa_node(gpu_index):
+    """One process per GPU: pin this process to the CPUs NVML reports as local to its GPU, so that the pinned
+    host batches are allocated (first touch) on that NUMA node and the H2D copies do not cross sockets."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            uuid = str(torch.cuda.get_device_properties(gpu_index).uuid)
+            h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(gpu_index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (int(w) >> b) & 1}
+        cpus &= set(os.sched_getaffinity(0))
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+    except Exception:
+        pass
+
+
 def run_ours(args, rank, world, local_rank):
     from oracle import nms_oracle, yolo_oracle  # checker / CPU baseline only
     from yolo_infer_pt_b200 import _lib, synth
@@ -174,6 +194,8 @@ def run_ours(args, rank, world, local_rank):
 
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
+    if world > 1:   # (the single-GPU run keeps every core for its CPU-baseline leg)
+        bind_to_gpu_numa_node(local_rank)   # before any pinned allocation: H2D then reads node-local host memory
     peaks = read_peaks()
     model = getattr(nn, f"yolo_v11_{args.model}")(80)
     synth.load_synth(model, 0, "survey")
