@@ -12,7 +12,7 @@ timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__byte
   python tools/ncu_target.py --model n --batch 256 --iters 2 > gpurun_out/${TAG}_ncu_dram.log 2>&1
 echo "conv dram rc=$?"
 timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum \
-  --clock-control none --launch-skip 95 -c 95 --csv --log-file gpurun_out/${TAG}_all_dram.csv \
+  --clock-control none --launch-skip 85 -c 85 --csv --log-file gpurun_out/${TAG}_all_dram.csv \
   python tools/ncu_target.py --model n --batch 256 --iters 2 --nms 1 > gpurun_out/${TAG}_ncu_all.log 2>&1
 echo "all dram rc=$?"
 bash tools/ncu_one.sh ${TAG} 0 3 61 64 66
