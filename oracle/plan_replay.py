@@ -83,8 +83,9 @@ class PlanReplay:
                 x = F.pad(x, (0, 0, pad, pad, pad, pad))         # zero padding like the kernel's OOB fill
                 x = x[:, dy:dy + s * op["Hout"]:s, dx:dx + s * op["Wout"]:s, :][:, :op["Hout"], :op["Wout"]]
                 x = x.reshape(self.B, op["Hout"] * op["Wout"], cp)
-                if op["a_tma"]:
-                    x = F.pad(x, (0, op["seg_kpad"][si] - cp))
+                # per-source K padding: 64-channel blocks for TMA-fed 1x1 layers and for tap-aligned 3x3
+                # layers (seg_kpad == cp everywhere else)
+                x = F.pad(x, (0, op["seg_kpad"][si] - cp))
                 cols.append(x)
         A = torch.cat(cols, 2)
         A = F.pad(A, (0, op["K_pad"] - A.shape[2]))

@@ -264,7 +264,7 @@ int yb_plan_pack_conv(const yb_plan* plan, int index, const float* w, const floa
     __nv_bfloat16* W = reinterpret_cast<__nv_bfloat16*>(dst);
     float* B = reinterpret_cast<float*>(dst + (size_t)op.N_pad * op.K_pad * 2);
     int per_tap = 0;
-    for (int s = 0; s < op.nseg; s++) per_tap += cpad8(op.src[s].C);
+    for (int s = 0; s < op.nseg; s++) per_tap += op.seg_kpad[s];   // (> padded channels for tap-aligned 3x3 layers)
     for (int co = 0; co < cout; co++) {
       __nv_bfloat16* row = W + (size_t)co * op.K_pad;
       for (int tap = 0; tap < k * k; tap++) {
@@ -276,7 +276,7 @@ int yb_plan_pack_conv(const yb_plan* plan, int index, const float* w, const floa
             row[kpos + c] = __float2bfloat16(v);
           }
           ci0 += op.src[s].C;
-          kpos += op.a_tma ? op.seg_kpad[s] : cpad8(op.src[s].C);
+          kpos += op.seg_kpad[s];
         }
       }
       B[co] = bias ? bias[co] : 0.f;

@@ -56,7 +56,8 @@ struct ConvParams {
   int Hin, Win, Hout, Wout;
   int M;              // B * Hout * Wout
   int K, num_kb;
-  int per_tap;        // sum of src_cp
+  int per_tap;        // sum of src_cp (tap-aligned layers: padded to a multiple of 64)
+  int tap_c;          // tap-aligned layers: channels >= tap_c of a tap are padding (never gathered)
   int seg_kb[4];      // a_tma: k-blocks per segment
   void* dst;
   int dst_ld;         // elements
@@ -667,12 +668,12 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
                 offb[i] = (uint32_t)(((y0 + i * P.stride) >> up) * Ws + (x0 >> up)) * ld2;
             }
             uint32_t deltab = (uint32_t)c * 2u;
-            uint32_t ok8 = (k0 < K) ? 0xFFu : 0u;
+            uint32_t ok8 = (k0 < K && c < P.tap_c) ? 0xFFu : 0u;
             if (ksize == 3) {
               const int dy = (tap * 11) >> 5;  // tap / 3 for tap < 16
               const int dx = tap - dy * 3;
               deltab += (uint32_t)(dy * Ws + dx) * ld2;
-              ok8 = (k0 < K && ((xbits >> dx) & 1u)) ? (dy == 0 ? ybits[0] : dy == 1 ? ybits[1] : ybits[2]) : 0u;
+              ok8 = (k0 < K && c < P.tap_c && ((xbits >> dx) & 1u)) ? (dy == 0 ? ybits[0] : dy == 1 ? ybits[1] : ybits[2]) : 0u;
             }
             mbar_wait(empty_bar(s), ph ^ 1u);
             const uint32_t a_s = a_base + (uint32_t)s * A_STAGE_BYTES + sw_off + (uint32_t)rbase * 128u;
@@ -713,9 +714,9 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
           const int s = stage;
           const uint32_t ph = phase;
           const int k0 = kb * BK + g * 8;
-          const bool k_ok = k0 < P.K;
           int tap = fast_div(k0, P.pt_mul, P.pt_shr, P.per_tap);
           int c = k0 - tap * P.per_tap;
+          const bool k_ok = k0 < P.K && c < P.tap_c;
           int seg = 0;
           while (seg + 1 < P.nseg && c >= P.src_cp[seg]) {
             c -= P.src_cp[seg];
@@ -1101,7 +1102,7 @@ __global__ void conv_direct_check_kernel(const ConvParams P) {
         for (int c = 0; c < P.src_c[s]; c++)
           acc += __bfloat162float(sp[c]) * __bfloat162float(wrow[kpos + c]);
       }
-      kpos += P.a_tma ? P.seg_kpad[s] : P.src_cp[s];
+      kpos += P.seg_kpad[s];
     }
   }
   float x = acc + P.bias[n];
@@ -1198,7 +1199,7 @@ static size_t conv_smem_bytes(int stages, int BN, size_t a_region = 0, int b_slo
 static bool patch_eligible(const yb_plan* p, const Op& op) {
   if (getenv("YB_NO_PATCH")) return false;
   if (op.k != 3 || op.stride != 1 || op.nseg != 1 || op.src[0].up || op.out_f32) return false;
-  const int C = op.src[0].C;
+  const int C = op.seg_kpad[0];   // channels per tap as packed (a multiple of 64 for tap-aligned layers)
   if (!(C == 8 || C == 16 || C == 32 || (C % 64 == 0 && C > 0))) return false;
   int min_hw = 40;  // below this the 16 x 8 tiles hang too far over the image edge
   if (const char* e = getenv("YB_PATCH_MIN_HW")) min_hw = atoi(e);
@@ -1248,7 +1249,7 @@ int conv_tc_prepare(yb_plan* p, Op& op) {
       return false;
     }
     if (op.patch) {
-      const int C = op.src[0].C, cblk = std::min(C, 64);
+      const int C = op.seg_kpad[0], cblk = std::min(C, 64);
       op.patch_stage_bytes = round_up(PP_H * PP_W * cblk * 2 + 16, 1024);
       for (int pst = MAX_PATCH_STAGES; pst >= 2; pst--) {
         const size_t a_region = (size_t)pst * op.patch_stage_bytes;
@@ -1269,8 +1270,10 @@ int conv_tc_prepare(yb_plan* p, Op& op) {
   bool found = false;
   op.b_resident = 0;
   struct Try { int occ; bool res; int cb; int min_st; };
+  // (patch layers: resident weights on one CTA per SM beat streamed weights on two - the streamed path
+  // re-reads the matrix per tile and runs the generic MMA issue loop)
   const Try tries[] = {
-      {occ, true, 2, 4}, {occ, true, 1, 4}, {occ, false, 2, 5}, {1, true, 2, 4}, {occ, false, 1, 4},
+      {occ, true, 2, 4}, {occ, true, 1, 4}, {1, true, 2, 4}, {1, true, 1, 4}, {occ, false, 2, 5}, {occ, false, 1, 4},
       {occ, true, 1, 3}, {occ, false, 1, 2}};
   for (const Try& t : tries) {
     if (t.res && !res_ok) continue;
@@ -1339,7 +1342,7 @@ int conv_tc_prepare(yb_plan* p, Op& op) {
     const Buf& b = p->bufs[op.src[0].buf];
     const uint8_t* base = buf_ptr(p, op.src[0].buf) + (size_t)op.src[0].c_off * 2;
     rc = make_tmap_nhwc(&op.tmap_a[0], base, (uint64_t)op.src[0].C, (uint64_t)b.W, (uint64_t)b.H, (uint64_t)p->B,
-                        (uint64_t)b.C, (uint32_t)std::min(op.src[0].C, 64), PP_W, PP_H);
+                        (uint64_t)b.C, (uint32_t)std::min(op.seg_kpad[0], 64), PP_W, PP_H);
     if (rc) return rc;
   }
   if (op.a_tma && !op.dw_fused) {
@@ -1400,8 +1403,9 @@ static void fill_params(const yb_plan* p, const Op& op, ConvParams& P) {
     P.src_up[i] = op.src[i].up;
     P.seg_kb[i] = op.seg_kpad[i] / BK;
     P.seg_kpad[i] = op.seg_kpad[i];
-    per_tap += P.src_cp[i];
+    per_tap += op.a_tma ? P.src_cp[i] : op.seg_kpad[i];   // tap-aligned 3x3 layers: per-tap K padded to 64
   }
+  P.tap_c = (!op.a_tma && op.nseg == 1 && op.seg_kpad[0] != P.src_cp[0]) ? P.src_cp[0] : 0x7fffffff;
   P.per_tap = per_tap;
   P.ksize = op.k;
   P.stride = op.stride;
@@ -1461,7 +1465,7 @@ static void fill_params(const yb_plan* p, const Op& op, ConvParams& P) {
   // measured: alternate tiles win except on patch layers with >= 32 output channels
   P.alt_epilogue = (getenv("YB_NO_ALT_EPI") || (op.patch && op.BN >= 32)) ? 0 : 1;
   if (op.patch) {
-    const int C = op.src[0].C;
+    const int C = op.seg_kpad[0];
     P.patch = 1;
     P.cblk = std::min(C, 64);
     P.ncb = (C + 63) / 64;

@@ -140,6 +140,16 @@ struct Builder {
         op.seg_kpad[i] = cpad8(op.src[i].C);
         per_tap += op.seg_kpad[i];
       }
+      // 3x3 / stride-1 layers that will read TMA halo patches need every tap's K range to start on a
+      // 64-channel block: channel counts that are no power of two <= 32 and no multiple of 64 (YOLO11x: 48,
+      // 96) get their per-tap K padded ("tap-aligned" packing; the pad columns hold zero weights)
+      int min_hw = 40;
+      if (const char* e = getenv("YB_PATCH_MIN_HW")) min_hw = atoi(e);
+      if (k == 3 && s == 1 && op.nseg == 1 && !op.src[0].up && !getenv("YB_NO_PATCH") && !getenv("YB_NO_TAP_ALIGN") &&
+          op.Hout >= min_hw && op.Wout >= min_hw && per_tap > 32 && per_tap % 64 != 0) {
+        op.seg_kpad[0] = round_up(per_tap, 64);
+        per_tap = op.seg_kpad[0];
+      }
       K = per_tap * k * k;
       Kp = round_up(K, 64);
     }
