@@ -472,9 +472,9 @@ long long yb_plan_describe(const yb_plan* plan, char* buf, size_t capacity) {
     const Op& o = plan->ops[i];
     snprintf(t, sizeof(t), "%s{\"kind\":%d,\"name\":\"%s\",\"k\":%d,\"stride\":%d,\"Hin\":%d,\"Win\":%d,"
              "\"Hout\":%d,\"Wout\":%d,\"act\":%d,\"out_f32\":%d,\"dst_row_off\":%d,\"conv_index\":%d,"
-             "\"a_tma\":%d,\"patch\":%d,\"dw_fused\":%d,\"fused_away\":%d,\"K\":%d,\"K_pad\":%d,\"N_pad\":%d,\"BN\":%d,\"has_res\":%d,",
+             "\"a_tma\":%d,\"patch\":%d,\"pair\":%d,\"resident\":%d,\"occ\":%d,\"stages\":%d,\"dw_fused\":%d,\"fused_away\":%d,\"K\":%d,\"K_pad\":%d,\"N_pad\":%d,\"BN\":%d,\"has_res\":%d,",
              i ? "," : "", (int)o.kind, o.name.c_str(), o.k, o.stride, o.Hin, o.Win, o.Hout, o.Wout, o.act,
-             o.out_f32, o.dst_row_off, o.conv_index, o.a_tma, o.patch, o.dw_fused, o.fused_away, o.K, o.K_pad, o.N_pad, o.BN, o.has_res);
+             o.out_f32, o.dst_row_off, o.conv_index, o.a_tma, o.patch, o.pair, o.b_resident, o.occ, o.stages, o.dw_fused, o.fused_away, o.K, o.K_pad, o.N_pad, o.BN, o.has_res);
     j += t;
     snprintf(t, sizeof(t), "\"seg_kpad\":[%d,%d,%d,%d],\"dw\":[%d,%d,%d,%d],\"heads\":%d,\"scale\":%.9g,",
              o.seg_kpad[0], o.seg_kpad[1], o.seg_kpad[2], o.seg_kpad[3], o.dw_gsz, o.dw_gstride, o.dw_goff,

@@ -44,7 +44,8 @@ static constexpr int MAX_PATCH_STAGES = 4;
 static constexpr int NUM_BARS = 3 * MAX_STAGES + 4 + 2 * MAX_PATCH_STAGES;
 static constexpr int PT_H = 16, PT_W = 8;          // PATCH mode output tile (pixels)
 static constexpr int PP_H = PT_H + 2, PP_W = PT_W + 2;  // its input halo patch
-enum { MODE_GATHER = 0, MODE_ATMA = 1, MODE_PATCH = 2, MODE_DW = 3 };
+enum { MODE_GATHER = 0, MODE_ATMA = 1, MODE_PATCH = 2, MODE_DW = 3, MODE_PATCH2 = 4 };
+static constexpr int PP2_W = 2 * PT_W + 2;        // MODE_PATCH2: one 18 x 18 patch feeds two 16 x 8 tiles side by side
 
 struct ConvParams {
   const __nv_bfloat16* src[4];
@@ -78,6 +79,8 @@ struct ConvParams {
   // 3x3 / stride-1 convs fed from TMA halo patches (mode PATCH): an 18 x 10 pixel patch of `cblk`
   // channels per 16 x 8 output tile; each tap is a shifted UMMA descriptor into the patch
   int patch, cblk, ncb, a_layout;
+  int patch_creal;      // real input channels (tap-aligned layers: K steps past them are zero padding and are skipped)
+  int pair;             // MODE_PATCH2: 16 x 16 pixel super-tiles = two accumulators sharing every weight k-block
   int patch_tx_bytes, patch_stage_bytes, patch_stages;
   int a_region_bytes;   // shared memory of the A ring (stages x 16 KB, or the patch ring)
   int b_resident;       // weights stay in shared memory for the whole kernel: slot kb, loaded during the first tile
@@ -175,7 +178,7 @@ struct TilePos {
   int m0;            // linear: first row
   int n, oy0, ox0;   // 2-D: image and patch origin
 };
-template <bool T2D, int TW>
+template <bool T2D, int TW, int TH = BM / TW>
 __device__ __forceinline__ TilePos tile_pos(const ConvParams& P, int mt) {
   TilePos t;
   t.m0 = mt * BM;
@@ -184,7 +187,7 @@ __device__ __forceinline__ TilePos tile_pos(const ConvParams& P, int mt) {
     t.n = fast_div(mt, P.tpi_mul, P.tpi_shr, P.tiles_per_img);
     int r = mt - t.n * P.tiles_per_img;
     int ty = fast_div(r, P.tx_mul, P.tx_shr, P.tiles_x);
-    t.oy0 = ty * (BM / TW);
+    t.oy0 = ty * TH;
     t.ox0 = (r - ty * P.tiles_x) * TW;
   }
   return t;
@@ -266,10 +269,12 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 // N <= 64 an MMA retires in ~48 cycles; a longer issue sequence is the bottleneck).
 // a_lo / b_lo: low descriptor words (address >> 4) of the patch and of weight slot `kb0`; bstep =
 // slot stride >> 4; first: the accumulator is overwritten by the first MMA.
-template <int CBLK>
+template <int CBLK, bool PAIR>
 __device__ __forceinline__ void issue_patch_steady(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
-                                                   uint32_t b_hi, uint32_t bstep, uint32_t idesc, bool first) {
+                                                   uint32_t b_hi, uint32_t bstep, uint32_t idesc, bool first,
+                                                   uint32_t bn, int kvalid) {
   constexpr int ROWB = CBLK * 2;
+  constexpr int PP_W = PAIR ? PP2_W : yb::PP_W;   // patch row pitch in pixels (shadows the single-tile constant)
   constexpr int NMMA = CBLK == 8 ? 5 : 9 * CBLK / 16;
 #pragma unroll
   for (int i = 0; i < NMMA; i++) {
@@ -287,10 +292,13 @@ __device__ __forceinline__ void issue_patch_steady(uint32_t d_tmem, uint32_t a_l
       a_off = ((tap / 3) * PP_W + tap % 3) * ROWB + cin * 2;
       kslot = kg / 64;
       k = (kg % 64) / 16;
+      if (CBLK == 64 && k >= kvalid) continue;   // zero-padded channels of a tap-aligned layer
     }
     const uint64_t da = ((uint64_t)a_hi << 32) | (uint64_t)((a_lo + (a_off >> 4)) & 0x3FFFu) | ((uint64_t)lbo << 16);
     const uint64_t db = ((uint64_t)b_hi << 32) | (uint64_t)((b_lo + (uint32_t)kslot * bstep + 2u * k) & 0x3FFFu) | (1ull << 16);
     umma_bf16(d_tmem, da, db, idesc, (uint32_t)(!(first && i == 0)));
+    if (PAIR)   // right half: same weights, patch shifted by 8 pixels, second accumulator
+      umma_bf16(d_tmem + bn, da + (uint64_t)((PT_W * ROWB) >> 4), db, idesc, (uint32_t)(!(first && i == 0)));
   }
 }
 
@@ -312,7 +320,7 @@ static constexpr int NUM_THREADS_DW = (DW_WARP0 + DW_THREADS / 32) * 32;
 // every instantiation carries only the code of its own roles, which keeps it inside the
 // instruction cache (11 warps run disjoint code).
 template <int MODE, bool T2D, bool HEAD>
-__global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS, MODE == MODE_PATCH ? 3 : MODE == MODE_DW ? 1 : 2)
+__global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS, MODE == MODE_PATCH ? 3 : MODE == MODE_DW ? 1 : 2)  // (PATCH2: 2)
     conv_gemm_tcgen05_kernel(const ConvParams P, const __grid_constant__ CUtensorMap tmap_b,
                              const __grid_constant__ CUtensorMap tmap_a0,
                              const __grid_constant__ CUtensorMap tmap_a1,
@@ -321,10 +329,14 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
                              const __grid_constant__ CUtensorMap tmap_c) {
   constexpr bool DW = MODE == MODE_DW;
   constexpr bool A_TMA = MODE != MODE_GATHER;   // warps 4-7 are not im2col producers: they join the epilogue
-  constexpr bool PATCH = MODE == MODE_PATCH;
+  constexpr bool PAIR = MODE == MODE_PATCH2;        // two 16 x 8 tiles per iteration (one 16 x 16 super-tile)
+  constexpr bool PATCH = MODE == MODE_PATCH || PAIR;
   constexpr bool PGEO = PATCH || DW;               // 16 x 8 pixel tiles
-  constexpr int TW = PGEO ? PT_W : 16;             // 2-D tile width (rows of the tile: r = ly * TW + lx)
-  constexpr int TWS = PGEO ? 3 : 4;
+  constexpr int TW = PAIR ? 16 : PGEO ? PT_W : 16; // 2-D tile width used to place the tile in the image
+  constexpr int TH = PAIR ? 16 : BM / TW;
+  constexpr int EW = PGEO ? PT_W : 16;             // width of one accumulator's pixel block (row r = ly * EW + lx)
+  constexpr int EWS = PGEO ? 3 : 4;
+  constexpr int PPW = PAIR ? PP2_W : PP_W;         // patch row pitch, pixels
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   const uint32_t base = (raw_addr + 1023u) & ~1023u;  // SWIZZLE_128B tiles need 1024 B alignment
@@ -339,7 +351,7 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
   const uint32_t c_groups = (uint32_t)(BN + 63) / 64;
   const uint32_t c_base = b_base + (uint32_t)P.b_slots * b_stage_bytes;
   uint8_t* tail = smem + (size_t)P.a_region_bytes + (size_t)P.b_slots * b_stage_bytes +
-                  (size_t)c_groups * C_GROUP_BYTES * (size_t)P.c_bufs;
+                  (size_t)c_groups * C_GROUP_BYTES * (size_t)P.c_bufs * (PAIR ? 2 : 1);
   const bool RES = P.b_resident != 0;
   const uint32_t ring_base = a_base + (DW ? (uint32_t)P.dw_patch_bytes : 0u);   // A stage ring
   // Two epilogue warp groups exist when no im2col producers are needed.  With one N tile and two
@@ -441,16 +453,17 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ti++) {
       if (alt_epi && (ti & 1) != grp) continue;
       const int mt = P.n_tiles == 1 ? tile : tile / P.n_tiles;
-      const TilePos tp = tile_pos<T2D, TW>(P, mt);
+      const TilePos tp = tile_pos<T2D, TW, TH>(P, mt);
       const int m0 = tp.m0;
       const int n0 = (tile - mt * P.n_tiles) * BN;
       const int acc = ti & 1;
+      for (int half = 0; half < (PAIR ? 2 : 1); half++) {   // PATCH2: left / right 16 x 8 block of the super-tile
       int m = m0 + etid;
       bool row_ok = m < P.M;
       int n_img = 0, r = 0;
       if (T2D) {
         n_img = tp.n;
-        const int oy = tp.oy0 + (etid >> TWS), ox = tp.ox0 + (etid & (TW - 1));
+        const int oy = tp.oy0 + (etid >> EWS), ox = tp.ox0 + PT_W * half + (etid & (EW - 1));
         r = oy * P.Wout + ox;
         m = n_img * P.hw_out + r;
         row_ok = !PGEO || (oy < P.Hout && ox < P.Wout);   // 16 x 8 tiles may hang over the image edge
@@ -473,9 +486,11 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
       };
       res_fetch(cfirst, ra0, ra1);
       res_fetch(cfirst + cstep, rb0, rb1);
+      if (half == 0) {
       mbar_wait(tmem_full_bar(acc), (uint32_t)(ti >> 1) & 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      if (!fast_flow && !(alt_epi && HEAD)) {
+      }
+      if (half == 0 && !fast_flow && !(alt_epi && HEAD)) {
         // the previous tile's TMA stores (this group's, when the groups alternate: issued a whole
         // tile ago) must have finished reading the staging buffer
         if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
@@ -483,8 +498,8 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
           for (int i = tid; i < BN; i += 128 * ngrp) bias_s[i] = __ldg(P.bias + n0 + i);
         epi_sync();
       }
-      const uint32_t c_buf = c_base + (((fast_flow && (ti & 1)) || (alt_epi && grp)) ? c_groups * C_GROUP_BYTES : 0u);
-      const uint32_t t_row = tmem_base + ((uint32_t)(qwarp * 32) << 16) + (uint32_t)(acc * BN);
+      const uint32_t c_buf = c_base + (((fast_flow && (ti & 1)) || (alt_epi && grp) || (PAIR && half)) ? c_groups * C_GROUP_BYTES : 0u);
+      const uint32_t t_row = tmem_base + ((uint32_t)(qwarp * 32) << 16) + (uint32_t)(acc * (PAIR ? 2 * BN : BN) + half * BN);
       float dist[4];
       auto do_chunk = [&](int c0, const uint4& rv0, const uint4& rv1) {
         uint32_t v[16];
@@ -570,6 +585,7 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
         ob[(size_t)2 * P.A_total] = (x2 - x1) * st;
         ob[(size_t)3 * P.A_total] = (y2 - y1) * st;
       }
+      }   // half
       // accumulator stage drained: hand it back to the MMA warp
       asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
       mbar_arrive(tmem_empty_bar(acc));
@@ -580,6 +596,8 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
         if (fast_flow && leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         epi_sync();
         if (leader) {
+          const uint32_t c_buf = c_base + (((fast_flow && (ti & 1)) || (alt_epi && grp)) ? c_groups * C_GROUP_BYTES : 0u);
+          for (int half = 0; half < (PAIR ? 2 : 1); half++)
           for (uint32_t g = 0; g < c_groups; g++) {
             const int cg0 = n0 + (int)g * 64;
             if (cg0 < P.cout_store) {
@@ -587,7 +605,8 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
                 asm volatile(
                     "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];" ::"l"(
                         (uint64_t)&tmap_c),
-                    "r"(cg0), "r"(tp.ox0), "r"(tp.oy0), "r"(tp.n), "r"(c_buf + g * C_GROUP_BYTES)
+                    "r"(cg0), "r"(tp.ox0 + PT_W * half), "r"(tp.oy0), "r"(tp.n),
+                    "r"(c_buf + (uint32_t)half * c_groups * C_GROUP_BYTES + g * C_GROUP_BYTES)
                     : "memory");
               } else {
                 asm volatile(
@@ -621,7 +640,7 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
       uint32_t phase = 0;
       const int ksize = P.ksize, Win = P.Win, Hin = P.Hin, K = P.K, per_tap = P.per_tap, nseg = P.nseg;
       for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-        const TilePos tp = tile_pos<T2D, TW>(P, P.n_tiles == 1 ? tile : tile / P.n_tiles);
+        const TilePos tp = tile_pos<T2D, TW, TH>(P, P.n_tiles == 1 ? tile : tile / P.n_tiles);
         if (T2D) {
           // ---- fast path: 8 x 16 spatial tile.  This thread's 8 rows are the 8 image rows of one
           // tile column (ly = i, lx = rbase), so x validity is shared and y validity per tap row is
@@ -787,7 +806,7 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
       const int acc = ti & 1;
       mbar_wait(tmem_empty_bar(acc), ((uint32_t)(ti >> 1) & 1u) ^ 1u);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * (PAIR ? 2 * BN : BN));
       if (PATCH) {
         // k-blocks in consumption order: (channel block, tap) for >= 64 channels, else the packed
         // (tap, channel) order.  Every K=16 step reads the patch through a descriptor shifted by the
@@ -795,7 +814,7 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
         // 16-byte-aligned start inside the TMA-written patch is a valid operand origin.
         const int cblk = P.cblk;
         const uint32_t row_bytes = (uint32_t)cblk * 2u;
-        const uint64_t adesc_hi = ((uint64_t)((PP_W * row_bytes) >> 4) << 32) | ((uint64_t)1 << 46) |
+        const uint64_t adesc_hi = ((uint64_t)((PPW * row_bytes) >> 4) << 32) | ((uint64_t)1 << 46) |
                                   ((uint64_t)P.a_layout << 61);
         if (RES && ti > 0) {
           // steady state with resident weights: nothing to wait for but the patches
@@ -808,10 +827,11 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
               const uint32_t bstep = b_stage_bytes >> 4;
               const uint32_t b_lo = (b_base >> 4) + (uint32_t)(cb * 9) * bstep;
               const bool first = cb == 0;
-              if (cblk == 64) issue_patch_steady<64>(d_tmem, a_lo, a_hi, b_lo, b_hi, bstep, idesc, first);
-              else if (cblk == 32) issue_patch_steady<32>(d_tmem, a_lo, a_hi, b_lo, b_hi, bstep, idesc, first);
-              else if (cblk == 16) issue_patch_steady<16>(d_tmem, a_lo, a_hi, b_lo, b_hi, bstep, idesc, first);
-              else issue_patch_steady<8>(d_tmem, a_lo, a_hi, b_lo, b_hi, bstep, idesc, first);
+              const int kvalid = min(4, (P.patch_creal - cb * 64 + 15) >> 4);
+              if (cblk == 64) issue_patch_steady<64, PAIR>(d_tmem, a_lo, a_hi, b_lo, b_hi, bstep, idesc, first, (uint32_t)BN, kvalid);
+              else if (cblk == 32) issue_patch_steady<32, PAIR>(d_tmem, a_lo, a_hi, b_lo, b_hi, bstep, idesc, first, (uint32_t)BN, kvalid);
+              else if (cblk == 16) issue_patch_steady<16, PAIR>(d_tmem, a_lo, a_hi, b_lo, b_hi, bstep, idesc, first, (uint32_t)BN, kvalid);
+              else issue_patch_steady<8, PAIR>(d_tmem, a_lo, a_hi, b_lo, b_hi, bstep, idesc, first, (uint32_t)BN, kvalid);
               umma_commit(patch_empty_bar(pstage));
               if (cb == P.ncb - 1) umma_commit(tmem_full_bar(acc));
             }
@@ -836,27 +856,31 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
               uint32_t a_addr;
               uint64_t lbo = 1;
               if (cblk >= 64) {
+                if ((kb / 9) * 64 + k * 16 >= P.patch_creal) break;   // zero-padded channels of a tap-aligned layer
                 const int tap = kb % 9, dy = (tap * 11) >> 5, dx = tap - dy * 3;
-                a_addr = pa + (uint32_t)(dy * PP_W + dx) * row_bytes + 32u * k;
+                a_addr = pa + (uint32_t)(dy * PPW + dx) * row_bytes + 32u * k;
               } else if (cblk >= 16) {
                 const int kg = kb * BK + k * 16;
                 const int tap = kg / cblk;
                 if (tap >= 9) break;
                 const int dy = (tap * 11) >> 5, dx = tap - dy * 3;
-                a_addr = pa + (uint32_t)(dy * PP_W + dx) * row_bytes + (uint32_t)(kg - tap * cblk) * 2u;
+                a_addr = pa + (uint32_t)(dy * PPW + dx) * row_bytes + (uint32_t)(kg - tap * cblk) * 2u;
               } else {
                 // 8 channels: one MMA covers taps (2j, 2j+1); LBO = distance between their pixels
                 const int j = kb * 4 + k;
                 if (j >= 5) break;
                 const int t0 = 2 * j, t1 = j < 4 ? 2 * j + 1 : 2 * j;
                 const int dy0 = (t0 * 11) >> 5, dy1 = (t1 * 11) >> 5;
-                const uint32_t o0 = (uint32_t)(dy0 * PP_W + (t0 - dy0 * 3)) * 16u;
-                const uint32_t o1 = (uint32_t)(dy1 * PP_W + (t1 - dy1 * 3)) * 16u;
+                const uint32_t o0 = (uint32_t)(dy0 * PPW + (t0 - dy0 * 3)) * 16u;
+                const uint32_t o1 = (uint32_t)(dy1 * PPW + (t1 - dy1 * 3)) * 16u;
                 a_addr = pa + o0;
                 lbo = j < 4 ? (uint64_t)((o1 - o0) >> 4) : 1;
               }
               const uint64_t da = adesc_hi | (lbo << 16) | (uint64_t)((a_addr >> 4) & 0x3FFF);
               umma_bf16(d_tmem, da, db + 2u * k, idesc, (uint32_t)((kb | k) != 0));
+              if (PAIR)
+                umma_bf16(d_tmem + (uint32_t)BN, da + (uint64_t)((PT_W * row_bytes) >> 4), db + 2u * k, idesc,
+                          (uint32_t)((kb | k) != 0));
             }
             umma_commit(empty_bar(stage));
             if (last_of_patch) umma_commit(patch_empty_bar(pstage));
@@ -990,7 +1014,7 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
       int pstage = 0;
       uint32_t pphase = 0;
       for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-        const TilePos tp = tile_pos<T2D, TW>(P, P.n_tiles == 1 ? tile : tile / P.n_tiles);
+        const TilePos tp = tile_pos<T2D, TW, TH>(P, P.n_tiles == 1 ? tile : tile / P.n_tiles);
         for (int cb = 0; cb < P.ncb; cb++) {
           mbar_wait(patch_empty_bar(pstage), pphase ^ 1u);
           mbar_expect_tx(patch_full_bar(pstage), (uint32_t)P.patch_tx_bytes);
@@ -1030,7 +1054,7 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
         if (PATCH && !load_b) break;   // nothing left to load: the MMA warp no longer waits on these barriers
         const uint32_t tx = a_tx + (load_b ? b_stage_bytes : 0u);
         const int mt = P.n_tiles == 1 ? tile : tile / P.n_tiles;
-        const TilePos tp = tile_pos<T2D, TW>(P, mt);
+        const TilePos tp = tile_pos<T2D, TW, TH>(P, mt);
         const int n0 = (tile - mt * P.n_tiles) * BN;
         int seg = 0, kk = 0;
         for (int kb = 0; kb < num_kb; kb++) {
@@ -1228,13 +1252,23 @@ int conv_tc_prepare(yb_plan* p, Op& op) {
   if (!op.a_tma)
     if (const char* e = getenv("YB_OCC_GATHER")) occ = std::max(1, std::min(occ, atoi(e)));
   op.patch = patch_eligible(p, op) ? 1 : 0;
+  // pair tiles: two accumulators share every weight k-block (halves the weight traffic per output pixel and
+  // the per-tile fixed costs); needs 4 x BN TMEM columns and one N tile
+  // (measured: wins on the wide 160 x 160 layers - YOLO11x C=48: 0.45 -> 0.34 ms; neutral on YOLO11n's 80 x 80 box
+  // branch, a loss on 40 x 40 maps and on the 8-32 channel layers, which prefer single tiles with alternating
+  // epilogue groups.  YB_PAIR=0/1 overrides)
+  const int pair_env = getenv("YB_PAIR") ? atoi(getenv("YB_PAIR")) : -1;
+  op.pair = (op.patch && op.N_pad == op.BN && 4 * tmem_cols_for(op.BN) / 2 <= 512 && op.Wout >= 16 &&
+             (pair_env < 0 ? (op.BN >= 48 && op.Hout >= 160) : pair_env != 0)) ? 1 : 0;
+  if (op.pair) occ = std::min(occ, std::max(1, 512 / tmem_cols_for(2 * op.BN)));
   const int num_kb = op.K_pad / BK;
   const size_t w_bytes = (size_t)num_kb * op.BN * 128;
   // Weights resident in shared memory (loaded once per CTA instead of once per tile) whenever the
   // whole [BN x K_pad] matrix fits next to a useful A ring: L2 -> SM bandwidth (~43 B/clk/SM) is the
   // scarce resource of the small-channel layers, and the weight tile is 30-60 % of their traffic.
   const bool res_ok = op.N_pad == op.BN && num_kb <= MAX_STAGES && getenv("YB_NO_RESIDENT") == nullptr;
-  const bool cb2_ok = op.N_pad == op.BN && op.BN <= 128 && !op.out_f32 && getenv("YB_ONE_CBUF") == nullptr;
+  const bool cb2_ok = op.N_pad == op.BN && op.BN <= 128 && !op.out_f32 && !op.pair && getenv("YB_ONE_CBUF") == nullptr;
+  const int halves = op.pair ? 2 : 1;   // staging buffers per tile iteration
   // shared-memory plan: (occupancy, resident weights, staging buffers, minimum A stages) -> stages
   auto plan_smem = [&](int occ_try, bool resident, int cb, int min_st, int& st_out, int& pst_out) -> bool {
     const size_t bud = SMEM_MAX / occ_try;
@@ -1250,14 +1284,14 @@ int conv_tc_prepare(yb_plan* p, Op& op) {
     }
     if (op.patch) {
       const int C = op.seg_kpad[0], cblk = std::min(C, 64);
-      op.patch_stage_bytes = round_up(PP_H * PP_W * cblk * 2 + 16, 1024);
+      op.patch_stage_bytes = round_up(PP_H * (op.pair ? PP2_W : PP_W) * cblk * 2 + 16, 1024);
       for (int pst = MAX_PATCH_STAGES; pst >= 2; pst--) {
         const size_t a_region = (size_t)pst * op.patch_stage_bytes;
         if (resident) {
-          if (conv_smem_bytes(num_kb, op.BN, a_region, num_kb, cb) <= bud) { st_out = num_kb; pst_out = pst; return true; }
+          if (conv_smem_bytes(num_kb, op.BN, a_region, num_kb, cb * halves) <= bud) { st_out = num_kb; pst_out = pst; return true; }
         } else {
           for (int st = std::min(MAX_STAGES, 8); st >= min_st; st--)
-            if (conv_smem_bytes(st, op.BN, a_region, 0, cb) <= bud) { st_out = st; pst_out = pst; return true; }
+            if (conv_smem_bytes(st, op.BN, a_region, 0, cb * halves) <= bud) { st_out = st; pst_out = pst; return true; }
         }
       }
       return false;
@@ -1310,13 +1344,14 @@ int conv_tc_prepare(yb_plan* p, Op& op) {
     plan_smem(occ, false, 1, 2, st, pst);
   }
   op.c_bufs = cb;
+  if (!op.patch) op.pair = 0;
   if (const char* e = getenv("YB_STAGES"))
     if (!op.b_resident && !op.patch) st = std::max(1, std::min(st, atoi(e)));
   op.stages = st;
   op.patch_stages = pst;
   const size_t a_region = op.patch ? (size_t)pst * op.patch_stage_bytes : 0;
   const size_t dw_extra = op.dw_fused ? (size_t)pst * op.patch_stage_bytes + (size_t)10 * num_kb * 64 * 4 : 0;
-  op.smem_bytes = std::max(conv_smem_bytes(st, op.BN, a_region, op.b_resident ? num_kb : 0, cb) + dw_extra,
+  op.smem_bytes = std::max(conv_smem_bytes(st, op.BN, a_region, op.b_resident ? num_kb : 0, cb * halves) + dw_extra,
                            SMEM_MAX / (occ + 1) + 1024);
   if (op.smem_bytes > SMEM_MAX) {
     set_error("conv %s: tile needs %zu bytes of shared memory", op.name.c_str(), op.smem_bytes);
@@ -1342,7 +1377,7 @@ int conv_tc_prepare(yb_plan* p, Op& op) {
     const Buf& b = p->bufs[op.src[0].buf];
     const uint8_t* base = buf_ptr(p, op.src[0].buf) + (size_t)op.src[0].c_off * 2;
     rc = make_tmap_nhwc(&op.tmap_a[0], base, (uint64_t)op.src[0].C, (uint64_t)b.W, (uint64_t)b.H, (uint64_t)p->B,
-                        (uint64_t)b.C, (uint32_t)std::min(op.seg_kpad[0], 64), PP_W, PP_H);
+                        (uint64_t)b.C, (uint32_t)std::min(op.seg_kpad[0], 64), op.pair ? PP2_W : PP_W, PP_H);
     if (rc) return rc;
   }
   if (op.a_tma && !op.dw_fused) {
@@ -1384,6 +1419,7 @@ int conv_tc_prepare(yb_plan* p, Op& op) {
     YB_CUDA(cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<MODE_GATHER, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
     YB_CUDA(cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<MODE_PATCH, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
     YB_CUDA(cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<MODE_DW, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
+    YB_CUDA(cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<MODE_PATCH2, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
     attr_set = true;
   }
   return YB_OK;
@@ -1439,7 +1475,7 @@ static void fill_params(const yb_plan* p, const Op& op, ConvParams& P) {
   P.BN = op.BN;
   P.stages = op.stages;
   P.a_tma = op.a_tma;
-  P.tmem_cols = tmem_cols_for(op.BN);
+  P.tmem_cols = tmem_cols_for(op.pair ? 2 * op.BN : op.BN);
   P.n_tiles = op.N_pad / op.BN;
   P.total_tiles = ((P.M + BM - 1) / BM) * P.n_tiles;
   auto magic = [](int d, uint32_t& mul, uint32_t& shr) {
@@ -1463,18 +1499,20 @@ static void fill_params(const yb_plan* p, const Op& op, ConvParams& P) {
   P.b_slots = op.b_resident ? P.num_kb : op.stages;
   P.c_bufs = op.c_bufs;
   // measured: alternate tiles win except on patch layers with >= 32 output channels
-  P.alt_epilogue = (getenv("YB_NO_ALT_EPI") || (op.patch && op.BN >= 32)) ? 0 : 1;
+  P.alt_epilogue = (getenv("YB_NO_ALT_EPI") || (op.patch && op.BN >= 32) || op.pair) ? 0 : 1;
   if (op.patch) {
     const int C = op.seg_kpad[0];
     P.patch = 1;
     P.cblk = std::min(C, 64);
     P.ncb = (C + 63) / 64;
     P.a_layout = P.cblk == 64 ? 2 : P.cblk == 32 ? 4 : P.cblk == 16 ? 6 : 0;
-    P.patch_tx_bytes = PP_H * PP_W * P.cblk * 2;
+    P.pair = op.pair;
+    P.patch_creal = op.src[0].C;
+    P.patch_tx_bytes = PP_H * (op.pair ? PP2_W : PP_W) * P.cblk * 2;
     P.patch_stage_bytes = op.patch_stage_bytes;
     P.patch_stages = op.patch_stages;
     P.a_region_bytes = op.patch_stages * op.patch_stage_bytes;
-    P.tiles_x = (op.Wout + PT_W - 1) / PT_W;
+    P.tiles_x = (op.Wout + (op.pair ? 2 : 1) * PT_W - 1) / ((op.pair ? 2 : 1) * PT_W);
     P.tiles_per_img = P.tiles_x * ((op.Hout + PT_H - 1) / PT_H);
     P.total_tiles = p->B * P.tiles_per_img * P.n_tiles;
     magic(P.tiles_per_img, P.tpi_mul, P.tpi_shr);
@@ -1531,6 +1569,8 @@ int launch_conv_tc(const yb_plan* p, const Op& op, cudaStream_t st, float* fused
     else YB_LAUNCH(MODE_GATHER, false, true);
   } else if (P.dw) {
     YB_LAUNCH(MODE_DW, true, false);
+  } else if (P.patch && P.pair) {
+    YB_LAUNCH(MODE_PATCH2, true, false);
   } else if (P.patch) {
     YB_LAUNCH(MODE_PATCH, true, false);
   } else if (P.a_tma) {

@@ -104,6 +104,7 @@ struct Op {
   int tile2d = 0;          // 8 x 16 spatial output tiles (else 128 consecutive flattened rows)
   int patch = 0;           // 3x3/s1: A operand read from TMA halo patches through shifted descriptors
   int patch_stage_bytes = 0, patch_stages = 0;
+  int pair = 0;            // patch layers: 16 x 16 pixel super-tiles (two accumulators per weight k-block)
   int b_resident = 0;      // weight matrix stays in shared memory across the CTA's tiles
   int c_bufs = 1;          // output staging buffers
   int dw_fused = 0;        // OP_CONV: the depthwise conv `dw_op` in front of this 1x1 is computed by its producer warps
