@@ -686,17 +686,21 @@ __global__ void __launch_bounds__(IMG_T) nms_image_kernel(const NmsArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------
-static int cap_for(int max_nms) {
+// Key-list capacity per image.  The list only has to hold max_nms keys for correctness, but an image whose
+// candidates all fit is banded from the list (8 B per candidate) instead of from the raw scores (4 B per
+// anchor x class, every band): room for 1/8 of the score slots, between 32 K and 256 K keys.
+static int cap_for(int max_nms, long long slots) {
   int c = SORT_TILE;
   while (c < max_nms) c <<= 1;
+  long long want = slots / 8;
+  if (want > 262144) want = 262144;
+  while (c < want) c <<= 1;
   return c;
 }
 
 size_t nms_workspace_bytes(int B, int nc, int A, int max_nms) {
-  (void)nc;
-  (void)A;
   size_t hdr = ((size_t)B * sizeof(NmsHeader) + 255) / 256 * 256;
-  size_t keys = (size_t)B * cap_for(max_nms) * 8;
+  size_t keys = (size_t)B * cap_for(max_nms, (long long)nc * A) * 8;
   return hdr + keys;
 }
 
@@ -728,7 +732,7 @@ int nms_run(const float* pred, int B, int nc, int A, float conf, double iou, int
   a.iou = iou;
   a.max_det = max_det;
   a.max_nms = max_nms;
-  a.cap = cap_for(max_nms);
+  a.cap = cap_for(max_nms, (long long)nc * A);
   a.first_band = FIRST_BAND;
   a.next_band = NEXT_BAND;
   if (const char* e = getenv("YB_NMS_FIRST_BAND")) a.first_band = std::max(32, std::min(SORT_TILE, atoi(e)));
