@@ -35,10 +35,12 @@ namespace yb {
 static constexpr int HIST_BINS = 2048;
 static constexpr int SORT_TILE = 4096;
 
-struct NmsHeader {  // per image, zeroed at the start of every call
+struct NmsHeader {  // per image, zero at the start of every call
   int cand_count;   // candidates found by the scan
   int sel_count;    // keys appended by the scan (may exceed capacity; clamp on read)
-  int pad[6];
+  int sel2_count;   // overflow images: keys re-appended by the select pass
+  int selected;     // overflow images: 1 = the list holds every key of the max_nms best (and possibly a few more)
+  int pad[4];
 };
 
 struct NmsArgs {
@@ -50,6 +52,7 @@ struct NmsArgs {
   int first_band, next_band;   // candidates per band (<= SORT_TILE)
   float max_wh;
   NmsHeader* hdr;
+  unsigned int* ghist;       // [B][HIST_BINS], zero between calls (overflow images only)
   unsigned long long* keys;  // [B][cap]
   float* out;
   int* out_counts;
@@ -342,6 +345,100 @@ __device__ __forceinline__ void walk_bins(ImgSmem& sm, const unsigned int* h, in
 #else
 #define YB_T(slot) do { } while (0)
 #endif
+// ---- images with more candidates than the key list holds (dense predictions, util.py:157's [:max_nms] cut) ----
+// Only the max_nms best candidates can ever reach the greedy step.  Two grid-wide passes over the scores of such
+// an image (every block of the other images returns at once) rebuild its key list so that it holds all of them:
+// a histogram of the score bins, then a compaction of every key up to the bin in which rank max_nms falls.  The
+// per-image kernel then bands from the list as usual; if even that prefix does not fit the list (a single fat
+// bin), it falls back to banding from the raw scores.
+__global__ void __launch_bounds__(256) nms_ovf_hist_kernel(const NmsArgs a) {
+  __shared__ unsigned int hs[HIST_BINS];
+  pdl_prologue_done();
+  pdl_wait();
+  const int b = blockIdx.y;
+  if (a.hdr[b].sel_count <= a.cap) return;
+  for (int i = threadIdx.x; i < HIST_BINS; i += 256) hs[i] = 0u;
+  __syncthreads();
+  const long long total = (long long)a.nc * a.A;
+  const float* sp = a.pred + ((size_t)b * (4 + a.nc) + 4) * a.A;
+  for (long long e = (long long)blockIdx.x * 256 + threadIdx.x; e < total; e += (long long)gridDim.x * 256) {
+    const float sc = __ldg(sp + e);
+    if (sc > a.conf) atomicAdd(&hs[bin_of(make_key(sc, 0u))], 1u);
+  }
+  __syncthreads();
+  unsigned int* g = a.ghist + (size_t)b * HIST_BINS;
+  for (int i = threadIdx.x; i < HIST_BINS; i += 256)
+    if (hs[i]) atomicAdd(&g[i], hs[i]);
+}
+
+__global__ void __launch_bounds__(256) nms_ovf_select_kernel(const NmsArgs a) {
+  __shared__ unsigned int part[256];
+  __shared__ int s_T;
+  pdl_prologue_done();
+  pdl_wait();
+  const int b = blockIdx.y;
+  NmsHeader* h = a.hdr + b;
+  if (h->sel_count <= a.cap) return;
+  // threshold bin: the first bin T with count(bins <= T) >= max_nms (every block derives it on its own)
+  const unsigned int* g = a.ghist + (size_t)b * HIST_BINS;
+  constexpr int BPT = HIST_BINS / 256;
+  unsigned int v[BPT], tot = 0;
+#pragma unroll
+  for (int q = 0; q < BPT; q++) {
+    v[q] = g[threadIdx.x * BPT + q];
+    tot += v[q];
+  }
+  part[threadIdx.x] = tot;
+  if (threadIdx.x == 0) s_T = HIST_BINS - 1;
+  __syncthreads();
+  unsigned int base = 0;
+  for (int i = 0; i < (int)threadIdx.x; i++) base += part[i];
+  unsigned int cum = base;
+#pragma unroll
+  for (int q = 0; q < BPT; q++) {
+    const unsigned int before = cum;
+    cum += v[q];
+    if (before < (unsigned int)a.max_nms && cum >= (unsigned int)a.max_nms) s_T = threadIdx.x * BPT + q;   // unique
+  }
+  __syncthreads();
+  const int T = s_T;
+  unsigned int upto = 0;   // keys with bin <= T
+  for (int i = 0; i <= T; i++) upto += g[i];
+  if (upto > (unsigned int)a.cap) return;   // does not fit: the per-image kernel bands from the raw scores
+  if (blockIdx.x == 0 && threadIdx.x == 0) h->selected = 1;
+  const long long total = (long long)a.nc * a.A;
+  const float* sp = a.pred + ((size_t)b * (4 + a.nc) + 4) * a.A;
+  unsigned long long* keys = a.keys + (size_t)b * a.cap;
+  const int lane = threadIdx.x & 31;
+  const long long stride = (long long)gridDim.x * 256;
+  const long long iters = (total + stride - 1) / stride;
+  long long e = (long long)blockIdx.x * 256 + threadIdx.x;
+  for (long long it = 0; it < iters; it++, e += stride) {
+    bool take = false;
+    unsigned long long key = 0;
+    if (e < total) {
+      const float sc = __ldg(sp + e);
+      if (sc > a.conf) {
+        const int c = (int)(e / a.A);
+        const int an = (int)(e - (long long)c * a.A);
+        key = make_key(sc, (unsigned int)an * (unsigned int)a.nc + (unsigned int)c);
+        take = bin_of(key) <= T;
+      }
+    }
+    const unsigned int m = __ballot_sync(0xffffffffu, take);
+    if (m) {
+      const int leader = __ffs(m) - 1;
+      int slot0 = 0;
+      if (lane == leader) slot0 = atomicAdd(&h->sel2_count, __popc(m));
+      slot0 = __shfl_sync(0xffffffffu, slot0, leader);
+      if (take) {
+        const int slot = slot0 + __popc(m & ((1u << lane) - 1u));
+        if (slot < a.cap) keys[slot] = key;
+      }
+    }
+  }
+}
+
 // IMG_T threads per image: 1024 for small batches (latency), 512 (two CTAs per SM) for large ones.
 template <int IMG_T>
 __global__ void __launch_bounds__(IMG_T) nms_image_kernel(const NmsArgs a) {
@@ -353,9 +450,9 @@ __global__ void __launch_bounds__(IMG_T) nms_image_kernel(const NmsArgs a) {
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const NmsHeader h = a.hdr[b];
   Src src;
-  src.complete = h.sel_count <= a.cap;
+  src.complete = h.sel_count <= a.cap || h.selected;   // selected: the list was rebuilt with the max_nms best
   src.keys = a.keys + (size_t)b * a.cap;
-  src.n = min(h.sel_count, a.cap);
+  src.n = h.selected ? min(h.sel2_count, a.cap) : min(h.sel_count, a.cap);
   src.sp = a.pred + ((size_t)b * (4 + a.nc) + 4) * a.A;
   src.total = (long long)a.nc * a.A;
   src.A = a.A;
@@ -666,12 +763,16 @@ __global__ void __launch_bounds__(IMG_T) nms_image_kernel(const NmsArgs a) {
     // leave the header zeroed for the next call on this workspace (yb_nms then needs no memset)
     a.hdr[b].cand_count = 0;
     a.hdr[b].sel_count = 0;
+    a.hdr[b].sel2_count = 0;
+    a.hdr[b].selected = 0;
 #ifdef YB_NMS_STATS
     for (int i = 0; i < 6; i++) a.hdr[b].pad[i] = sm.st_cyc[i + 2];   // (stats build only: the header is not left zero)
     a.hdr[b].cand_count = sm.st_cyc[0];
     a.hdr[b].sel_count = sm.st_cyc[1];
 #endif
   }
+  if (h.sel_count > a.cap)   // overflow image: leave its global histogram zeroed for the next call
+    for (int i = tid; i < HIST_BINS; i += IMG_T) a.ghist[(size_t)b * HIST_BINS + i] = 0u;
   for (int k = tid; k < K; k += IMG_T) {
     BoxF tmp;
     float r[6];
@@ -700,8 +801,9 @@ static int cap_for(int max_nms, long long slots) {
 
 size_t nms_workspace_bytes(int B, int nc, int A, int max_nms) {
   size_t hdr = ((size_t)B * sizeof(NmsHeader) + 255) / 256 * 256;
+  size_t hist = (size_t)B * HIST_BINS * 4;
   size_t keys = (size_t)B * cap_for(max_nms, (long long)nc * A) * 8;
-  return hdr + keys;
+  return hdr + hist + keys;
 }
 
 int nms_run(const float* pred, int B, int nc, int A, float conf, double iou, int max_det, int max_nms,
@@ -740,7 +842,8 @@ int nms_run(const float* pred, int B, int nc, int A, float conf, double iou, int
   a.max_wh = max_wh;
   size_t hdr_bytes = ((size_t)B * sizeof(NmsHeader) + 255) / 256 * 256;
   a.hdr = reinterpret_cast<NmsHeader*>(ws);
-  a.keys = reinterpret_cast<unsigned long long*>((uint8_t*)ws + hdr_bytes);
+  a.ghist = reinterpret_cast<unsigned int*>((uint8_t*)ws + hdr_bytes);
+  a.keys = reinterpret_cast<unsigned long long*>((uint8_t*)ws + hdr_bytes + (size_t)B * HIST_BINS * 4);
   a.out = out;
   a.out_counts = out_counts;
   static bool attr_set = false;
@@ -753,11 +856,16 @@ int nms_run(const float* pred, int B, int nc, int A, float conf, double iou, int
   }
   // the per-image kernel leaves the headers zeroed; a workspace last used by yb_nms / yb_nms_workspace_init
   // with the same batch needs no memset node in front of the append kernel
-  if (!ws_clean) YB_CUDA(cudaMemsetAsync(ws, 0, hdr_bytes, st));
+  if (!ws_clean) YB_CUDA(cudaMemsetAsync(ws, 0, hdr_bytes + (size_t)B * HIST_BINS * 4, st));
   long long total = (long long)nc * A;
   int gx = (int)std::min<long long>((total + 256 * 16 - 1) / (256 * 16), 1024);
   int vec4 = (A % 4 == 0) && ((reinterpret_cast<uintptr_t>(pred) & 15) == 0);
   YB_CUDA(launch_pdl(nms_append_kernel, dim3(gx, B), dim3(256), 0, st, a, vec4));
+  count_launch();
+  // overflow images only (every other block exits at once)
+  YB_CUDA(launch_pdl(nms_ovf_hist_kernel, dim3(std::min(gx, 128), B), dim3(256), 0, st, a));
+  count_launch();
+  YB_CUDA(launch_pdl(nms_ovf_select_kernel, dim3(std::min(gx, 128), B), dim3(256), 0, st, a));
   count_launch();
   if (B <= 160) YB_CUDA(launch_pdl(nms_image_kernel<1024>, dim3(B), dim3(1024), sizeof(ImgSmem), st, a));
   else YB_CUDA(launch_pdl(nms_image_kernel<512>, dim3(B), dim3(512), sizeof(ImgSmem), st, a));
