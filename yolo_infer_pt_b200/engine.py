@@ -147,14 +147,20 @@ class Engine:
             raise RuntimeError(f"unsupported input dtype {x.dtype}")
         return x if x.is_contiguous() else x.contiguous()
 
-    def forward(self, x):
+    def forward(self, x, out=None):
         """(B,3,H,W) image tensor -> the engine's static (B, 4+nc, A) fp32 prediction tensor
-        (layout of reference nets/nn.py:262-270). The returned tensor is overwritten by the next call."""
+        (layout of reference nets/nn.py:262-270). The returned tensor is overwritten by the next call;
+        pass `out` (same shape, fp32, contiguous) to write somewhere else - pipelines that overlap the
+        NMS of one batch with the forward of the next alternate between two such tensors."""
         x = self._check_input(x)
+        if out is None:
+            out = self.out
+        elif out.shape != self.out.shape or out.dtype != torch.float32 or not out.is_contiguous() or out.device != self.out.device:
+            raise ValueError("Engine.forward: `out` must be a contiguous fp32 tensor shaped like the prediction tensor")
         stream = torch.cuda.current_stream(self.device).cuda_stream
-        _lib.check(self.L.yb_forward(self.plan, x.data_ptr(), _DTYPES[x.dtype], self.out.data_ptr(),
+        _lib.check(self.L.yb_forward(self.plan, x.data_ptr(), _DTYPES[x.dtype], out.data_ptr(),
                                      ctypes.c_void_p(stream)), "yb_forward")
-        return self.out
+        return out
 
     def forward_raw(self, x):
         """Pre-decode head logits (B, A, 64+nc) fp32 (reference training-mode output, nn.py:256-259)."""

@@ -1,10 +1,15 @@
 """Host-to-device streaming around the hot path: the loop the reference's `test()` runs
-(main.py:264-273: `samples.to(device)`, `model(samples)`, `non_max_suppression(outputs)`), with the
-H2D copy of batch i+1 overlapped with the kernels of batch i.
+(main.py:264-273: `samples.to(device)`, `model(samples)`, `non_max_suppression(outputs)`), software
+pipelined over four CUDA streams:
 
-`StreamingDetector` owns two device input buffers, a copy stream and a compute stream.  Pinned host
-batches go in, padded detections `(det (B, 300, 6) fp32, counts (B,) int32)` come out on the host.
-PyTorch provides memory, streams and events only; every kernel is libyolob200's.
+    copy    H2D of batch i+1          (pinned host memory -> one of two device input buffers)
+    compute forward of batch i        (-> one of two prediction tensors)
+    nms     NMS of batch i-1          (reads the other prediction tensor)
+    d2h     detections of batch i-1   (-> pinned host landing buffers)
+
+`StreamingDetector` owns the buffers and events.  Pinned host batches (or, with `resident=True`, batches that
+already live on the device) go in, padded detections `(det (B, 300, 6) fp32, counts (B,) int32)` come out on
+the host.  PyTorch provides memory, streams and events only; every kernel is libyolob200's.
 """
 import torch
 
@@ -12,42 +17,58 @@ from .utils import util
 
 
 class StreamingDetector:
-    def __init__(self, model, batch_shape, dtype=torch.uint8, device="cuda", conf=0.001, iou=0.65):
+    def __init__(self, model, batch_shape, dtype=torch.uint8, device="cuda", conf=0.001, iou=0.65, resident=False):
         self.model = model
         self.device = torch.device(device)
         self.conf, self.iou = conf, iou
+        self.resident = resident
         self.copy_stream = torch.cuda.Stream(self.device)
         self.compute_stream = torch.cuda.Stream(self.device)
+        self.nms_stream = torch.cuda.Stream(self.device)
         self.d2h_stream = torch.cuda.Stream(self.device)
-        self.inputs = [torch.empty(batch_shape, dtype=dtype, device=self.device) for _ in range(2)]
+        self.inputs = [None, None] if resident else [torch.empty(batch_shape, dtype=dtype, device=self.device) for _ in range(2)]
         self.copied = [torch.cuda.Event() for _ in range(2)]
         self.consumed = [torch.cuda.Event() for _ in range(2)]
-        for e in self.consumed:
+        self.fwd_done = [torch.cuda.Event() for _ in range(2)]
+        self.nms_done = [torch.cuda.Event() for _ in range(2)]
+        for e in self.consumed + self.nms_done:
             e.record(self.compute_stream)
-        self.h2d_bytes = self.inputs[0].numel() * self.inputs[0].element_size()
+        self.preds = None                       # two prediction tensors, allocated at the first batch
+        self.h2d_bytes = 0 if resident else self.inputs[0].numel() * self.inputs[0].element_size()
         b = batch_shape[0]
         # pinned host landing buffers for the detections (two slots; a result stays valid for two steps)
         self.det_host = [torch.empty(b, util.MAX_DET, 6, dtype=torch.float32).pin_memory() for _ in range(2)]
         self.cnt_host = [torch.empty(b, dtype=torch.int32).pin_memory() for _ in range(2)]
 
-    def _upload(self, slot, host_batch):
+    def _upload(self, slot, batch):
+        if self.resident:
+            self.inputs[slot] = batch           # already on the device, owned by the caller
+            return
         with torch.cuda.stream(self.copy_stream):
             self.copy_stream.wait_event(self.consumed[slot])      # the kernels that read this buffer are done
-            self.inputs[slot].copy_(host_batch, non_blocking=True)
+            self.inputs[slot].copy_(batch, non_blocking=True)
             self.copied[slot].record(self.copy_stream)
 
     def _detect(self, slot):
+        x = self.inputs[slot]
         with torch.cuda.stream(self.compute_stream):
-            self.compute_stream.wait_event(self.copied[slot])
-            y = self.model(self.inputs[slot])
-            det, counts = util.nms_padded(y, self.conf, self.iou)
+            if not self.resident:
+                self.compute_stream.wait_event(self.copied[slot])
+            self.compute_stream.wait_event(self.nms_done[slot])   # the NMS that read this prediction tensor two batches ago
+            eng = self.model._engine_for(x)
+            if self.preds is None:
+                self.preds = [torch.empty_like(eng.out) for _ in range(2)]
+            y = eng.forward(x, out=self.preds[slot])
             self.consumed[slot].record(self.compute_stream)
-            computed = torch.cuda.Event()
-            computed.record(self.compute_stream)
-        # detections go back on their own stream: the next batch's kernels do not queue behind the copy
+            self.fwd_done[slot].record(self.compute_stream)
+        with torch.cuda.stream(self.nms_stream):                  # overlaps the next batch's forward
+            self.nms_stream.wait_event(self.fwd_done[slot])
+            det, counts = util.nms_padded(y, self.conf, self.iou)
+            self.nms_done[slot].record(self.nms_stream)
+        # detections go back on their own stream: no kernel queues behind the copy
         det_h, cnt_h = self.det_host[slot], self.cnt_host[slot]
         with torch.cuda.stream(self.d2h_stream):
-            self.d2h_stream.wait_event(computed)
+            self.d2h_stream.wait_event(self.nms_done[slot])
             det.record_stream(self.d2h_stream)
             counts.record_stream(self.d2h_stream)
             det_h.copy_(det, non_blocking=True)
@@ -56,10 +77,10 @@ class StreamingDetector:
             done.record(self.d2h_stream)
         return det_h, cnt_h, done
 
-    def run(self, host_batches):
-        """Generator over pinned host batches -> (det, counts) host tensors, in order.  The H2D copy
-        of the next batch is in flight while the current batch computes."""
-        it = iter(host_batches)
+    def run(self, batches):
+        """Generator over batches -> (det, counts) host tensors, in order.  The H2D copy of the next batch and
+        the NMS of the previous one are in flight while the current batch's forward runs."""
+        it = iter(batches)
         try:
             nxt = next(it)
         except StopIteration:
