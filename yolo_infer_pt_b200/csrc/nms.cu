@@ -862,10 +862,11 @@ int nms_run(const float* pred, int B, int nc, int A, float conf, double iou, int
   int vec4 = (A % 4 == 0) && ((reinterpret_cast<uintptr_t>(pred) & 15) == 0);
   YB_CUDA(launch_pdl(nms_append_kernel, dim3(gx, B), dim3(256), 0, st, a, vec4));
   count_launch();
-  // overflow images only (every other block exits at once)
-  YB_CUDA(launch_pdl(nms_ovf_hist_kernel, dim3(std::min(gx, 128), B), dim3(256), 0, st, a));
+  // overflow images only (every other block exits at once: keep the grids small, ~2 K CTAs)
+  const int ogx = std::max(8, std::min(std::min(gx, 128), 2048 / B));
+  YB_CUDA(launch_pdl(nms_ovf_hist_kernel, dim3(ogx, B), dim3(256), 0, st, a));
   count_launch();
-  YB_CUDA(launch_pdl(nms_ovf_select_kernel, dim3(std::min(gx, 128), B), dim3(256), 0, st, a));
+  YB_CUDA(launch_pdl(nms_ovf_select_kernel, dim3(ogx, B), dim3(256), 0, st, a));
   count_launch();
   if (B <= 160) YB_CUDA(launch_pdl(nms_image_kernel<1024>, dim3(B), dim3(1024), sizeof(ImgSmem), st, a));
   else YB_CUDA(launch_pdl(nms_image_kernel<512>, dim3(B), dim3(512), sizeof(ImgSmem), st, a));
