@@ -1,0 +1,3 @@
+for v in "A=1" "YB_STEM_MINB4=1" "YB_STEM_CTAS=2" "YB_STEM_CTAS=2 YB_STEM_MINB4=1"; do
+  echo "== $v"; env $v python tools/layer_table.py n 256 2>/dev/null | sed -n 2,2p
+done

@@ -11,6 +11,11 @@
 
 namespace yb {
 
+__device__ __forceinline__ float silu_half(float h) {  // SiLU(2h) = h + h*tanh(h)
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
 __device__ __forceinline__ float silu_acc(float x) {  // h + h*tanh(h), h = x/2 (one MUFU op)
   float h = 0.5f * x, t;
   asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
@@ -299,25 +304,22 @@ __device__ __forceinline__ float vec_elem<uint8_t>(const uint4& v, int j) {
 // staged as hi + lo bf16 pairs and multiplied as hi*W_hi + hi*W_lo + lo*W_hi, which matches an fp32
 // convolution to ~2^-16 relative.  uint8 / bf16 images are exact in bf16 and use bf16 weights like
 // every other layer of the network.
-template <typename T, int NT, bool SPLIT>
-__global__ void __launch_bounds__(256)
+template <typename T, int NT, bool SPLIT, int MINB = 1>
+__global__ void __launch_bounds__(256, MINB)
     stem_mma_kernel(const T* __restrict__ in, __nv_bfloat16* __restrict__ out, const float* __restrict__ wgt,
-                    int B, int H, int W, int Ho, int Wo, int Cp, int out_ld, float in_scale) {
+                    int B, int H, int W, int Ho, int Wo, int Cp, int out_ld, float in_scale, int total_tiles) {
   constexpr int EPV = 16 / (int)sizeof(T);
   constexpr int NVEC = (2 * STEM_TW + 1 + EPV + EPV - 1) / EPV;
   constexpr int PITCH = NVEC * EPV + 8;   // bf16 elements per patch row
   constexpr int PSZ = 3 * STEM_IH * PITCH;
+  // uint8 pixels are always finite, so the K padding (k = 27..31, zero weights) may read any patch
+  // element instead of a predicated zero
+  constexpr bool FINITE = sizeof(T) == 1;
   extern __shared__ __align__(16) uint8_t stem_smem[];
   __nv_bfloat16* patch = reinterpret_cast<__nv_bfloat16*>(stem_smem);          // [hi|lo][3][IH][PITCH]
   __nv_bfloat16* stage = patch + (SPLIT ? 2 : 1) * PSZ;                         // [8 warps][16 px][NT*8]
   pdl_prologue_done();
-  pdl_wait();
   const int tiles_x = (Wo + STEM_TW - 1) / STEM_TW, tiles_y = (Ho + STEM_TH - 1) / STEM_TH;
-  int bid = blockIdx.x;
-  const int tx = bid % tiles_x;
-  bid /= tiles_x;
-  const int ty = bid % tiles_y;
-  const int b = bid / tiles_y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   // ---- per-thread tap offsets of its 8 K columns (k = 2t, 2t+1, 2t+8, 2t+9 of each k-step)
@@ -326,34 +328,67 @@ __global__ void __launch_bounds__(256)
   for (int j = 0; j < 8; j++) {
     const int k = (j >> 2) * 16 + ((j >> 1) & 1) * 8 + 2 * t + (j & 1);
     const int ci = k / 9, r9 = k - ci * 9, ky = r9 / 3, kx = r9 - ky * 3;
-    koff[j] = k < 27 ? (ci * STEM_IH + ky) * PITCH + kx : -1;
+    koff[j] = k < 27 ? (ci * STEM_IH + ky) * PITCH + kx : (FINITE ? 0 : -1);
   }
-  // ---- stage the input patch as bf16 (hi, and lo = x - hi when SPLIT)
-  const int gy0 = 2 * ty * STEM_TH - 1;
-  const int gxa = 2 * tx * STEM_TW - EPV;
-  for (int i = tid; i < 3 * STEM_IH * NVEC; i += 256) {
-    const int vx = i % NVEC;
-    const int row = i / NVEC;  // ci * IH + iy
-    const int iy = row % STEM_IH, ci = row / STEM_IH;
-    const int gy = gy0 + iy, gx = gxa + vx * EPV;
-    __align__(16) __nv_bfloat16 o[EPV], ol[EPV];
-    if ((unsigned)gy < (unsigned)H && gx >= 0 && gx < W) {
-      const uint4 v = __ldg(reinterpret_cast<const uint4*>(in + (((size_t)b * 3 + ci) * H + gy) * W + gx));
-      if (SPLIT) {
+  // ---- weights of a channel group -> B fragments (n = g per n-tile), hi + lo split.  The input scale
+  // and the 1/2 of SiLU(x) = h + h*tanh(h), h = x/2, are folded into weights and bias (exact: power of 2
+  // for the half; the scale is folded before the bf16 rounding exactly like the packed conv weights).
+  const float* bias = wgt + 27 * Cp;
+  uint32_t bhi[NT][2][2], blo[NT][2][2];
+  float bia[NT][2];
+  auto load_weights = [&](int c0) {
 #pragma unroll
-        for (int j = 0; j < EPV; j++) {
-          const float x = vec_elem<T>(v, j);
-          o[j] = __float2bfloat16(x);
-          ol[j] = __float2bfloat16(x - __bfloat162float(o[j]));
+    for (int nt = 0; nt < NT; nt++) {
+      const int n = c0 + nt * 8 + g;
+#pragma unroll
+      for (int ks = 0; ks < 2; ks++)
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          const int k0 = ks * 16 + h * 8 + 2 * t;
+          const float w0 = (k0 < 27 && n < Cp) ? 0.5f * (__ldg(wgt + k0 * Cp + n) * in_scale) : 0.f;
+          const float w1 = (k0 + 1 < 27 && n < Cp) ? 0.5f * (__ldg(wgt + (k0 + 1) * Cp + n) * in_scale) : 0.f;
+          const __nv_bfloat16 h0 = __float2bfloat16(w0), h1 = __float2bfloat16(w1);
+          bhi[nt][ks][h] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+          blo[nt][ks][h] = pack2_bf16(w0 - __bfloat162float(h0), w1 - __bfloat162float(h1));
         }
-      } else {
-        unpack_bf16<T>(v, o);
+      const int cb = c0 + nt * 8 + 2 * t;
+      bia[nt][0] = cb < Cp ? 0.5f * __ldg(bias + cb) : 0.f;
+      bia[nt][1] = cb + 1 < Cp ? 0.5f * __ldg(bias + cb + 1) : 0.f;
+    }
+  };
+  const bool single = Cp <= NT * 8;   // one channel group: its fragments stay in registers for all tiles
+  if (single) load_weights(0);
+  const unsigned short* pu = reinterpret_cast<const unsigned short*>(patch);
+  __nv_bfloat16* wstage = stage + warp * 16 * NT * 8;
+  // ---- staging descriptors of this thread's 16-byte vectors (tile independent; kept in registers when few)
+  constexpr int NIT = (3 * STEM_IH * NVEC + 255) / 256;
+  constexpr bool HOIST = NIT <= 2;
+  int st_iy[HOIST ? NIT : 1], st_vxe[HOIST ? NIT : 1], st_soff[HOIST ? NIT : 1], st_goff[HOIST ? NIT : 1];
+  if (HOIST) {
+#pragma unroll
+    for (int it = 0; it < (HOIST ? NIT : 1); it++) {
+      const int i = tid + it * 256;
+      const int vx = i % NVEC, row = i / NVEC;
+      st_iy[it] = row % STEM_IH;
+      st_vxe[it] = vx * EPV;
+      st_soff[it] = i < 3 * STEM_IH * NVEC ? row * PITCH + vx * EPV : -1;
+      st_goff[it] = ((row / STEM_IH) * H + st_iy[it]) * W + vx * EPV;
+    }
+  }
+  // 16 input elements -> bf16 (hi | lo) patch row; an all-zero vector is the padding
+  auto convert_store = [&](const uint4& v, int soff) {
+    __align__(16) __nv_bfloat16 o[EPV], ol[EPV];
+    if (SPLIT) {
+#pragma unroll
+      for (int j = 0; j < EPV; j++) {
+        const float x = vec_elem<T>(v, j);
+        o[j] = __float2bfloat16(x);
+        ol[j] = __float2bfloat16(x - __bfloat162float(o[j]));
       }
     } else {
-#pragma unroll
-      for (int j = 0; j < EPV; j++) o[j] = ol[j] = __float2bfloat16(0.f);
+      unpack_bf16<T>(v, o);
     }
-    __nv_bfloat16* dp = patch + row * PITCH + vx * EPV;
+    __nv_bfloat16* dp = patch + soff;
     if (EPV >= 8) {
 #pragma unroll
       for (int j = 0; j < EPV; j += 8) {
@@ -364,86 +399,118 @@ __global__ void __launch_bounds__(256)
       *reinterpret_cast<uint2*>(dp) = *reinterpret_cast<const uint2*>(o);
       if (SPLIT) *reinterpret_cast<uint2*>(dp + PSZ) = *reinterpret_cast<const uint2*>(ol);
     }
-  }
-  __syncthreads();
-  const int oy = ty * STEM_TH + warp;
-  if (oy >= Ho) return;
-  const float* bias = wgt + 27 * Cp;
-  const unsigned short* pu = reinterpret_cast<const unsigned short*>(patch);
-  __nv_bfloat16* wstage = stage + warp * 16 * NT * 8;
-#pragma unroll 1
-  for (int c0 = 0; c0 < Cp; c0 += NT * 8) {
-    // weights of this channel group -> B fragments (n = g per n-tile), scale folded, hi + lo split
-    uint32_t bhi[NT][2][2], blo[NT][2][2];
-    float bia[NT][2];
+  };
+  // register prefetch of a tile's vectors (hoisted variant): issued one tile ahead of their use
+  uint4 pv[HOIST ? NIT : 1];
+  auto fetch_tile = [&](int tl) {
+    const int tx = tl % tiles_x;
+    tl /= tiles_x;
+    const int ty = tl % tiles_y, b = tl / tiles_y;
+    const int gy0 = 2 * ty * STEM_TH - 1, gxa = 2 * tx * STEM_TW - EPV;
+    const T* tile_in = in + ((size_t)b * 3 * H + gy0) * (size_t)W + gxa;   // may point before the image: only in-bounds offsets are read
 #pragma unroll
-    for (int nt = 0; nt < NT; nt++) {
-      const int n = c0 + nt * 8 + g;
-#pragma unroll
-      for (int ks = 0; ks < 2; ks++)
-#pragma unroll
-        for (int h = 0; h < 2; h++) {
-          const int k0 = ks * 16 + h * 8 + 2 * t;
-          const float w0 = (k0 < 27 && n < Cp) ? __ldg(wgt + k0 * Cp + n) * in_scale : 0.f;
-          const float w1 = (k0 + 1 < 27 && n < Cp) ? __ldg(wgt + (k0 + 1) * Cp + n) * in_scale : 0.f;
-          const __nv_bfloat16 h0 = __float2bfloat16(w0), h1 = __float2bfloat16(w1);
-          bhi[nt][ks][h] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-          blo[nt][ks][h] = pack2_bf16(w0 - __bfloat162float(h0), w1 - __bfloat162float(h1));
-        }
-      const int cb = c0 + nt * 8 + 2 * t;
-      bia[nt][0] = cb < Cp ? __ldg(bias + cb) : 0.f;
-      bia[nt][1] = cb + 1 < Cp ? __ldg(bias + cb + 1) : 0.f;
+    for (int it = 0; it < (HOIST ? NIT : 1); it++) {
+      const int gy = gy0 + st_iy[it], gx = gxa + st_vxe[it];
+      pv[it] = make_uint4(0u, 0u, 0u, 0u);
+      if (st_soff[it] >= 0 && (unsigned)gy < (unsigned)H && gx >= 0 && gx < W)
+        pv[it] = __ldg(reinterpret_cast<const uint4*>(tile_in + st_goff[it]));
     }
+  };
+  pdl_wait();
+  if (HOIST && (int)blockIdx.x < total_tiles) fetch_tile(blockIdx.x);
 #pragma unroll 1
-    for (int mi = 0; mi < STEM_TW / 16; mi++) {
-      // input column of tap kx for output column lx: EPV + 2*lx + kx - 1
-      const int base0 = (2 * warp) * PITCH + EPV - 1 + 2 * (mi * 16 + g);
-      const int base1 = base0 + 16;
-      uint32_t afr[SPLIT ? 2 : 1][2][4];
+  for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    int bid = tile;
+    const int tx = bid % tiles_x;
+    bid /= tiles_x;
+    const int ty = bid % tiles_y;
+    const int b = bid / tiles_y;
+    if (tile != (int)blockIdx.x) __syncthreads();   // every warp is done with the previous patch
+    // ---- stage the input patch as bf16 (hi, and lo = x - hi when SPLIT)
+    if (HOIST) {
 #pragma unroll
-      for (int part = 0; part < (SPLIT ? 2 : 1); part++)
-#pragma unroll
-        for (int ks = 0; ks < 2; ks++)
-#pragma unroll
-          for (int h = 0; h < 2; h++) {
-            const int o0 = koff[ks * 4 + h * 2], o1 = koff[ks * 4 + h * 2 + 1];
-            const unsigned short* pp = pu + part * PSZ;
-            const uint32_t a00 = o0 >= 0 ? pp[base0 + o0] : 0u, a01 = o1 >= 0 ? pp[base0 + o1] : 0u;
-            const uint32_t a10 = o0 >= 0 ? pp[base1 + o0] : 0u, a11 = o1 >= 0 ? pp[base1 + o1] : 0u;
-            afr[part][ks][h * 2] = a00 | (a01 << 16);       // row g
-            afr[part][ks][h * 2 + 1] = a10 | (a11 << 16);   // row g + 8
-          }
-      float d[NT][4];
-#pragma unroll
-      for (int nt = 0; nt < NT; nt++) {
-        d[nt][0] = d[nt][2] = bia[nt][0];
-        d[nt][1] = d[nt][3] = bia[nt][1];
-#pragma unroll
-        for (int ks = 0; ks < 2; ks++) {
-          if (SPLIT) {
-            mma_bf16_16816(d[nt], afr[0][ks], blo[nt][ks][0], blo[nt][ks][1]);
-            mma_bf16_16816(d[nt], afr[SPLIT ? 1 : 0][ks], bhi[nt][ks][0], bhi[nt][ks][1]);
-          }
-          mma_bf16_16816(d[nt], afr[0][ks], bhi[nt][ks][0], bhi[nt][ks][1]);
-        }
-      }
-      // SiLU -> bf16 -> per-warp staging [16 px][NT*8] -> 16-byte contiguous global stores
-      __syncwarp();
-#pragma unroll
-      for (int nt = 0; nt < NT; nt++) {
-        *reinterpret_cast<uint32_t*>(wstage + g * NT * 8 + nt * 8 + 2 * t) = pack2_bf16(silu_acc(d[nt][0]), silu_acc(d[nt][1]));
-        *reinterpret_cast<uint32_t*>(wstage + (g + 8) * NT * 8 + nt * 8 + 2 * t) = pack2_bf16(silu_acc(d[nt][2]), silu_acc(d[nt][3]));
-      }
-      __syncwarp();
-      const int ox0 = tx * STEM_TW + mi * 16;
-      for (int c = lane; c < 16 * NT; c += 32) {   // 16-byte chunks of the 16 x (NT*8) tile
-        const int px = c / NT, cg = c - px * NT;
-        if (ox0 + px < Wo && c0 + cg * 8 < Cp)
-          *reinterpret_cast<uint4*>(out + (((size_t)b * Ho + oy) * Wo + ox0 + px) * out_ld + c0 + cg * 8) =
-              *reinterpret_cast<const uint4*>(wstage + px * NT * 8 + cg * 8);
+      for (int it = 0; it < (HOIST ? NIT : 1); it++)
+        if (st_soff[it] >= 0) convert_store(pv[it], st_soff[it]);
+    } else {
+      const int gy0 = 2 * ty * STEM_TH - 1;
+      const int gxa = 2 * tx * STEM_TW - EPV;
+      const T* tile_in = in + ((size_t)b * 3 * H + gy0) * (size_t)W + gxa;
+#pragma unroll 1
+      for (int i = tid; i < 3 * STEM_IH * NVEC; i += 256) {
+        const int vx = i % NVEC, row = i / NVEC;  // row = ci * IH + iy
+        const int iy = row % STEM_IH, vxe = vx * EPV;
+        const int gy = gy0 + iy, gx = gxa + vxe;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if ((unsigned)gy < (unsigned)H && gx >= 0 && gx < W)
+          v = __ldg(reinterpret_cast<const uint4*>(tile_in + ((row / STEM_IH) * H + iy) * W + vxe));
+        convert_store(v, row * PITCH + vxe);
       }
     }
+    __syncthreads();
+    // the next tile's pixels travel while this one is computed
+    if (HOIST && tile + (int)gridDim.x < total_tiles) fetch_tile(tile + (int)gridDim.x);
+    const int oy = ty * STEM_TH + warp;
+    if (oy >= Ho) continue;
+#pragma unroll 1
+    for (int c0 = 0; c0 < Cp; c0 += NT * 8) {
+      if (!single) load_weights(c0);
+#pragma unroll 1
+      for (int mi = 0; mi < STEM_TW / 16; mi++) {
+        // input column of tap kx for output column lx: EPV + 2*lx + kx - 1
+        const int base0 = (2 * warp) * PITCH + EPV - 1 + 2 * (mi * 16 + g);
+        const int base1 = base0 + 16;
+        uint32_t afr[SPLIT ? 2 : 1][2][4];
+#pragma unroll
+        for (int part = 0; part < (SPLIT ? 2 : 1); part++)
+#pragma unroll
+          for (int ks = 0; ks < 2; ks++)
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+              const int o0 = koff[ks * 4 + h * 2], o1 = koff[ks * 4 + h * 2 + 1];
+              const unsigned short* pp = pu + part * PSZ;
+              const bool v0 = FINITE || o0 >= 0, v1 = FINITE || o1 >= 0;
+              const uint32_t a00 = v0 ? pp[base0 + o0] : 0u, a01 = v1 ? pp[base0 + o1] : 0u;
+              const uint32_t a10 = v0 ? pp[base1 + o0] : 0u, a11 = v1 ? pp[base1 + o1] : 0u;
+              afr[part][ks][h * 2] = a00 | (a01 << 16);       // row g
+              afr[part][ks][h * 2 + 1] = a10 | (a11 << 16);   // row g + 8
+            }
+        float d[NT][4];
+#pragma unroll
+        for (int nt = 0; nt < NT; nt++) {
+          d[nt][0] = d[nt][2] = bia[nt][0];
+          d[nt][1] = d[nt][3] = bia[nt][1];
+#pragma unroll
+          for (int ks = 0; ks < 2; ks++) {
+            if (SPLIT) {
+              mma_bf16_16816(d[nt], afr[0][ks], blo[nt][ks][0], blo[nt][ks][1]);
+              mma_bf16_16816(d[nt], afr[SPLIT ? 1 : 0][ks], bhi[nt][ks][0], bhi[nt][ks][1]);
+            }
+            mma_bf16_16816(d[nt], afr[0][ks], bhi[nt][ks][0], bhi[nt][ks][1]);
+          }
+        }
+        // SiLU (accumulators hold x/2) -> bf16 -> per-warp staging [16 px][NT*8] -> 16-byte global stores
+        __syncwarp();
+#pragma unroll
+        for (int nt = 0; nt < NT; nt++) {
+          *reinterpret_cast<uint32_t*>(wstage + g * NT * 8 + nt * 8 + 2 * t) = pack2_bf16(silu_half(d[nt][0]), silu_half(d[nt][1]));
+          *reinterpret_cast<uint32_t*>(wstage + (g + 8) * NT * 8 + nt * 8 + 2 * t) = pack2_bf16(silu_half(d[nt][2]), silu_half(d[nt][3]));
+        }
+        __syncwarp();
+        const int ox0 = tx * STEM_TW + mi * 16;
+        for (int c = lane; c < 16 * NT; c += 32) {   // 16-byte chunks of the 16 x (NT*8) tile
+          const int px = c / NT, cg = c - px * NT;
+          if (ox0 + px < Wo && c0 + cg * 8 < Cp)
+            *reinterpret_cast<uint4*>(out + (((size_t)b * Ho + oy) * Wo + ox0 + px) * out_ld + c0 + cg * 8) =
+                *reinterpret_cast<const uint4*>(wstage + px * NT * 8 + cg * 8);
+        }
+      }
+    }
   }
+}
+
+static int stem_ctas_per_sm() {
+  static const int v = getenv("YB_STEM_CTAS") ? atoi(getenv("YB_STEM_CTAS")) : 8;
+  return v;
 }
 
 template <typename T, bool SPLIT>
@@ -454,7 +521,8 @@ static int launch_stem_t(const yb_plan* p, const Op& op, const void* in, float s
   __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(buf_ptr(p, op.dst.buf)) + op.dst.c_off;
   const int Cp = cpad8(op.dst.C);
   const unsigned blocks = (unsigned)(p->B * ((op.Hout + STEM_TH - 1) / STEM_TH) * ((op.Wout + STEM_TW - 1) / STEM_TW));
-  if (getenv("YB_STEM_DIRECT")) {  // CUDA-core version (cross-check)
+  static const bool direct = getenv("YB_STEM_DIRECT") != nullptr;
+  if (direct) {  // CUDA-core version (cross-check)
     const size_t smem = ((size_t)28 * Cp + 2 * 3 * STEM_IH * STEM_HP) * 4;
     YB_CUDA(launch_pdl(stem_conv_kernel<T>, dim3(blocks), dim3(256), smem, st, (const T*)in, out, w, p->B, p->H, p->W,
                        op.Hout, op.Wout, Cp, db.C, scale));
@@ -465,12 +533,24 @@ static int launch_stem_t(const yb_plan* p, const Op& op, const void* in, float s
   constexpr int PITCH = NVEC * EPV + 8;
   const int nt = (Cp / 8) % 3 == 0 ? 3 : ((Cp / 8) % 4 == 0 ? 4 : 2);   // n-tiles per pass
   const size_t smem = ((size_t)(SPLIT ? 2 : 1) * 3 * STEM_IH * PITCH + (size_t)8 * 16 * nt * 8) * 2;
-#define YB_STEM_MMA(NT)                                                                                         \
-  YB_CUDA(launch_pdl(stem_mma_kernel<T, NT, SPLIT>, dim3(blocks), dim3(256), smem, st, (const T*)in, out, w, p->B, \
-                     p->H, p->W, op.Hout, op.Wout, Cp, db.C, scale))
-  if (nt == 3) YB_STEM_MMA(3);
-  else if (nt == 4) YB_STEM_MMA(4);
-  else YB_STEM_MMA(2);
+  // persistent (grid = resident CTAs): the tap offsets and, with one channel group, the weight fragments
+  // are set up once per CTA instead of once per tile
+#define YB_STEM_MMA(NT, MINB)                                                                                    \
+  do {                                                                                                           \
+    static int occ = 0;                                                                                          \
+    if (occ == 0) {                                                                                              \
+      YB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stem_mma_kernel<T, NT, SPLIT, MINB>, 256, smem)); \
+      occ = std::max(1, std::min(occ, stem_ctas_per_sm()));                                                      \
+    }                                                                                                            \
+    const unsigned grid = std::min(blocks, (unsigned)(p->num_sms * occ));                                        \
+    YB_CUDA(launch_pdl(stem_mma_kernel<T, NT, SPLIT, MINB>, dim3(grid), dim3(256), smem, st, (const T*)in, out, w, \
+                       p->B, p->H, p->W, op.Hout, op.Wout, Cp, db.C, scale, (int)blocks));                       \
+  } while (0)
+  static const bool minb4 = getenv("YB_STEM_MINB1") == nullptr;
+  if (nt == 3) YB_STEM_MMA(3, 1);
+  else if (nt == 4) YB_STEM_MMA(4, 1);
+  else if (minb4) YB_STEM_MMA(2, 4);
+  else YB_STEM_MMA(2, 1);
 #undef YB_STEM_MMA
   return YB_OK;
 }
