@@ -299,6 +299,23 @@ __device__ __forceinline__ float vec_elem<uint8_t>(const uint4& v, int j) {
   return (float)((w >> (8 * (j & 3))) & 0xFFu);
 }
 
+// Shared-memory layout of the stem patch: three "tap column" planes per input channel.  The conv has
+// stride 2, so output column x reads input columns 2x-1, 2x, 2x+1; plane kx holds input column
+// 2x + kx - 1 at element x, which makes the 8 output pixels of an MMA row block contiguous (16 bytes) for
+// every tap - exactly one row of an ldmatrix 8x8 tile.  ldmatrix.trans of [tap][pixel] tiles yields the
+// [pixel][tap] A fragments of mma.m16n8k16 (two ldmatrix.x4 per 16 pixels x 32 taps instead of 32
+// 16-bit loads).  Row pitch 144 B and plane stride 459 x 16 B spread the 8 taps of a tile over the banks.
+static constexpr int STEM_PWB = (STEM_TW + 8) * 2;                  // plane row pitch, bytes
+static constexpr int STEM_PLANE_B = 3 * STEM_IH * STEM_PWB;         // one kx plane (3 channels), bytes
+static constexpr int STEM_PART_B = 3 * STEM_PLANE_B;                // all planes of the hi (or lo) part
+static constexpr int STEM_ZERO_B = 128;                             // zero rows for the K padding (k = 27..31)
+
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t* r, uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+               : "r"(addr));
+}
+
 // NT: n-tiles (8 channels each) per pass over the tile; wider stems take several passes.
 // SPLIT: the input is not exactly representable in bf16 (fp32 / fp16 images): input and weights are
 // staged as hi + lo bf16 pairs and multiplied as hi*W_hi + hi*W_lo + lo*W_hi, which matches an fp32
@@ -309,26 +326,28 @@ __global__ void __launch_bounds__(256, MINB)
     stem_mma_kernel(const T* __restrict__ in, __nv_bfloat16* __restrict__ out, const float* __restrict__ wgt,
                     int B, int H, int W, int Ho, int Wo, int Cp, int out_ld, float in_scale, int total_tiles) {
   constexpr int EPV = 16 / (int)sizeof(T);
+  constexpr bool U8 = sizeof(T) == 1;
+  // generic staging walks every 16-byte vector that overlaps patch columns [EPV-1, EPV-1 + 2*TW]
   constexpr int NVEC = (2 * STEM_TW + 1 + EPV + EPV - 1) / EPV;
-  constexpr int PITCH = NVEC * EPV + 8;   // bf16 elements per patch row
-  constexpr int PSZ = 3 * STEM_IH * PITCH;
-  // uint8 pixels are always finite, so the K padding (k = 27..31, zero weights) may read any patch
-  // element instead of a predicated zero
-  constexpr bool FINITE = sizeof(T) == 1;
+  constexpr int PARTS = SPLIT ? 2 : 1;
   extern __shared__ __align__(16) uint8_t stem_smem[];
-  __nv_bfloat16* patch = reinterpret_cast<__nv_bfloat16*>(stem_smem);          // [hi|lo][3][IH][PITCH]
-  __nv_bfloat16* stage = patch + (SPLIT ? 2 : 1) * PSZ;                         // [8 warps][16 px][NT*8]
+  uint8_t* zero_rows = stem_smem + PARTS * STEM_PART_B;
+  __nv_bfloat16* stage = reinterpret_cast<__nv_bfloat16*>(zero_rows + STEM_ZERO_B);   // [8 warps][16 px][NT*8]
   pdl_prologue_done();
   const int tiles_x = (Wo + STEM_TW - 1) / STEM_TW, tiles_y = (Ho + STEM_TH - 1) / STEM_TH;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
-  // ---- per-thread tap offsets of its 8 K columns (k = 2t, 2t+1, 2t+8, 2t+9 of each k-step)
-  int koff[8];
+  if (tid < STEM_ZERO_B / 4) reinterpret_cast<uint32_t*>(zero_rows)[tid] = 0u;
+  // ---- ldmatrix row address of this lane per k-step: tile (lane >> 3) = {px 0-7 | px 8-15} x {k 0-7 | k 8-15},
+  // row (lane & 7) = tap k
+  const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(stem_smem);
+  uint32_t aoff[2];
 #pragma unroll
-  for (int j = 0; j < 8; j++) {
-    const int k = (j >> 2) * 16 + ((j >> 1) & 1) * 8 + 2 * t + (j & 1);
+  for (int ks = 0; ks < 2; ks++) {
+    const int k = ks * 16 + ((lane >> 4) & 1) * 8 + (lane & 7);
     const int ci = k / 9, r9 = k - ci * 9, ky = r9 / 3, kx = r9 - ky * 3;
-    koff[j] = k < 27 ? (ci * STEM_IH + ky) * PITCH + kx : (FINITE ? 0 : -1);
+    aoff[ks] = k < 27 ? (uint32_t)(kx * STEM_PLANE_B + (ci * STEM_IH + 2 * warp + ky) * STEM_PWB + ((lane >> 3) & 1) * 16)
+                      : (uint32_t)(PARTS * STEM_PART_B);
   }
   // ---- weights of a channel group -> B fragments (n = g per n-tile), hi + lo split.  The input scale
   // and the 1/2 of SiLU(x) = h + h*tanh(h), h = x/2, are folded into weights and bias (exact: power of 2
@@ -358,66 +377,59 @@ __global__ void __launch_bounds__(256, MINB)
   };
   const bool single = Cp <= NT * 8;   // one channel group: its fragments stay in registers for all tiles
   if (single) load_weights(0);
-  const unsigned short* pu = reinterpret_cast<const unsigned short*>(patch);
   __nv_bfloat16* wstage = stage + warp * 16 * NT * 8;
-  // ---- staging descriptors of this thread's 16-byte vectors (tile independent; kept in registers when few)
-  constexpr int NIT = (3 * STEM_IH * NVEC + 255) / 256;
-  constexpr bool HOIST = NIT <= 2;
-  int st_iy[HOIST ? NIT : 1], st_vxe[HOIST ? NIT : 1], st_soff[HOIST ? NIT : 1], st_goff[HOIST ? NIT : 1];
-  if (HOIST) {
-#pragma unroll
-    for (int it = 0; it < (HOIST ? NIT : 1); it++) {
-      const int i = tid + it * 256;
-      const int vx = i % NVEC, row = i / NVEC;
-      st_iy[it] = row % STEM_IH;
-      st_vxe[it] = vx * EPV;
-      st_soff[it] = i < 3 * STEM_IH * NVEC ? row * PITCH + vx * EPV : -1;
-      st_goff[it] = ((row / STEM_IH) * H + st_iy[it]) * W + vx * EPV;
-    }
-  }
-  // 16 input elements -> bf16 (hi | lo) patch row; an all-zero vector is the padding
-  auto convert_store = [&](const uint4& v, int soff) {
-    __align__(16) __nv_bfloat16 o[EPV], ol[EPV];
-    if (SPLIT) {
-#pragma unroll
-      for (int j = 0; j < EPV; j++) {
-        const float x = vec_elem<T>(v, j);
-        o[j] = __float2bfloat16(x);
-        ol[j] = __float2bfloat16(x - __bfloat162float(o[j]));
-      }
-    } else {
-      unpack_bf16<T>(v, o);
-    }
-    __nv_bfloat16* dp = patch + soff;
-    if (EPV >= 8) {
-#pragma unroll
-      for (int j = 0; j < EPV; j += 8) {
-        *reinterpret_cast<uint4*>(dp + j) = *reinterpret_cast<const uint4*>(o + j);
-        if (SPLIT) *reinterpret_cast<uint4*>(dp + PSZ + j) = *reinterpret_cast<const uint4*>(ol + j);
-      }
-    } else {
-      *reinterpret_cast<uint2*>(dp) = *reinterpret_cast<const uint2*>(o);
-      if (SPLIT) *reinterpret_cast<uint2*>(dp + PSZ) = *reinterpret_cast<const uint2*>(ol);
-    }
-  };
-  // register prefetch of a tile's vectors (hoisted variant): issued one tile ahead of their use
-  uint4 pv[HOIST ? NIT : 1];
+
+  // ---- uint8 staging: a thread owns 16-byte vectors (16 pixels of one input row) whose even / odd
+  // pixels are whole 16-byte plane rows; the kx = 0 plane is the kx = 2 plane shifted by one pixel and
+  // needs the byte in front of the vector.  Loads run one tile ahead (registers).
+  constexpr int NV8 = STEM_TW / 8;                                  // vectors per patch row (uint8)
+  constexpr int NIT = (3 * STEM_IH * NV8 + 255) / 256;
+  uint4 pv[U8 ? NIT : 1];
+  uint32_t pb[U8 ? NIT : 1];
   auto fetch_tile = [&](int tl) {
     const int tx = tl % tiles_x;
     tl /= tiles_x;
     const int ty = tl % tiles_y, b = tl / tiles_y;
-    const int gy0 = 2 * ty * STEM_TH - 1, gxa = 2 * tx * STEM_TW - EPV;
-    const T* tile_in = in + ((size_t)b * 3 * H + gy0) * (size_t)W + gxa;   // may point before the image: only in-bounds offsets are read
+    const int gy0 = 2 * ty * STEM_TH - 1, gx0 = 2 * tx * STEM_TW;
 #pragma unroll
-    for (int it = 0; it < (HOIST ? NIT : 1); it++) {
-      const int gy = gy0 + st_iy[it], gx = gxa + st_vxe[it];
+    for (int it = 0; it < (U8 ? NIT : 1); it++) {
+      const int i = tid + it * 256;
+      const int vx = i % NV8, row = i / NV8;   // row = ci * IH + iy
+      const int ci = row / STEM_IH, iy = row - ci * STEM_IH;
+      const int gy = gy0 + iy, gx = gx0 + vx * 16;
       pv[it] = make_uint4(0u, 0u, 0u, 0u);
-      if (st_soff[it] >= 0 && (unsigned)gy < (unsigned)H && gx >= 0 && gx < W)
-        pv[it] = __ldg(reinterpret_cast<const uint4*>(tile_in + st_goff[it]));
+      pb[it] = 0u;
+      if (row < 3 * STEM_IH && (unsigned)gy < (unsigned)H && gx < W) {
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(in) + (((size_t)b * 3 + ci) * H + gy) * (size_t)W + gx;
+        pv[it] = __ldg(reinterpret_cast<const uint4*>(src));
+        if (gx > 0) pb[it] = __ldg(src - 1);
+      }
+    }
+  };
+  auto store_tile_u8 = [&]() {
+#pragma unroll
+    for (int it = 0; it < (U8 ? NIT : 1); it++) {
+      const int i = tid + it * 256;
+      const int vx = i % NV8, row = i / NV8;
+      if (row >= 3 * STEM_IH) break;
+      const uint32_t w[4] = {pv[it].x, pv[it].y, pv[it].z, pv[it].w};
+      float f[16];
+#pragma unroll
+      for (int j = 0; j < 16; j++) f[j] = (float)((w[j >> 2] >> (8 * (j & 3))) & 0xFFu);
+      const float fp = (float)pb[it];
+      // input column gx0 + 16 vx + j is patch column r = 16 vx + j + 1 (r = 2x + kx)
+      uint4 p0, p1, p2;
+      p1 = make_uint4(pack2_bf16(f[0], f[2]), pack2_bf16(f[4], f[6]), pack2_bf16(f[8], f[10]), pack2_bf16(f[12], f[14]));
+      p2 = make_uint4(pack2_bf16(f[1], f[3]), pack2_bf16(f[5], f[7]), pack2_bf16(f[9], f[11]), pack2_bf16(f[13], f[15]));
+      p0 = make_uint4(pack2_bf16(fp, f[1]), pack2_bf16(f[3], f[5]), pack2_bf16(f[7], f[9]), pack2_bf16(f[11], f[13]));
+      uint8_t* dst = stem_smem + row * STEM_PWB + vx * 16;
+      *reinterpret_cast<uint4*>(dst) = p0;
+      *reinterpret_cast<uint4*>(dst + STEM_PLANE_B) = p1;
+      *reinterpret_cast<uint4*>(dst + 2 * STEM_PLANE_B) = p2;
     }
   };
   pdl_wait();
-  if (HOIST && (int)blockIdx.x < total_tiles) fetch_tile(blockIdx.x);
+  if (U8 && (int)blockIdx.x < total_tiles) fetch_tile(blockIdx.x);
 #pragma unroll 1
   for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
     int bid = tile;
@@ -426,15 +438,13 @@ __global__ void __launch_bounds__(256, MINB)
     const int ty = bid % tiles_y;
     const int b = bid / tiles_y;
     if (tile != (int)blockIdx.x) __syncthreads();   // every warp is done with the previous patch
-    // ---- stage the input patch as bf16 (hi, and lo = x - hi when SPLIT)
-    if (HOIST) {
-#pragma unroll
-      for (int it = 0; it < (HOIST ? NIT : 1); it++)
-        if (st_soff[it] >= 0) convert_store(pv[it], st_soff[it]);
+    if (U8) {
+      store_tile_u8();
     } else {
+      // ---- generic staging (bf16 / fp16 / fp32 images): element-wise plane stores, hi and lo parts
       const int gy0 = 2 * ty * STEM_TH - 1;
-      const int gxa = 2 * tx * STEM_TW - EPV;
-      const T* tile_in = in + ((size_t)b * 3 * H + gy0) * (size_t)W + gxa;
+      const int gxa = 2 * tx * STEM_TW - EPV;   // patch column pc = EPV - 1 + r
+      const T* tile_in = in + ((size_t)b * 3 * H + gy0) * (size_t)W + gxa;   // only in-bounds offsets are read
 #pragma unroll 1
       for (int i = tid; i < 3 * STEM_IH * NVEC; i += 256) {
         const int vx = i % NVEC, row = i / NVEC;  // row = ci * IH + iy
@@ -443,12 +453,34 @@ __global__ void __launch_bounds__(256, MINB)
         uint4 v = make_uint4(0u, 0u, 0u, 0u);
         if ((unsigned)gy < (unsigned)H && gx >= 0 && gx < W)
           v = __ldg(reinterpret_cast<const uint4*>(tile_in + ((row / STEM_IH) * H + iy) * W + vxe));
-        convert_store(v, row * PITCH + vxe);
+        unsigned short* prow = reinterpret_cast<unsigned short*>(stem_smem + row * STEM_PWB);
+#pragma unroll
+        for (int j = 0; j < EPV; j++) {
+          const float x = vec_elem<T>(v, j);
+          const __nv_bfloat16 hi = __float2bfloat16(x);
+          const unsigned short uh = __bfloat16_as_ushort(hi);
+          const unsigned short ul = SPLIT ? __bfloat16_as_ushort(__float2bfloat16(x - __bfloat162float(hi))) : (unsigned short)0;
+          const int r = vxe + j - (EPV - 1);   // parity of r is a compile-time property of j
+          if (r < 0 || r > 2 * STEM_TW) continue;
+          if (r & 1) {
+            prow[STEM_PLANE_B / 2 + (r >> 1)] = uh;
+            if (SPLIT) prow[(STEM_PART_B + STEM_PLANE_B) / 2 + (r >> 1)] = ul;
+          } else {
+            if (r < 2 * STEM_TW) {
+              prow[r >> 1] = uh;
+              if (SPLIT) prow[STEM_PART_B / 2 + (r >> 1)] = ul;
+            }
+            if (r >= 2) {
+              prow[STEM_PLANE_B + (r >> 1) - 1] = uh;
+              if (SPLIT) prow[STEM_PART_B / 2 + STEM_PLANE_B + (r >> 1) - 1] = ul;
+            }
+          }
+        }
       }
     }
     __syncthreads();
     // the next tile's pixels travel while this one is computed
-    if (HOIST && tile + (int)gridDim.x < total_tiles) fetch_tile(tile + (int)gridDim.x);
+    if (U8 && tile + (int)gridDim.x < total_tiles) fetch_tile(tile + (int)gridDim.x);
     const int oy = ty * STEM_TH + warp;
     if (oy >= Ho) continue;
 #pragma unroll 1
@@ -456,24 +488,13 @@ __global__ void __launch_bounds__(256, MINB)
       if (!single) load_weights(c0);
 #pragma unroll 1
       for (int mi = 0; mi < STEM_TW / 16; mi++) {
-        // input column of tap kx for output column lx: EPV + 2*lx + kx - 1
-        const int base0 = (2 * warp) * PITCH + EPV - 1 + 2 * (mi * 16 + g);
-        const int base1 = base0 + 16;
-        uint32_t afr[SPLIT ? 2 : 1][2][4];
+        uint32_t afr[PARTS][2][4];
 #pragma unroll
-        for (int part = 0; part < (SPLIT ? 2 : 1); part++)
+        for (int part = 0; part < PARTS; part++)
 #pragma unroll
           for (int ks = 0; ks < 2; ks++)
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-              const int o0 = koff[ks * 4 + h * 2], o1 = koff[ks * 4 + h * 2 + 1];
-              const unsigned short* pp = pu + part * PSZ;
-              const bool v0 = FINITE || o0 >= 0, v1 = FINITE || o1 >= 0;
-              const uint32_t a00 = v0 ? pp[base0 + o0] : 0u, a01 = v1 ? pp[base0 + o1] : 0u;
-              const uint32_t a10 = v0 ? pp[base1 + o0] : 0u, a11 = v1 ? pp[base1 + o1] : 0u;
-              afr[part][ks][h * 2] = a00 | (a01 << 16);       // row g
-              afr[part][ks][h * 2 + 1] = a10 | (a11 << 16);   // row g + 8
-            }
+            ldmatrix_x4_trans(afr[part][ks], smem_base + aoff[ks] + (uint32_t)(mi * 32) +
+                                                 ((part && aoff[ks] < (uint32_t)STEM_PART_B) ? (uint32_t)STEM_PART_B : 0u));
         float d[NT][4];
 #pragma unroll
         for (int nt = 0; nt < NT; nt++) {
@@ -528,17 +549,16 @@ static int launch_stem_t(const yb_plan* p, const Op& op, const void* in, float s
                        op.Hout, op.Wout, Cp, db.C, scale));
     return YB_OK;
   }
-  constexpr int EPV = 16 / (int)sizeof(T);
-  constexpr int NVEC = (2 * STEM_TW + 1 + EPV + EPV - 1) / EPV;
-  constexpr int PITCH = NVEC * EPV + 8;
   const int nt = (Cp / 8) % 3 == 0 ? 3 : ((Cp / 8) % 4 == 0 ? 4 : 2);   // n-tiles per pass
-  const size_t smem = ((size_t)(SPLIT ? 2 : 1) * 3 * STEM_IH * PITCH + (size_t)8 * 16 * nt * 8) * 2;
+  const size_t smem = (size_t)(SPLIT ? 2 : 1) * STEM_PART_B + STEM_ZERO_B + (size_t)8 * 16 * nt * 8 * 2;
   // persistent (grid = resident CTAs): the tap offsets and, with one channel group, the weight fragments
   // are set up once per CTA instead of once per tile
 #define YB_STEM_MMA(NT, MINB)                                                                                    \
   do {                                                                                                           \
     static int occ = 0;                                                                                          \
     if (occ == 0) {                                                                                              \
+      YB_CUDA(cudaFuncSetAttribute(stem_mma_kernel<T, NT, SPLIT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                   (int)(2 * STEM_PART_B + STEM_ZERO_B + 8 * 16 * 4 * 8 * 2)));                  \
       YB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stem_mma_kernel<T, NT, SPLIT, MINB>, 256, smem)); \
       occ = std::max(1, std::min(occ, stem_ctas_per_sm()));                                                      \
     }                                                                                                            \
