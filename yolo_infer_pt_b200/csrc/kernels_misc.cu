@@ -308,7 +308,11 @@ __device__ __forceinline__ float vec_elem<uint8_t>(const uint4& v, int j) {
 static constexpr int STEM_PWB = (STEM_TW + 8) * 2;                  // plane row pitch, bytes
 static constexpr int STEM_PLANE_B = 3 * STEM_IH * STEM_PWB;         // one kx plane (3 channels), bytes
 static constexpr int STEM_PART_B = 3 * STEM_PLANE_B;                // all planes of the hi (or lo) part
-static constexpr int STEM_ZERO_B = 128;                             // zero rows for the K padding (k = 27..31)
+static constexpr int STEM_ZERO_B = 128;
+#ifndef YB_STEM_MI_UNROLL
+#define YB_STEM_MI_UNROLL 1
+#endif
+static constexpr int STEM_MI_UNROLL = YB_STEM_MI_UNROLL;                             // zero rows for the K padding (k = 27..31)
 
 __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t* r, uint32_t addr) {
   asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0, %1, %2, %3}, [%4];"
@@ -486,7 +490,7 @@ __global__ void __launch_bounds__(256, MINB)
 #pragma unroll 1
     for (int c0 = 0; c0 < Cp; c0 += NT * 8) {
       if (!single) load_weights(c0);
-#pragma unroll 1
+#pragma unroll(STEM_MI_UNROLL)
       for (int mi = 0; mi < STEM_TW / 16; mi++) {
         uint32_t afr[PARTS][2][4];
 #pragma unroll
