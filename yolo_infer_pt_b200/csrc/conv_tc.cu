@@ -258,6 +258,12 @@ __device__ __forceinline__ float silu_f(float x) {
   return fmaf(h, t, h);
 }
 
+__device__ __forceinline__ float silu_half(float h) {  // SiLU(2h)
+  float t;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(h));
+  return fmaf(h, t, h);
+}
+
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
   __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
@@ -445,8 +451,10 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
     // tile's store: that one is drained (wait_group.read) a full tile later.
     const bool bias_once = P.n_tiles == 1;
     const bool fast_flow = !alt_epi && bias_once && (HEAD || P.c_bufs == 2);
+    // SiLU(x) = h + h*tanh(h) with h = x/2: the 1/2 is folded into the accumulator FMA (h = acc*0.5 +
+    // bias*0.5, bit-identical to (acc + bias)*0.5), so a SiLU element costs FFMA + MUFU + FFMA
     if (bias_once) {
-      for (int i = tid; i < BN; i += 128 * ngrp) bias_s[i] = __ldg(P.bias + i);
+      for (int i = tid; i < BN; i += 128 * ngrp) bias_s[i] = (P.act ? 0.5f : 1.f) * __ldg(P.bias + i);
       if (ngrp == 2) asm volatile("bar.sync 1, 256;" ::: "memory");
       else asm volatile("bar.sync 1, 128;" ::: "memory");
     }
@@ -495,7 +503,7 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
         // tile ago) must have finished reading the staging buffer
         if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
         if (!bias_once)
-          for (int i = tid; i < BN; i += 128 * ngrp) bias_s[i] = __ldg(P.bias + n0 + i);
+          for (int i = tid; i < BN; i += 128 * ngrp) bias_s[i] = (P.act ? 0.5f : 1.f) * __ldg(P.bias + n0 + i);
         epi_sync();
       }
       const uint32_t c_buf = c_base + (((fast_flow && (ti & 1)) || (alt_epi && grp) || (PAIR && half)) ? c_groups * C_GROUP_BYTES : 0u);
@@ -509,9 +517,16 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
         if (nb >= P.cout_store || (!row_ok && HEAD)) return;
         float f[16];
 #pragma unroll
-        for (int j = 0; j < 16; j++) {
-          float x = __uint_as_float(v[j]) + bias_s[c0 + j];
-          f[j] = P.act ? silu_f(x) : x;
+        for (int q = 0; q < 4; q++) {
+          const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c0 + 4 * q);   // broadcast LDS.128
+          const float bq[4] = {b4.x, b4.y, b4.z, b4.w};
+          if (P.act) {   // uniform
+#pragma unroll
+            for (int j = 0; j < 4; j++) f[4 * q + j] = silu_half(fmaf(__uint_as_float(v[4 * q + j]), 0.5f, bq[j]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; j++) f[4 * q + j] = __uint_as_float(v[4 * q + j]) + bq[j];
+          }
         }
         if (!HEAD) {
           // bf16 tile staged in shared memory in the TMA SWIZZLE_128B layout (16-byte chunk index
@@ -571,9 +586,11 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
       };
       for (int c0 = cfirst; c0 < BN; c0 += cstep) {  // one inlined copy of the chunk body (code size)
         do_chunk(c0, ra0, ra1);
-        ra0 = rb0;
-        ra1 = rb1;
-        res_fetch(c0 + 2 * cstep, rb0, rb1);
+        if (!HEAD && P.res != nullptr) {   // uniform branch: layers without a residual skip the register rotation
+          ra0 = rb0;
+          ra1 = rb1;
+          res_fetch(c0 + 2 * cstep, rb0, rb1);
+        }
       }
       if (HEAD && P.out_mode == 2 && row_ok && (alt_epi || grp == 0)) {
         const int y = fast_div(r, P.w_mul, P.w_shr, P.Wout), x = r - y * P.Wout;
