@@ -1177,6 +1177,18 @@ static PFN_encodeTiled get_encode() {
   return fn;
 }
 
+// L2 promotion (the granularity at which a TMA miss fetches from DRAM) must not exceed the bytes a row
+// of the box really uses: a 16-channel slice of a 32-channel buffer is 32 useful bytes per 64-byte pixel,
+// and 256-byte promotion would drag the other slice through DRAM as well (measured: 3x the algorithmic
+// reads on the C2f/C3k2 bottleneck inputs).
+static CUtensorMapL2promotion promo_for(uint64_t used_bytes, uint64_t pitch_bytes) {
+  static const bool force256 = getenv("YB_TMA_PROMO256") != nullptr;
+  if (force256 || used_bytes >= pitch_bytes || used_bytes >= 256) return CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+  if (used_bytes >= 128) return CU_TENSOR_MAP_L2_PROMOTION_L2_128B;
+  if (used_bytes >= 64) return CU_TENSOR_MAP_L2_PROMOTION_L2_64B;
+  return CU_TENSOR_MAP_L2_PROMOTION_NONE;
+}
+
 static int make_tmap_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows,
                         uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_rows) {
   PFN_encodeTiled enc = get_encode();
@@ -1190,7 +1202,8 @@ static int make_tmap_2d(CUtensorMap* map, const void* base, uint64_t inner, uint
   cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   promo_for(std::min<uint64_t>(box_inner, inner) * 2, row_stride_bytes),
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed with %d (inner=%llu rows=%llu stride=%llu box=%ux%u)",
               (int)r, (unsigned long long)inner, (unsigned long long)rows,
@@ -1219,7 +1232,7 @@ static int make_tmap_nhwc(CUtensorMap* map, const void* base, uint64_t C, uint64
                                 : box_c == 32 ? CU_TENSOR_MAP_SWIZZLE_64B
                                 : box_c == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, promo_for(std::min<uint64_t>(box_c, C) * 2, ld_elems * 2),
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled (4-D NHWC) failed with %d (C=%llu W=%llu H=%llu N=%llu ld=%llu)", (int)r,
