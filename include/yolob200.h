@@ -101,6 +101,14 @@ int yb_plan_bind(yb_plan* plan, const void* dev_weights, void* dev_workspace);
  *           anchors ordered level 8,16,32, row-major (nets/nn.py:262-270). */
 int yb_forward(yb_plan* plan, const void* in_nchw, int in_dtype, float* out, void* cuda_stream);
 
+/* yb_forward whose class-score epilogues also do non_max_suppression's candidate filter (utils/util.py:130,
+ * 147: scores > conf): every such (anchor, class) is appended to the per-image key lists of
+ * `nms_workspace` (yb_nms_workspace_bytes bytes, headers zero: yb_nms_workspace_init, or last used by a
+ * yb_nms* call of the same batch) while the scores are still in registers, instead of re-reading the
+ * (B, nc, A) scores in the NMS.  Follow with yb_nms_prefiltered on the same workspace, conf and max_nms. */
+int yb_forward_nms(yb_plan* plan, const void* in_nchw, int in_dtype, float* out, float conf, int max_nms,
+                   void* nms_workspace, size_t nms_workspace_bytes, void* cuda_stream);
+
 /* Same, but stops before the DFL decode and returns the pre-decode logits:
  * raw : (B, A, 64+nc) fp32, channel order [box 4x16, cls nc] — the training-mode head output
  * of nets/nn.py:256-259 flattened and level-concatenated (a transposed view of nn.py:262). */
@@ -160,6 +168,13 @@ int yb_nms_workspace_init(void* workspace, size_t workspace_bytes, void* cuda_st
 int yb_nms_clean(const float* pred, int batch, int num_classes, int num_anchors, float conf, double iou,
                  int max_det, int max_nms, float max_wh, float* out, int* out_counts, void* workspace,
                  size_t workspace_bytes, void* cuda_stream);
+
+/* yb_nms for predictions produced by yb_forward_nms with this workspace: the candidate lists are already
+ * filled, the pass over the scores is skipped (images that overflowed their list are still rebuilt from
+ * pred).  Results are identical to yb_nms. */
+int yb_nms_prefiltered(const float* pred, int batch, int num_classes, int num_anchors, float conf, double iou,
+                       int max_det, int max_nms, float max_wh, float* out, int* out_counts, void* workspace,
+                       size_t workspace_bytes, void* cuda_stream);
 
 /* ---- misc ---- */
 /* ---- pre-processing (the step in front of YOLO.forward) ------------------------

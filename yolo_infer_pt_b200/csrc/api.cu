@@ -30,6 +30,8 @@ void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 size_t nms_workspace_bytes(int B, int nc, int A, int max_nms);
 int nms_run(const float* pred, int B, int nc, int A, float conf, double iou, int max_det, int max_nms,
             float max_wh, float* out, int* out_counts, void* ws, size_t ws_bytes, cudaStream_t st, int ws_clean);
+int nms_sink_layout(void* ws, size_t ws_bytes, int B, int nc, int A, int max_nms, int** hdr,
+                    unsigned long long** keys, int* cap);
 
 int metric_run(const float* det, const int* counts, const float* tgt, const int* tcounts, int B, int max_det,
                int max_t, const float* iou_v, int n_iou, uint8_t* correct, cudaStream_t st);
@@ -128,7 +130,7 @@ static int forward_impl(yb_plan* p, const void* in, int in_dtype, float* out, in
   if (!p->use_graph) return run_ops(p, in, in_dtype, out, raw, st);
   for (GraphEntry& g : p->graphs) {
     if (g.in == in && g.out == out && g.stream == stream && g.dtype == in_dtype && g.raw == raw &&
-        g.impl == p->conv_impl) {
+        g.impl == p->conv_impl && g.sink == (const void*)p->sink_keys && g.sink_conf == p->sink_conf) {
       YB_CUDA(cudaGraphLaunch(g.exec, st));
       g_launches.fetch_add((unsigned long long)yb_plan_num_launches(p), std::memory_order_relaxed);
       return YB_OK;
@@ -159,6 +161,8 @@ static int forward_impl(yb_plan* p, const void* in, int in_dtype, float* out, in
   g.dtype = in_dtype;
   g.raw = raw;
   g.impl = p->conv_impl;
+  g.sink = p->sink_keys;
+  g.sink_conf = p->sink_conf;
   e = cudaGraphInstantiate(&g.exec, graph, 0);
   cudaGraphDestroy(graph);
   if (e != cudaSuccess) {
@@ -323,7 +327,28 @@ int yb_plan_bind(yb_plan* plan, const void* dev_weights, void* dev_workspace) {
 }
 
 int yb_forward(yb_plan* plan, const void* in_nchw, int in_dtype, float* out, void* cuda_stream) {
+  if (plan) plan->sink_keys = nullptr, plan->sink_hdr = nullptr;
   return forward_impl(plan, in_nchw, in_dtype, out, 0, cuda_stream);
+}
+
+int yb_forward_nms(yb_plan* plan, const void* in_nchw, int in_dtype, float* out, float conf, int max_nms,
+                   void* nms_workspace, size_t nms_workspace_bytes, void* cuda_stream) {
+  if (!plan || !nms_workspace) {
+    set_error("yb_forward_nms: null argument");
+    return YB_ERR_ARG;
+  }
+  if (!plan->fuse_decode || plan->conv_impl != 0) {
+    set_error("yb_forward_nms: needs the fused head epilogues (tensor-core path, decode fusion on)");
+    return YB_ERR_STATE;
+  }
+  int rc = nms_sink_layout(nms_workspace, nms_workspace_bytes, plan->B, plan->nc, plan->A, max_nms, &plan->sink_hdr,
+                           &plan->sink_keys, &plan->sink_cap);
+  if (rc) return rc;
+  plan->sink_conf = conf;
+  rc = forward_impl(plan, in_nchw, in_dtype, out, 0, cuda_stream);
+  plan->sink_keys = nullptr;
+  plan->sink_hdr = nullptr;
+  return rc;
 }
 
 int yb_forward_raw(yb_plan* plan, const void* in_nchw, int in_dtype, float* raw, void* cuda_stream) {
@@ -502,6 +527,17 @@ int yb_nms(const float* pred, int batch, int num_classes, int num_anchors, float
   }
   return nms_run(pred, batch, num_classes, num_anchors, conf, iou, max_det, max_nms, max_wh, out,
                  out_counts, workspace, workspace_bytes, (cudaStream_t)cuda_stream, 0);
+}
+
+int yb_nms_prefiltered(const float* pred, int batch, int num_classes, int num_anchors, float conf, double iou,
+                       int max_det, int max_nms, float max_wh, float* out, int* out_counts, void* workspace,
+                       size_t workspace_bytes, void* cuda_stream) {
+  if (!pred || !out || !out_counts) {
+    set_error("yb_nms_prefiltered: null argument");
+    return YB_ERR_ARG;
+  }
+  return nms_run(pred, batch, num_classes, num_anchors, conf, iou, max_det, max_nms, max_wh, out,
+                 out_counts, workspace, workspace_bytes, (cudaStream_t)cuda_stream, 2);
 }
 
 int yb_nms_workspace_init(void* workspace, size_t workspace_bytes, void* cuda_stream) {

@@ -97,6 +97,12 @@ struct ConvParams {
   // fused head decode (out_mode 2 / 3): dst is the (B, 4+nc, A) fp32 output tensor
   int out_mode;       // 0 bf16 slice, 1 fp32 logits, 2 DFL box decode, 3 class sigmoid
   int A_total, nc;
+  // out_mode 3 with a candidate sink: every score > nms_conf also becomes a key of the image's NMS list
+  // (what nms_append_kernel would find by re-reading the scores)
+  int* nms_hdr;                   // [B] NmsHeader (8 ints): [0] cand_count, [1] sel_count
+  unsigned long long* nms_keys;   // [B][nms_cap]
+  int nms_cap;
+  float nms_conf;
   float lvl_stride;
   // naive path only
   const __nv_bfloat16* w;
@@ -514,7 +520,7 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
         tmem_ld16(t_row + (uint32_t)c0, v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         const int nb = n0 + c0;
-        if (nb >= P.cout_store || (!row_ok && HEAD)) return;
+        if (nb >= P.cout_store || (!row_ok && HEAD && P.out_mode != 3)) return;   // class mode keeps the warp whole (shuffles)
         float f[16];
 #pragma unroll
         for (int q = 0; q < 4; q++) {
@@ -578,9 +584,59 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
           // class scores: plane-major fp32 stores, one anchor per lane -> 128 B per warp store
           float* ob = reinterpret_cast<float*>(P.dst) + ((size_t)n_img * (4 + P.nc) + 4 + nb) * P.A_total +
                       P.dst_row_off + r;
+          int cnt = 0;
 #pragma unroll
           for (int j = 0; j < 16; j++) {
-            if (nb + j < P.nc) ob[(size_t)j * P.A_total] = __fdividef(1.f, 1.f + __expf(-f[j]));  // 2-ulp reciprocal: MUFU.RCP + FMUL
+            f[j] = __fdividef(1.f, 1.f + __expf(-f[j]));  // 2-ulp reciprocal: MUFU.RCP + FMUL
+            if (row_ok && nb + j < P.nc) {
+              ob[(size_t)j * P.A_total] = f[j];
+              cnt += f[j] > P.nms_conf ? 1 : 0;
+            }
+          }
+          if (P.nms_keys) {
+            // warp-aggregated append (the whole warp is here: rows outside the tensor carry cnt = 0): one
+            // scan + one pair of atomics per image the warp's 32 anchors belong to (one or two, more only on
+            // feature maps smaller than a warp)
+            unsigned rem = __ballot_sync(0xffffffffu, cnt > 0);
+            if (rem) {
+              const int lane_ = (int)(tid & 31);
+              int slot = 0;
+              while (rem) {
+                const int leader = __ffs((int)rem) - 1;
+                const int img = __shfl_sync(0xffffffffu, n_img, leader);
+                const bool in = n_img == img;
+                int incl = in ? cnt : 0;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                  const int tt = __shfl_up_sync(0xffffffffu, incl, o);
+                  if (lane_ >= o) incl += tt;
+                }
+                const int tot = __shfl_sync(0xffffffffu, incl, 31);
+                int base = 0;
+                if (lane_ == leader) {
+                  base = atomicAdd(P.nms_hdr + 8 * img + 1, tot);   // sel_count: slots handed out
+                  atomicAdd(P.nms_hdr + 8 * img, tot);              // cand_count
+                }
+                base = __shfl_sync(0xffffffffu, base, leader);
+                if (in) slot = base + incl - cnt;
+                rem &= ~__ballot_sync(0xffffffffu, in);
+              }
+              if (cnt) {
+                unsigned long long* kl = P.nms_keys + (size_t)n_img * P.nms_cap;
+                const unsigned int anchor = (unsigned int)(P.dst_row_off + r);
+#pragma unroll
+                for (int j = 0; j < 16; j++) {
+                  if (nb + j < P.nc && f[j] > P.nms_conf) {
+                    if (slot < P.nms_cap) {
+                      const unsigned int u = __float_as_uint(f[j]);
+                      const unsigned int ord = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+                      kl[slot] = ((unsigned long long)(~ord) << 32) | (anchor * (unsigned int)P.nc + (unsigned int)(nb + j));
+                    }
+                    slot++;
+                  }
+                }
+              }
+            }
           }
         }
       };
@@ -946,7 +1002,8 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
       float* dww = bias_s + 256;   // [10][CW]: 9 taps + bias, zero beyond the real channels
       for (int i = ptid; i < 10 * CW; i += DW_THREADS) {
         const int tap = i / CW, c = i - tap * CW;
-        dww[i] = c < P.dw_C ? __ldg(P.dw_w + tap * P.dw_cp + c) : 0.f;
+        // SiLU(x) = h + h*tanh(h), h = x/2: the 1/2 is folded into the depthwise weights and bias (exact)
+        dww[i] = c < P.dw_C ? (P.dw_act ? 0.5f : 1.f) * __ldg(P.dw_w + tap * P.dw_cp + c) : 0.f;
       }
       asm volatile("bar.sync 3, %0;" ::"n"(DW_THREADS) : "memory");
       int stage = 0, pstage = 0;
@@ -995,8 +1052,8 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
                 for (int px = 0; px < 4; px++) {
                   float2 o = acc[slot][px];
                   if (P.dw_act) {
-                    o.x = silu_f(o.x);
-                    o.y = silu_f(o.y);
+                    o.x = silu_half(o.x);
+                    o.y = silu_half(o.y);
                   }
                   const uint32_t m = (uint32_t)((RPT * rq + r) * PT_W + 4 * xh + px);
                   const uint32_t addr = sbase + m * 128u + ((((uint32_t)cpair >> 2) ^ (m & 7u)) << 4);
@@ -1575,6 +1632,10 @@ static void fill_params(const yb_plan* p, const Op& op, ConvParams& P) {
   P.out_mode = op.out_f32 ? 1 : 0;
   P.A_total = p->A;
   P.nc = p->nc;
+  P.nms_hdr = nullptr;
+  P.nms_keys = nullptr;
+  P.nms_cap = 0;
+  P.nms_conf = INFINITY;
 }
 
 int launch_conv_tc(const yb_plan* p, const Op& op, cudaStream_t st, float* fused_out) {
@@ -1587,6 +1648,12 @@ int launch_conv_tc(const yb_plan* p, const Op& op, cudaStream_t st, float* fused
     P.cout_store = op.head_part == 1 ? 64 : round_up(p->nc, 16);
     int lvl = op.dst_row_off == p->lvl_off[2] ? 2 : op.dst_row_off == p->lvl_off[1] ? 1 : 0;
     P.lvl_stride = p->lvl_stride[lvl];
+    if (op.head_part == 2 && p->sink_keys) {   // class scores also feed the NMS candidate lists
+      P.nms_hdr = p->sink_hdr;
+      P.nms_keys = p->sink_keys;
+      P.nms_cap = p->sink_cap;
+      P.nms_conf = p->sink_conf;
+    }
   }
   int grid = std::min(P.total_tiles, p->num_sms * op.occ);
 #define YB_LAUNCH(ATMA, T2D, HEAD)                                                                       \

@@ -806,6 +806,24 @@ size_t nms_workspace_bytes(int B, int nc, int A, int max_nms) {
   return hdr + hist + keys;
 }
 
+// Where the class-score epilogues of the forward (conv_tc.cu, out_mode 3) append candidate keys when the
+// caller runs yb_forward_nms + yb_nms_prefiltered instead of yb_forward + yb_nms.
+int nms_sink_layout(void* ws, size_t ws_bytes, int B, int nc, int A, int max_nms, int** hdr,
+                    unsigned long long** keys, int* cap) {
+  static_assert(sizeof(NmsHeader) == 32, "conv_tc.cu indexes the header as 8 ints per image");
+  if (B <= 0 || nc <= 0 || A <= 0 || max_nms <= 0 || ws_bytes < nms_workspace_bytes(B, nc, A, max_nms)) {
+    set_error("yb_forward_nms: NMS workspace too small or bad sizes");
+    return YB_ERR_ARG;
+  }
+  size_t hdr_bytes = ((size_t)B * sizeof(NmsHeader) + 255) / 256 * 256;
+  *hdr = reinterpret_cast<int*>(ws);
+  *keys = reinterpret_cast<unsigned long long*>((uint8_t*)ws + hdr_bytes + (size_t)B * HIST_BINS * 4);
+  *cap = cap_for(max_nms, (long long)nc * A);
+  return YB_OK;
+}
+
+// ws_clean: 0 = clear the headers first, 1 = headers known to be zero, 2 = the candidate lists were already
+// filled by the forward's epilogues (skip the append pass)
 int nms_run(const float* pred, int B, int nc, int A, float conf, double iou, int max_det, int max_nms,
             float max_wh, float* out, int* out_counts, void* ws, size_t ws_bytes, cudaStream_t st, int ws_clean) {
   if (B <= 0 || nc <= 0 || A <= 0 || max_det <= 0 || max_nms <= 0) {
@@ -860,8 +878,10 @@ int nms_run(const float* pred, int B, int nc, int A, float conf, double iou, int
   long long total = (long long)nc * A;
   int gx = (int)std::min<long long>((total + 256 * 16 - 1) / (256 * 16), 1024);
   int vec4 = (A % 4 == 0) && ((reinterpret_cast<uintptr_t>(pred) & 15) == 0);
-  YB_CUDA(launch_pdl(nms_append_kernel, dim3(gx, B), dim3(256), 0, st, a, vec4));
-  count_launch();
+  if (ws_clean != 2) {
+    YB_CUDA(launch_pdl(nms_append_kernel, dim3(gx, B), dim3(256), 0, st, a, vec4));
+    count_launch();
+  }
   // overflow images only (every other block exits at once: keep the grids small, ~2 K CTAs)
   const int ogx = std::max(8, std::min(std::min(gx, 128), 2048 / B));
   YB_CUDA(launch_pdl(nms_ovf_hist_kernel, dim3(ogx, B), dim3(256), 0, st, a));

@@ -133,6 +133,8 @@ struct GraphEntry {
   void* out = nullptr;
   void* stream = nullptr;
   int dtype = 0, raw = 0, impl = 0;
+  const void* sink = nullptr;   // NMS candidate sink captured in the graph (yb_forward_nms)
+  float sink_conf = 0.f;
   cudaGraphExec_t exec = nullptr;
 };
 
@@ -156,6 +158,11 @@ struct yb_plan {
   int use_graph = 0;
   int fuse_decode = 1;     // head tails decode in their epilogue; the logits buffer is skipped
   int num_sms = 148;
+  // candidate sink of the current forward (yb_forward_nms): NMS key lists filled by the class-score epilogues
+  int* sink_hdr = nullptr;
+  unsigned long long* sink_keys = nullptr;
+  int sink_cap = 0;
+  float sink_conf = 0.f;
   std::vector<yb::GraphEntry> graphs;
   cudaStream_t capture_stream = nullptr;
   int profiling = 0;

@@ -147,17 +147,27 @@ class Engine:
             raise RuntimeError(f"unsupported input dtype {x.dtype}")
         return x if x.is_contiguous() else x.contiguous()
 
-    def forward(self, x, out=None):
+    def forward(self, x, out=None, nms_sink=None):
         """(B,3,H,W) image tensor -> the engine's static (B, 4+nc, A) fp32 prediction tensor
         (layout of reference nets/nn.py:262-270). The returned tensor is overwritten by the next call;
         pass `out` (same shape, fp32, contiguous) to write somewhere else - pipelines that overlap the
-        NMS of one batch with the forward of the next alternate between two such tensors."""
+        NMS of one batch with the forward of the next alternate between two such tensors.
+        `nms_sink=(workspace, conf, max_nms)`: the class-score epilogues also append every score > conf to
+        the NMS candidate lists of `workspace` (util.nms_workspace); follow with
+        util.nms_padded(..., workspace=workspace, prefiltered=True)."""
         x = self._check_input(x)
         if out is None:
             out = self.out
         elif out.shape != self.out.shape or out.dtype != torch.float32 or not out.is_contiguous() or out.device != self.out.device:
             raise ValueError("Engine.forward: `out` must be a contiguous fp32 tensor shaped like the prediction tensor")
         stream = torch.cuda.current_stream(self.device).cuda_stream
+        if nms_sink is not None:
+            ws, conf, max_nms = nms_sink
+            conf32 = float(np.float32(conf))   # the NMS compares fp32 scores with an fp32 threshold
+            _lib.check(self.L.yb_forward_nms(self.plan, x.data_ptr(), _DTYPES[x.dtype], out.data_ptr(), conf32,
+                                             int(max_nms), ws.data_ptr(), ws.numel(), ctypes.c_void_p(stream)),
+                       "yb_forward_nms")
+            return out
         _lib.check(self.L.yb_forward(self.plan, x.data_ptr(), _DTYPES[x.dtype], out.data_ptr(),
                                      ctypes.c_void_p(stream)), "yb_forward")
         return out

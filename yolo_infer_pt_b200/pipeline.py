@@ -17,7 +17,8 @@ from .utils import util
 
 
 class StreamingDetector:
-    def __init__(self, model, batch_shape, dtype=torch.uint8, device="cuda", conf=0.001, iou=0.65, resident=False):
+    def __init__(self, model, batch_shape, dtype=torch.uint8, device="cuda", conf=0.001, iou=0.65, resident=False,
+                 fuse_filter=True):
         self.model = model
         self.device = torch.device(device)
         self.conf, self.iou = conf, iou
@@ -34,6 +35,10 @@ class StreamingDetector:
         for e in self.consumed + self.nms_done:
             e.record(self.compute_stream)
         self.preds = None                       # two prediction tensors, allocated at the first batch
+        # fuse_filter: the forward's class-score epilogues apply the NMS confidence filter (one candidate
+        # workspace per slot); the NMS then never re-reads the (B, nc, A) scores
+        self.fuse_filter = fuse_filter
+        self.nms_ws = None
         self.h2d_bytes = 0 if resident else self.inputs[0].numel() * self.inputs[0].element_size()
         b = batch_shape[0]
         # pinned host landing buffers for the detections (two slots; a result stays valid for two steps)
@@ -58,12 +63,19 @@ class StreamingDetector:
             eng = self.model._engine_for(x)
             if self.preds is None:
                 self.preds = [torch.empty_like(eng.out) for _ in range(2)]
-            y = eng.forward(x, out=self.preds[slot])
+                if self.fuse_filter:
+                    self.nms_ws = [util.nms_workspace(eng.batch, eng.num_outputs - 4, eng.num_anchors, self.device)
+                                   for _ in range(2)]
+            sink = (self.nms_ws[slot], self.conf, util.MAX_NMS) if self.fuse_filter else None
+            y = eng.forward(x, out=self.preds[slot], nms_sink=sink)
             self.consumed[slot].record(self.compute_stream)
             self.fwd_done[slot].record(self.compute_stream)
         with torch.cuda.stream(self.nms_stream):                  # overlaps the next batch's forward
             self.nms_stream.wait_event(self.fwd_done[slot])
-            det, counts = util.nms_padded(y, self.conf, self.iou)
+            if self.fuse_filter:
+                det, counts = util.nms_padded(y, self.conf, self.iou, workspace=self.nms_ws[slot], prefiltered=True)
+            else:
+                det, counts = util.nms_padded(y, self.conf, self.iou)
             self.nms_done[slot].record(self.nms_stream)
         # detections go back on their own stream: no kernel queues behind the copy
         det_h, cnt_h = self.det_host[slot], self.cnt_host[slot]

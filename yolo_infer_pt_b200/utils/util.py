@@ -57,10 +57,20 @@ def make_anchors(x, strides, offset=0.5):
 _workspaces = {}
 
 
+def nms_workspace(batch, num_classes, num_anchors, device, max_nms=MAX_NMS):
+    """A private NMS workspace (zeroed headers) for `Engine.forward(..., nms_sink=)` + `nms_padded(...,
+    workspace=, prefiltered=True)`: the forward's class-score epilogues fill its candidate lists."""
+    L = _lib_module().lib()
+    return torch.zeros(L.yb_nms_workspace_bytes(batch, num_classes, num_anchors, max_nms), dtype=torch.uint8,
+                       device=device)
+
+
 def nms_padded(outputs, confidence_threshold=0.001, iou_threshold=0.65, max_det=MAX_DET, max_nms=MAX_NMS,
-               max_wh=MAX_WH):
+               max_wh=MAX_WH, workspace=None, prefiltered=False):
     """Device-resident NMS: returns (det, counts) with det (B, max_det, 6) fp32 rows
-    [x1, y1, x2, y2, score, class] and counts (B,) int32 — no host synchronisation."""
+    [x1, y1, x2, y2, score, class] and counts (B,) int32 — no host synchronisation.
+    `prefiltered`: `outputs` came from `Engine.forward(x, nms_sink=(workspace, conf, max_nms))` with the same
+    threshold, so the candidate lists in `workspace` are already filled and the score pass is skipped."""
     if not (isinstance(outputs, torch.Tensor) and outputs.is_cuda):
         raise RuntimeError("yolo_infer_pt_b200.non_max_suppression needs a CUDA tensor; "
                            "there is no CPU fallback on the inference path")
@@ -74,7 +84,9 @@ def nms_padded(outputs, confidence_threshold=0.001, iou_threshold=0.65, max_det=
     nc = no - 4
     dev = pred.device
     key = (dev.index, B, nc, A, max_nms)
-    ws = _workspaces.get(key)
+    if prefiltered and workspace is None:
+        raise ValueError("prefiltered NMS needs the workspace the forward appended its candidates to")
+    ws = workspace if workspace is not None else _workspaces.get(key)
     if ws is None:
         nbytes = L.yb_nms_workspace_bytes(B, nc, A, max_nms)
         ws = torch.zeros(nbytes, dtype=torch.uint8, device=dev)   # zero headers once; the kernel keeps them zero
@@ -85,9 +97,10 @@ def nms_padded(outputs, confidence_threshold=0.001, iou_threshold=0.65, max_det=
     counts = torch.empty(B, dtype=torch.int32, device=dev)
     conf32 = float(numpy.float32(confidence_threshold))  # torch compares an fp32 tensor in fp32
     stream = torch.cuda.current_stream(dev).cuda_stream
-    _lib.check(L.yb_nms_clean(pred.data_ptr(), B, nc, A, conf32, float(iou_threshold), max_det, max_nms,
-                              float(max_wh), det.data_ptr(), counts.data_ptr(), ws.data_ptr(), ws.numel(),
-                              ctypes.c_void_p(stream)), "yb_nms")
+    fn = L.yb_nms_prefiltered if prefiltered else L.yb_nms_clean
+    _lib.check(fn(pred.data_ptr(), B, nc, A, conf32, float(iou_threshold), max_det, max_nms,
+                  float(max_wh), det.data_ptr(), counts.data_ptr(), ws.data_ptr(), ws.numel(),
+                  ctypes.c_void_p(stream)), "yb_nms")
     return det, counts
 
 
