@@ -769,10 +769,12 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
             }
             mbar_wait(empty_bar(s), ph ^ 1u);
             const uint32_t a_s = a_base + (uint32_t)s * A_STAGE_BYTES + sw_off + (uint32_t)rbase * 128u;
+            if (k0 < ((K + 15) & ~15)) {   // granules of K16 steps past the real K are never read by the MMA
 #pragma unroll
-            for (int i = 0; i < 8; i++)  // masked taps are zero-filled; their source is never read
-              cp_async16(a_s + (uint32_t)i * 2048u, img_base + (uint32_t)(offb[i] + deltab),
-                         ((ok8 >> i) & 1u) ? 16u : 0u);
+              for (int i = 0; i < 8; i++)  // masked taps are zero-filled; their source is never read
+                cp_async16(a_s + (uint32_t)i * 2048u, img_base + (uint32_t)(offb[i] + deltab),
+                           ((ok8 >> i) & 1u) ? 16u : 0u);
+            }
             asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(gathered_bar(s)) : "memory");
             if (++stage == S) {
               stage = 0;
@@ -850,11 +852,13 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
           const int ld = P.src_ld[seg];
           mbar_wait(empty_bar(s), ph ^ 1u);
           const uint32_t a_s = a_base + (uint32_t)s * A_STAGE_BYTES + sw_off;
+          if (k0 < ((P.K + 15) & ~15)) {   // granules of K16 steps past the real K are never read by the MMA
 #pragma unroll
-          for (int i = 0; i < 8; i++) {
-            const bool ok = k_ok && ((okmask[i] >> tbit) & 1u);
-            const int idx = ok ? pix[i] + delta : 0;
-            cp_async16(a_s + (uint32_t)(rbase + 16 * i) * 128u, sp + (long long)idx * ld, ok ? 16u : 0u);
+            for (int i = 0; i < 8; i++) {
+              const bool ok = k_ok && ((okmask[i] >> tbit) & 1u);
+              const int idx = ok ? pix[i] + delta : 0;
+              cp_async16(a_s + (uint32_t)(rbase + 16 * i) * 128u, sp + (long long)idx * ld, ok ? 16u : 0u);
+            }
           }
           asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(gathered_bar(s)) : "memory");
           if (++stage == S) {
@@ -875,6 +879,8 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
                              ((uint64_t)1 << 16);
     int ti = 0, stage = 0, pstage = 0;
     uint32_t phase = 0, pphase = 0;
+    // K is one contiguous run (gathered im2col rows, or a single TMA-fed source): only its tail is padding
+    const bool k_tail_ok = MODE == MODE_GATHER || P.nseg == 1;
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ti++) {
       const int acc = ti & 1;
       mbar_wait(tmem_empty_bar(acc), ((uint32_t)(ti >> 1) & 1u) ^ 1u);
@@ -976,9 +982,12 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
         {
           const uint64_t da = desc_hi | (uint64_t)(((ring_base + (uint32_t)stage * A_STAGE_BYTES) >> 4) & 0x3FFF);
           const uint64_t db = desc_hi | (uint64_t)(((b_base + (uint32_t)(RES ? kb : stage) * b_stage_bytes) >> 4) & 0x3FFF);
+          // K16 steps past the real K (K padded to the 64-wide k-block) hold zeros: not issued
+          const int kv = k_tail_ok ? min(BK / 16, (P.K - kb * BK + 15) >> 4) : BK / 16;
 #pragma unroll
-          for (int k = 0; k < BK / 16; k++)  // +32 bytes (2 x 16 B units) per K=16 step inside the swizzle atom
-            umma_bf16(d_tmem, da + 2u * k, db + 2u * k, idesc, (uint32_t)((kb | k) != 0));
+          for (int k = 0; k < BK / 16; k++) {  // +32 bytes (2 x 16 B units) per K=16 step inside the swizzle atom
+            if (k < kv) umma_bf16(d_tmem, da + 2u * k, db + 2u * k, idesc, (uint32_t)((kb | k) != 0));
+          }
           umma_commit(empty_bar(stage));  // frees the smem stage once these MMAs have read it
           if (kb == num_kb - 1) umma_commit(tmem_full_bar(acc));  // accumulator complete -> epilogue
         }
