@@ -109,6 +109,22 @@ def test_forward_within_north_star_tolerance(size, hw, batch):
     assert cls_err <= SCORE_TOL
 
 
+@pytest.mark.parametrize("size,h,w,batch", [("n", 96, 160, 3), ("n", 320, 192, 1), ("s", 160, 64, 5)])
+def test_forward_rectangular_inputs_and_odd_batches(size, h, w, batch):
+    """Letterboxed batches need not be square (any multiple of the largest stride, nn.py:262-270 builds the
+    anchors from the feature-map shapes); tiles hang over right / bottom edges differently per level."""
+    model = _model(size, "survey")
+    x = synth.synth_images(batch, h, w, seed=7)
+    ref = _oracle(model, x)
+    with torch.no_grad():
+        y = model.to("cuda:0")(x.to("cuda:0")).cpu()
+    assert tuple(y.shape) == tuple(ref.shape) == (batch, 84, (h // 8) * (w // 8) + (h // 16) * (w // 16) + (h // 32) * (w // 32))
+    box_err = (y[:, :4] - ref[:, :4]).abs().max().item()
+    cls_err = (y[:, 4:] - ref[:, 4:]).abs().max().item()
+    print(f"{size}@{h}x{w} B={batch}: box max-abs {box_err:.4f} px, score max-abs {cls_err:.2e}")
+    assert box_err <= BOX_TOL_PX and cls_err <= SCORE_TOL
+
+
 @pytest.mark.parametrize("size", ["n", "x"])
 def test_forward_matches_golden_reference_output(size, golden_dir):
     g = np.load(os.path.join(golden_dir, f"fwdsv_{size}_64.npz"))

@@ -2,7 +2,7 @@
 (main.py:264-273: `samples.to(device)`, `model(samples)`, `non_max_suppression(outputs)`), software
 pipelined over four CUDA streams:
 
-    copy    H2D of batch i+1          (pinned host memory -> one of two device input buffers)
+    copy    H2D of batches i+1, i+2   (pinned host memory -> one of three device input buffers)
     compute forward of batch i        (-> one of two prediction tensors)
     nms     NMS of batch i-1          (reads the other prediction tensor)
     d2h     detections of batch i-1   (-> pinned host landing buffers)
@@ -18,7 +18,7 @@ from .utils import util
 
 class StreamingDetector:
     def __init__(self, model, batch_shape, dtype=torch.uint8, device="cuda", conf=0.001, iou=0.65, resident=False,
-                 fuse_filter=True):
+                 fuse_filter=True, input_buffers=3):
         self.model = model
         self.device = torch.device(device)
         self.conf, self.iou = conf, iou
@@ -27,9 +27,13 @@ class StreamingDetector:
         self.compute_stream = torch.cuda.Stream(self.device)
         self.nms_stream = torch.cuda.Stream(self.device)
         self.d2h_stream = torch.cuda.Stream(self.device)
-        self.inputs = [None, None] if resident else [torch.empty(batch_shape, dtype=dtype, device=self.device) for _ in range(2)]
-        self.copied = [torch.cuda.Event() for _ in range(2)]
-        self.consumed = [torch.cuda.Event() for _ in range(2)]
+        # input ring: with three buffers the copy engine always has a free target, so a copy that takes about
+        # as long as a forward (PCIe-bound uint8 batches) never waits for the kernels, nor they for it
+        self.n_in = 2 if resident else max(2, int(input_buffers))
+        self.inputs = [None] * self.n_in if resident else [torch.empty(batch_shape, dtype=dtype, device=self.device)
+                                                           for _ in range(self.n_in)]
+        self.copied = [torch.cuda.Event() for _ in range(self.n_in)]
+        self.consumed = [torch.cuda.Event() for _ in range(self.n_in)]
         self.fwd_done = [torch.cuda.Event() for _ in range(2)]
         self.nms_done = [torch.cuda.Event() for _ in range(2)]
         for e in self.consumed + self.nms_done:
@@ -45,20 +49,22 @@ class StreamingDetector:
         self.det_host = [torch.empty(b, util.MAX_DET, 6, dtype=torch.float32).pin_memory() for _ in range(2)]
         self.cnt_host = [torch.empty(b, dtype=torch.int32).pin_memory() for _ in range(2)]
 
-    def _upload(self, slot, batch):
+    def _upload(self, index, batch):
+        islot = index % self.n_in
         if self.resident:
-            self.inputs[slot] = batch           # already on the device, owned by the caller
+            self.inputs[islot] = batch          # already on the device, owned by the caller
             return
         with torch.cuda.stream(self.copy_stream):
-            self.copy_stream.wait_event(self.consumed[slot])      # the kernels that read this buffer are done
-            self.inputs[slot].copy_(batch, non_blocking=True)
-            self.copied[slot].record(self.copy_stream)
+            self.copy_stream.wait_event(self.consumed[islot])     # the kernels that read this buffer are done
+            self.inputs[islot].copy_(batch, non_blocking=True)
+            self.copied[islot].record(self.copy_stream)
 
-    def _detect(self, slot):
-        x = self.inputs[slot]
+    def _detect(self, index):
+        islot, slot = index % self.n_in, index & 1      # input ring slot; prediction / NMS workspace / landing slot
+        x = self.inputs[islot]
         with torch.cuda.stream(self.compute_stream):
             if not self.resident:
-                self.compute_stream.wait_event(self.copied[slot])
+                self.compute_stream.wait_event(self.copied[islot])
             self.compute_stream.wait_event(self.nms_done[slot])   # the NMS that read this prediction tensor two batches ago
             eng = self.model._engine_for(x)
             if self.preds is None:
@@ -68,7 +74,7 @@ class StreamingDetector:
                                    for _ in range(2)]
             sink = (self.nms_ws[slot], self.conf, util.MAX_NMS) if self.fuse_filter else None
             y = eng.forward(x, out=self.preds[slot], nms_sink=sink)
-            self.consumed[slot].record(self.compute_stream)
+            self.consumed[islot].record(self.compute_stream)
             self.fwd_done[slot].record(self.compute_stream)
         with torch.cuda.stream(self.nms_stream):                  # overlaps the next batch's forward
             self.nms_stream.wait_event(self.fwd_done[slot])
@@ -93,24 +99,30 @@ class StreamingDetector:
         """Generator over batches -> (det, counts) host tensors, in order.  The H2D copy of the next batch and
         the NMS of the previous one are in flight while the current batch's forward runs."""
         it = iter(batches)
-        try:
-            nxt = next(it)
-        except StopIteration:
-            return
-        self._upload(0, nxt)
-        slot, pending = 0, None
-        while nxt is not None:
-            try:
-                following = next(it)
-            except StopIteration:
-                following = None
-            if following is not None:
-                self._upload(slot ^ 1, following)
-            result = self._detect(slot)
+        ahead = []                 # indices uploaded (or uploading) and not yet run
+        state = {"next": 0, "more": True}
+
+        def fill():
+            while state["more"] and len(ahead) < self.n_in - 1:
+                try:
+                    b = next(it)
+                except StopIteration:
+                    state["more"] = False
+                    return
+                self._upload(state["next"], b)
+                ahead.append(state["next"])
+                state["next"] += 1
+
+        fill()
+        pending = None
+        while ahead:
+            index = ahead.pop(0)
+            fill()                 # the ring minus the batch about to run is in flight
+            result = self._detect(index)
             if pending is not None:
                 pending[2].synchronize()
                 yield pending[0], pending[1]
             pending = result
-            nxt, slot = following, slot ^ 1
-        pending[2].synchronize()
-        yield pending[0], pending[1]
+        if pending is not None:
+            pending[2].synchronize()
+            yield pending[0], pending[1]
