@@ -425,10 +425,10 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
-  // prologue done (barriers, TMEM): let the next kernel start its own, then wait for the producer of
-  // our inputs before the first global-memory access
+  // prologue done (barriers, TMEM): let the next kernel start its own.  Each role waits for the producer
+  // kernel of our inputs (griddepcontrol.wait) right before its first access to activations; bias and
+  // weights are constants of the plan and are fetched before that wait, under the previous kernel's tail
   pdl_prologue_done();
-  pdl_wait();
 
   // With A fed by TMA the im2col warps have nothing to gather: they join the epilogue as a second
   // group that converts the odd 16-column chunks of the accumulator (same TMEM lane quadrants).
@@ -464,6 +464,7 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
       if (ngrp == 2) asm volatile("bar.sync 1, 256;" ::: "memory");
       else asm volatile("bar.sync 1, 128;" ::: "memory");
     }
+    pdl_wait();
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ti++) {
       if (alt_epi && (ti & 1) != grp) continue;
       const int mt = P.n_tiles == 1 ? tile : tile / P.n_tiles;
@@ -697,6 +698,7 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
     if (leader) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
   } else if (warp < MMA_WARP) {
     // ============================ im2col producer ==========================================
+    pdl_wait();
     {
       const int ptid = tid - PROD_WARP0 * 32;
       const int g = ptid & 7;       // 16-byte granule (8 channels) inside the 128-byte K row
@@ -1015,6 +1017,7 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
         dww[i] = c < P.dw_C ? (P.dw_act ? 0.5f : 1.f) * __ldg(P.dw_w + tap * P.dw_cp + c) : 0.f;
       }
       asm volatile("bar.sync 3, %0;" ::"n"(DW_THREADS) : "memory");
+      pdl_wait();
       int stage = 0, pstage = 0;
       uint32_t phase = 0, pphase = 0;
       for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
@@ -1090,6 +1093,7 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
     // im2col data is written by cp.async (generic proxy) but read by the tensor core through the
     // async proxy.  This thread acquires a gathered stage, issues the proxy fence and forwards the
     // arrival to the MMA warp, keeping the (expensive) fence off the MMA issue path.
+    pdl_wait();
     if (PGEO && lane == 0) {
       // ---- halo-patch producer: one 4-D TMA box {cblk, 10, 18, 1} per (tile, channel block);
       // coordinates start one pixel above / left of the tile, out-of-image pixels are zero-filled
@@ -1131,6 +1135,19 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
       const uint32_t a_tx = MODE == MODE_ATMA ? (uint32_t)A_STAGE_BYTES : 0u;
       int stage = 0;
       uint32_t phase = 0;
+      // The weight k-blocks of the CTA's first tile that fit the (still empty) stage ring are requested
+      // before the wait for the previous kernel: their DRAM / L2 latency is off the critical path.
+      int pre = 0;
+      if ((int)blockIdx.x < P.total_tiles) {
+        const int n0f = ((int)blockIdx.x - (P.n_tiles == 1 ? (int)blockIdx.x : (int)blockIdx.x / P.n_tiles) * P.n_tiles) * BN;
+        pre = min(num_kb, S);
+        for (int kb = 0; kb < pre; kb++) {
+          mbar_expect_tx(full_bar(kb), a_tx + b_stage_bytes);
+          const int kb_w = (PATCH && P.cblk >= 64) ? (kb % 9) * P.ncb + kb / 9 : kb;
+          tma_load_2d(b_base + (uint32_t)kb * b_stage_bytes, &tmap_b, kb_w * BK, n0f, full_bar(kb));
+        }
+      }
+      pdl_wait();
       for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
         // resident weights are fetched during the CTA's first tile only
         const bool load_b = !RES || tile == (int)blockIdx.x;
@@ -1143,12 +1160,15 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
         for (int kb = 0; kb < num_kb; kb++) {
           const int s = stage;
           const uint32_t ph = phase;
-          mbar_wait(empty_bar(s), ph ^ 1u);
-          if (tx) mbar_expect_tx(full_bar(s), tx);
-          else mbar_arrive(full_bar(s));   // im2col layer with resident weights: only the gather feeds this stage
+          const bool early = tile == (int)blockIdx.x && kb < pre;   // expect_tx + weight load already issued
+          if (!early) {
+            mbar_wait(empty_bar(s), ph ^ 1u);
+            if (tx) mbar_expect_tx(full_bar(s), tx);
+            else mbar_arrive(full_bar(s));   // im2col layer with resident weights: only the gather feeds this stage
+          }
           // PATCH with >= 64 channels consumes k-blocks channel-block-major; they are packed tap-major
           const int kb_w = (PATCH && P.cblk >= 64) ? (kb % 9) * P.ncb + kb / 9 : kb;
-          if (load_b)
+          if (load_b && !early)
             tma_load_2d(b_base + (uint32_t)(RES ? kb : s) * b_stage_bytes, &tmap_b, kb_w * BK, n0, full_bar(s));
           if (MODE == MODE_ATMA) {
             const CUtensorMap* ma =
