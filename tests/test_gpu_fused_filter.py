@@ -75,3 +75,19 @@ def test_streaming_detector_fused_equals_unfused():
         assert torch.equal(c0, c1)
         for b in range(c0.numel()):
             assert torch.equal(d0[b, :int(c0[b])], d1[b, :int(c1[b])])
+
+
+def test_prefiltered_nms_rejects_mismatched_threshold_or_tensor():
+    model = _model()
+    x = (synth.synth_images(2, 64, 64, seed=1) * 255).round().to(torch.uint8).to("cuda:0")
+    with torch.no_grad():
+        eng = model._engine_for(x)
+        ws = util.nms_workspace(eng.batch, eng.num_outputs - 4, eng.num_anchors, x.device)
+        with pytest.raises(ValueError):
+            util.nms_padded(eng.forward(x), 0.001, 0.65, workspace=ws, prefiltered=True)     # no sink was attached
+        y = eng.forward(x, nms_sink=(ws, 0.001, util.MAX_NMS))
+        with pytest.raises(ValueError):
+            util.nms_padded(y, 0.25, 0.65, workspace=ws, prefiltered=True)                   # other threshold
+        with pytest.raises(ValueError):
+            util.nms_padded(y.clone(), 0.001, 0.65, workspace=ws, prefiltered=True)          # other tensor
+        util.nms_padded(y, 0.001, 0.65, workspace=ws, prefiltered=True)                      # consumes (and re-zeroes) the lists

@@ -30,6 +30,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <type_traits>
 
 #include "yb_internal.h"
 
@@ -516,7 +517,8 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
       const uint32_t c_buf = c_base + (((fast_flow && (ti & 1)) || (alt_epi && grp) || (PAIR && half)) ? c_groups * C_GROUP_BYTES : 0u);
       const uint32_t t_row = tmem_base + ((uint32_t)(qwarp * 32) << 16) + (uint32_t)(acc * (PAIR ? 2 * BN : BN) + half * BN);
       float dist[4];
-      auto do_chunk = [&](int c0, const uint4& rv0, const uint4& rv1) {
+      auto do_chunk = [&](int c0, const uint4& rv0, const uint4& rv1, auto with_res) {
+        constexpr bool WITH_RES = decltype(with_res)::value;
         uint32_t v[16];
         tmem_ld16(t_row + (uint32_t)c0, v);
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
@@ -542,7 +544,7 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
 #pragma unroll
           for (int h = 0; h < 2; h++) {
             if (nb + 8 * h < P.cout_store) {
-              if (resp) {
+              if (WITH_RES && resp) {
                 const uint4 rv = h ? rv1 : rv0;
                 const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
 #pragma unroll
@@ -641,13 +643,18 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
           }
         }
       };
-      for (int c0 = cfirst; c0 < BN; c0 += cstep) {  // one inlined copy of the chunk body (code size)
-        do_chunk(c0, ra0, ra1);
-        if (!HEAD && P.res != nullptr) {   // uniform branch: layers without a residual skip the register rotation
+      // two copies of the chunk body; a kernel only ever runs one of them.  The copy without a residual
+      // carries no prefetch registers and no rotation moves.
+      if (!HEAD && P.res != nullptr) {
+        for (int c0 = cfirst; c0 < BN; c0 += cstep) {
+          do_chunk(c0, ra0, ra1, std::true_type{});
           ra0 = rb0;
           ra1 = rb1;
           res_fetch(c0 + 2 * cstep, rb0, rb1);
         }
+      } else {
+        const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+        for (int c0 = cfirst; c0 < BN; c0 += cstep) do_chunk(c0, z, z, std::false_type{});
       }
       if (HEAD && P.out_mode == 2 && row_ok && (alt_epi || grp == 0)) {
         const int y = fast_div(r, P.w_mul, P.w_shr, P.Wout), x = r - y * P.Wout;

@@ -167,6 +167,7 @@ class Engine:
             _lib.check(self.L.yb_forward_nms(self.plan, x.data_ptr(), _DTYPES[x.dtype], out.data_ptr(), conf32,
                                              int(max_nms), ws.data_ptr(), ws.numel(), ctypes.c_void_p(stream)),
                        "yb_forward_nms")
+            ws._yb_sink_tag = (conf32, int(max_nms), out.data_ptr())   # checked by util.nms_padded(prefiltered=True)
             return out
         _lib.check(self.L.yb_forward(self.plan, x.data_ptr(), _DTYPES[x.dtype], out.data_ptr(),
                                      ctypes.c_void_p(stream)), "yb_forward")

@@ -96,6 +96,9 @@ def nms_padded(outputs, confidence_threshold=0.001, iou_threshold=0.65, max_det=
     det = torch.empty(B, max_det, 6, dtype=torch.float32, device=dev)
     counts = torch.empty(B, dtype=torch.int32, device=dev)
     conf32 = float(numpy.float32(confidence_threshold))  # torch compares an fp32 tensor in fp32
+    if prefiltered and getattr(ws, "_yb_sink_tag", None) != (conf32, int(max_nms), pred.data_ptr()):
+        raise ValueError("prefiltered NMS: the workspace was not filled by a forward of these predictions with "
+                         "the same confidence threshold and max_nms")
     stream = torch.cuda.current_stream(dev).cuda_stream
     fn = L.yb_nms_prefiltered if prefiltered else L.yb_nms_clean
     _lib.check(fn(pred.data_ptr(), B, nc, A, conf32, float(iou_threshold), max_det, max_nms,
