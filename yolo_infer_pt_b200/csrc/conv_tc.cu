@@ -7,24 +7,34 @@
 //                                           n = output channel
 //                                           k = (tap, source slice, channel)
 //
-//   A : NHWC bf16 activations.  1x1/stride-1 convs over plain slices fetch 128x64 tiles with TMA
-//       (one 2-D tensor map per source slice of the concat).  3x3, stride-2 and upsampled sources
-//       use a software im2col producer: 128 threads gather 16-byte channel granules and store
-//       them in the 128B-swizzled K-major layout the UMMA descriptor expects.
-//   W : packed bf16 [N_pad][K_pad], K-major, fetched with TMA (SWIZZLE_128B).
+//   A : NHWC bf16 activations, four ways into shared memory (template parameter MODE):
+//       MODE_ATMA   1x1/stride-1 over plain slices: 128x64 tiles by TMA, one tensor map per source of a concat;
+//       MODE_PATCH  3x3/stride-1: the halo patch of a 16x8 pixel tile by one 4-D TMA box (zero-filled outside
+//                   the image = padding); every tap is a UMMA descriptor shifted by the tap's pixel offset
+//                   (the swizzle is a function of the smem address bits).  MODE_PATCH2: 16x16 super-tiles,
+//                   two accumulators share each weight k-block;
+//       MODE_DW     depthwise 3x3 + bias + SiLU computed by 8 extra warps from a TMA patch straight into the
+//                   swizzled A stage of the 1x1 conv that follows (nn.py:248-251);
+//       MODE_GATHER stride-2 and upsampled sources: 128 threads gather 16-byte channel granules with cp.async
+//                   into the 128B-swizzled K-major layout.
+//   W : packed bf16 [N_pad][K_pad], K-major, fetched with TMA (SWIZZLE_128B); resident in shared memory for
+//       the whole kernel when the matrix fits next to the A ring.
 //   D : fp32 accumulators in TMEM (128 lanes x BN columns), tcgen05.mma cta_group::1 kind::f16,
 //       issued by one thread; tcgen05.commit releases smem stages and signals the epilogue.
-//   Epilogue: tcgen05.ld -> +bias -> SiLU -> +residual -> bf16 (or fp32 head logits) stored
-//       straight into the channel slice of the consumer's buffer.
+//   Epilogue: tcgen05.ld -> bias + SiLU -> +residual -> bf16 staged in swizzled smem -> TMA store into the
+//       channel slice of the consumer's buffer (or fp32 head outputs, below).
 //
 // The kernel is persistent: grid = SMs x resident CTAs, each CTA walks tiles t = blockIdx.x + i*grid.
-// Warp roles (352 threads): warps 0-3 epilogue (TMEM lane = output row), warps 4-7 im2col
-// producers, warp 8 TMEM allocator + MMA issuer, warp 9 TMA producer, warp 10 proxy-fence relay.  Two accumulator stages in
+// Warp roles (352 threads; 608 with the depthwise warps): warps 0-3 epilogue (TMEM lane = output row), warps
+// 4-7 im2col producers or a second epilogue group, warp 8 TMEM allocator + MMA issuer, warp 9 TMA producer,
+// warp 10 halo-patch producer / proxy-fence relay.  Each role executes griddepcontrol.wait right before its
+// first access to activations (constants - bias, weights - are requested before it).  Two accumulator stages in
 // TMEM (2 x BN columns) let the epilogue of tile i overlap the main loop of tile i+1; the smem
 // stage ring runs continuously across tiles.
 // Epilogue modes: bf16 NHWC slice (+residual) | fp32 head logits | fused DFL box decode
 // (nets/nn.py:222-225,265-268 + make_anchors utils/util.py:85-96) | fused class sigmoid (nn.py:270),
-// the last two writing the final (B, 4+nc, A) fp32 tensor directly.
+// the last two writing the final (B, 4+nc, A) fp32 tensor directly; the class mode can also append the NMS
+// candidate keys of its scores > conf (utils/util.py:130,147) to per-image lists (yb_forward_nms).
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
