@@ -178,6 +178,23 @@ def test_unsupported_configs_fail_loudly():
         Engine([3, 16, 32, 64, 128, 200], [1] * 6, [False, True], 80, 1, 64, 64, host_only=True)
 
 
+def test_c_abi_rejects_bad_arguments_without_touching_the_gpu():
+    """Error behaviour of the entry points added around the candidate sink: negative code + message, no crash."""
+    import ctypes
+    from yolo_infer_pt_b200 import _lib
+    L = _lib.lib()
+    e = Engine(*nn.yolo_v11_n(80)._arch, 2, 64, 64, host_only=True)
+    null = ctypes.c_void_p(0)
+    # no workspace / no plan
+    assert L.yb_forward_nms(e.plan, null, 3, null, ctypes.c_float(0.001), 30000, null, 0, null) < 0
+    assert L.yb_forward_nms(null, null, 3, null, ctypes.c_float(0.001), 30000, null, 0, null) < 0
+    assert b"yb_forward_nms" in L.yb_last_error()
+    assert L.yb_nms_prefiltered(null, 2, 80, 84, ctypes.c_float(0.001), 0.65, 300, 30000, ctypes.c_float(7680.0), null, null,
+                                null, 0, null) < 0
+    # workspace size is a pure function of the sizes (same formula the sink uses)
+    assert L.yb_nms_workspace_bytes(2, 80, 84, 30000) >= 2 * 32 + 2 * 2048 * 4 + 2 * 32768 * 8
+
+
 def test_wh2xy_and_make_anchors():
     x = torch.tensor([[10.0, 20.0, 4.0, 6.0]])
     assert torch.equal(util.wh2xy(x), torch.tensor([[8.0, 17.0, 12.0, 23.0]]))
