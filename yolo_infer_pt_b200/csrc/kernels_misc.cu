@@ -728,44 +728,46 @@ __device__ __forceinline__ uint4 max_bf16x8(const uint4& a, const uint4& b) {
   return o;
 }
 
+// G: 8-channel groups per CTA (a pixel's G x 16 bytes are contiguous: full sectors, fewer and fatter CTAs)
+template <int G>
 __global__ void __launch_bounds__(256)
     sppf_pool_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* dst, int ld, int H, int W,
                      int Chalf) {
-  extern __shared__ uint4 pl[];  // cur[HW], tmp[HW]
+  extern __shared__ uint4 pl[];  // cur[HW][G], tmp[HW][G]
   pdl_prologue_done();
   pdl_wait();
-  const int HW = H * W;
+  const int HW = H * W, n = HW * G;
   uint4* cur = pl;
-  uint4* tmp = pl + HW;
-  const int cgs = Chalf >> 3;
+  uint4* tmp = pl + n;
+  const int cgs = (Chalf >> 3) / G;
   const int b = blockIdx.x / cgs;
   const int cg = blockIdx.x % cgs;
-  const size_t img_base = (size_t)b * HW * ld + cg * 8;
-  for (int i = threadIdx.x; i < HW; i += blockDim.x)
-    cur[i] = __ldg(reinterpret_cast<const uint4*>(src + img_base + (size_t)i * ld));
+  const size_t img_base = (size_t)b * HW * ld + cg * 8 * G;
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+    cur[i] = __ldg(reinterpret_cast<const uint4*>(src + img_base + (size_t)(i / G) * ld + (i % G) * 8));
   __syncthreads();
   for (int stage = 0; stage < 3; stage++) {
-    for (int i = threadIdx.x; i < HW; i += blockDim.x) {
-      int y = i / W, x = i - y * W;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const int pix = i / G, y = pix / W, x = pix - y * W;
       uint4 m = cur[i];
 #pragma unroll
       for (int d = -2; d <= 2; d++) {
         int xx = x + d;
-        if (d != 0 && (unsigned)xx < (unsigned)W) m = max_bf16x8(m, cur[y * W + xx]);
+        if (d != 0 && (unsigned)xx < (unsigned)W) m = max_bf16x8(m, cur[i + d * G]);
       }
       tmp[i] = m;
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < HW; i += blockDim.x) {
-      int y = i / W, x = i - y * W;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const int pix = i / G, g = i % G, y = pix / W;
       uint4 m = tmp[i];
 #pragma unroll
       for (int d = -2; d <= 2; d++) {
         int yy = y + d;
-        if (d != 0 && (unsigned)yy < (unsigned)H) m = max_bf16x8(m, tmp[yy * W + x]);
+        if (d != 0 && (unsigned)yy < (unsigned)H) m = max_bf16x8(m, tmp[i + d * W * G]);
       }
       // dst points at slice 1 of the concat buffer; slices are Chalf channels apart
-      *reinterpret_cast<uint4*>(dst + img_base + (size_t)i * ld + (size_t)stage * Chalf) = m;
+      *reinterpret_cast<uint4*>(dst + img_base + (size_t)pix * ld + g * 8 + (size_t)stage * Chalf) = m;
       cur[i] = m;  // each thread rewrites only the pixels it owns; tmp is the read set
     }
     __syncthreads();
@@ -779,20 +781,29 @@ int launch_pool(const yb_plan* p, const Op& op, cudaStream_t st) {
   __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(buf_ptr(p, op.dst.buf)) + op.dst.c_off;
   int Chalf = op.src[0].C;
   int HW = op.Hin * op.Win;
-  size_t smem = (size_t)2 * HW * 16;
+  const int cg_all = Chalf >> 3;
+  const int G = (cg_all % 4 == 0 && (size_t)2 * HW * 4 * 16 <= 96 * 1024) ? 4 : (cg_all % 2 == 0 ? 2 : 1);
+  size_t smem = (size_t)2 * HW * G * 16;
   if (smem > 200 * 1024) {
     set_error("SPPF plane %dx%d does not fit shared memory", op.Hin, op.Win);
     return YB_ERR_UNSUPPORTED;
   }
-  static size_t attr = 0;
-  if (smem > 48 * 1024 && smem > attr) {
-    YB_CUDA(cudaFuncSetAttribute(sppf_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)smem));
-    attr = smem;
-  }
   // src (slice 0) and dst (slices 1..3) live in the same concat buffer
-  unsigned blocks = (unsigned)(p->B * (Chalf >> 3));
-  YB_CUDA(launch_pdl(sppf_pool_kernel, dim3(blocks), dim3(256), smem, st, src, dst, sb.C, op.Hin, op.Win, Chalf));
+  unsigned blocks = (unsigned)(p->B * (cg_all / G));
+#define YB_SPPF(GG)                                                                                              \
+  do {                                                                                                           \
+    static size_t attr = 0;                                                                                      \
+    if (smem > 48 * 1024 && smem > attr) {                                                                       \
+      YB_CUDA(cudaFuncSetAttribute(sppf_pool_kernel<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      attr = smem;                                                                                               \
+    }                                                                                                            \
+    YB_CUDA(launch_pdl(sppf_pool_kernel<GG>, dim3(blocks), dim3(256), smem, st, src, dst, sb.C, op.Hin, op.Win,  \
+                       Chalf));                                                                                  \
+  } while (0)
+  if (G == 4) YB_SPPF(4);
+  else if (G == 2) YB_SPPF(2);
+  else YB_SPPF(1);
+#undef YB_SPPF
   count_launch();
   YB_CUDA(cudaGetLastError());
   return YB_OK;
