@@ -730,7 +730,7 @@ __device__ __forceinline__ uint4 max_bf16x8(const uint4& a, const uint4& b) {
 
 // G: 8-channel groups per CTA (a pixel's G x 16 bytes are contiguous: full sectors, fewer and fatter CTAs)
 template <int G>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(G >= 4 ? 512 : 256)
     sppf_pool_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* dst, int ld, int H, int W,
                      int Chalf) {
   extern __shared__ uint4 pl[];  // cur[HW][G], tmp[HW][G]
@@ -797,7 +797,7 @@ int launch_pool(const yb_plan* p, const Op& op, cudaStream_t st) {
       YB_CUDA(cudaFuncSetAttribute(sppf_pool_kernel<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
       attr = smem;                                                                                               \
     }                                                                                                            \
-    YB_CUDA(launch_pdl(sppf_pool_kernel<GG>, dim3(blocks), dim3(256), smem, st, src, dst, sb.C, op.Hin, op.Win,  \
+    YB_CUDA(launch_pdl(sppf_pool_kernel<GG>, dim3(blocks), dim3(GG >= 4 ? 512 : 256), smem, st, src, dst, sb.C, op.Hin, op.Win, \
                        Chalf));                                                                                  \
   } while (0)
   if (G == 4) YB_SPPF(4);
