@@ -71,8 +71,12 @@ typedef struct yb_conv_info {
 
 /* Build the static execution plan (op list, activation-buffer aliasing, TMA descriptors) for one
  * (architecture, batch, height, width) on `device`. H and W must be multiples of 32
- * (nets/nn.py:205-206 concatenates stride-2 pyramids). */
-int yb_plan_create(const yb_arch_desc* arch, int batch, int height, int width, int device,
+ * (nets/nn.py:205-206 concatenates stride-2 pyramids).
+ * act_dtype: storage type of activations and packed weights, YB_F16 or YB_BF16 (accumulation, bias,
+ * SiLU, DFL decode and sigmoid are always fp32).  YB_F16 is what the reference's own evaluation uses
+ * (main.py:251 `model.half()`, main.py:266 `samples.half()`) and is the default of the Python host side;
+ * YB_BF16 trades 3 mantissa bits for range.  device < 0: host-only plan (layout / packer, never bound). */
+int yb_plan_create(const yb_arch_desc* arch, int batch, int height, int width, int act_dtype, int device,
                    yb_plan** out);
 void yb_plan_destroy(yb_plan* plan);
 

@@ -3,7 +3,8 @@
 Takes the plan description (`Engine.describe()`: buffers, ops, channel slices, GEMM K layouts) and
 the packed weight blob (`Engine.pack_from_model`) and executes every op with fp32 torch ops over
 NHWC buffers, exactly as the CUDA kernels are specified to: same slices, same K ordering of the
-packed weights, same padded channels, optional bf16 rounding at every activation store.  Buffers
+packed weights, same padded channels, optional rounding to the plan's 16-bit storage type (fp16 or
+bf16, `desc["act_f16"]`) at every activation store.  Buffers
 start as NaN, so an op that reads a channel nobody wrote poisons the output.
 
 This validates the *host logic* (plan builder, buffer aliasing, weight packer) without a GPU, and
@@ -18,16 +19,24 @@ def _bf16(t):
     return t.to(torch.bfloat16).to(torch.float32)
 
 
+def _fp16(t):
+    return t.to(torch.float16).to(torch.float32)
+
+
 def _cpad8(c):
     return (c + 7) // 8 * 8
 
 
 class PlanReplay:
     def __init__(self, desc, convs, blob, emulate_bf16=True):
+        """emulate_bf16 (historic name): round every 16-bit activation store to the plan's storage type."""
         self.d = desc
         self.convs = convs
         self.blob = np.asarray(blob, dtype=np.uint8)
         self.bf16 = emulate_bf16
+        self.f16 = bool(desc.get("act_f16", 0))
+        self.rnd = _fp16 if self.f16 else _bf16
+        self.tdtype = torch.float16 if self.f16 else torch.bfloat16
         self.B = desc["B"]
         self.bufs = {}
 
@@ -41,7 +50,7 @@ class PlanReplay:
         """rows: (B, n_rows, C_store) -> dst slice (bf16-rounded unless the buffer is fp32)."""
         buf = self._buf(sl["buf"])
         if self.bf16 and self.d["bufs"][sl["buf"]]["elem_bytes"] == 2:
-            rows = _bf16(rows)
+            rows = self.rnd(rows)
         buf[:, row_off:row_off + rows.shape[1], sl["c_off"]:sl["c_off"] + rows.shape[2]] = rows
 
     def _load_nhwc(self, sl, channels=None):
@@ -57,8 +66,11 @@ class PlanReplay:
         cw = self.convs[op["conv_index"]]
         raw = self.blob[cw["blob_offset"]:cw["blob_offset"] + cw["blob_bytes"]]
         nw = op["N_pad"] * op["K_pad"]
-        w16 = raw[:nw * 2].view(np.uint16).astype(np.uint32) << 16
-        W = torch.from_numpy(w16.view(np.float32).reshape(op["N_pad"], op["K_pad"]).copy())
+        if self.f16:
+            W = torch.from_numpy(raw[:nw * 2].view(np.float16).astype(np.float32).reshape(op["N_pad"], op["K_pad"]))
+        else:
+            w16 = raw[:nw * 2].view(np.uint16).astype(np.uint32) << 16
+            W = torch.from_numpy(w16.view(np.float32).reshape(op["N_pad"], op["K_pad"]).copy())
         bias = torch.from_numpy(raw[nw * 2:nw * 2 + op["N_pad"] * 4].view(np.float32).copy())
         return W, bias
 
@@ -90,7 +102,7 @@ class PlanReplay:
         A = torch.cat(cols, 2)
         A = F.pad(A, (0, op["K_pad"] - A.shape[2]))
         if self.bf16:
-            A = _bf16(A)  # activations are stored in bf16 already; NaN stays NaN
+            A = self.rnd(A)  # activations are stored in 16 bits already; NaN stays NaN
         D = A @ W.t() + bias
         if op["act"]:
             D = F.silu(D)
@@ -187,9 +199,9 @@ class PlanReplay:
         return None
 
     def buffer_bytes(self, i):
-        """Buffer i in the GPU's storage format (bf16 or fp32 NHWC); unwritten (NaN) entries as 0."""
+        """Buffer i in the GPU's storage format (fp16 / bf16 or fp32 NHWC); unwritten (NaN) entries as 0."""
         t = torch.nan_to_num(self._buf(i), nan=0.0)
-        return t.to(torch.bfloat16) if self.d["bufs"][i]["elem_bytes"] == 2 else t.float()
+        return t.to(self.tdtype) if self.d["bufs"][i]["elem_bytes"] == 2 else t.float()
 
     def run(self, x, taps=None):
         """x: (B,3,H,W) fp32 -> (B, 4+nc, A).  taps: optional dict filled with each op's dst slice

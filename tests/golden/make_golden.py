@@ -50,7 +50,7 @@ def save(name, **arrays):
 
 def main():
     # ---- forward, every size, 2 x 3 x 64 x 64 -------------------------------------------------
-    for size in "ntsmlx":
+    for size in ("" if os.environ.get("YB_GOLDEN_ONLY_NEW") else "ntsmlx"):
         m = ref_model(size)
         x = synth.synth_images(2, 64, 64, seed=1)
         with torch.no_grad():
@@ -62,14 +62,14 @@ def main():
         save(f"fwd_{size}_64.npz", out=fused.numpy(), out_unfused=unfused.numpy(),
              raw0=raw[0].numpy(), raw1=raw[1].numpy(), raw2=raw[2].numpy())
     # ---- forward on the SURVEY §8(d) recipe (the tolerance gate's weights) -----------------------
-    for size in "nx":
+    for size in ("" if os.environ.get("YB_GOLDEN_ONLY_NEW") else "nx"):
         m = ref_model(size, recipe="survey").fuse().eval()
         x = synth.synth_images(2, 64, 64, seed=1)
         with torch.no_grad():
             y = m(x)
         save(f"fwdsv_{size}_64.npz", out=y.numpy())
     # ---- forward, n and s at 640 (BASELINE config 1), sub-sampled anchors ----------------------
-    for size in "ns":
+    for size in ("" if os.environ.get("YB_GOLDEN_ONLY_NEW") else "ns"):
         m = ref_model(size, recipe="survey").fuse().eval()
         x = synth.synth_images(1, 640, 640, seed=0)
         with torch.no_grad():
@@ -81,6 +81,24 @@ def main():
         if size == "n":
             dets = ref_util.non_max_suppression(y, 0.001, 0.65)
             save("e2e_n_640_nms.npz", det=dets[0].numpy())
+    # ---- the falsifiable gate's recipes (tests/test_gpu_parity.py): scores spread over (0, 1) ----------
+    for size, hw in (("n", 320), ("x", 128)):
+        m = ref_model(size, recipe="survey_widehead").fuse().eval()
+        x = synth.synth_images(2, hw, hw, seed=0)
+        with torch.no_grad():
+            y = m(x)
+        idx = np.arange(0, y.shape[2], 4)
+        sc = y[:, 4:]
+        save(f"fwdwh_{size}_{hw}.npz", out_sub=y[:, :, idx].numpy(), idx=idx,
+             stats=np.array([float(((sc > 0.1) & (sc < 0.9)).float().mean()), float(sc.max())], dtype=np.float64))
+    m = ref_model("n", recipe="calibrated_damped").fuse().eval()
+    with torch.no_grad():
+        y = m(synth.synth_images(1, 640, 640, seed=0))
+    dets = ref_util.non_max_suppression(y, 0.25, 0.65)
+    save("e2e_cd_n_640_nms.npz", det=dets[0].numpy(), conf=np.float64(0.25), iou=np.float64(0.65),
+         ncand=np.array(int((y[0, 4:] > 0.25).sum())))
+    if os.environ.get("YB_GOLDEN_ONLY_NEW"):
+        return
     # ---- non_max_suppression -------------------------------------------------------------------
     cases = [
         ("sparse_640", dict(batch=2, nc=80, anchors=8400, img=640, mode="sparse", seed=0), 0.001, 0.65),

@@ -11,6 +11,7 @@ from oracle.plan_replay import PlanReplay
 from yolo_infer_pt_b200 import _lib, synth
 from yolo_infer_pt_b200.engine import Engine
 from yolo_infer_pt_b200.nets import nn
+from yolo_infer_pt_b200.utils import util
 
 pytestmark = pytest.mark.gpu
 
@@ -18,9 +19,9 @@ BOX_TOL_PX = 0.5     # north star: max abs error on box coordinates
 SCORE_TOL = 1e-2     # north star: max abs error on class scores
 
 
-def _model(size, recipe):
+def _model(size, recipe, **kw):
     m = getattr(nn, f"yolo_v11_{size}")(80)
-    synth.load_synth(m, 0, recipe)
+    synth.load_synth(m, 0, recipe, **kw)
     return m.fuse().eval()
 
 
@@ -229,10 +230,15 @@ def test_batch_independence():
         assert torch.equal(e1.forward(x[i:i + 1].contiguous())[0], y3[i])
 
 
-@pytest.mark.parametrize("size,hw,patch_min_hw", [("n", 64, None), ("n", 160, None), ("t", 64, None), ("x", 64, None),
-                                                   ("s", 96, None), ("n", 160, "1"), ("s", 96, "1"), ("x", 64, "1"),
-                                                   ("m", 64, "1"), ("n", 320, None)])
-def test_every_op_teacher_forced(size, hw, patch_min_hw, monkeypatch):
+F16, BF16 = torch.float16, torch.bfloat16
+
+
+@pytest.mark.parametrize("size,hw,patch_min_hw,act", [("n", 64, None, F16), ("n", 160, None, F16), ("t", 64, None, F16),
+                                                       ("x", 64, None, F16), ("s", 96, None, F16), ("n", 160, "1", F16),
+                                                       ("s", 96, "1", F16), ("x", 64, "1", F16), ("m", 64, "1", F16),
+                                                       ("n", 320, None, F16), ("n", 160, None, BF16), ("x", 64, "1", BF16),
+                                                       ("s", 96, None, BF16), ("n", 320, None, BF16)])
+def test_every_op_teacher_forced(size, hw, patch_min_hw, act, monkeypatch):
     """Per-op parity with identical inputs: before each op the GPU buffers are overwritten with the CPU
     replay's (bf16-exact) state, the op runs alone through both conv implementations, and its output
     slice is compared with the replay's.  No error can accumulate, so the tolerance is a couple of
@@ -242,10 +248,11 @@ def test_every_op_teacher_forced(size, hw, patch_min_hw, monkeypatch):
         monkeypatch.setenv("YB_PATCH_MIN_HW", patch_min_hw)
     model = _model(size, "calibrated")
     x = synth.synth_images(2, hw, hw, seed=1)
-    eng = Engine(*model._arch, 2, hw, hw, "cuda:0")
+    eng = Engine(*model._arch, 2, hw, hw, "cuda:0", act_dtype=act)
     blob = eng.pack_from_model(model)
     desc = eng.describe()
-    rep = PlanReplay(desc, eng.convs, blob, emulate_bf16=True)
+    assert desc["act_f16"] == (1 if act == F16 else 0)
+    rep = PlanReplay(desc, eng.convs, blob, emulate_bf16=True)   # rounds to the plan's storage type
     xg = x.to("cuda:0")
     report, worst = [], 0.0
     with torch.no_grad():
@@ -273,9 +280,72 @@ def test_every_op_teacher_forced(size, hw, patch_min_hw, monkeypatch):
                 scale = max(1.0, want.abs().max().item())
                 err = (got - want).abs().max().item() / scale
                 worst = max(worst, err)
-                if err > 0.01:
+                if err > (0.01 if act == BF16 else 0.004):   # a couple of ulps of the storage type (+ tanh.approx SiLU)
                     report.append(f"{op['name']} impl={impl} k{op['k']} s{op['stride']} tma{op['a_tma']} patch{op.get('patch', 0)} dwf{op.get('dw_fused', 0)} "
                                   f"K{op['K_pad']} N{op['N_pad']}/BN{op['BN']}: max err {err:.4f} of max |x|")
             eng.set_conv_impl(0)
-    print(f"{size}@{hw} patch_min_hw={patch_min_hw}: worst per-op error {worst:.5f} of the layer's max |activation|")
+    print(f"{size}@{hw} patch_min_hw={patch_min_hw} {act}: worst per-op error {worst:.5f} of the layer's max |activation|")
     assert not report, "\n".join(report)
+
+
+def test_engine_follows_weight_updates():
+    """The packed copy must never outlive the module's weights: in-place parameter updates, re-assignment,
+    dtype moves of a submodule and load_state_dict all re-pack; `.data` in-place writes need invalidate_engine()."""
+    model = _model("n", "survey_widehead").to("cuda:0")
+    x = synth.synth_images(1, 64, 64, seed=1).to("cuda:0")
+    with torch.no_grad():
+        y0 = model(x).clone()
+        bias = model.head.cls[0][4].bias
+        bias.add_(2.0)                                   # in-place on the parameter: _version bumps
+        y1 = model(x).clone()
+        assert not torch.equal(y0[:, 4:, :64], y1[:, 4:, :64])
+        bias.data = bias.data - 2.0                      # re-assignment: new storage
+        y2 = model(x).clone()
+        assert torch.equal(y0, y2)
+        sd = {k: v.clone() for k, v in model.state_dict().items()}
+        sd["head.cls.0.4.bias"] += 1.0
+        model.load_state_dict(sd, assign=True)
+        y3 = model(x).clone()
+        assert not torch.equal(y0[:, 4:, :64], y3[:, 4:, :64])
+        model.head.cls[0][4].bias.data[:] -= 1.0         # through .data in place: invisible, documented
+        model.invalidate_engine()
+        y4 = model(x).clone()
+        assert (y0 - y4).abs().max() < 1e-5
+        model.head.half()                                # submodule dtype move (bypasses YOLO._apply)
+        y5 = model(x).clone()
+        assert (y0[:, :4] - y5[:, :4]).abs().max() < 1.0 and (y0[:, 4:] - y5[:, 4:]).abs().max() < 1e-2
+
+
+def test_eval_forward_returns_fresh_tensors_and_head_anchors():
+    """Like the reference, two predictions kept alive do not alias; head.anchors / head.strides are populated."""
+    model = _model("n", "survey").to("cuda:0")
+    a = synth.synth_images(1, 64, 64, seed=1).to("cuda:0")
+    b = synth.synth_images(1, 64, 64, seed=2).to("cuda:0")
+    with torch.no_grad():
+        ya = model(a)
+        yb = model(b)
+        ya2 = model(a)
+    assert ya.data_ptr() != yb.data_ptr() and torch.equal(ya, ya2) and not torch.equal(ya, yb)
+    assert tuple(model.head.anchors.shape) == (2, 84) and tuple(model.head.strides.shape) == (1, 84)
+    assert model.head.anchors[:, 0].tolist() == [0.5, 0.5] and model.head.strides[0, -1].item() == 32.0
+    # engine cache is bounded (variable shapes must not grow memory without bound)
+    with torch.no_grad():
+        for hw in (32, 64, 96, 128, 160, 192):
+            model(torch.zeros(1, 3, hw, hw, device="cuda:0"))
+    assert len(model.__dict__["_yb_engines"]) <= model.MAX_ENGINES
+
+
+def test_second_device_and_current_device_preserved():
+    """Per-device function attributes + device guard: a plan on cuda:1 works and leaves cuda:0 current."""
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    model = _model("n", "survey")
+    x = synth.synth_images(1, 128, 128, seed=1)
+    with torch.no_grad():
+        y0 = model.to("cuda:0")(x.to("cuda:0")).cpu()
+        torch.cuda.set_device(0)
+        m1 = _model("n", "survey").to("cuda:1")
+        y1 = m1(x.to("cuda:1"))
+        det = util.non_max_suppression(y1, 0.001, 0.65)
+        assert torch.cuda.current_device() == 0
+    assert torch.equal(y0, y1.cpu()) and det[0].device.index == 1

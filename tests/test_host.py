@@ -80,29 +80,30 @@ def test_fuse_matches_batchnorm():
     assert (torch.nn.functional.silu(fused(x)) - ref).abs().max() < 1e-5
 
 
-def bf16_weight_state(model):
-    """Fused state_dict whose dense-conv weights are rounded to bf16 — what the packed blob holds
-    (stem and depthwise weights stay fp32 in the blob)."""
+def bf16_weight_state(model, dtype=torch.bfloat16):
+    """Fused state_dict whose dense-conv weights are rounded to the plan's 16-bit storage type — what the
+    packed blob holds (stem and depthwise weights stay fp32 in the blob)."""
     m = copy.deepcopy(model).fuse()
     sd = {k: v.float().clone() for k, v in m.state_dict().items()}
     for name, mod in m.named_modules():
         if isinstance(mod, torch.nn.Conv2d) and mod.groups == 1 and name not in ("net.p1.0.conv", "head.dfl.conv"):
-            sd[name + ".weight"] = sd[name + ".weight"].to(torch.bfloat16).float()
+            sd[name + ".weight"] = sd[name + ".weight"].to(dtype).float()
     return sd
 
 
-@pytest.mark.parametrize("size,hw", [("n", 64), ("t", 64), ("s", 64), ("m", 64), ("x", 64), ("n", 96)])
-def test_plan_replay_matches_oracle(size, hw):
+@pytest.mark.parametrize("size,hw,act", [("n", 64, torch.float16), ("t", 64, torch.float16), ("s", 64, torch.float16),
+                                         ("m", 64, torch.float16), ("x", 64, torch.bfloat16), ("n", 96, torch.bfloat16)])
+def test_plan_replay_matches_oracle(size, hw, act):
     """Plan + aliasing + packed weights, replayed in fp32 on the CPU, reproduce the oracle forward
-    run on the same bf16-rounded weights — layer by layer and end to end."""
+    run on the same 16-bit-rounded weights — layer by layer and end to end, for both storage types."""
     model = getattr(nn, f"yolo_v11_{size}")(80)
     synth.load_synth(model, 0)
-    eng = Engine(*model._arch, 2, hw, hw, host_only=True)
+    eng = Engine(*model._arch, 2, hw, hw, host_only=True, act_dtype=act)
     blob = eng.pack_from_model(model)
     desc = eng.describe()
     x = synth.synth_images(2, hw, hw, seed=1)
     taps_o, taps_r = {}, {}
-    sd = bf16_weight_state(model)
+    sd = bf16_weight_state(model, act)
     with torch.no_grad():
         ref = yolo_oracle.forward(sd, *model._arch, x, taps=taps_o)
         rep = PlanReplay(desc, eng.convs, blob, emulate_bf16=False)
@@ -242,3 +243,46 @@ def test_reference_checkpoint_imports(tmp_path):
     """)
     out = subprocess.run([sys.executable, "-c", code2], check=True, capture_output=True, text=True)
     assert "ok" in out.stdout
+
+
+def test_weights_fingerprint_sees_every_kind_of_update():
+    """YOLO._weights_version (host logic of the engine cache): in-place updates, re-assignment, submodule dtype
+    moves and submodule load_state_dict(assign=True) all change it; reading it does not."""
+    m = nn.yolo_v11_n(80).fuse().eval()
+    v = m._weights_version()
+    assert v == m._weights_version()
+    p = m.head.box[0][2].bias
+    with torch.no_grad():
+        p.add_(1)
+    v1 = m._weights_version()
+    assert v1 != v
+    p.data = p.data.clone()
+    v2 = m._weights_version()
+    assert v2 != v1
+    m.net.half()
+    v3 = m._weights_version()
+    assert v3 != v2
+    m.head.load_state_dict(m.head.state_dict(), assign=True)
+    assert m._weights_version() != v3
+
+
+def test_widehead_recipe_spreads_scores_and_boxes():
+    """The falsifiable gate's recipe really has scores across (0, 1) and DFL expectations across bins - checked on
+    the fp32 oracle and against the fixture written from the reference itself."""
+    m = nn.yolo_v11_n(80)
+    synth.load_synth(m, 0, "survey_widehead")
+    m = m.fuse().eval()
+    sd = {k: v.float() for k, v in m.state_dict().items()}
+    x = synth.synth_images(2, 320, 320, seed=0)
+    with torch.no_grad():
+        maps = yolo_oracle.forward_raw(sd, *m._arch, x)
+        y = yolo_oracle.decode(maps, 80)
+    sc = y[:, 4:]
+    assert ((sc > 0.1) & (sc < 0.9)).float().mean() >= 0.05 and sc.max() > 0.5
+    dist = torch.cat([(t[:, :64].reshape(2, 4, 16, -1).softmax(2) * torch.arange(16.0).view(1, 1, 16, 1)).sum(2).flatten()
+                      for t in maps])
+    assert dist.std() >= 2.0
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "fwdwh_n_320.npz"))
+    ref = torch.from_numpy(g["out_sub"])
+    sub = y[:, :, torch.from_numpy(g["idx"])]
+    assert (sub[:, :4] - ref[:, :4]).abs().max() < 2e-2 and (sub[:, 4:] - ref[:, 4:]).abs().max() < 1e-5

@@ -42,7 +42,7 @@ class ConvInfo(ctypes.Structure):
 # name -> (restype, argtypes); every symbol include/yolob200.h declares
 SYMBOLS = {
     "yb_plan_create": (ctypes.c_int, [ctypes.POINTER(ArchDesc), ctypes.c_int, ctypes.c_int, ctypes.c_int,
-                                      ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
+                                      ctypes.c_int, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p)]),
     "yb_plan_destroy": (None, [ctypes.c_void_p]),
     "yb_plan_workspace_bytes": (ctypes.c_size_t, [ctypes.c_void_p]),
     "yb_plan_weight_bytes": (ctypes.c_size_t, [ctypes.c_void_p]),

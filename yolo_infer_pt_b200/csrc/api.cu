@@ -125,12 +125,14 @@ static int forward_impl(yb_plan* p, const void* in, int in_dtype, float* out, in
     set_error("yb_forward: plan has no weights/workspace bound (call yb_plan_bind)");
     return YB_ERR_STATE;
   }
-  YB_CUDA(cudaSetDevice(p->device));
+  DeviceGuard guard(p->device);
+  if (guard.rc) return guard.rc;
   cudaStream_t st = (cudaStream_t)stream;
   if (!p->use_graph) return run_ops(p, in, in_dtype, out, raw, st);
   for (GraphEntry& g : p->graphs) {
     if (g.in == in && g.out == out && g.stream == stream && g.dtype == in_dtype && g.raw == raw &&
-        g.impl == p->conv_impl && g.sink == (const void*)p->sink_keys && g.sink_conf == p->sink_conf) {
+        g.impl == p->conv_impl && g.sink == (const void*)p->sink_keys && g.sink_conf == p->sink_conf &&
+        g.sink_hdr == (const void*)p->sink_hdr && g.sink_cap == p->sink_cap) {
       YB_CUDA(cudaGraphLaunch(g.exec, st));
       g_launches.fetch_add((unsigned long long)yb_plan_num_launches(p), std::memory_order_relaxed);
       return YB_OK;
@@ -163,6 +165,8 @@ static int forward_impl(yb_plan* p, const void* in, int in_dtype, float* out, in
   g.impl = p->conv_impl;
   g.sink = p->sink_keys;
   g.sink_conf = p->sink_conf;
+  g.sink_hdr = p->sink_hdr;
+  g.sink_cap = p->sink_cap;
   e = cudaGraphInstantiate(&g.exec, graph, 0);
   cudaGraphDestroy(graph);
   if (e != cudaSuccess) {
@@ -191,10 +195,14 @@ using namespace yb;
 
 extern "C" {
 
-int yb_plan_create(const yb_arch_desc* arch, int batch, int height, int width, int device,
+int yb_plan_create(const yb_arch_desc* arch, int batch, int height, int width, int act_dtype, int device,
                    yb_plan** out) {
   if (!arch || !out || batch <= 0) {
     set_error("yb_plan_create: bad argument");
+    return YB_ERR_ARG;
+  }
+  if (act_dtype != YB_F16 && act_dtype != YB_BF16) {
+    set_error("yb_plan_create: act_dtype must be YB_F16 or YB_BF16 (got %d)", act_dtype);
     return YB_ERR_ARG;
   }
   *out = nullptr;
@@ -213,6 +221,7 @@ int yb_plan_create(const yb_arch_desc* arch, int batch, int height, int width, i
   p->H = height;
   p->W = width;
   p->device = device;
+  p->act_f16 = act_dtype == YB_F16 ? 1 : 0;
   cudaDeviceProp prop;
   if (device >= 0 && cudaGetDeviceProperties(&prop, device) == cudaSuccess)
     p->num_sms = prop.multiProcessorCount;
@@ -265,19 +274,20 @@ int yb_plan_pack_conv(const yb_plan* plan, int index, const float* w, const floa
   memset(dst, 0, cw.info.blob_bytes);
   const int cout = cw.info.cout, cin = cw.info.cin, k = cw.info.ksize;
   if (cw.info.kind == 1) {
-    __nv_bfloat16* W = reinterpret_cast<__nv_bfloat16*>(dst);
+    act_t* W = reinterpret_cast<act_t*>(dst);
     float* B = reinterpret_cast<float*>(dst + (size_t)op.N_pad * op.K_pad * 2);
+    const bool f16 = plan->act_f16 != 0;
     int per_tap = 0;
     for (int s = 0; s < op.nseg; s++) per_tap += op.seg_kpad[s];   // (> padded channels for tap-aligned 3x3 layers)
     for (int co = 0; co < cout; co++) {
-      __nv_bfloat16* row = W + (size_t)co * op.K_pad;
+      act_t* row = W + (size_t)co * op.K_pad;
       for (int tap = 0; tap < k * k; tap++) {
         int kpos = op.a_tma ? 0 : tap * per_tap;
         int ci0 = 0;
         for (int s = 0; s < op.nseg; s++) {
           for (int c = 0; c < op.src[s].C; c++) {
             float v = w[((size_t)co * cin + (ci0 + c)) * k * k + tap];
-            row[kpos + c] = __float2bfloat16(v);
+            row[kpos + c] = host_to_act16(v, f16);
           }
           ci0 += op.src[s].C;
           kpos += op.seg_kpad[s];
@@ -312,7 +322,8 @@ int yb_plan_bind(yb_plan* plan, const void* dev_weights, void* dev_workspace) {
     set_error("yb_plan_bind: host-only plan (created with device < 0) cannot run");
     return YB_ERR_STATE;
   }
-  YB_CUDA(cudaSetDevice(plan->device));
+  DeviceGuard guard(plan->device);
+  if (guard.rc) return guard.rc;
   drop_graphs(plan);
   plan->d_weights = reinterpret_cast<const uint8_t*>(dev_weights);
   plan->d_ws = reinterpret_cast<uint8_t*>(dev_workspace);
@@ -374,7 +385,8 @@ int yb_plan_profile_read(yb_plan* plan, float* op_ms, int capacity) {
     set_error("yb_plan_profile_read: bad argument");
     return YB_ERR_ARG;
   }
-  YB_CUDA(cudaSetDevice(plan->device));
+  DeviceGuard guard(plan->device);
+  if (guard.rc) return guard.rc;
   YB_CUDA(cudaDeviceSynchronize());
   int n = plan->prof_used;
   for (size_t i = 0; i < plan->ops.size(); i++) op_ms[i] = 0.f;
@@ -416,7 +428,8 @@ long long yb_plan_debug_read(yb_plan* plan, const char* conv_name, float* host_o
       set_error("yb_plan_debug_read: host buffer too small (%zu floats needed)", n);
       return YB_ERR_ARG;
     }
-    YB_CUDA(cudaSetDevice(plan->device));
+    DeviceGuard guard(plan->device);
+  if (guard.rc) return guard.rc;
     YB_CUDA(cudaDeviceSynchronize());
     size_t row_bytes = (size_t)b.C * b.elem_bytes;
     std::vector<uint8_t> tmp(rows * row_bytes);
@@ -428,8 +441,7 @@ long long yb_plan_debug_read(yb_plan* plan, const char* conv_name, float* host_o
         if (b.elem_bytes == 4) {
           v = reinterpret_cast<const float*>(rp)[c];
         } else {
-          uint32_t bits = (uint32_t)reinterpret_cast<const uint16_t*>(rp)[c] << 16;
-          memcpy(&v, &bits, 4);
+          v = host_from_act16(reinterpret_cast<const uint16_t*>(rp)[c], plan->act_f16 != 0);
         }
         host_out[r * C + c] = v;
       }
@@ -449,7 +461,8 @@ int yb_plan_debug_write(yb_plan* plan, int buf_index, const void* host_data, siz
     set_error("yb_plan_debug_write: bad argument (buffer %d, %zu bytes)", buf_index, bytes);
     return YB_ERR_ARG;
   }
-  YB_CUDA(cudaSetDevice(plan->device));
+  DeviceGuard guard(plan->device);
+  if (guard.rc) return guard.rc;
   YB_CUDA(cudaDeviceSynchronize());
   YB_CUDA(cudaMemcpy(buf_ptr(plan, buf_index), host_data, bytes, cudaMemcpyHostToDevice));
   return YB_OK;
@@ -461,7 +474,8 @@ int yb_plan_run_op(yb_plan* plan, int op_index, const void* in_nchw, int in_dtyp
     set_error("yb_plan_run_op: bad argument");
     return YB_ERR_ARG;
   }
-  YB_CUDA(cudaSetDevice(plan->device));
+  DeviceGuard guard(plan->device);
+  if (guard.rc) return guard.rc;
   int saved = plan->fuse_decode;
   plan->fuse_decode = 0;  // head tails write their logits slice, so the test can read it back
   int rc = run_one(plan, plan->ops[op_index], in_nchw, in_dtype, out, 0, (cudaStream_t)cuda_stream);
@@ -479,7 +493,9 @@ long long yb_plan_describe(const yb_plan* plan, char* buf, size_t capacity) {
     snprintf(t, sizeof(t), "{\"buf\":%d,\"c_off\":%d,\"C\":%d,\"up\":%d}", s.buf, s.c_off, s.C, s.up);
     return std::string(t);
   };
-  snprintf(t, sizeof(t), "{\"B\":%d,\"H\":%d,\"W\":%d,\"nc\":%d,\"A\":%d,\"logits_buf\":%d,"
+  snprintf(t, sizeof(t), "{\"act_f16\":%d,", plan->act_f16);
+  j += t;
+  snprintf(t, sizeof(t), "\"B\":%d,\"H\":%d,\"W\":%d,\"nc\":%d,\"A\":%d,\"logits_buf\":%d,"
            "\"workspace_bytes\":%zu,\"weight_bytes\":%zu,\"lvl_off\":[%d,%d,%d],\"bufs\":[",
            plan->B, plan->H, plan->W, plan->nc, plan->A, plan->logits_buf, plan->workspace_bytes,
            plan->weight_bytes, plan->lvl_off[0], plan->lvl_off[1], plan->lvl_off[2]);
@@ -514,6 +530,16 @@ long long yb_plan_describe(const yb_plan* plan, char* buf, size_t capacity) {
   return (long long)j.size() + 1;
 }
 
+// device that owns a device pointer (the NMS / metric / letterbox entry points take no plan)
+static int device_of(const void* ptr) {
+  cudaPointerAttributes at;
+  if (ptr && cudaPointerGetAttributes(&at, ptr) == cudaSuccess && at.type == cudaMemoryTypeDevice) return at.device;
+  cudaGetLastError();
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev;
+}
+
 size_t yb_nms_workspace_bytes(int batch, int num_classes, int num_anchors, int max_nms) {
   return nms_workspace_bytes(batch, num_classes, num_anchors, max_nms);
 }
@@ -525,6 +551,8 @@ int yb_nms(const float* pred, int batch, int num_classes, int num_anchors, float
     set_error("yb_nms: null argument");
     return YB_ERR_ARG;
   }
+  DeviceGuard guard(device_of(pred));
+  if (guard.rc) return guard.rc;
   return nms_run(pred, batch, num_classes, num_anchors, conf, iou, max_det, max_nms, max_wh, out,
                  out_counts, workspace, workspace_bytes, (cudaStream_t)cuda_stream, 0);
 }
@@ -536,6 +564,8 @@ int yb_nms_prefiltered(const float* pred, int batch, int num_classes, int num_an
     set_error("yb_nms_prefiltered: null argument");
     return YB_ERR_ARG;
   }
+  DeviceGuard guard(device_of(pred));
+  if (guard.rc) return guard.rc;
   return nms_run(pred, batch, num_classes, num_anchors, conf, iou, max_det, max_nms, max_wh, out,
                  out_counts, workspace, workspace_bytes, (cudaStream_t)cuda_stream, 2);
 }
@@ -545,6 +575,8 @@ int yb_nms_workspace_init(void* workspace, size_t workspace_bytes, void* cuda_st
     set_error("yb_nms_workspace_init: null workspace");
     return YB_ERR_ARG;
   }
+  DeviceGuard guard(device_of(workspace));
+  if (guard.rc) return guard.rc;
   YB_CUDA(cudaMemsetAsync(workspace, 0, workspace_bytes, (cudaStream_t)cuda_stream));
   return YB_OK;
 }
@@ -556,24 +588,30 @@ int yb_nms_clean(const float* pred, int batch, int num_classes, int num_anchors,
     set_error("yb_nms: null argument");
     return YB_ERR_ARG;
   }
+  DeviceGuard guard(device_of(pred));
+  if (guard.rc) return guard.rc;
   return nms_run(pred, batch, num_classes, num_anchors, conf, iou, max_det, max_nms, max_wh, out,
                  out_counts, workspace, workspace_bytes, (cudaStream_t)cuda_stream, 1);
 }
 
 int yb_letterbox(const long long* desc, int batch, int input_size, uint8_t* out_nchw_rgb, double* meta,
                  void* cuda_stream) {
+  DeviceGuard guard(device_of(out_nchw_rgb));
+  if (guard.rc) return guard.rc;
   return letterbox_run(desc, batch, input_size, out_nchw_rgb, meta, (cudaStream_t)cuda_stream);
 }
 
 int yb_compute_metric(const float* det, const int* counts, const float* targets, const int* target_counts,
                       int batch, int max_det, int max_targets, const float* iou_v, int n_iou, uint8_t* correct,
                       void* cuda_stream) {
+  DeviceGuard guard(device_of(det));
+  if (guard.rc) return guard.rc;
   return metric_run(det, counts, targets, target_counts, batch, max_det, max_targets, iou_v, n_iou, correct,
                     (cudaStream_t)cuda_stream);
 }
 
 const char* yb_last_error(void) { return g_err; }
 unsigned long long yb_launch_count(void) { return g_launches.load(); }
-int yb_version(void) { return 100; }
+int yb_version(void) { return 200; }
 
 }  // extern "C"

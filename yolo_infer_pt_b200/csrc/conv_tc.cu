@@ -59,7 +59,7 @@ enum { MODE_GATHER = 0, MODE_ATMA = 1, MODE_PATCH = 2, MODE_DW = 3, MODE_PATCH2 
 static constexpr int PP2_W = 2 * PT_W + 2;        // MODE_PATCH2: one 18 x 18 patch feeds two 16 x 8 tiles side by side
 
 struct ConvParams {
-  const __nv_bfloat16* src[4];
+  const act_t* src[4];   // fp16 or bf16 bits (template parameter F16)
   int src_cp[4];      // padded channels of the slice (multiple of 8): its K extent per tap
   int src_ld[4];      // row stride of the source buffer, elements
   int src_up[4];
@@ -77,7 +77,7 @@ struct ConvParams {
   int cout_store;     // channels actually stored (padded to 8 for bf16, 4 for fp32)
   int out_f32;
   const float* bias;
-  const __nv_bfloat16* res;
+  const act_t* res;
   int res_ld;
   int act;
   int BN, stages, a_tma, tmem_cols;
@@ -116,7 +116,7 @@ struct ConvParams {
   float nms_conf;
   float lvl_stride;
   // naive path only
-  const __nv_bfloat16* w;
+  const act_t* w;
   int K_pad, cout;
   int src_c[4];       // real channels
   int seg_kpad[4];
@@ -281,10 +281,6 @@ __device__ __forceinline__ float silu_half(float h) {  // SiLU(2h)
   return fmaf(h, t, h);
 }
 
-__device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
 
 // All MMAs of one halo patch (one channel block, 9 taps) against weights resident in shared memory,
 // fully unrolled: tap offsets and K steps are compile-time constants, so the single issuing thread
@@ -342,7 +338,7 @@ static constexpr int NUM_THREADS_DW = (DW_WARP0 + DW_THREADS / 32) * 32;
 // (8x16 spatial patch vs 128 flattened rows) and the epilogue family (bf16 slice vs head modes):
 // every instantiation carries only the code of its own roles, which keeps it inside the
 // instruction cache (11 warps run disjoint code).
-template <int MODE, bool T2D, bool HEAD>
+template <int MODE, bool T2D, bool HEAD, bool F16>
 __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS, MODE == MODE_PATCH ? 3 : MODE == MODE_DW ? 1 : 2)  // (PATCH2: 2)
     conv_gemm_tcgen05_kernel(const ConvParams P, const __grid_constant__ CUtensorMap tmap_b,
                              const __grid_constant__ CUtensorMap tmap_a0,
@@ -350,6 +346,7 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
                              const __grid_constant__ CUtensorMap tmap_a2,
                              const __grid_constant__ CUtensorMap tmap_a3,
                              const __grid_constant__ CUtensorMap tmap_c) {
+  using A16 = Act16<F16>;   // 16-bit storage / operand type of activations and weights
   constexpr bool DW = MODE == MODE_DW;
   constexpr bool A_TMA = MODE != MODE_GATHER;   // warps 4-7 are not im2col producers: they join the epilogue
   constexpr bool PAIR = MODE == MODE_PATCH2;        // two 16 x 8 tiles per iteration (one 16 x 16 super-tile)
@@ -498,7 +495,7 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
         r = m - n_img * P.hw_out;
       }
       const size_t drow = (size_t)n_img * P.dst_rows_per_img + P.dst_row_off + r;
-      const __nv_bfloat16* resp = (!HEAD && P.res && row_ok) ? P.res + (size_t)m * P.res_ld : nullptr;
+      const act_t* resp = (!HEAD && P.res && row_ok) ? P.res + (size_t)m * P.res_ld : nullptr;
       // residual operand: prefetched two chunks ahead so its global-load latency hides behind the
       // wait for the accumulator and the math of the previous chunks
       uint4 ra0, ra1, rb0, rb1;
@@ -556,10 +553,10 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
             if (nb + 8 * h < P.cout_store) {
               if (WITH_RES && resp) {
                 const uint4 rv = h ? rv1 : rv0;
-                const __nv_bfloat162* r2 = reinterpret_cast<const __nv_bfloat162*>(&rv);
+                const uint32_t r2[4] = {rv.x, rv.y, rv.z, rv.w};
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                  float2 rf = __bfloat1622float2(r2[j]);
+                  float2 rf = A16::unpack2(r2[j]);
                   f[8 * h + 2 * j] += rf.x;
                   f[8 * h + 2 * j + 1] += rf.y;
                 }
@@ -567,8 +564,8 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
               const uint32_t chunk = (uint32_t)(((c0 & 63) >> 3) + h);
               const uint32_t addr = srow + ((chunk ^ (uint32_t)(etid & 7)) << 4);
               asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr),
-                           "r"(pack_bf16(f[8 * h + 0], f[8 * h + 1])), "r"(pack_bf16(f[8 * h + 2], f[8 * h + 3])),
-                           "r"(pack_bf16(f[8 * h + 4], f[8 * h + 5])), "r"(pack_bf16(f[8 * h + 6], f[8 * h + 7]))
+                           "r"(A16::pack2(f[8 * h + 0], f[8 * h + 1])), "r"(A16::pack2(f[8 * h + 2], f[8 * h + 3])),
+                           "r"(A16::pack2(f[8 * h + 4], f[8 * h + 5])), "r"(A16::pack2(f[8 * h + 6], f[8 * h + 7]))
                            : "memory");
             }
           }
@@ -867,7 +864,7 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
             delta = dy * Ws + (tap - dy * 3);
             tbit = tap;
           }
-          const __nv_bfloat16* sp = P.src[seg] + c;
+          const act_t* sp = P.src[seg] + c;
           const int ld = P.src_ld[seg];
           mbar_wait(empty_bar(s), ph ^ 1u);
           const uint32_t a_s = a_base + (uint32_t)s * A_STAGE_BYTES + sw_off;
@@ -892,7 +889,8 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
     // One thread runs the whole issue loop (tcgen05.mma / commit are single-thread instructions):
     // with N <= 64 an MMA retires in ~48 cycles, so every instruction on this thread's path counts.
     if (lane == 0) {
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
+    // instruction descriptor: D fp32, A/B format 0 = fp16 / 1 = bf16, K-major both, N, M
+    const uint32_t idesc = (1u << 4) | (F16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(BN >> 3) << 17) |
                            ((uint32_t)(BM >> 4) << 24);
     const uint64_t desc_hi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61) |
                              ((uint64_t)1 << 16);
@@ -1056,7 +1054,7 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
             for (int i = 0; i < 6; i++) {
               uint32_t v;
               asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(pbase + (uint32_t)(pr * PP_W + i) * 128u));
-              f[i] = make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xFFFF0000u));
+              f[i] = A16::unpack2(v);
             }
 #pragma unroll
             for (int ky = 0; ky < 3; ky++) {
@@ -1086,7 +1084,7 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
                   }
                   const uint32_t m = (uint32_t)((RPT * rq + r) * PT_W + 4 * xh + px);
                   const uint32_t addr = sbase + m * 128u + ((((uint32_t)cpair >> 2) ^ (m & 7u)) << 4);
-                  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(pack_bf16(o.x, o.y)) : "memory");
+                  asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(A16::pack2(o.x, o.y)) : "memory");
                 }
               }
             }
@@ -1220,6 +1218,7 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
 // Scalar cross-check kernel (validation only; selected with yb_plan_set_conv_impl(plan, 1)).
 // One thread per (output row, output channel), same packed weights, fp32 accumulation.
 // ------------------------------------------------------------------------------------------
+template <bool F16>
 __global__ void conv_direct_check_kernel(const ConvParams P) {
   long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   int cs = P.cout_store;
@@ -1230,7 +1229,7 @@ __global__ void conv_direct_check_kernel(const ConvParams P) {
   int r = m - img * P.hw_out;
   int oy = r / P.Wout, ox = r - oy * P.Wout;
   float acc = 0.f;
-  const __nv_bfloat16* wrow = P.w + (size_t)n * P.K_pad;
+  const act_t* wrow = P.w + (size_t)n * P.K_pad;
   int taps = P.ksize * P.ksize;
   for (int tap = 0; tap < taps; tap++) {
     int dy = P.ksize == 3 ? tap / 3 : 0, dx = P.ksize == 3 ? tap % 3 : 0;
@@ -1241,10 +1240,10 @@ __global__ void conv_direct_check_kernel(const ConvParams P) {
       if (ok) {
         int up = P.src_up[s];
         int Hs = P.Hin >> up, Ws = P.Win >> up;
-        const __nv_bfloat16* sp =
+        const act_t* sp =
             P.src[s] + ((size_t)(img * Hs + (iy >> up)) * Ws + (ix >> up)) * (size_t)P.src_ld[s];
         for (int c = 0; c < P.src_c[s]; c++)
-          acc += __bfloat162float(sp[c]) * __bfloat162float(wrow[kpos + c]);
+          acc += Act16<F16>::unpack1(sp[c]) * Act16<F16>::unpack1(wrow[kpos + c]);
       }
       kpos += P.seg_kpad[s];
     }
@@ -1255,8 +1254,8 @@ __global__ void conv_direct_check_kernel(const ConvParams P) {
   if (P.out_f32) {
     reinterpret_cast<float*>(P.dst)[drow * (size_t)P.dst_ld + n] = x;
   } else {
-    if (P.res) x += __bfloat162float(P.res[(size_t)m * P.res_ld + n]);
-    reinterpret_cast<__nv_bfloat16*>(P.dst)[drow * (size_t)P.dst_ld + n] = __float2bfloat16(x);
+    if (P.res) x += Act16<F16>::unpack1(P.res[(size_t)m * P.res_ld + n]);
+    reinterpret_cast<act_t*>(P.dst)[drow * (size_t)P.dst_ld + n] = Act16<F16>::pack1(x);
   }
 }
 
@@ -1292,6 +1291,8 @@ static CUtensorMapL2promotion promo_for(uint64_t used_bytes, uint64_t pitch_byte
   return CU_TENSOR_MAP_L2_PROMOTION_NONE;
 }
 
+static thread_local bool g_tmap_f16 = true;   // element type of the maps being encoded (set by conv_tc_prepare)
+
 static int make_tmap_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t rows,
                         uint64_t row_stride_bytes, uint32_t box_inner, uint32_t box_rows) {
   PFN_encodeTiled enc = get_encode();
@@ -1303,7 +1304,7 @@ static int make_tmap_2d(CUtensorMap* map, const void* base, uint64_t inner, uint
   cuuint64_t strides[1] = {row_stride_bytes};
   cuuint32_t box[2] = {box_inner, box_rows};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
+  CUresult r = enc(map, g_tmap_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides,
                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                    promo_for(std::min<uint64_t>(box_inner, inner) * 2, row_stride_bytes),
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
@@ -1334,7 +1335,7 @@ static int make_tmap_nhwc(CUtensorMap* map, const void* base, uint64_t C, uint64
   const CUtensorMapSwizzle sw = no_swizzle ? CU_TENSOR_MAP_SWIZZLE_NONE : box_c >= 64 ? CU_TENSOR_MAP_SWIZZLE_128B
                                 : box_c == 32 ? CU_TENSOR_MAP_SWIZZLE_64B
                                 : box_c == 16 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
+  CUresult r = enc(map, g_tmap_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, sw, promo_for(std::min<uint64_t>(box_c, C) * 2, ld_elems * 2),
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
@@ -1371,6 +1372,7 @@ static int tmem_cols_for(int BN) {
 }
 
 int conv_tc_prepare(yb_plan* p, Op& op) {
+  g_tmap_f16 = p->act_f16 != 0;
   const ConvW& cw = p->convs[op.conv_index];
   const uint8_t* wbase = p->d_weights + cw.info.blob_offset;
   // Resident CTAs per SM: bounded by TMEM (512 columns per SM, 2 accumulator stages per CTA) and
@@ -1541,19 +1543,25 @@ int conv_tc_prepare(yb_plan* p, Op& op) {
                         (uint64_t)db.C * 2, 64, BM);
     if (rc) return rc;
   }
-  static bool attr_set = false;
-  if (!attr_set) {
+  // the opt-in to > 48 KB of dynamic shared memory is a per-device function attribute
+  static bool attr_set[YB_MAX_DEVICES] = {false};
+  bool& done = attr_set[p->device & (YB_MAX_DEVICES - 1)];
+  if (!done) {
     const int smem_max = 227 * 1024;
-    YB_CUDA(cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<MODE_ATMA, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-    YB_CUDA(cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<MODE_GATHER, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-    YB_CUDA(cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<MODE_ATMA, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-    YB_CUDA(cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<MODE_ATMA, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-    YB_CUDA(cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<MODE_GATHER, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-    YB_CUDA(cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<MODE_GATHER, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-    YB_CUDA(cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<MODE_PATCH, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-    YB_CUDA(cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<MODE_DW, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-    YB_CUDA(cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<MODE_PATCH2, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));
-    attr_set = true;
+#define YB_ATTR(MODE, T2D, HEAD)                                                                                                                                   \
+    YB_CUDA(cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<MODE, T2D, HEAD, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max));  \
+    YB_CUDA(cudaFuncSetAttribute(conv_gemm_tcgen05_kernel<MODE, T2D, HEAD, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_max))
+    YB_ATTR(MODE_ATMA, false, true);
+    YB_ATTR(MODE_GATHER, false, true);
+    YB_ATTR(MODE_ATMA, true, false);
+    YB_ATTR(MODE_ATMA, false, false);
+    YB_ATTR(MODE_GATHER, true, false);
+    YB_ATTR(MODE_GATHER, false, false);
+    YB_ATTR(MODE_PATCH, true, false);
+    YB_ATTR(MODE_DW, true, false);
+    YB_ATTR(MODE_PATCH2, true, false);
+#undef YB_ATTR
+    done = true;
   }
   return YB_OK;
 }
@@ -1565,7 +1573,7 @@ static void fill_params(const yb_plan* p, const Op& op, ConvParams& P) {
   int per_tap = 0;
   for (int i = 0; i < op.nseg; i++) {
     const Buf& b = p->bufs[op.src[i].buf];
-    P.src[i] = reinterpret_cast<const __nv_bfloat16*>(buf_ptr(p, op.src[i].buf)) + op.src[i].c_off;
+    P.src[i] = reinterpret_cast<const act_t*>(buf_ptr(p, op.src[i].buf)) + op.src[i].c_off;
     P.src_cp[i] = cpad8(op.src[i].C);
     P.src_c[i] = op.src[i].C;
     P.src_ld[i] = b.C;
@@ -1597,11 +1605,11 @@ static void fill_params(const yb_plan* p, const Op& op, ConvParams& P) {
   P.cout = op.dst.C;
   P.cout_store = op.out_f32 ? round_up(op.dst.C, 4) : cpad8(op.dst.C);
   const uint8_t* wbase = p->d_weights + cw.info.blob_offset;
-  P.w = reinterpret_cast<const __nv_bfloat16*>(wbase);
+  P.w = reinterpret_cast<const act_t*>(wbase);
   P.bias = reinterpret_cast<const float*>(wbase + (size_t)op.N_pad * op.K_pad * 2);
   if (op.has_res) {
     const Buf& rb = p->bufs[op.res.buf];
-    P.res = reinterpret_cast<const __nv_bfloat16*>(buf_ptr(p, op.res.buf)) + op.res.c_off;
+    P.res = reinterpret_cast<const act_t*>(buf_ptr(p, op.res.buf)) + op.res.c_off;
     P.res_ld = rb.C;
   }
   P.act = op.act;
@@ -1703,9 +1711,16 @@ int launch_conv_tc(const yb_plan* p, const Op& op, cudaStream_t st, float* fused
   }
   int grid = std::min(P.total_tiles, p->num_sms * op.occ);
 #define YB_LAUNCH(ATMA, T2D, HEAD)                                                                       \
-  YB_CUDA(launch_pdl(conv_gemm_tcgen05_kernel<ATMA, T2D, HEAD>, dim3(grid),                                \
-                     dim3(ATMA == MODE_DW ? NUM_THREADS_DW : NUM_THREADS), op.smem_bytes, st,              \
-                     P, op.tmap_b, op.tmap_a[0], op.tmap_a[1], op.tmap_a[2], op.tmap_a[3], op.tmap_c))
+  do {                                                                                                   \
+    if (p->act_f16)                                                                                      \
+      YB_CUDA(launch_pdl(conv_gemm_tcgen05_kernel<ATMA, T2D, HEAD, true>, dim3(grid),                    \
+                         dim3(ATMA == MODE_DW ? NUM_THREADS_DW : NUM_THREADS), op.smem_bytes, st,        \
+                         P, op.tmap_b, op.tmap_a[0], op.tmap_a[1], op.tmap_a[2], op.tmap_a[3], op.tmap_c)); \
+    else                                                                                                 \
+      YB_CUDA(launch_pdl(conv_gemm_tcgen05_kernel<ATMA, T2D, HEAD, false>, dim3(grid),                   \
+                         dim3(ATMA == MODE_DW ? NUM_THREADS_DW : NUM_THREADS), op.smem_bytes, st,        \
+                         P, op.tmap_b, op.tmap_a[0], op.tmap_a[1], op.tmap_a[2], op.tmap_a[3], op.tmap_c)); \
+  } while (0)
   const bool head = P.out_mode != 0;
   if (head) {
     if (P.a_tma) YB_LAUNCH(MODE_ATMA, false, true);
@@ -1735,7 +1750,8 @@ int launch_conv_naive(const yb_plan* p, const Op& op, cudaStream_t st) {
   long long total = (long long)P.M * P.cout_store;
   int threads = 256;
   long long blocks = (total + threads - 1) / threads;
-  conv_direct_check_kernel<<<(unsigned)blocks, threads, 0, st>>>(P);
+  if (p->act_f16) conv_direct_check_kernel<true><<<(unsigned)blocks, threads, 0, st>>>(P);
+  else conv_direct_check_kernel<false><<<(unsigned)blocks, threads, 0, st>>>(P);
   count_launch();
   YB_CUDA(cudaGetLastError());
   return YB_OK;

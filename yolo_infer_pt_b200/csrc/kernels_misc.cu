@@ -1,5 +1,6 @@
 // Memory-bound kernels of the YOLOv11 forward: stem conv, depthwise 3x3, SPPF pooling, the C2PSA
-// attention core and the DFL box decode.  All activations are NHWC bf16; arithmetic is fp32.
+// attention core and the DFL box decode.  All activations are NHWC fp16 or bf16 (template parameter F16,
+// plan->act_f16); arithmetic is fp32.
 #include <math.h>
 #include <algorithm>
 #include <stdio.h>
@@ -31,33 +32,20 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
   return *reinterpret_cast<float2*>(&rd);
 }
 
-__device__ __forceinline__ void bf16x8_to_float(const uint4& v, float* f) {
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&v);
+template <bool F16>
+__device__ __forceinline__ void act8_to_float(const uint4& v, float* f) {
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
   for (int j = 0; j < 4; j++) {
-    float2 t = __bfloat1622float2(h[j]);
+    float2 t = Act16<F16>::unpack2(w[j]);
     f[2 * j] = t.x;
     f[2 * j + 1] = t.y;
   }
 }
-__device__ __forceinline__ uint4 float_to_bf16x8(const float* f) {
-  uint4 o;
-  __nv_bfloat162* h = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-  for (int j = 0; j < 4; j++) h[j] = __floats2bfloat162_rn(f[2 * j], f[2 * j + 1]);
-  return o;
-}
-
-__device__ __forceinline__ void mma_bf16_16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
-  asm volatile(
-      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
-      "{%0,%1,%2,%3};"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-__device__ __forceinline__ uint32_t pack2_bf16(float a, float b) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
+template <bool F16>
+__device__ __forceinline__ uint4 float_to_act8(const float* f) {
+  return make_uint4(Act16<F16>::pack2(f[0], f[1]), Act16<F16>::pack2(f[2], f[3]), Act16<F16>::pack2(f[4], f[5]),
+                    Act16<F16>::pack2(f[6], f[7]));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -124,9 +112,9 @@ __device__ __forceinline__ void unpack_eo<uint8_t>(const uint4& v, float* ev, fl
   }
 }
 
-template <typename T>
+template <typename T, bool F16>
 __global__ void __launch_bounds__(256)
-    stem_conv_kernel(const T* __restrict__ in, __nv_bfloat16* __restrict__ out,
+    stem_conv_kernel(const T* __restrict__ in, act_t* __restrict__ out,
                      const float* __restrict__ wgt, int B, int H, int W, int Ho, int Wo, int Cp,
                      int out_ld, float in_scale) {
   constexpr int EPV = 16 / (int)sizeof(T);  // elements per 16-byte vector (W % 32 == 0 keeps rows aligned)
@@ -201,7 +189,7 @@ __global__ void __launch_bounds__(256)
       x1[t + 1] = re[32];
       x1[t + 2] = ro[32];
     }
-  __nv_bfloat16* op = out + (((size_t)b * Ho + oy) * Wo + ox) * out_ld;
+  act_t* op = out + (((size_t)b * Ho + oy) * Wo + ox) * out_ld;
   const bool two = ox + 32 < Wo;
   for (int c0 = 0; c0 < Cp; c0 += 8) {
     float2 a0[4], a1[4];
@@ -229,14 +217,14 @@ __global__ void __launch_bounds__(256)
       o[2 * j] = silu_acc(a0[j].x);
       o[2 * j + 1] = silu_acc(a0[j].y);
     }
-    *reinterpret_cast<uint4*>(op + c0) = float_to_bf16x8(o);
+    *reinterpret_cast<uint4*>(op + c0) = float_to_act8<F16>(o);
     if (two) {
 #pragma unroll
       for (int j = 0; j < 4; j++) {
         o[2 * j] = silu_acc(a1[j].x);
         o[2 * j + 1] = silu_acc(a1[j].y);
       }
-      *reinterpret_cast<uint4*>(op + (size_t)32 * out_ld + c0) = float_to_bf16x8(o);
+      *reinterpret_cast<uint4*>(op + (size_t)32 * out_ld + c0) = float_to_act8<F16>(o);
     }
   }
 }
@@ -251,32 +239,6 @@ __global__ void __launch_bounds__(256)
 // 16 pixels; the output tile goes through a per-warp staging buffer so that global stores are 16 B
 // per lane and contiguous.
 // ---------------------------------------------------------------------------------------------
-template <typename T>
-__device__ __forceinline__ void unpack_bf16(const uint4& v, __nv_bfloat16* o);
-template <>
-__device__ __forceinline__ void unpack_bf16<float>(const uint4& v, __nv_bfloat16* o) {
-  o[0] = __float2bfloat16(__uint_as_float(v.x));
-  o[1] = __float2bfloat16(__uint_as_float(v.y));
-  o[2] = __float2bfloat16(__uint_as_float(v.z));
-  o[3] = __float2bfloat16(__uint_as_float(v.w));
-}
-template <>
-__device__ __forceinline__ void unpack_bf16<__half>(const uint4& v, __nv_bfloat16* o) {
-  const __half* h = reinterpret_cast<const __half*>(&v);
-#pragma unroll
-  for (int j = 0; j < 8; j++) o[j] = __float2bfloat16(__half2float(h[j]));
-}
-template <>
-__device__ __forceinline__ void unpack_bf16<__nv_bfloat16>(const uint4& v, __nv_bfloat16* o) {
-  *reinterpret_cast<uint4*>(o) = v;
-}
-template <>
-__device__ __forceinline__ void unpack_bf16<uint8_t>(const uint4& v, __nv_bfloat16* o) {
-  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-  for (int j = 0; j < 16; j++) o[j] = __float2bfloat16((float)((w[j >> 2] >> (8 * (j & 3))) & 0xFFu));
-}
-
 template <typename T>
 __device__ __forceinline__ float vec_elem(const uint4& v, int j);   // element j of a 16-byte vector as fp32
 template <>
@@ -321,22 +283,27 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t* r, uint32_t addr) {
 }
 
 // NT: n-tiles (8 channels each) per pass over the tile; wider stems take several passes.
-// SPLIT: the input is not exactly representable in bf16 (fp32 / fp16 images): input and weights are
-// staged as hi + lo bf16 pairs and multiplied as hi*W_hi + hi*W_lo + lo*W_hi, which matches an fp32
-// convolution to ~2^-16 relative.  uint8 / bf16 images are exact in bf16 and use bf16 weights like
-// every other layer of the network.
-template <typename T, int NT, bool SPLIT, int MINB = 1>
+// SPLIT: the input is not exactly representable in the 16-bit operand type (fp32 images; fp16 images with bf16
+// operands and vice versa): input and weights are staged as hi + lo pairs and multiplied as
+// hi*W_hi + hi*W_lo + lo*W_hi, which matches an fp32 convolution to ~2^-16 relative.  uint8 images (and images
+// already in the operand type) are exact and use 16-bit weights like every other layer of the network.
+// F16: operand / output type (Act16).  uint8 pixels with fp16 operands are staged as v * 2^-8 (exact) and the
+// weights carry 256/255 instead of 1/255, which keeps them clear of the fp16 subnormal range.
+template <typename T, int NT, bool SPLIT, bool F16, int MINB = 1>
 __global__ void __launch_bounds__(256, MINB)
-    stem_mma_kernel(const T* __restrict__ in, __nv_bfloat16* __restrict__ out, const float* __restrict__ wgt,
+    stem_mma_kernel(const T* __restrict__ in, act_t* __restrict__ out, const float* __restrict__ wgt,
                     int B, int H, int W, int Ho, int Wo, int Cp, int out_ld, float in_scale, int total_tiles) {
+  using A16 = Act16<F16>;
   constexpr int EPV = 16 / (int)sizeof(T);
   constexpr bool U8 = sizeof(T) == 1;
+  constexpr float PXS = (U8 && F16) ? 1.f / 256.f : 1.f;   // pixel staging scale (a power of two)
+  const float wscale = in_scale / PXS;
   // generic staging walks every 16-byte vector that overlaps patch columns [EPV-1, EPV-1 + 2*TW]
   constexpr int NVEC = (2 * STEM_TW + 1 + EPV + EPV - 1) / EPV;
   constexpr int PARTS = SPLIT ? 2 : 1;
   extern __shared__ __align__(16) uint8_t stem_smem[];
   uint8_t* zero_rows = stem_smem + PARTS * STEM_PART_B;
-  __nv_bfloat16* stage = reinterpret_cast<__nv_bfloat16*>(zero_rows + STEM_ZERO_B);   // [8 warps][16 px][NT*8]
+  act_t* stage = reinterpret_cast<act_t*>(zero_rows + STEM_ZERO_B);   // [8 warps][16 px][NT*8]
   pdl_prologue_done();
   const int tiles_x = (Wo + STEM_TW - 1) / STEM_TW, tiles_y = (Ho + STEM_TH - 1) / STEM_TH;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -368,11 +335,11 @@ __global__ void __launch_bounds__(256, MINB)
 #pragma unroll
         for (int h = 0; h < 2; h++) {
           const int k0 = ks * 16 + h * 8 + 2 * t;
-          const float w0 = (k0 < 27 && n < Cp) ? 0.5f * (__ldg(wgt + k0 * Cp + n) * in_scale) : 0.f;
-          const float w1 = (k0 + 1 < 27 && n < Cp) ? 0.5f * (__ldg(wgt + (k0 + 1) * Cp + n) * in_scale) : 0.f;
-          const __nv_bfloat16 h0 = __float2bfloat16(w0), h1 = __float2bfloat16(w1);
-          bhi[nt][ks][h] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-          blo[nt][ks][h] = pack2_bf16(w0 - __bfloat162float(h0), w1 - __bfloat162float(h1));
+          const float w0 = (k0 < 27 && n < Cp) ? 0.5f * (__ldg(wgt + k0 * Cp + n) * wscale) : 0.f;
+          const float w1 = (k0 + 1 < 27 && n < Cp) ? 0.5f * (__ldg(wgt + (k0 + 1) * Cp + n) * wscale) : 0.f;
+          const uint16_t h0 = A16::pack1(w0), h1 = A16::pack1(w1);
+          bhi[nt][ks][h] = (uint32_t)h0 | ((uint32_t)h1 << 16);
+          blo[nt][ks][h] = A16::pack2(w0 - A16::unpack1(h0), w1 - A16::unpack1(h1));
         }
       const int cb = c0 + nt * 8 + 2 * t;
       bia[nt][0] = cb < Cp ? 0.5f * __ldg(bias + cb) : 0.f;
@@ -381,7 +348,7 @@ __global__ void __launch_bounds__(256, MINB)
   };
   const bool single = Cp <= NT * 8;   // one channel group: its fragments stay in registers for all tiles
   if (single) load_weights(0);
-  __nv_bfloat16* wstage = stage + warp * 16 * NT * 8;
+  act_t* wstage = stage + warp * 16 * NT * 8;
 
   // ---- uint8 staging: a thread owns 16-byte vectors (16 pixels of one input row) whose even / odd
   // pixels are whole 16-byte plane rows; the kx = 0 plane is the kx = 2 plane shifted by one pixel and
@@ -419,13 +386,13 @@ __global__ void __launch_bounds__(256, MINB)
       const uint32_t w[4] = {pv[it].x, pv[it].y, pv[it].z, pv[it].w};
       float f[16];
 #pragma unroll
-      for (int j = 0; j < 16; j++) f[j] = (float)((w[j >> 2] >> (8 * (j & 3))) & 0xFFu);
-      const float fp = (float)pb[it];
+      for (int j = 0; j < 16; j++) f[j] = (float)((w[j >> 2] >> (8 * (j & 3))) & 0xFFu) * PXS;
+      const float fp = (float)pb[it] * PXS;
       // input column gx0 + 16 vx + j is patch column r = 16 vx + j + 1 (r = 2x + kx)
       uint4 p0, p1, p2;
-      p1 = make_uint4(pack2_bf16(f[0], f[2]), pack2_bf16(f[4], f[6]), pack2_bf16(f[8], f[10]), pack2_bf16(f[12], f[14]));
-      p2 = make_uint4(pack2_bf16(f[1], f[3]), pack2_bf16(f[5], f[7]), pack2_bf16(f[9], f[11]), pack2_bf16(f[13], f[15]));
-      p0 = make_uint4(pack2_bf16(fp, f[1]), pack2_bf16(f[3], f[5]), pack2_bf16(f[7], f[9]), pack2_bf16(f[11], f[13]));
+      p1 = make_uint4(A16::pack2(f[0], f[2]), A16::pack2(f[4], f[6]), A16::pack2(f[8], f[10]), A16::pack2(f[12], f[14]));
+      p2 = make_uint4(A16::pack2(f[1], f[3]), A16::pack2(f[5], f[7]), A16::pack2(f[9], f[11]), A16::pack2(f[13], f[15]));
+      p0 = make_uint4(A16::pack2(fp, f[1]), A16::pack2(f[3], f[5]), A16::pack2(f[7], f[9]), A16::pack2(f[11], f[13]));
       uint8_t* dst = stem_smem + row * STEM_PWB + vx * 16;
       *reinterpret_cast<uint4*>(dst) = p0;
       *reinterpret_cast<uint4*>(dst + STEM_PLANE_B) = p1;
@@ -461,9 +428,8 @@ __global__ void __launch_bounds__(256, MINB)
 #pragma unroll
         for (int j = 0; j < EPV; j++) {
           const float x = vec_elem<T>(v, j);
-          const __nv_bfloat16 hi = __float2bfloat16(x);
-          const unsigned short uh = __bfloat16_as_ushort(hi);
-          const unsigned short ul = SPLIT ? __bfloat16_as_ushort(__float2bfloat16(x - __bfloat162float(hi))) : (unsigned short)0;
+          const unsigned short uh = A16::pack1(x);
+          const unsigned short ul = SPLIT ? A16::pack1(x - A16::unpack1(uh)) : (unsigned short)0;
           const int r = vxe + j - (EPV - 1);   // parity of r is a compile-time property of j
           if (r < 0 || r > 2 * STEM_TW) continue;
           if (r & 1) {
@@ -507,18 +473,18 @@ __global__ void __launch_bounds__(256, MINB)
 #pragma unroll
           for (int ks = 0; ks < 2; ks++) {
             if (SPLIT) {
-              mma_bf16_16816(d[nt], afr[0][ks], blo[nt][ks][0], blo[nt][ks][1]);
-              mma_bf16_16816(d[nt], afr[SPLIT ? 1 : 0][ks], bhi[nt][ks][0], bhi[nt][ks][1]);
+              A16::mma16816(d[nt], afr[0][ks], blo[nt][ks][0], blo[nt][ks][1]);
+              A16::mma16816(d[nt], afr[SPLIT ? 1 : 0][ks], bhi[nt][ks][0], bhi[nt][ks][1]);
             }
-            mma_bf16_16816(d[nt], afr[0][ks], bhi[nt][ks][0], bhi[nt][ks][1]);
+            A16::mma16816(d[nt], afr[0][ks], bhi[nt][ks][0], bhi[nt][ks][1]);
           }
         }
         // SiLU (accumulators hold x/2) -> bf16 -> per-warp staging [16 px][NT*8] -> 16-byte global stores
         __syncwarp();
 #pragma unroll
         for (int nt = 0; nt < NT; nt++) {
-          *reinterpret_cast<uint32_t*>(wstage + g * NT * 8 + nt * 8 + 2 * t) = pack2_bf16(silu_half(d[nt][0]), silu_half(d[nt][1]));
-          *reinterpret_cast<uint32_t*>(wstage + (g + 8) * NT * 8 + nt * 8 + 2 * t) = pack2_bf16(silu_half(d[nt][2]), silu_half(d[nt][3]));
+          *reinterpret_cast<uint32_t*>(wstage + g * NT * 8 + nt * 8 + 2 * t) = A16::pack2(silu_half(d[nt][0]), silu_half(d[nt][1]));
+          *reinterpret_cast<uint32_t*>(wstage + (g + 8) * NT * 8 + nt * 8 + 2 * t) = A16::pack2(silu_half(d[nt][2]), silu_half(d[nt][3]));
         }
         __syncwarp();
         const int ox0 = tx * STEM_TW + mi * 16;
@@ -538,18 +504,18 @@ static int stem_ctas_per_sm() {
   return v;
 }
 
-template <typename T, bool SPLIT>
+template <typename T, bool SPLIT, bool F16>
 static int launch_stem_t(const yb_plan* p, const Op& op, const void* in, float scale, cudaStream_t st) {
   const ConvW& cw = p->convs[op.conv_index];
   const float* w = reinterpret_cast<const float*>(p->d_weights + cw.info.blob_offset);
   const Buf& db = p->bufs[op.dst.buf];
-  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(buf_ptr(p, op.dst.buf)) + op.dst.c_off;
+  act_t* out = reinterpret_cast<act_t*>(buf_ptr(p, op.dst.buf)) + op.dst.c_off;
   const int Cp = cpad8(op.dst.C);
   const unsigned blocks = (unsigned)(p->B * ((op.Hout + STEM_TH - 1) / STEM_TH) * ((op.Wout + STEM_TW - 1) / STEM_TW));
   static const bool direct = getenv("YB_STEM_DIRECT") != nullptr;
   if (direct) {  // CUDA-core version (cross-check)
     const size_t smem = ((size_t)28 * Cp + 2 * 3 * STEM_IH * STEM_HP) * 4;
-    YB_CUDA(launch_pdl(stem_conv_kernel<T>, dim3(blocks), dim3(256), smem, st, (const T*)in, out, w, p->B, p->H, p->W,
+    YB_CUDA(launch_pdl(stem_conv_kernel<T, F16>, dim3(blocks), dim3(256), smem, st, (const T*)in, out, w, p->B, p->H, p->W,
                        op.Hout, op.Wout, Cp, db.C, scale));
     return YB_OK;
   }
@@ -559,15 +525,16 @@ static int launch_stem_t(const yb_plan* p, const Op& op, const void* in, float s
   // are set up once per CTA instead of once per tile
 #define YB_STEM_MMA(NT, MINB)                                                                                    \
   do {                                                                                                           \
-    static int occ = 0;                                                                                          \
+    static int occ_dev[YB_MAX_DEVICES] = {0};   /* the attribute and the occupancy are per device */           \
+    int& occ = occ_dev[p->device & (YB_MAX_DEVICES - 1)];                                                        \
     if (occ == 0) {                                                                                              \
-      YB_CUDA(cudaFuncSetAttribute(stem_mma_kernel<T, NT, SPLIT, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+      YB_CUDA(cudaFuncSetAttribute(stem_mma_kernel<T, NT, SPLIT, F16, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
                                    (int)(2 * STEM_PART_B + STEM_ZERO_B + 8 * 16 * 4 * 8 * 2)));                  \
-      YB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stem_mma_kernel<T, NT, SPLIT, MINB>, 256, smem)); \
+      YB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, stem_mma_kernel<T, NT, SPLIT, F16, MINB>, 256, smem)); \
       occ = std::max(1, std::min(occ, stem_ctas_per_sm()));                                                      \
     }                                                                                                            \
     const unsigned grid = std::min(blocks, (unsigned)(p->num_sms * occ));                                        \
-    YB_CUDA(launch_pdl(stem_mma_kernel<T, NT, SPLIT, MINB>, dim3(grid), dim3(256), smem, st, (const T*)in, out, w, \
+    YB_CUDA(launch_pdl(stem_mma_kernel<T, NT, SPLIT, F16, MINB>, dim3(grid), dim3(256), smem, st, (const T*)in, out, w, \
                        p->B, p->H, p->W, op.Hout, op.Wout, Cp, db.C, scale, (int)blocks));                       \
   } while (0)
   static const bool minb4 = getenv("YB_STEM_MINB1") == nullptr;
@@ -581,11 +548,12 @@ static int launch_stem_t(const yb_plan* p, const Op& op, const void* in, float s
 
 int launch_stem(const yb_plan* p, const Op& op, const void* in, int in_dtype, cudaStream_t st) {
   int rc;
+  const bool f16 = p->act_f16 != 0;
   switch (in_dtype) {
-    case YB_F32: rc = launch_stem_t<float, true>(p, op, in, 1.f, st); break;
-    case YB_F16: rc = launch_stem_t<__half, true>(p, op, in, 1.f, st); break;
-    case YB_BF16: rc = launch_stem_t<__nv_bfloat16, false>(p, op, in, 1.f, st); break;
-    case YB_U8: rc = launch_stem_t<uint8_t, false>(p, op, in, 1.f / 255.f, st); break;
+    case YB_F32: rc = f16 ? launch_stem_t<float, true, true>(p, op, in, 1.f, st) : launch_stem_t<float, true, false>(p, op, in, 1.f, st); break;
+    case YB_F16: rc = f16 ? launch_stem_t<__half, false, true>(p, op, in, 1.f, st) : launch_stem_t<__half, true, false>(p, op, in, 1.f, st); break;
+    case YB_BF16: rc = f16 ? launch_stem_t<__nv_bfloat16, true, true>(p, op, in, 1.f, st) : launch_stem_t<__nv_bfloat16, false, false>(p, op, in, 1.f, st); break;
+    case YB_U8: rc = f16 ? launch_stem_t<uint8_t, false, true>(p, op, in, 1.f / 255.f, st) : launch_stem_t<uint8_t, false, false>(p, op, in, 1.f / 255.f, st); break;
     default:
       set_error("unsupported input dtype %d", in_dtype);
       return YB_ERR_ARG;
@@ -604,8 +572,9 @@ int launch_stem(const yb_plan* p, const Op& op, const void* in, int in_dtype, cu
 // ---------------------------------------------------------------------------------------------
 static constexpr int DW_PX = 4;  // output pixels along x per thread: 18 tap loads for 4 outputs
 
+template <bool F16>
 __global__ void __launch_bounds__(256, 3)
-    dwconv3x3_kernel(const __nv_bfloat16* __restrict__ src, int src_ld, __nv_bfloat16* dst, int dst_ld,
+    dwconv3x3_kernel(const act_t* __restrict__ src, int src_ld, act_t* dst, int dst_ld,
                      const float* __restrict__ wgt, int Cp, int B, int H, int W, int C, int gsz,
                      int gstride, int goff, int act, int add) {
   pdl_prologue_done();
@@ -635,7 +604,7 @@ __global__ void __launch_bounds__(256, 3)
   for (int ky = 0; ky < 3; ky++) {
     const int iy = y - 1 + ky;
     const bool row_ok = (unsigned)iy < (unsigned)H;
-    const __nv_bfloat16* rowp = src + ((size_t)(b * H + (row_ok ? iy : y)) * W) * src_ld + sc;
+    const act_t* rowp = src + ((size_t)(b * H + (row_ok ? iy : y)) * W) * src_ld + sc;
 #pragma unroll
     for (int col = 0; col < DW_PX + 2; col++) {
       const int ix = x0 - 1 + col;
@@ -658,10 +627,10 @@ __global__ void __launch_bounds__(256, 3)
     }
 #pragma unroll
     for (int col = 0; col < DW_PX + 2; col++) {
-      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&v[ky][col]);
+      const uint32_t h2[4] = {v[ky][col].x, v[ky][col].y, v[ky][col].z, v[ky][col].w};
       float2 f[4];
 #pragma unroll
-      for (int j = 0; j < 4; j++) f[j] = __bfloat1622float2(h2[j]);
+      for (int j = 0; j < 4; j++) f[j] = Act16<F16>::unpack2(h2[j]);
 #pragma unroll
       for (int kx = 0; kx < 3; kx++) {
         const int p = col - kx;  // output pixel this column feeds through tap kx
@@ -682,14 +651,14 @@ __global__ void __launch_bounds__(256, 3)
       o[2 * j] = act ? silu_acc(acc[p][j].x) : acc[p][j].x;
       o[2 * j + 1] = act ? silu_acc(acc[p][j].y) : acc[p][j].y;
     }
-    __nv_bfloat16* dp = dst + ((size_t)(b * H + y) * W + x) * dst_ld + c;
+    act_t* dp = dst + ((size_t)(b * H + y) * W + x) * dst_ld + c;
     if (add) {
       float f[8];
-      bf16x8_to_float(*reinterpret_cast<const uint4*>(dp), f);
+      act8_to_float<F16>(*reinterpret_cast<const uint4*>(dp), f);
 #pragma unroll
       for (int j = 0; j < 8; j++) o[j] += f[j];
     }
-    *reinterpret_cast<uint4*>(dp) = float_to_bf16x8(o);
+    *reinterpret_cast<uint4*>(dp) = float_to_act8<F16>(o);
   }
 }
 
@@ -698,16 +667,19 @@ int launch_dw(const yb_plan* p, const Op& op, cudaStream_t st) {
   const float* w = reinterpret_cast<const float*>(p->d_weights + cw.info.blob_offset);
   const Buf& sb = p->bufs[op.src[0].buf];
   const Buf& db = p->bufs[op.dst.buf];
-  const __nv_bfloat16* src =
-      reinterpret_cast<const __nv_bfloat16*>(buf_ptr(p, op.src[0].buf)) + op.src[0].c_off;
-  __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(buf_ptr(p, op.dst.buf)) + op.dst.c_off;
+  const act_t* src = reinterpret_cast<const act_t*>(buf_ptr(p, op.src[0].buf)) + op.src[0].c_off;
+  act_t* dst = reinterpret_cast<act_t*>(buf_ptr(p, op.dst.buf)) + op.dst.c_off;
   int C = op.dst.C;
   const int per_row = ((op.Wout + DW_PX - 1) / DW_PX) * (C >> 3);
   int threads = std::min(256, round_up(per_row, 32));
   if (per_row > 256) threads = round_up((per_row + (per_row + 255) / 256 - 1) / ((per_row + 255) / 256), 32);
   dim3 blocks((unsigned)((per_row + threads - 1) / threads), (unsigned)op.Hout, (unsigned)p->B);
-  YB_CUDA(launch_pdl(dwconv3x3_kernel, blocks, dim3(threads), 0, st, src, sb.C, dst, db.C, w, cpad8(C), p->B,
-                     op.Hout, op.Wout, C, op.dw_gsz, op.dw_gstride, op.dw_goff, op.act, op.dw_add));
+  if (p->act_f16)
+    YB_CUDA(launch_pdl(dwconv3x3_kernel<true>, blocks, dim3(threads), 0, st, src, sb.C, dst, db.C, w, cpad8(C), p->B,
+                       op.Hout, op.Wout, C, op.dw_gsz, op.dw_gstride, op.dw_goff, op.act, op.dw_add));
+  else
+    YB_CUDA(launch_pdl(dwconv3x3_kernel<false>, blocks, dim3(threads), 0, st, src, sb.C, dst, db.C, w, cpad8(C), p->B,
+                       op.Hout, op.Wout, C, op.dw_gsz, op.dw_gstride, op.dw_goff, op.act, op.dw_add));
   count_launch();
   YB_CUDA(cudaGetLastError());
   return YB_OK;
@@ -718,20 +690,16 @@ int launch_dw(const yb_plan* p, const Op& op, cudaStream_t st) {
 // (image, 8-channel group) plane in shared memory and runs the cascade as separable row/column
 // 5-max passes; slice 0 of the concat buffer is read once, slices 1..3 are written once.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ uint4 max_bf16x8(const uint4& a, const uint4& b) {
-  uint4 o;
-  const __nv_bfloat162* x = reinterpret_cast<const __nv_bfloat162*>(&a);
-  const __nv_bfloat162* y = reinterpret_cast<const __nv_bfloat162*>(&b);
-  __nv_bfloat162* z = reinterpret_cast<__nv_bfloat162*>(&o);
-#pragma unroll
-  for (int j = 0; j < 4; j++) z[j] = __hmax2(x[j], y[j]);
-  return o;
+template <bool F16>
+__device__ __forceinline__ uint4 max_act8(const uint4& a, const uint4& b) {
+  return make_uint4(Act16<F16>::max2(a.x, b.x), Act16<F16>::max2(a.y, b.y), Act16<F16>::max2(a.z, b.z),
+                    Act16<F16>::max2(a.w, b.w));
 }
 
 // G: 8-channel groups per CTA (a pixel's G x 16 bytes are contiguous: full sectors, fewer and fatter CTAs)
-template <int G>
+template <int G, bool F16>
 __global__ void __launch_bounds__(G >= 4 ? 512 : 256)
-    sppf_pool_kernel(const __nv_bfloat16* __restrict__ src, __nv_bfloat16* dst, int ld, int H, int W,
+    sppf_pool_kernel(const act_t* __restrict__ src, act_t* dst, int ld, int H, int W,
                      int Chalf) {
   extern __shared__ uint4 pl[];  // cur[HW][G], tmp[HW][G]
   pdl_prologue_done();
@@ -753,7 +721,7 @@ __global__ void __launch_bounds__(G >= 4 ? 512 : 256)
 #pragma unroll
       for (int d = -2; d <= 2; d++) {
         int xx = x + d;
-        if (d != 0 && (unsigned)xx < (unsigned)W) m = max_bf16x8(m, cur[i + d * G]);
+        if (d != 0 && (unsigned)xx < (unsigned)W) m = max_act8<F16>(m, cur[i + d * G]);
       }
       tmp[i] = m;
     }
@@ -764,7 +732,7 @@ __global__ void __launch_bounds__(G >= 4 ? 512 : 256)
 #pragma unroll
       for (int d = -2; d <= 2; d++) {
         int yy = y + d;
-        if (d != 0 && (unsigned)yy < (unsigned)H) m = max_bf16x8(m, tmp[i + d * W * G]);
+        if (d != 0 && (unsigned)yy < (unsigned)H) m = max_act8<F16>(m, tmp[i + d * W * G]);
       }
       // dst points at slice 1 of the concat buffer; slices are Chalf channels apart
       *reinterpret_cast<uint4*>(dst + img_base + (size_t)pix * ld + g * 8 + (size_t)stage * Chalf) = m;
@@ -776,9 +744,8 @@ __global__ void __launch_bounds__(G >= 4 ? 512 : 256)
 
 int launch_pool(const yb_plan* p, const Op& op, cudaStream_t st) {
   const Buf& sb = p->bufs[op.src[0].buf];
-  const __nv_bfloat16* src =
-      reinterpret_cast<const __nv_bfloat16*>(buf_ptr(p, op.src[0].buf)) + op.src[0].c_off;
-  __nv_bfloat16* dst = reinterpret_cast<__nv_bfloat16*>(buf_ptr(p, op.dst.buf)) + op.dst.c_off;
+  const act_t* src = reinterpret_cast<const act_t*>(buf_ptr(p, op.src[0].buf)) + op.src[0].c_off;
+  act_t* dst = reinterpret_cast<act_t*>(buf_ptr(p, op.dst.buf)) + op.dst.c_off;
   int Chalf = op.src[0].C;
   int HW = op.Hin * op.Win;
   const int cg_all = Chalf >> 3;
@@ -790,19 +757,26 @@ int launch_pool(const yb_plan* p, const Op& op, cudaStream_t st) {
   }
   // src (slice 0) and dst (slices 1..3) live in the same concat buffer
   unsigned blocks = (unsigned)(p->B * (cg_all / G));
-#define YB_SPPF(GG)                                                                                              \
+#define YB_SPPF(GG, FF)                                                                                          \
   do {                                                                                                           \
-    static size_t attr = 0;                                                                                      \
+    static size_t attr_dev[YB_MAX_DEVICES] = {0};   /* per device */                                             \
+    size_t& attr = attr_dev[p->device & (YB_MAX_DEVICES - 1)];                                                   \
     if (smem > 48 * 1024 && smem > attr) {                                                                       \
-      YB_CUDA(cudaFuncSetAttribute(sppf_pool_kernel<GG>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+      YB_CUDA(cudaFuncSetAttribute(sppf_pool_kernel<GG, FF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
       attr = smem;                                                                                               \
     }                                                                                                            \
-    YB_CUDA(launch_pdl(sppf_pool_kernel<GG>, dim3(blocks), dim3(GG >= 4 ? 512 : 256), smem, st, src, dst, sb.C, op.Hin, op.Win, \
+    YB_CUDA(launch_pdl(sppf_pool_kernel<GG, FF>, dim3(blocks), dim3(GG >= 4 ? 512 : 256), smem, st, src, dst, sb.C, op.Hin, op.Win, \
                        Chalf));                                                                                  \
   } while (0)
-  if (G == 4) YB_SPPF(4);
-  else if (G == 2) YB_SPPF(2);
-  else YB_SPPF(1);
+  if (p->act_f16) {
+    if (G == 4) YB_SPPF(4, true);
+    else if (G == 2) YB_SPPF(2, true);
+    else YB_SPPF(1, true);
+  } else {
+    if (G == 4) YB_SPPF(4, false);
+    else if (G == 2) YB_SPPF(2, false);
+    else YB_SPPF(1, false);
+  }
 #undef YB_SPPF
   count_launch();
   YB_CUDA(cudaGetLastError());
@@ -825,23 +799,25 @@ static constexpr int ATT_KC = 128;  // keys per shared-memory chunk
 static constexpr int ATT_KP = 40;   // K row pitch, bf16 (80 B)
 static constexpr int ATT_VP = 72;   // V row pitch, bf16 (144 B)
 
+template <bool F16>
 __global__ void __launch_bounds__(256)
-    attention_kernel(const __nv_bfloat16* __restrict__ qkv, int qkv_ld, __nv_bfloat16* __restrict__ out,
+    attention_kernel(const act_t* __restrict__ qkv, int qkv_ld, act_t* __restrict__ out,
                      int out_ld, int N, int heads, float scale_log2e) {
-  __shared__ __align__(16) __nv_bfloat16 Ks[ATT_KC * ATT_KP];
-  __shared__ __align__(16) __nv_bfloat16 Vs[ATT_KC * ATT_VP];
+  using A16 = Act16<F16>;
+  __shared__ __align__(16) act_t Ks[ATT_KC * ATT_KP];
+  __shared__ __align__(16) act_t Vs[ATT_KC * ATT_VP];
   pdl_prologue_done();
   pdl_wait();
   const int h = blockIdx.y, b = blockIdx.z;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int g = lane >> 2, t = lane & 3;
   const int q0 = blockIdx.x * ATT_Q + warp * 16;
-  const __nv_bfloat16* base = qkv + (size_t)b * N * qkv_ld + h * 128;
+  const act_t* base = qkv + (size_t)b * N * qkv_ld + h * 128;
   // Q fragments (A operand, 16 queries x 32 channels = 2 k-steps), rows clamped into the image
   uint32_t qa[2][4];
   {
-    const __nv_bfloat16* r0 = base + (size_t)min(q0 + g, N - 1) * qkv_ld;
-    const __nv_bfloat16* r1 = base + (size_t)min(q0 + g + 8, N - 1) * qkv_ld;
+    const act_t* r0 = base + (size_t)min(q0 + g, N - 1) * qkv_ld;
+    const act_t* r1 = base + (size_t)min(q0 + g + 8, N - 1) * qkv_ld;
 #pragma unroll
     for (int ks = 0; ks < 2; ks++) {
       qa[ks][0] = __ldg(reinterpret_cast<const uint32_t*>(r0 + ks * 16 + 2 * t));
@@ -863,7 +839,7 @@ __global__ void __launch_bounds__(256)
     for (int i = tid; i < ATT_KC * 12; i += 256) {
       const int key = i / 12, gr = i - key * 12;
       const bool ok = k0 + key < N;
-      const __nv_bfloat16* sp = base + (size_t)(ok ? k0 + key : 0) * qkv_ld + 32 + gr * 8;
+      const act_t* sp = base + (size_t)(ok ? k0 + key : 0) * qkv_ld + 32 + gr * 8;
       const uint32_t dp = gr < 4 ? ks_s + (uint32_t)(key * ATT_KP + gr * 8) * 2u
                                  : vs_s + (uint32_t)(key * ATT_VP + (gr - 4) * 8) * 2u;
       asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dp), "l"(sp), "r"(ok ? 16u : 0u)
@@ -877,10 +853,10 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
       for (int nt = 0; nt < 8; nt++) {
         s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
-        const __nv_bfloat16* kr = Ks + (kb + nt * 8 + g) * ATT_KP + 2 * t;
+        const act_t* kr = Ks + (kb + nt * 8 + g) * ATT_KP + 2 * t;
 #pragma unroll
         for (int ks = 0; ks < 2; ks++)
-          mma_bf16_16816(s[nt], qa[ks], *reinterpret_cast<const uint32_t*>(kr + ks * 16),
+          A16::mma16816(s[nt], qa[ks], *reinterpret_cast<const uint32_t*>(kr + ks * 16),
                          *reinterpret_cast<const uint32_t*>(kr + ks * 16 + 8));
       }
       float mx0 = -INFINITY, mx1 = -INFINITY;
@@ -919,8 +895,8 @@ __global__ void __launch_bounds__(256)
         const float p2 = exp2f(s[nt][2] - mn1), p3 = exp2f(s[nt][3] - mn1);
         l0 += p0 + p1;
         l1 += p2 + p3;
-        pa[nt >> 1][(nt & 1) * 2] = pack2_bf16(p0, p1);
-        pa[nt >> 1][(nt & 1) * 2 + 1] = pack2_bf16(p2, p3);
+        pa[nt >> 1][(nt & 1) * 2] = A16::pack2(p0, p1);
+        pa[nt >> 1][(nt & 1) * 2 + 1] = A16::pack2(p2, p3);
       }
 #pragma unroll
       for (int j = 0; j < 4; j++) {
@@ -933,8 +909,8 @@ __global__ void __launch_bounds__(256)
           asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
                        : "=r"(r0), "=r"(r1), "=r"(r2), "=r"(r3)
                        : "r"(vrow + (uint32_t)dp * 32u));
-          mma_bf16_16816(o[2 * dp], pa[j], r0, r1);
-          mma_bf16_16816(o[2 * dp + 1], pa[j], r2, r3);
+          A16::mma16816(o[2 * dp], pa[j], r0, r1);
+          A16::mma16816(o[2 * dp + 1], pa[j], r2, r3);
         }
       }
     }
@@ -944,35 +920,38 @@ __global__ void __launch_bounds__(256)
   l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
   l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
   const float i0 = 1.f / l0, i1 = 1.f / l1;
-  __nv_bfloat16* ob = out + (size_t)b * N * out_ld + h * 64 + 2 * t;
+  act_t* ob = out + (size_t)b * N * out_ld + h * 64 + 2 * t;
   if (q0 + g < N) {
-    __nv_bfloat16* op = ob + (size_t)(q0 + g) * out_ld;
+    act_t* op = ob + (size_t)(q0 + g) * out_ld;
 #pragma unroll
     for (int nt = 0; nt < 8; nt++)
-      *reinterpret_cast<uint32_t*>(op + nt * 8) = pack2_bf16(o[nt][0] * i0, o[nt][1] * i0);
+      *reinterpret_cast<uint32_t*>(op + nt * 8) = A16::pack2(o[nt][0] * i0, o[nt][1] * i0);
   }
   if (q0 + g + 8 < N) {
-    __nv_bfloat16* op = ob + (size_t)(q0 + g + 8) * out_ld;
+    act_t* op = ob + (size_t)(q0 + g + 8) * out_ld;
 #pragma unroll
     for (int nt = 0; nt < 8; nt++)
-      *reinterpret_cast<uint32_t*>(op + nt * 8) = pack2_bf16(o[nt][2] * i1, o[nt][3] * i1);
+      *reinterpret_cast<uint32_t*>(op + nt * 8) = A16::pack2(o[nt][2] * i1, o[nt][3] * i1);
   }
 }
 
 int launch_attn(const yb_plan* p, const Op& op, cudaStream_t st) {
   const Buf& sb = p->bufs[op.src[0].buf];
   const Buf& db = p->bufs[op.dst.buf];
-  const __nv_bfloat16* qkv =
-      reinterpret_cast<const __nv_bfloat16*>(buf_ptr(p, op.src[0].buf)) + op.src[0].c_off;
-  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(buf_ptr(p, op.dst.buf)) + op.dst.c_off;
+  const act_t* qkv = reinterpret_cast<const act_t*>(buf_ptr(p, op.src[0].buf)) + op.src[0].c_off;
+  act_t* out = reinterpret_cast<act_t*>(buf_ptr(p, op.dst.buf)) + op.dst.c_off;
   if (op.dk != 32 || op.dh != 64) {
     set_error("attention kernel is specialised for dim_key 32 / dim_head 64 (got %d / %d)", op.dk, op.dh);
     return YB_ERR_UNSUPPORTED;
   }
   int N = op.Hin * op.Win;
   dim3 grid((N + ATT_Q - 1) / ATT_Q, op.heads, p->B);
-  YB_CUDA(launch_pdl(attention_kernel, grid, dim3(256), 0, st, qkv, sb.C, out, db.C, N, op.heads,
-                     op.scale * 1.4426950408889634f));
+  if (p->act_f16)
+    YB_CUDA(launch_pdl(attention_kernel<true>, grid, dim3(256), 0, st, qkv, sb.C, out, db.C, N, op.heads,
+                       op.scale * 1.4426950408889634f));
+  else
+    YB_CUDA(launch_pdl(attention_kernel<false>, grid, dim3(256), 0, st, qkv, sb.C, out, db.C, N, op.heads,
+                       op.scale * 1.4426950408889634f));
   count_launch();
   YB_CUDA(cudaGetLastError());
   return YB_OK;
@@ -1063,7 +1042,8 @@ int launch_decode(const yb_plan* p, const float* logits, float* out, cudaStream_
   }
   int no = 64 + p->nc;
   size_t smem = ((size_t)DEC_T * (no | 1) + DEC_T * 4) * 4;
-  static size_t attr = 0;
+  static size_t attr_dev[YB_MAX_DEVICES] = {0};   // per device
+  size_t& attr = attr_dev[p->device & (YB_MAX_DEVICES - 1)];
   if (smem > 48 * 1024 && smem > attr) {
     YB_CUDA(cudaFuncSetAttribute(head_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)smem));

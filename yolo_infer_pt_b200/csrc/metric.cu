@@ -79,7 +79,10 @@ int metric_run(const float* det, const int* counts, const float* tgt, const int*
     set_error("yb_compute_metric: %d labels x %d detections do not fit shared memory", max_t, max_det);
     return YB_ERR_UNSUPPORTED;
   }
-  static size_t attr = 0;
+  static size_t attr_dev[YB_MAX_DEVICES] = {0};   // per-device function attribute
+  int cur_dev = 0;
+  YB_CUDA(cudaGetDevice(&cur_dev));
+  size_t& attr = attr_dev[cur_dev & (YB_MAX_DEVICES - 1)];
   if (smem > 48 * 1024 && smem > attr) {
     YB_CUDA(cudaFuncSetAttribute(metric_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = smem;

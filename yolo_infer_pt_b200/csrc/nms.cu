@@ -864,7 +864,11 @@ int nms_run(const float* pred, int B, int nc, int A, float conf, double iou, int
   a.keys = reinterpret_cast<unsigned long long*>((uint8_t*)ws + hdr_bytes + (size_t)B * HIST_BINS * 4);
   a.out = out;
   a.out_counts = out_counts;
-  static bool attr_set = false;
+  // per-device function attribute (the caller has made the tensor's device current)
+  static bool attr_dev[YB_MAX_DEVICES] = {false};
+  int cur_dev = 0;
+  YB_CUDA(cudaGetDevice(&cur_dev));
+  bool& attr_set = attr_dev[cur_dev & (YB_MAX_DEVICES - 1)];
   if (!attr_set) {
     YB_CUDA(cudaFuncSetAttribute(nms_image_kernel<1024>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)sizeof(ImgSmem)));

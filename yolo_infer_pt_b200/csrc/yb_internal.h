@@ -3,6 +3,7 @@
 #include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <string>
 #include <vector>
@@ -51,6 +52,88 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
 __device__ __forceinline__ void pdl_prologue_done() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 #endif
+
+#ifdef __CUDACC__
+// The two 16-bit activation / weight storage types (plan->act_f16).  Arithmetic is fp32 everywhere; only
+// the pack / unpack at loads and stores and the tensor-core operand format differ.
+template <bool F16>
+struct Act16 {
+  static __device__ __forceinline__ uint32_t pack2(float a, float b) {
+    if (F16) {
+      __half2 h = __floats2half2_rn(a, b);
+      return *reinterpret_cast<uint32_t*>(&h);
+    }
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  static __device__ __forceinline__ float2 unpack2(uint32_t v) {
+    if (F16) return __half22float2(*reinterpret_cast<const __half2*>(&v));
+    return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xFFFF0000u));
+  }
+  static __device__ __forceinline__ uint16_t pack1(float a) {
+    if (F16) return __half_as_ushort(__float2half_rn(a));
+    return __bfloat16_as_ushort(__float2bfloat16(a));
+  }
+  static __device__ __forceinline__ float unpack1(uint16_t v) {
+    if (F16) return __half2float(__ushort_as_half(v));
+    return __uint_as_float((uint32_t)v << 16);
+  }
+  static __device__ __forceinline__ uint32_t max2(uint32_t a, uint32_t b) {
+    if (F16) {
+      __half2 r = __hmax2(*reinterpret_cast<const __half2*>(&a), *reinterpret_cast<const __half2*>(&b));
+      return *reinterpret_cast<uint32_t*>(&r);
+    }
+    __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+    return *reinterpret_cast<uint32_t*>(&r);
+  }
+  // mma.sync.m16n8k16, fp32 accumulate
+  static __device__ __forceinline__ void mma16816(float* c, const uint32_t* a, uint32_t b0, uint32_t b1) {
+    if (F16)
+      asm volatile(
+          "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+          : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+          : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+    else
+      asm volatile(
+          "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+          : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+          : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+  }
+};
+#endif
+// host-side conversion of one fp32 value to the plan's 16-bit storage type
+static inline uint16_t host_to_act16(float v, bool f16) {
+  if (f16) return __half_as_ushort(__float2half_rn(v));
+  return __bfloat16_as_ushort(__float2bfloat16(v));
+}
+static inline float host_from_act16(uint16_t v, bool f16) {
+  if (f16) return __half2float(__ushort_as_half(v));
+  return __bfloat162float(__ushort_as_bfloat16(v));
+}
+static constexpr int YB_MAX_DEVICES = 64;   // per-device caches of function attributes (power of two)
+typedef uint16_t act_t;   // one activation / weight element in global memory (fp16 or bf16 bits)
+
+// Selects a device for the duration of a yb_* call and restores the caller's current device on exit
+// (torch tracks the current device itself; a library call must not change it behind its back).
+struct DeviceGuard {
+  int prev = -1, rc = YB_OK;
+  explicit DeviceGuard(int dev) {
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+    if (prev != dev) {
+      cudaError_t e = cudaSetDevice(dev);
+      if (e != cudaSuccess) {
+        yb::set_error("cudaSetDevice(%d) failed: %s", dev, cudaGetErrorString(e));
+        rc = YB_ERR_CUDA;
+        prev = -1;
+      }
+    } else {
+      prev = -1;
+    }
+  }
+  ~DeviceGuard() {
+    if (prev >= 0) cudaSetDevice(prev);
+  }
+};
 
 static inline int round_up(int x, int m) { return (x + m - 1) / m * m; }
 static inline int cpad8(int c) { return round_up(c, 8); }
@@ -135,6 +218,8 @@ struct GraphEntry {
   int dtype = 0, raw = 0, impl = 0;
   const void* sink = nullptr;   // NMS candidate sink captured in the graph (yb_forward_nms)
   float sink_conf = 0.f;
+  const void* sink_hdr = nullptr;   // the sink's header block and per-image key stride are baked into the graph too
+  int sink_cap = 0;
   cudaGraphExec_t exec = nullptr;
 };
 
@@ -143,6 +228,7 @@ struct GraphEntry {
 struct yb_plan {
   yb_arch_desc arch;
   int B = 0, H = 0, W = 0, device = 0;
+  int act_f16 = 1;         // activation / weight storage type: 1 = IEEE fp16 (default), 0 = bf16
   int nc = 0, no = 0, A = 0;
   int lvl_h[3], lvl_w[3], lvl_off[3];
   float lvl_stride[3];

@@ -7,6 +7,7 @@ An Engine owns, for one (architecture, batch, height, width, device):
 PyTorch is used for device memory and streams only; every kernel on the path lives in the .so.
 """
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -32,10 +33,22 @@ def fold_conv_bn(conv, norm=None):
     return w.contiguous(), b.contiguous()
 
 
+def default_act_dtype():
+    """Storage type of activations and packed weights: fp16 unless YB_ACT_DTYPE=bf16.
+    fp16 is what the reference's own evaluation runs in (main.py:251,266 `.half()`); with fp32 accumulation
+    and fp32 decode it keeps the head outputs within the north-star tolerance (0.5 px / 1e-2) on networks
+    whose head actually spreads scores over (0, 1), where bf16 storage does not (tests/test_gpu_parity.py)."""
+    return torch.bfloat16 if os.environ.get("YB_ACT_DTYPE", "fp16").lower() in ("bf16", "bfloat16") else torch.float16
+
+
 class Engine:
     def __init__(self, width, depth, csp, num_classes, batch, height, width_px, device=None,
-                 host_only=False):
+                 host_only=False, act_dtype=None):
         L = _lib.lib()
+        act_dtype = default_act_dtype() if act_dtype is None else act_dtype
+        if act_dtype not in (torch.float16, torch.bfloat16):
+            raise ValueError("act_dtype must be torch.float16 or torch.bfloat16")
+        self.act_dtype = act_dtype
         self.L = L
         arch = _lib.ArchDesc()
         arch.width[:] = list(width)
@@ -55,8 +68,8 @@ class Engine:
             dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
             self.device = torch.device("cuda", dev_index)
         handle = ctypes.c_void_p()
-        _lib.check(L.yb_plan_create(ctypes.byref(arch), self.batch, self.height, self.width, dev_index,
-                                    ctypes.byref(handle)), "yb_plan_create")
+        _lib.check(L.yb_plan_create(ctypes.byref(arch), self.batch, self.height, self.width, _DTYPES[act_dtype],
+                                    dev_index, ctypes.byref(handle)), "yb_plan_create")
         self.plan = handle
         self.num_anchors = L.yb_plan_num_anchors(self.plan)
         self.num_outputs = L.yb_plan_num_outputs(self.plan)
@@ -164,14 +177,33 @@ class Engine:
         if nms_sink is not None:
             ws, conf, max_nms = nms_sink
             conf32 = float(np.float32(conf))   # the NMS compares fp32 scores with an fp32 threshold
+            if getattr(ws, "_yb_sink_pending", False):
+                # a previous forward filled this workspace and no NMS consumed it: its counters would be
+                # double-counted, so clear the headers first (stream-ordered memset)
+                _lib.check(self.L.yb_nms_workspace_init(ws.data_ptr(), ws.numel(), ctypes.c_void_p(stream)),
+                           "yb_nms_workspace_init")
             _lib.check(self.L.yb_forward_nms(self.plan, x.data_ptr(), _DTYPES[x.dtype], out.data_ptr(), conf32,
                                              int(max_nms), ws.data_ptr(), ws.numel(), ctypes.c_void_p(stream)),
                        "yb_forward_nms")
             ws._yb_sink_tag = (conf32, int(max_nms), out.data_ptr())   # checked by util.nms_padded(prefiltered=True)
+            ws._yb_sink_pending = True
             return out
         _lib.check(self.L.yb_forward(self.plan, x.data_ptr(), _DTYPES[x.dtype], out.data_ptr(),
                                      ctypes.c_void_p(stream)), "yb_forward")
         return out
+
+    def forward_static(self, x):
+        """Graph-mode forward for callers that hand in a fresh tensor every call (the drop-in `model(x)`): the
+        CUDA graph is keyed on its input / output pointers, so `x` is copied into a static input buffer, the
+        graph replays into the static output and a fresh copy of it is returned (two small device copies
+        instead of a re-capture per call)."""
+        x = self._check_input(x)
+        pool = self.__dict__.setdefault("_static_in", {})
+        buf = pool.get(x.dtype)
+        if buf is None:
+            buf = pool[x.dtype] = torch.empty_like(x)
+        buf.copy_(x)
+        return self.forward(buf).clone()
 
     def forward_raw(self, x):
         """Pre-decode head logits (B, A, 64+nc) fp32 (reference training-mode output, nn.py:256-259)."""

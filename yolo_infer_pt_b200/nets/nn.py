@@ -12,7 +12,7 @@ What is kept identical to the reference, so that checkpoints, pickles and caller
 What is different:
   * eval forward requires a CUDA (sm_100) input and the built extension; it raises otherwise —
     there is no CPU or eager-PyTorch fallback for inference;
-  * the eval output is always fp32 (bf16 activations, fp32 accumulation and decode);
+  * the eval output is always fp32 (fp16 - or bf16 - activations, fp32 accumulation and decode);
   * the modules below describe *parameters and topology*; their torch `forward`s are only the
     differentiable training-mode graph (autograd for ComputeLoss, utils/util.py:863-930) and are
     never reached from eval mode.
@@ -44,10 +44,11 @@ def fuse_conv(conv, norm):
     """BatchNorm folding, reference nn.py:8-25: W' = diag(g / sqrt(var + eps)) W, b' = g (b - mean) / sqrt(var + eps) + beta."""
     out = torch.nn.Conv2d(conv.in_channels, conv.out_channels, conv.kernel_size, conv.stride, conv.padding,
                           groups=conv.groups, bias=True).requires_grad_(False).to(conv.weight.device)
-    scale = norm.weight / torch.sqrt(norm.running_var + norm.eps)
-    out.weight.copy_(conv.weight * scale.view(-1, 1, 1, 1))
-    bias = conv.bias if conv.bias is not None else torch.zeros_like(norm.running_mean)
-    out.bias.copy_(scale * (bias - norm.running_mean) + norm.bias)
+    with torch.no_grad():
+        scale = norm.weight / torch.sqrt(norm.running_var + norm.eps)
+        out.weight.copy_(conv.weight * scale.view(-1, 1, 1, 1))
+        bias = conv.bias if conv.bias is not None else torch.zeros_like(norm.running_mean)
+        out.bias.copy_(scale * (bias - norm.running_mean) + norm.bias)
     return out
 
 
@@ -270,7 +271,13 @@ class YOLO(torch.nn.Module):
     def forward(self, x):
         if self.training:
             return self.head(list(self.fpn(self.net(x))))
-        return self._engine_for(x).forward(x)
+        eng = self._engine_for(x)
+        self._set_head_anchors(eng, x.device)
+        # a fresh tensor per call, like the reference (two live predictions never alias); the Engine /
+        # StreamingDetector API keeps static buffers for callers that want them
+        if eng.graph:
+            return eng.forward_static(x)
+        return eng.forward(x, out=torch.empty_like(eng.out))
 
     def fuse(self):
         for m in self.modules():
@@ -281,22 +288,42 @@ class YOLO(torch.nn.Module):
         return self
 
     # ---- B200 engine management ------------------------------------------------------------
+    MAX_ENGINES = 4          # cached plans (+ multi-GB workspaces) per model; least recently used is dropped
+
     def forward_raw(self, x):
         """Pre-decode head logits (B, A, 64+nc) fp32 computed by the CUDA engine."""
         return self._engine_for(x).forward_raw(x)
 
     def invalidate_engine(self):
+        """Drop every cached engine (packed weights, plans, workspaces).  Called automatically by fuse(),
+        .to()/.half()/.float() on the model and load_state_dict(); call it by hand after writing weights
+        through `.data` IN PLACE (`p.data.copy_(w)`, `bias.data[:] = v`): such writes leave no trace
+        (`.data` has its own version counter) and the engine would keep serving the packed copy."""
         self.__dict__["_yb_engines"] = {}
-        self.__dict__.pop("_yb_tensors", None)
+        self.__dict__.pop("_yb_slots", None)
 
     def _weights_version(self):
-        # in-place updates (load_state_dict, optimizer steps) bump Tensor._version; module surgery
-        # (fuse, .to(), .half()) goes through invalidate_engine
-        tensors = self.__dict__.get("_yb_tensors")
-        if tensors is None:
-            tensors = list(self.state_dict(keep_vars=True).values())
-            self.__dict__["_yb_tensors"] = tensors
-        return sum(t._version for t in tensors)
+        """Fingerprint of the tensors the engine packed: (data_ptr, _version) of every parameter and buffer,
+        plus the identity of the tensor each module slot currently holds.  Catches in-place updates of the
+        parameters themselves (optimizer steps, `load_state_dict`), re-assignment (`p.data = w`,
+        `load_state_dict(assign=True)` on a submodule) and dtype/device moves of submodules (`.half()` swaps
+        the storage).  Not caught: in-place writes through `.data` and replacing whole modules by hand -
+        call invalidate_engine() after those."""
+        slots = self.__dict__.get("_yb_slots")
+        if slots is None:
+            slots = []
+            for m in self.modules():
+                slots += [(m._parameters, k, m._parameters[k]) for k in m._parameters if m._parameters[k] is not None]
+                slots += [(m._buffers, k, m._buffers[k]) for k in m._buffers if m._buffers[k] is not None]
+            self.__dict__["_yb_slots"] = slots
+        h = 0
+        for d, k, t in slots:
+            if d[k] is not t:           # the slot holds another tensor now: rebuild the list, force a re-pack
+                self.__dict__.pop("_yb_slots", None)
+                self.__dict__["_yb_epoch"] = self.__dict__.get("_yb_epoch", 0) + 1
+                return self._weights_version()
+            h += t.data_ptr() + t._version
+        return h + (self.__dict__.get("_yb_epoch", 0) << 56)
 
     def _engine_for(self, x):
         if not (isinstance(x, torch.Tensor) and x.is_cuda):
@@ -307,18 +334,57 @@ class YOLO(torch.nn.Module):
             raise RuntimeError(f"expected a (B,3,H,W) image tensor, got {tuple(x.shape)}")
         Engine = _engine_class()
         engines = self.__dict__.setdefault("_yb_engines", {})
-        key = (x.device.index, x.shape[0], x.shape[2], x.shape[3])
+        key = (x.device.index, x.shape[0], x.shape[2], x.shape[3], self.__dict__.get("_yb_act_dtype"))
         version = self._weights_version()
         entry = engines.get(key)
         if entry is None or entry[1] != version:
             width, depth, csp, nc = self._arch
             eng = entry[0] if entry is not None else Engine(width, depth, csp, nc, x.shape[0], x.shape[2],
-                                                           x.shape[3], x.device)
+                                                           x.shape[3], x.device,
+                                                           act_dtype=self.__dict__.get("_yb_act_dtype"))
             eng.pack_from_model(self)
             if entry is None and x.shape[0] <= 8:
                 eng.use_graph(True)  # small batches are launch-bound: replay one CUDA graph
+            engines.pop(key, None)
             engines[key] = entry = (eng, version)
+            while len(engines) > self.MAX_ENGINES:   # variable shapes must not grow memory without bound
+                engines.pop(next(iter(engines)))
+        elif next(reversed(engines)) != key:
+            engines[key] = engines.pop(key)          # most recently used last
         return entry[0]
+
+    def set_activation_dtype(self, dtype):
+        """Storage type of the engine's activations and packed weights: torch.float16 (default; what the
+        reference's own evaluation runs in, main.py:251,266) or torch.bfloat16.  Accumulation, bias, SiLU,
+        DFL decode and sigmoid are fp32 either way."""
+        if dtype not in (torch.float16, torch.bfloat16, None):
+            raise ValueError("activation dtype must be torch.float16 or torch.bfloat16")
+        self.__dict__["_yb_act_dtype"] = dtype
+        return self
+
+    def _set_head_anchors(self, eng, device):
+        """`head.anchors` / `head.strides` as the reference's eval forward leaves them (nn.py:261; (2, A) and
+        (1, A)); the CUDA decode computes them from the anchor index, so they are built once per shape here."""
+        key = (eng.height, eng.width, device)
+        cache = self.__dict__.setdefault("_yb_anchor_cache", {})
+        if key not in cache:
+            if len(cache) > 8:
+                cache.clear()
+            pts, scl = [], []
+            for s in (8, 16, 32):
+                h, w = eng.height // s, eng.width // s
+                ys = torch.arange(h, device=device, dtype=torch.float32) + 0.5
+                xs = torch.arange(w, device=device, dtype=torch.float32) + 0.5
+                gy, gx = torch.meshgrid(ys, xs, indexing="ij")
+                pts.append(torch.stack((gx, gy), -1).view(-1, 2))
+                scl.append(torch.full((h * w, 1), float(s), device=device))
+            cache[key] = (torch.cat(pts).transpose(0, 1), torch.cat(scl).transpose(0, 1))
+        self.head.anchors, self.head.strides = cache[key]
+
+    def load_state_dict(self, *args, **kwargs):
+        out = super().load_state_dict(*args, **kwargs)
+        self.invalidate_engine()
+        return out
 
     def _apply(self, fn, *args, **kwargs):
         self.invalidate_engine()
@@ -326,8 +392,8 @@ class YOLO(torch.nn.Module):
 
     def __getstate__(self):
         state = self.__dict__.copy()
-        state.pop("_yb_engines", None)
-        state.pop("_yb_tensors", None)
+        for k in ("_yb_engines", "_yb_slots", "_yb_anchor_cache"):
+            state.pop(k, None)
         return state
 
     def __setstate__(self, state):
@@ -337,8 +403,8 @@ class YOLO(torch.nn.Module):
         self.__dict__.update(state)
         if "_arch" not in self.__dict__:
             self.__dict__["_arch"] = self._infer_arch()
-        self.__dict__.pop("_yb_engines", None)
-        self.__dict__.pop("_yb_tensors", None)
+        for k in ("_yb_engines", "_yb_slots", "_yb_anchor_cache"):
+            self.__dict__.pop(k, None)
 
     def _infer_arch(self):
         """(width, depth, csp, num_classes) of the constructor call (nn.py:308-347) from the modules."""
@@ -357,7 +423,7 @@ class YOLO(torch.nn.Module):
         new = cls.__new__(cls)
         memo[id(self)] = new
         for k, v in self.__dict__.items():
-            if k in ("_yb_engines", "_yb_tensors"):
+            if k in ("_yb_engines", "_yb_slots", "_yb_anchor_cache"):
                 continue
             new.__dict__[k] = copy.deepcopy(v, memo)
         return new

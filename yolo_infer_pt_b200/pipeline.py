@@ -45,9 +45,11 @@ class StreamingDetector:
         self.nms_ws = None
         self.h2d_bytes = 0 if resident else self.inputs[0].numel() * self.inputs[0].element_size()
         b = batch_shape[0]
-        # pinned host landing buffers for the detections (two slots; a result stays valid for two steps)
-        self.det_host = [torch.empty(b, util.MAX_DET, 6, dtype=torch.float32).pin_memory() for _ in range(2)]
-        self.cnt_host = [torch.empty(b, dtype=torch.int32).pin_memory() for _ in range(2)]
+        # pinned host landing buffers for the detections: three slots, because the D2H copy of batch i+2 is
+        # enqueued before result i+1 is handed out - a yielded result therefore stays valid until the consumer
+        # has asked for the NEXT one (hold two results at most; clone to keep more, e.g. list(pipe.run(...)))
+        self.det_host = [torch.empty(b, util.MAX_DET, 6, dtype=torch.float32).pin_memory() for _ in range(3)]
+        self.cnt_host = [torch.empty(b, dtype=torch.int32).pin_memory() for _ in range(3)]
 
     def _upload(self, index, batch):
         islot = index % self.n_in
@@ -84,7 +86,7 @@ class StreamingDetector:
                 det, counts = util.nms_padded(y, self.conf, self.iou)
             self.nms_done[slot].record(self.nms_stream)
         # detections go back on their own stream: no kernel queues behind the copy
-        det_h, cnt_h = self.det_host[slot], self.cnt_host[slot]
+        det_h, cnt_h = self.det_host[index % 3], self.cnt_host[index % 3]
         with torch.cuda.stream(self.d2h_stream):
             self.d2h_stream.wait_event(self.nms_done[slot])
             det.record_stream(self.d2h_stream)
@@ -96,8 +98,10 @@ class StreamingDetector:
         return det_h, cnt_h, done
 
     def run(self, batches):
-        """Generator over batches -> (det, counts) host tensors, in order.  The H2D copy of the next batch and
-        the NMS of the previous one are in flight while the current batch's forward runs."""
+        """Generator over batches -> (det, counts) pinned host tensors, in order.  The H2D copy of the next batch
+        and the NMS of the previous one are in flight while the current batch's forward runs.  A yielded pair is
+        a view of a landing buffer that is reused three batches later: it is valid while the consumer holds at
+        most the current and the previous result; clone what must live longer."""
         it = iter(batches)
         ahead = []                 # indices uploaded (or uploading) and not yet run
         state = {"next": 0, "more": True}

@@ -29,20 +29,44 @@ def _variant_name(model):
     return table.get((width[0], width[1], depth))
 
 
-def synth_state_dict(model, seed=0, recipe="calibrated", calibrated=True):
+WIDEHEAD_TAIL = 64.0      # survey_widehead: factor on the weights of the six head tail convs
+WIDEHEAD_CLS_BIAS = -5.0  # survey_widehead: centre of the class-tail biases
+
+
+def synth_state_dict(model, seed=0, recipe="calibrated", calibrated=True, gain=None, bn_gain=1.0, tail=None):
     """Seeded weights for `model` (reference or product YOLO, same state_dict keys).
 
     recipe="survey"      SURVEY.md §8(d) `synth_weights`: torch-default conv init range
                          U(+-1/sqrt(fan_in)), arbitrary BatchNorm statistics.  Activations shrink
-                         with depth, so round-off is barely amplified: this is the recipe the
-                         0.5 px / 1e-2 tolerance of the north star was probed on.
+                         with depth, so round-off is barely amplified - but the head is nearly constant
+                         (every score < 0.003): a parity gate on it cannot fail.
+    recipe="survey_widehead"  the same backbone with the six head tail convs (head.box.*.2, head.cls.*.4)
+                         scaled by WIDEHEAD_TAIL and the class-tail biases centred on WIDEHEAD_CLS_BIAS:
+                         class scores spread over (0, 1) (> 5 % inside (0.1, 0.9)), DFL distributions
+                         vary by side and level, and 16-bit round-off arriving at the head is amplified
+                         64x - the recipe of the falsifiable tolerance gate (tests/test_gpu_parity.py).
     recipe="calibrated"  variance-preserving conv init and BatchNorm running statistics taken from
                          tests/golden/synth_bn_<size>_seed<seed>.npz (per-channel batch statistics
                          recorded by tests/golden/make_synth_bn.py, stored as fp16 so every machine
                          loads identical values).  Every layer keeps unit scale and spatial
                          structure — the recipe for layer-level parity (a tap-order or slice bug is
-                         invisible on a collapsed network) and a round-off stress test.
+                         invisible on a collapsed network).  At bn_gain = 1 the network is chaotic (a
+                         1-ulp input perturbation moves the fp32 oracle's boxes by hundreds of pixels).
+    gain      conv init bound = gain / sqrt(fan_in) (default 1 for survey, sqrt(3) for calibrated)
+    bn_gain   factor on every BatchNorm weight: < 1 damps the calibrated network below the edge of chaos
+    tail      factor on the head tail weights (default WIDEHEAD_TAIL for survey_widehead, else 1)
     """
+    wide = recipe == "survey_widehead"
+    if wide:
+        recipe = "survey"
+    if recipe == "calibrated_damped":
+        # calibrated network pulled below the edge of chaos (BatchNorm weights x0.8: a 1-ulp input perturbation
+        # moves the fp32 oracle by < 0.5 px instead of hundreds) with the head tails x30: spatially structured
+        # scores and boxes - the recipe of the detection-level end-to-end test
+        recipe, bn_gain = "calibrated", 0.8 if bn_gain == 1.0 else bn_gain
+        tail = 30.0 if tail is None else tail
+    if tail is None:
+        tail = WIDEHEAD_TAIL if wide else 1.0
     rng = np.random.RandomState(seed)
     out = {}
     bn = None
@@ -68,13 +92,13 @@ def synth_state_dict(model, seed=0, recipe="calibrated", calibrated=True):
             val = rng.normal(0.0, 0.1, shape)
         elif key.endswith(".weight"):  # conv weight OIHW, variance preserving: std = 1/sqrt(fan_in)
             fan_in = int(np.prod(shape[1:]))
-            bound = np.sqrt((1.0 if survey else 3.0) / fan_in)
+            bound = (gain if gain is not None else (1.0 if survey else np.sqrt(3.0))) / np.sqrt(fan_in)
             val = rng.uniform(-bound, bound, shape)
         elif key.endswith(".bias"):
             if key.startswith("head.box."):
                 val = np.full(shape, 1.0)
             elif key.startswith("head.cls."):
-                val = (np.full(shape, -9.0) + rng.normal(0.0, 1.0, shape)) if survey else \
+                val = (np.full(shape, WIDEHEAD_CLS_BIAS if wide else -9.0) + rng.normal(0.0, 1.0, shape)) if survey else \
                     (np.full(shape, CLS_BIAS) + rng.normal(0.0, 0.5, shape))
             else:
                 val = rng.normal(0.0, 0.1, shape)
@@ -82,12 +106,18 @@ def synth_state_dict(model, seed=0, recipe="calibrated", calibrated=True):
             raise KeyError(key)
         if bn is not None and key in bn.files:
             val = bn[key].astype(np.float32)
+        if key.endswith("norm.weight"):
+            val = np.asarray(val) * bn_gain
+        if tail != 1.0 and key.endswith(".weight") and (
+                (key.startswith("head.box.") and key.split(".")[3] == "2") or
+                (key.startswith("head.cls.") and key.split(".")[3] == "4")):
+            val = np.asarray(val) * tail
         out[key] = torch.from_numpy(np.asarray(val)).to(ref.dtype)
     return out
 
 
-def load_synth(model, seed=0, recipe="calibrated"):
-    model.load_state_dict(synth_state_dict(model, seed, recipe))
+def load_synth(model, seed=0, recipe="calibrated", **kw):
+    model.load_state_dict(synth_state_dict(model, seed, recipe, **kw))
     return model
 
 

@@ -36,11 +36,14 @@ def letterbox_batch(images, input_size, out=None, stream=None):
         keep.append(im)
         rows.append((im.data_ptr(), im.shape[0], im.shape[1]))
     B, S = len(rows), int(input_size)
-    desc = torch.tensor(rows, dtype=torch.int64).pin_memory().to(dev, non_blocking=True)
-    if out is None:
-        out = torch.empty((B, 3, S, S), dtype=torch.uint8, device=dev)
-    meta = torch.empty((B, 3), dtype=torch.float64, device=dev)
     st = stream if stream is not None else torch.cuda.current_stream(dev)
+    # the descriptor upload and the kernel that reads it are ordered on the SAME stream (`stream=` may differ
+    # from the current one)
+    with torch.cuda.stream(st):
+        desc = torch.tensor(rows, dtype=torch.int64).pin_memory().to(dev, non_blocking=True)
+        if out is None:
+            out = torch.empty((B, 3, S, S), dtype=torch.uint8, device=dev)
+        meta = torch.empty((B, 3), dtype=torch.float64, device=dev)
     L = _lib.lib()
     with torch.cuda.device(dev):
         _lib.check(L.yb_letterbox(ctypes.c_void_p(desc.data_ptr()), B, S, ctypes.c_void_p(out.data_ptr()),

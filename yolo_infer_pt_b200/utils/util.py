@@ -101,9 +101,12 @@ def nms_padded(outputs, confidence_threshold=0.001, iou_threshold=0.65, max_det=
                          "the same confidence threshold and max_nms")
     stream = torch.cuda.current_stream(dev).cuda_stream
     fn = L.yb_nms_prefiltered if prefiltered else L.yb_nms_clean
-    _lib.check(fn(pred.data_ptr(), B, nc, A, conf32, float(iou_threshold), max_det, max_nms,
-                  float(max_wh), det.data_ptr(), counts.data_ptr(), ws.data_ptr(), ws.numel(),
-                  ctypes.c_void_p(stream)), "yb_nms")
+    with torch.cuda.device(dev):
+        _lib.check(fn(pred.data_ptr(), B, nc, A, conf32, float(iou_threshold), max_det, max_nms,
+                      float(max_wh), det.data_ptr(), counts.data_ptr(), ws.data_ptr(), ws.numel(),
+                      ctypes.c_void_p(stream)), "yb_nms")
+    if prefiltered:
+        ws._yb_sink_pending = False     # consumed: the per-image kernel left the headers zeroed
     return det, counts
 
 
