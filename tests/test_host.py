@@ -286,3 +286,81 @@ def test_widehead_recipe_spreads_scores_and_boxes():
     ref = torch.from_numpy(g["out_sub"])
     sub = y[:, :, torch.from_numpy(g["idx"])]
     assert (sub[:, :4] - ref[:, :4]).abs().max() < 2e-2 and (sub[:, 4:] - ref[:, 4:]).abs().max() < 1e-5
+
+
+def _to_ultralytics_keys(model):
+    """Inverse of util.ultralytics_key, written independently from the Ultralytics module layout (yolo11.yaml +
+    ultralytics/nn/modules: Conv{conv,bn}, C3k2{cv1,cv2,m}, C3k{cv1,cv2,cv3,m}, Bottleneck{cv1,cv2}, SPPF{cv1,cv2},
+    C2PSA{cv1,cv2,m[PSABlock{attn{qkv,proj,pe},ffn}]}, Detect{cv2,cv3,dfl})."""
+    layer = {"net.p1.0": 0, "net.p2.0": 1, "net.p2.1": 2, "net.p3.0": 3, "net.p3.1": 4, "net.p4.0": 5, "net.p4.1": 6,
+             "net.p5.0": 7, "net.p5.1": 8, "net.p5.2": 9, "net.p5.3": 10, "fpn.h1": 13, "fpn.h2": 16, "fpn.h3": 17,
+             "fpn.h4": 19, "fpn.h5": 20, "fpn.h6": 22}
+    out = {}
+    for key in model.state_dict():
+        p = key.split(".")
+        if p[0] == "head":
+            if p[1] == "dfl":
+                u = "model.23." + ".".join(p[1:])
+            elif p[1] == "box":
+                u = f"model.23.cv2.{p[2]}.{p[3]}." + ".".join(p[4:]).replace("norm", "bn")
+            else:
+                j = int(p[3])
+                u = (f"model.23.cv3.{p[2]}.2." + ".".join(p[4:])) if j == 4 else \
+                    (f"model.23.cv3.{p[2]}.{j // 2}.{j % 2}." + ".".join(p[4:]).replace("norm", "bn"))
+        else:
+            pre = ".".join(p[:3]) if p[0] == "net" else ".".join(p[:2])
+            rest = p[3:] if p[0] == "net" else p[2:]
+            if pre == "net.p5.3" and rest[0] == "res_m":      # PSABlock
+                blk, sub = rest[1], rest[2:]
+                if sub[0] == "conv1":
+                    name = {"qkv": "qkv", "conv2": "proj", "conv1": "pe"}[sub[1]]
+                    r = ["m", blk, "attn", name] + sub[2:]
+                else:
+                    r = ["m", blk, "ffn"] + sub[1:]
+            else:
+                r = [{"conv1": "cv1", "conv2": "cv2", "conv3": "cv3", "res_m": "m"}.get(t, t) for t in rest]
+            u = f"model.{layer[pre]}." + ".".join("bn" if t == "norm" else t for t in r)
+        out[u] = key
+    return out
+
+
+@pytest.mark.parametrize("size", ["n", "s", "m", "x"])
+def test_ultralytics_key_map_hits_every_key(size):
+    """Corrected Ultralytics -> nets.nn key map (reference util.py:358-516 drops the head, the nested C3k blocks,
+    C2PSA and most BatchNorm statistics): every tensor of the model is reached exactly once, for every size."""
+    model = getattr(nn, f"yolo_v11_{size}")(80)
+    inv = _to_ultralytics_keys(model)
+    assert len(inv) == len(model.state_dict()) and (size != "n" or len(inv) == 499)
+    mapped = {u: util.ultralytics_key(u) for u in inv}
+    assert mapped == inv
+    # names as they appear in a real yolo11n.pt, with the shapes its tensors have
+    if size == "n":
+        sd = model.state_dict()
+        known = {"model.0.conv.weight": ("net.p1.0.conv.weight", (16, 3, 3, 3)),
+                 "model.2.m.0.cv1.conv.weight": ("net.p2.1.res_m.0.conv1.conv.weight", (8, 16, 3, 3)),
+                 "model.6.m.0.m.1.cv2.bn.running_var": ("net.p4.1.res_m.0.res_m.1.conv2.norm.running_var", (32,)),
+                 "model.9.cv2.conv.weight": ("net.p5.2.conv2.conv.weight", (256, 512, 1, 1)),
+                 "model.10.m.0.attn.qkv.conv.weight": ("net.p5.3.res_m.0.conv1.qkv.conv.weight", (256, 128, 1, 1)),
+                 "model.10.m.0.attn.pe.conv.weight": ("net.p5.3.res_m.0.conv1.conv1.conv.weight", (128, 1, 3, 3)),
+                 "model.10.m.0.attn.proj.bn.bias": ("net.p5.3.res_m.0.conv1.conv2.norm.bias", (128,)),
+                 "model.10.m.0.ffn.1.conv.weight": ("net.p5.3.res_m.0.conv2.1.conv.weight", (128, 256, 1, 1)),
+                 "model.22.m.0.cv3.conv.weight": ("fpn.h6.res_m.0.conv3.conv.weight", (128, 128, 1, 1)),
+                 "model.23.cv2.0.2.weight": ("head.box.0.2.weight", (64, 64, 1, 1)),
+                 "model.23.cv2.2.0.conv.weight": ("head.box.2.0.conv.weight", (64, 256, 3, 3)),
+                 "model.23.cv3.0.0.0.conv.weight": ("head.cls.0.0.conv.weight", (64, 1, 3, 3)),
+                 "model.23.cv3.1.1.1.bn.weight": ("head.cls.1.3.norm.weight", (80,)),
+                 "model.23.cv3.2.2.bias": ("head.cls.2.4.bias", (80,)),
+                 "model.23.dfl.conv.weight": ("head.dfl.conv.weight", (1, 16, 1, 1))}
+        for u, (ours, shape) in known.items():
+            assert util.ultralytics_key(u) == ours and tuple(sd[ours].shape) == shape, u
+    # loading an Ultralytics-named state_dict reproduces the donor model exactly; a checkpoint that lacks a branch fails loudly
+    donor = getattr(nn, f"yolo_v11_{size}")(80)
+    synth.load_synth(donor, 0, "survey")
+    usd = {u: donor.state_dict()[k].clone() for u, k in inv.items()}
+    util.load_ultralytics_weight(model, {"model": usd})
+    for k, v in donor.state_dict().items():
+        assert torch.equal(model.state_dict()[k], v), k
+    broken = {u: v for u, v in usd.items() if ".cv3." not in u}
+    with pytest.raises(KeyError):
+        util.load_ultralytics_weight(getattr(nn, f"yolo_v11_{size}")(80), {"model": broken})
+    assert util.ultralytics_key("model.11.foo") is None and util.ultralytics_key("model.23.cv4.0.0") is None

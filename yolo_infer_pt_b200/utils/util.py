@@ -168,3 +168,93 @@ def load_weight(model, ckpt):
     keep = {k: v.float() for k, v in src.items() if k in dst and v.shape == dst[k].shape}
     model.load_state_dict(state_dict=keep, strict=False)
     return model
+
+
+# ---- Ultralytics checkpoint import (reference util.py:358-516, corrected) -----------------------------------
+# Ultralytics YOLO11 numbers its layers 0..23 (yolo11.yaml): 0-10 backbone (Conv, Conv, C3k2, Conv, C3k2, Conv, C3k2,
+# Conv, C3k2, SPPF, C2PSA), 11-22 neck (13/16/19/22 C3k2, 17/20 Conv; the rest are Upsample / Concat without
+# weights), 23 Detect.  The reference's table (util.py:372-475) gets three families of keys wrong and silently skips
+# them ("Skipping ... missing key"):
+#   * util.py:406-409,425-429  nested C3k bottlenecks `6.m.0.m.0.cv1` are mapped to `...res_m.0.m.0.conv1`; the module
+#     is `res_m.0.res_m.0.conv1` (nets/nn.py:52-63), and C2PSA `10.m.0.attn.qkv / proj / pe / ffn.N` are mapped to
+#     `net.p5.3.m.0.attn.*`; the modules are `net.p5.3.res_m.0.conv1.{qkv, conv2, conv1}` / `.conv2.N` (nn.py:97-148);
+#   * util.py:454-477  Detect: Ultralytics `cv2` is the BOX branch (Conv, Conv, Conv2d) and `cv3` the CLASS branch
+#     (two DWConv+Conv pairs, Conv2d); the table sends cv2 -> head.cls and cv3 -> head.box with indices that do not
+#     exist, so the whole head keeps its random initialisation;
+#   * every direct table hit skips the `.bn.` -> `.norm.` rename (only the fallback path applies it), so the
+#     BatchNorm statistics of all C3k2 / SPPF / C2PSA convs are dropped as well.
+# Here the map is derived from the structure instead of a table, for every model size.
+_ULTRA_LAYERS = {0: "net.p1.0", 1: "net.p2.0", 2: "net.p2.1", 3: "net.p3.0", 4: "net.p3.1", 5: "net.p4.0", 6: "net.p4.1",
+                 7: "net.p5.0", 8: "net.p5.1", 9: "net.p5.2", 10: "net.p5.3", 13: "fpn.h1", 16: "fpn.h2", 17: "fpn.h3",
+                 19: "fpn.h4", 20: "fpn.h5", 22: "fpn.h6"}
+_ULTRA_TOKENS = {"cv1": "conv1", "cv2": "conv2", "cv3": "conv3", "m": "res_m", "bn": "norm"}
+_ULTRA_ATTN = {"qkv": "qkv", "proj": "conv2", "pe": "conv1"}
+
+
+def ultralytics_key(key):
+    """Ultralytics YOLO11 state_dict key ('model.6.m.0.m.1.cv2.bn.weight') -> this package's / the reference's key
+    ('net.p4.1.res_m.0.res_m.1.conv2.norm.weight'), or None for keys that have no counterpart."""
+    parts = key.split(".")
+    if parts[0] == "model":
+        parts = parts[1:]
+    if len(parts) < 2 or not parts[0].isdigit():
+        return None
+    idx, rest = int(parts[0]), parts[1:]
+    if idx == 23:                                            # Detect
+        if rest[0] == "dfl":
+            return "head." + ".".join(rest)
+        if rest[0] == "cv2" and len(rest) >= 4:              # box branch: Conv, Conv, Conv2d
+            lvl, j, tail = rest[1], int(rest[2]), rest[3:]
+            return f"head.box.{lvl}.{j}." + ".".join("norm" if t == "bn" else t for t in tail)
+        if rest[0] == "cv3" and len(rest) >= 4:              # class branch: (DWConv, Conv), (DWConv, Conv), Conv2d
+            lvl, a = rest[1], int(rest[2])
+            if a == 2:
+                return f"head.cls.{lvl}.4." + ".".join(rest[3:])
+            if len(rest) < 5:
+                return None
+            return f"head.cls.{lvl}.{2 * a + int(rest[3])}." + ".".join("norm" if t == "bn" else t for t in rest[4:])
+        return None
+    if idx not in _ULTRA_LAYERS:
+        return None
+    out, i = [_ULTRA_LAYERS[idx]], 0
+    while i < len(rest):
+        t = rest[i]
+        if t == "attn" and i + 1 < len(rest):                # PSABlock.attn.{qkv,proj,pe} -> conv1.{qkv,conv2,conv1}
+            out += ["conv1", _ULTRA_ATTN.get(rest[i + 1], rest[i + 1])]
+            i += 2
+        elif t == "ffn":                                     # PSABlock.ffn.N -> conv2.N
+            out.append("conv2")
+            i += 1
+        else:
+            out.append(_ULTRA_TOKENS.get(t, t))
+            i += 1
+    return ".".join(out)
+
+
+def load_ultralytics_weight(model, ckpt, strict=True, verbose=False):
+    """Reference util.py:358-516 with the key map corrected (see above): load an Ultralytics-format YOLO11
+    checkpoint (`yolo11n.pt`: {'model': DetectionModel}) or a plain Ultralytics state_dict into `model`.
+    strict: raise unless every tensor of `model` was found with the right shape (the reference prints and goes on,
+    which leaves whole branches at their random initialisation)."""
+    obj = ckpt if isinstance(ckpt, dict) else torch.load(ckpt, map_location="cpu", weights_only=False)
+    src = obj["model"] if "model" in obj and not isinstance(obj["model"], torch.Tensor) else obj
+    src = src.float().state_dict() if isinstance(src, torch.nn.Module) else src
+    dst = model.state_dict()
+    new, skipped = {}, []
+    for k, v in src.items():
+        dk = ultralytics_key(k)
+        if dk is None and k in dst:
+            dk = k
+        if dk in dst and tuple(v.shape) == tuple(dst[dk].shape):
+            new[dk] = v.to(dst[dk].dtype) if v.is_floating_point() else v
+        else:
+            skipped.append((k, dk))
+    missing = [k for k in dst if k not in new]
+    if verbose:
+        for k, dk in skipped:
+            print(f"load_ultralytics_weight: skipped {k} -> {dk}")
+    if strict and missing:
+        raise KeyError(f"load_ultralytics_weight: {len(missing)} tensors of the model were not found in the checkpoint "
+                       f"(first: {missing[:4]}); {len(skipped)} checkpoint tensors had no target (first: {skipped[:4]})")
+    model.load_state_dict(new, strict=False)
+    return model
