@@ -364,3 +364,34 @@ def test_ultralytics_key_map_hits_every_key(size):
     with pytest.raises(KeyError):
         util.load_ultralytics_weight(getattr(nn, f"yolo_v11_{size}")(80), {"model": broken})
     assert util.ultralytics_key("model.11.foo") is None and util.ultralytics_key("model.23.cv4.0.0") is None
+
+
+@pytest.mark.parametrize("size,batch,hw", [("n", 256, 640), ("n", 2, 64), ("s", 3, 320), ("x", 8, 640), ("m", 1, 1280)])
+def test_arena_never_overlaps_live_buffers(size, batch, hw):
+    """Lifetime-based arena reuse: two buffers whose lifetimes intersect never share memory.  Lifetimes are
+    recomputed here from the op list, INCLUDING the reads a fused kernel makes on behalf of an op that is no
+    longer launched (a 1x1 conv with the depthwise conv in front fused in reads that conv's input: round 1
+    placed the 1x1's own output on top of it, a cross-CTA race that showed as rare 1-ulp score differences
+    between identical images of a batch)."""
+    m = getattr(nn, f"yolo_v11_{size}")(80)
+    d = Engine(*m._arch, batch, hw, hw, host_only=True).describe()
+    ops, bufs = d["ops"], d["bufs"]
+    live = {}
+    for i, op in enumerate(ops):
+        used = [s["buf"] for s in op["src"]] + [op["dst"]["buf"]] + ([op["res"]["buf"]] if op["has_res"] else [])
+        if op.get("dw_fused"):
+            assert ops[i - 1]["fused_away"]
+            used += [s["buf"] for s in ops[i - 1]["src"]]
+        for b in used:
+            if b >= 0:
+                lo, hi = live.get(b, (10 ** 9, -1))
+                live[b] = (min(lo, i), max(hi, i))
+    assert any(op.get("dw_fused") for op in ops) or hw < 160 or size == "x"   # (x: 384-channel class branch is not fused)
+    ids = sorted(live)
+    for a in ids:
+        for b in ids:
+            if a < b and not (live[a][1] < live[b][0] or live[b][1] < live[a][0]):
+                A, Bb = bufs[a], bufs[b]
+                assert not (A["offset"] < Bb["offset"] + Bb["bytes"] and Bb["offset"] < A["offset"] + A["bytes"]), \
+                    f"{A['tag']} {live[a]} and {Bb['tag']} {live[b]} overlap in the arena"
+        assert bufs[a]["offset"] + bufs[a]["bytes"] <= d["workspace_bytes"]

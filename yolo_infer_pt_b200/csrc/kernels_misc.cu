@@ -384,15 +384,39 @@ __global__ void __launch_bounds__(256, MINB)
       const int vx = i % NV8, row = i / NV8;
       if (row >= 3 * STEM_IH) break;
       const uint32_t w[4] = {pv[it].x, pv[it].y, pv[it].z, pv[it].w};
+      // input column gx0 + 16 vx + j is patch column r = 16 vx + j + 1 (r = 2x + kx)
+      uint4 p0, p1, p2;
+      if constexpr (F16) {
+        // bytes -> fp16 without integer conversions: 0x6400 | b is the fp16 number 1024 + b, and
+        // (1024 + b) * 2^-8 - 4 = b / 256 exactly; one PRMT builds a pair, one HFMA2 rescales it
+        const uint32_t sc = 0x1C001C00u, off = 0xC400C400u;   // half2(2^-8), half2(-4.0)
+        uint32_t ev[4], od[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          uint32_t a, b;
+          asm("prmt.b32 %0, %1, %2, 0x7270;" : "=r"(a) : "r"(w[k]), "r"(0x64646464u));   // pixels 4k, 4k+2
+          asm("prmt.b32 %0, %1, %2, 0x7371;" : "=r"(b) : "r"(w[k]), "r"(0x64646464u));   // pixels 4k+1, 4k+3
+          asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(ev[k]) : "r"(a), "r"(sc), "r"(off));
+          asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(od[k]) : "r"(b), "r"(sc), "r"(off));
+        }
+        uint32_t hp;
+        asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(hp) : "r"(0x64006400u | pb[it]), "r"(sc), "r"(off));
+        uint32_t sh[4];   // odd pixels shifted by one: (prev, 1), (3, 5), (7, 9), (11, 13)
+        asm("prmt.b32 %0, %1, %2, 0x5410;" : "=r"(sh[0]) : "r"(hp), "r"(od[0]));
+#pragma unroll
+        for (int k = 1; k < 4; k++) asm("prmt.b32 %0, %1, %2, 0x5432;" : "=r"(sh[k]) : "r"(od[k - 1]), "r"(od[k]));
+        p0 = make_uint4(sh[0], sh[1], sh[2], sh[3]);
+        p1 = make_uint4(ev[0], ev[1], ev[2], ev[3]);
+        p2 = make_uint4(od[0], od[1], od[2], od[3]);
+      } else {
       float f[16];
 #pragma unroll
       for (int j = 0; j < 16; j++) f[j] = (float)((w[j >> 2] >> (8 * (j & 3))) & 0xFFu) * PXS;
       const float fp = (float)pb[it] * PXS;
-      // input column gx0 + 16 vx + j is patch column r = 16 vx + j + 1 (r = 2x + kx)
-      uint4 p0, p1, p2;
       p1 = make_uint4(A16::pack2(f[0], f[2]), A16::pack2(f[4], f[6]), A16::pack2(f[8], f[10]), A16::pack2(f[12], f[14]));
       p2 = make_uint4(A16::pack2(f[1], f[3]), A16::pack2(f[5], f[7]), A16::pack2(f[9], f[11]), A16::pack2(f[13], f[15]));
       p0 = make_uint4(A16::pack2(fp, f[1]), A16::pack2(f[3], f[5]), A16::pack2(f[7], f[9]), A16::pack2(f[11], f[13]));
+      }
       uint8_t* dst = stem_smem + row * STEM_PWB + vx * 16;
       *reinterpret_cast<uint4*>(dst) = p0;
       *reinterpret_cast<uint4*>(dst + STEM_PLANE_B) = p1;

@@ -440,6 +440,10 @@ int build_plan(yb_plan* p) {
       c.dw_fused = 1;
       c.dw_op = (int)i;
       d.fused_away = 1;
+      // the consumer's kernel now reads the depthwise conv's INPUT: keep that buffer alive through op i + 1,
+      // or the arena may place the consumer's own output (first defined at i + 1) on top of it
+      Buf& in = p->bufs[d.src[0].buf];
+      in.last_use = std::max(in.last_use, (int)i + 1);
     }
   }
   if (getenv("YB_NO_FUSE_DECODE")) p->fuse_decode = 0;
