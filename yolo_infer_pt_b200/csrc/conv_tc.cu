@@ -51,7 +51,7 @@ static constexpr int BK = 64;
 static constexpr int A_STAGE_BYTES = BM * BK * 2;  // 16 KB
 static constexpr int MAX_STAGES = 12;
 static constexpr int C_GROUP_BYTES = BM * 128;    // 128 rows x 64 bf16 output staging sub-tile
-static constexpr int MAX_PATCH_STAGES = 4;
+static constexpr int MAX_PATCH_STAGES = 6;
 static constexpr int NUM_BARS = 3 * MAX_STAGES + 4 + 2 * MAX_PATCH_STAGES;
 static constexpr int PT_H = 16, PT_W = 8;          // PATCH mode output tile (pixels)
 static constexpr int PP_H = PT_H + 2, PP_W = PT_W + 2;  // its input halo patch
@@ -105,6 +105,7 @@ struct ConvParams {
   const float* dw_w;    // [9][dw_cp] fp32 taps + [dw_cp] bias
   int dw_C, dw_cp, dw_act;
   int dw_patch_bytes;   // shared memory of the patch ring (the A ring follows it)
+  int wait_sleep_ns;    // sleep between polls of the off-critical-path waits (YB_WAIT_SLEEP_NS, 0 = tight try_wait)
   int dw_dbg;           // YB_DW_DBG bit 0: fp32 depthwise math, bit 1: fp32 SiLU in the epilogue (A/B switches)
   // fused head decode (out_mode 2 / 3): dst is the (B, 4+nc, A) fp32 output tensor
   int out_mode;       // 0 bf16 slice, 1 fp32 logits, 2 DFL box decode, 3 class sigmoid
@@ -169,6 +170,29 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "r"(parity)
       : "memory");
 #endif
+}
+// Wait for roles that are NOT on the critical path (epilogue warps waiting for an accumulator, the TMA / patch
+// producers waiting for a free stage): poll with test_wait and sleep between polls.  A warp parked in try_wait is
+// woken by every mbarrier event of the CTA and re-executes the check (ncu: the try_wait loop was 35 % of all warp
+// instructions of a fused-depthwise launch, issued from the same schedulers the math warps need); a sleeping
+// warp issues nothing.  `ns` bounds the extra latency; sleep_ns == 0 falls back to the tight wait.
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity, uint32_t sleep_ns) {
+  if (sleep_ns == 0) {
+    mbar_wait(bar, parity);
+    return;
+  }
+  while (true) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) break;
+    asm volatile("nanosleep.u32 %0;" ::"r"(sleep_ns));
+  }
 }
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1,
                                             uint32_t bar) {
@@ -304,33 +328,40 @@ __device__ __forceinline__ uint32_t hfma2_u32(uint32_t a, uint32_t b, uint32_t c
 // N <= 64 an MMA retires in ~48 cycles; a longer issue sequence is the bottleneck).
 // a_lo / b_lo: low descriptor words (address >> 4) of the patch and of weight slot `kb0`; bstep =
 // slot stride >> 4; first: the accumulator is overwritten by the first MMA.
-template <int CBLK, bool PAIR>
+template <int CBLK, bool PAIR, bool FULLK>
 __device__ __forceinline__ void issue_patch_steady(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
                                                    uint32_t b_hi, uint32_t bstep, uint32_t idesc, bool first,
                                                    uint32_t bn, int kvalid) {
   constexpr int ROWB = CBLK * 2;
   constexpr int PP_W = PAIR ? PP2_W : yb::PP_W;   // patch row pitch in pixels (shadows the single-tile constant)
   constexpr int NMMA = CBLK == 8 ? 5 : 9 * CBLK / 16;
+  // Low descriptor words: (shared-memory address >> 4) in bits 0-13, LBO in bits 16-29.  Every operand lies
+  // inside the CTA's shared-memory window (< 256 KB), so base + offset never carries out of the 14 address bits:
+  // one 32-bit add with a compile-time constant (offset and, for 8-channel patches, the tap-pair LBO) per MMA
+  // for A, and a running weight-slot base for B.
+  const uint32_t a0 = a_lo | (1u << 16), b0 = b_lo | (1u << 16);
+  uint32_t bslot = b0;
 #pragma unroll
   for (int i = 0; i < NMMA; i++) {
-    uint32_t a_off, lbo = 1;
+    uint32_t a_add;   // compile-time: (offset >> 4) + ((lbo - 1) << 16)
     int kslot, k;
     if (CBLK == 8) {
       const int t0 = 2 * i, t1 = i < 4 ? 2 * i + 1 : 2 * i;
       const int o0 = ((t0 / 3) * PP_W + t0 % 3) * 16, o1 = ((t1 / 3) * PP_W + t1 % 3) * 16;
-      a_off = o0;
-      lbo = i < 4 ? (uint32_t)((o1 - o0) >> 4) : 1u;
+      const uint32_t lbo = i < 4 ? (uint32_t)((o1 - o0) >> 4) : 1u;
+      a_add = (uint32_t)(o0 >> 4) + ((lbo - 1u) << 16);
       kslot = i / 4;
       k = i % 4;
     } else {
       const int kg = i * 16, tap = kg / CBLK, cin = kg % CBLK;
-      a_off = ((tap / 3) * PP_W + tap % 3) * ROWB + cin * 2;
+      a_add = (uint32_t)((((tap / 3) * PP_W + tap % 3) * ROWB + cin * 2) >> 4);
       kslot = kg / 64;
       k = (kg % 64) / 16;
-      if (CBLK == 64 && k >= kvalid) continue;   // zero-padded channels of a tap-aligned layer
     }
-    const uint64_t da = ((uint64_t)a_hi << 32) | (uint64_t)((a_lo + (a_off >> 4)) & 0x3FFFu) | ((uint64_t)lbo << 16);
-    const uint64_t db = ((uint64_t)b_hi << 32) | (uint64_t)((b_lo + (uint32_t)kslot * bstep + 2u * k) & 0x3FFFu) | (1ull << 16);
+    if (i > 0 && k == 0 && kslot > 0) bslot += bstep;       // next weight k-block (compile-time condition)
+    if (!FULLK && CBLK == 64 && k >= kvalid) continue;      // zero-padded channels of a tap-aligned layer
+    const uint64_t da = ((uint64_t)a_hi << 32) | (uint64_t)(a0 + a_add);
+    const uint64_t db = ((uint64_t)b_hi << 32) | (uint64_t)(bslot + 2u * (uint32_t)k);
     umma_bf16(d_tmem, da, db, idesc, (uint32_t)(!(first && i == 0)));
     if (PAIR)   // right half: same weights, patch shifted by 8 pixels, second accumulator
       umma_bf16(d_tmem + bn, da + (uint64_t)((PT_W * ROWB) >> 4), db, idesc, (uint32_t)(!(first && i == 0)));
@@ -527,7 +558,7 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
       res_fetch(cfirst, ra0, ra1);
       res_fetch(cfirst + cstep, rb0, rb1);
       if (half == 0) {
-      mbar_wait(tmem_full_bar(acc), (uint32_t)(ti >> 1) & 1u);
+      mbar_wait_sleep(tmem_full_bar(acc), (uint32_t)(ti >> 1) & 1u, (uint32_t)P.wait_sleep_ns);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       }
       if (half == 0 && !fast_flow && !(alt_epi && HEAD)) {
@@ -678,7 +709,9 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
       };
       // two copies of the chunk body; a kernel only ever runs one of them.  The copy without a residual
       // carries no prefetch registers and no rotation moves.
-      if (!HEAD && P.res != nullptr) {
+      if ((DW && (P.dw_dbg & 8)) || (!HEAD && (P.dw_dbg & 16))) {
+        // (ablation switch: epilogue without TMEM loads / math / staging)
+      } else if (!HEAD && P.res != nullptr) {
         for (int c0 = cfirst; c0 < BN; c0 += cstep) {
           do_chunk(c0, ra0, ra1, std::true_type{});
           ra0 = rb0;
@@ -915,7 +948,9 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
     // ============================ MMA issuer ==============================================
     // One thread runs the whole issue loop (tcgen05.mma / commit are single-thread instructions):
     // with N <= 64 an MMA retires in ~48 cycles, so every instruction on this thread's path counts.
-    if (lane == 0) {
+    // (elect.sync instead of lane == 0: the compiler then knows a single thread issues and drops the
+    // elect / retry wrapper it otherwise puts around every tcgen05.mma)
+    if (elect_one()) {
     // instruction descriptor: D fp32, A/B format 0 = fp16 / 1 = bf16, K-major both, N, M
     const uint32_t idesc = (1u << 4) | (F16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(BN >> 3) << 17) |
                            ((uint32_t)(BM >> 4) << 24);
@@ -951,10 +986,12 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
               const uint32_t b_lo = (b_base >> 4) + (uint32_t)(cb * 9) * bstep;
               const bool first = cb == 0;
               const int kvalid = min(4, (P.patch_creal - cb * 64 + 15) >> 4);
-              if (cblk == 64) issue_patch_steady<64, PAIR>(d_tmem, a_lo, a_hi, b_lo, b_hi, bstep, idesc, first, (uint32_t)BN, kvalid);
-              else if (cblk == 32) issue_patch_steady<32, PAIR>(d_tmem, a_lo, a_hi, b_lo, b_hi, bstep, idesc, first, (uint32_t)BN, kvalid);
-              else if (cblk == 16) issue_patch_steady<16, PAIR>(d_tmem, a_lo, a_hi, b_lo, b_hi, bstep, idesc, first, (uint32_t)BN, kvalid);
-              else issue_patch_steady<8, PAIR>(d_tmem, a_lo, a_hi, b_lo, b_hi, bstep, idesc, first, (uint32_t)BN, kvalid);
+              if (cblk == 64) {
+                if (kvalid >= 4) issue_patch_steady<64, PAIR, true>(d_tmem, a_lo, a_hi, b_lo, b_hi, bstep, idesc, first, (uint32_t)BN, 4);
+                else issue_patch_steady<64, PAIR, false>(d_tmem, a_lo, a_hi, b_lo, b_hi, bstep, idesc, first, (uint32_t)BN, kvalid);
+              } else if (cblk == 32) issue_patch_steady<32, PAIR, true>(d_tmem, a_lo, a_hi, b_lo, b_hi, bstep, idesc, first, (uint32_t)BN, 4);
+              else if (cblk == 16) issue_patch_steady<16, PAIR, true>(d_tmem, a_lo, a_hi, b_lo, b_hi, bstep, idesc, first, (uint32_t)BN, 4);
+              else issue_patch_steady<8, PAIR, true>(d_tmem, a_lo, a_hi, b_lo, b_hi, bstep, idesc, first, (uint32_t)BN, 4);
               umma_commit(patch_empty_bar(pstage));
               if (cb == P.ncb - 1) umma_commit(tmem_full_bar(acc));
             }
@@ -1020,17 +1057,32 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
         }
         continue;
       }
+      // Low descriptor words as running 32-bit values (address >> 4; every operand lies inside the CTA's shared
+      // memory window, so adding offsets never carries out of the 14 address bits): per k-block two adds, then
+      // four MMAs at compile-time offsets.  Only the last k-block can hold K16 steps past the real K.
+      const uint32_t dhi = (uint32_t)(desc_hi >> 32);
+      const uint32_t a_ring = (ring_base >> 4) | (1u << 16), b_ring = (b_base >> 4) | (1u << 16);
+      const uint32_t a_step = A_STAGE_BYTES >> 4, b_step = b_stage_bytes >> 4;
+      const int kv_last = k_tail_ok ? min(BK / 16, (P.K - (num_kb - 1) * BK + 15) >> 4) : BK / 16;
       for (int kb = 0; kb < num_kb; kb++) {
         mbar_wait(full_bar(stage), phase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         {
-          const uint64_t da = desc_hi | (uint64_t)(((ring_base + (uint32_t)stage * A_STAGE_BYTES) >> 4) & 0x3FFF);
-          const uint64_t db = desc_hi | (uint64_t)(((b_base + (uint32_t)(RES ? kb : stage) * b_stage_bytes) >> 4) & 0x3FFF);
-          // K16 steps past the real K (K padded to the 64-wide k-block) hold zeros: not issued
-          const int kv = k_tail_ok ? min(BK / 16, (P.K - kb * BK + 15) >> 4) : BK / 16;
+          const uint32_t da_lo = a_ring + (uint32_t)stage * a_step;
+          const uint32_t db_lo = b_ring + (uint32_t)(RES ? kb : stage) * b_step;
+          const uint64_t da = ((uint64_t)dhi << 32) | da_lo, db = ((uint64_t)dhi << 32) | db_lo;
+          if (kb == 0) {
+            umma_bf16(d_tmem, da, db, idesc, 0u);
+          } else {
+            umma_bf16(d_tmem, da, db, idesc, 1u);
+          }
+          if (kb < num_kb - 1 || kv_last == BK / 16) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; k++) {  // +32 bytes (2 x 16 B units) per K=16 step inside the swizzle atom
-            if (k < kv) umma_bf16(d_tmem, da + 2u * k, db + 2u * k, idesc, (uint32_t)((kb | k) != 0));
+            for (int k = 1; k < BK / 16; k++) umma_bf16(d_tmem, da + 2u * k, db + 2u * k, idesc, 1u);
+          } else {
+#pragma unroll
+            for (int k = 1; k < BK / 16; k++)
+              if (k < kv_last) umma_bf16(d_tmem, da + 2u * k, db + 2u * k, idesc, 1u);
           }
           umma_commit(empty_bar(stage));  // frees the smem stage once these MMAs have read it
           if (kb == num_kb - 1) umma_commit(tmem_full_bar(acc));  // accumulator complete -> epilogue
@@ -1073,7 +1125,9 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
           const uint32_t pbase = a_base + (uint32_t)pstage * (uint32_t)P.patch_stage_bytes +
                                  (uint32_t)((RPT * rq) * PP_W + 4 * xh) * 128u + (uint32_t)cpair * 4u;
           const uint32_t sbase = ring_base + (uint32_t)stage * A_STAGE_BYTES + (uint32_t)(cpair & 3) * 4u;
-          if (F16 && !(P.dw_dbg & 1)) {
+          if (P.dw_dbg & 4) {
+            // (ablation switch: no depthwise math at all)
+          } else if (F16 && !(P.dw_dbg & 1)) {
             // fp16 storage: the whole depthwise conv runs on packed halves - the loaded channel pair IS the HFMA2
             // operand (no unpack), the accumulator pair goes through one tanh.approx.f16x2 + one HFMA2 for SiLU
             // and is stored as is (no pack).  9 fp16 roundings on the accumulator instead of one on the output:
@@ -1188,7 +1242,7 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
       for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
         const TilePos tp = tile_pos<T2D, TW, TH>(P, P.n_tiles == 1 ? tile : tile / P.n_tiles);
         for (int cb = 0; cb < P.ncb; cb++) {
-          mbar_wait(patch_empty_bar(pstage), pphase ^ 1u);
+          mbar_wait_sleep(patch_empty_bar(pstage), pphase ^ 1u, (uint32_t)P.wait_sleep_ns);
           mbar_expect_tx(patch_full_bar(pstage), (uint32_t)P.patch_tx_bytes);
           tma_load_4d(a_base + (uint32_t)pstage * (uint32_t)P.patch_stage_bytes, &tmap_a0, cb * 64, tp.ox0 - 1,
                       tp.oy0 - 1, tp.n, patch_full_bar(pstage));
@@ -1247,7 +1301,7 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
           const uint32_t ph = phase;
           const bool early = tile == (int)blockIdx.x && kb < pre;   // expect_tx + weight load already issued
           if (!early) {
-            mbar_wait(empty_bar(s), ph ^ 1u);
+            mbar_wait_sleep(empty_bar(s), ph ^ 1u, (uint32_t)P.wait_sleep_ns);
             if (tx) mbar_expect_tx(full_bar(s), tx);
             else mbar_arrive(full_bar(s));   // im2col layer with resident weights: only the gather feeds this stage
           }
@@ -1480,11 +1534,18 @@ int conv_tc_prepare(yb_plan* p, Op& op) {
     if (op.dw_fused) {
       // patch ring (2 stages) + depthwise weights sit next to the usual A ring
       op.patch_stage_bytes = round_up(PP_H * PP_W * 128, 1024);
-      for (int pst = 3; pst >= 2; pst--) {
+      // measured (B200, ablations in DESIGN.md): these layers are bound by the instruction streams of the depthwise
+      // and epilogue warps, not by patch bytes in flight - more patch stages at the cost of the second output
+      // staging buffer (alternating epilogue groups) lose 30 %; three patch stages + four A stages + two staging
+      // buffers is the best split of the 227 KB
+      const int pst_max = getenv("YB_DW_PST") ? atoi(getenv("YB_DW_PST")) : 3;
+      const int st_want = getenv("YB_DW_ST") ? atoi(getenv("YB_DW_ST")) : 4;
+      for (int pst = std::min(pst_max, MAX_PATCH_STAGES); pst >= 2; pst--) {
         const size_t extra = (size_t)pst * op.patch_stage_bytes + (size_t)10 * num_kb * 64 * 4;
-        for (int st = std::min(MAX_STAGES, 4); st >= std::min(min_st, 3); st--)   // min_st 2 only as the last resort
+        for (int st = std::max(2, std::min(st_want, 4)); st >= 2; st--)
           if (conv_smem_bytes(st, op.BN, 0, resident ? num_kb : 0, cb) + extra <= bud) { st_out = st; pst_out = pst; return true; }
       }
+      (void)min_st;
       return false;
     }
     if (op.patch) {
@@ -1514,9 +1575,11 @@ int conv_tc_prepare(yb_plan* p, Op& op) {
   const Try tries[] = {
       {occ, true, 2, 4}, {occ, true, 1, 4}, {1, true, 2, 4}, {1, true, 1, 4}, {occ, false, 2, 5}, {occ, false, 1, 4},
       {occ, true, 1, 3}, {occ, false, 1, 2}};
+  const int dw_cb = getenv("YB_DW_CB") ? atoi(getenv("YB_DW_CB")) : 2;
   for (const Try& t : tries) {
     if (t.res && !res_ok) continue;
     if (t.cb == 2 && !cb2_ok) continue;
+    if (op.dw_fused && t.cb != dw_cb && cb2_ok) continue;   // (A/B switch YB_DW_CB)
     if (t.occ != occ && !op.dw_fused &&
         !(op.patch && occ > 1 && w_bytes >= 24 * 1024 && getenv("YB_NO_RESIDENT_OCC1") == nullptr))
       continue;
@@ -1736,7 +1799,7 @@ static void fill_params(const yb_plan* p, const Op& op, ConvParams& P) {
     P.dw_C = dwop.dst.C;
     P.dw_cp = cpad8(dwop.dst.C);
     P.dw_act = dwop.act;
-    P.dw_dbg = getenv("YB_DW_DBG") ? atoi(getenv("YB_DW_DBG")) : 0;
+
     P.ncb = P.num_kb;
     P.patch_tx_bytes = PP_H * PP_W * 128;
     P.patch_stage_bytes = op.patch_stage_bytes;
@@ -1754,6 +1817,11 @@ static void fill_params(const yb_plan* p, const Op& op, ConvParams& P) {
     magic(P.tiles_per_img, P.tpi_mul, P.tpi_shr);
     magic(P.tiles_x, P.tx_mul, P.tx_shr);
   }
+  {
+    static const int sleep_ns = getenv("YB_WAIT_SLEEP_NS") ? atoi(getenv("YB_WAIT_SLEEP_NS")) : 0;
+    P.wait_sleep_ns = sleep_ns;
+  }
+  P.dw_dbg = getenv("YB_DW_DBG") ? atoi(getenv("YB_DW_DBG")) : 0;
   P.out_mode = op.out_f32 ? 1 : 0;
   P.A_total = p->A;
   P.nc = p->nc;

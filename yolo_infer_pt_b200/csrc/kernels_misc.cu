@@ -543,7 +543,10 @@ static int launch_stem_t(const yb_plan* p, const Op& op, const void* in, float s
                        op.Hout, op.Wout, Cp, db.C, scale));
     return YB_OK;
   }
-  const int nt = (Cp / 8) % 3 == 0 ? 3 : ((Cp / 8) % 4 == 0 ? 4 : 2);   // n-tiles per pass
+  // n-tiles (8 channels) per pass.  A pass writes nt * 16 bytes of every pixel: 4 n-tiles = 64-byte pieces (whole
+  // sectors) wherever the channel count allows (YOLO11x: 96 channels = 3 passes of 32, not 4 passes of 24 whose
+  // 48-byte pieces straddle sectors); 3 n-tiles only when that is the whole pixel (YOLO11t: 24 channels)
+  const int nt = (Cp / 8) % 4 == 0 ? 4 : ((Cp / 8) % 3 == 0 ? 3 : 2);
   const size_t smem = (size_t)(SPLIT ? 2 : 1) * STEM_PART_B + STEM_ZERO_B + (size_t)8 * 16 * nt * 8 * 2;
   // persistent (grid = resident CTAs): the tap offsets and, with one channel group, the weight fragments
   // are set up once per CTA instead of once per tile
