@@ -91,3 +91,29 @@ def test_prefiltered_nms_rejects_mismatched_threshold_or_tensor():
         with pytest.raises(ValueError):
             util.nms_padded(y.clone(), 0.001, 0.65, workspace=ws, prefiltered=True)          # other tensor
         util.nms_padded(y, 0.001, 0.65, workspace=ws, prefiltered=True)                      # consumes (and re-zeroes) the lists
+
+
+def test_raw_frame_pipeline_letterboxes_on_the_device():
+    """StreamingDetector(raw_frames=(h, w)): HWC BGR frames in, the device-side letterbox in front of the forward;
+    detections equal those of the same frames letterboxed by utils.dataset.letterbox_batch and fed as NCHW batches."""
+    from yolo_infer_pt_b200.pipeline import StreamingDetector
+    from yolo_infer_pt_b200.utils import dataset
+    model = nn.yolo_v11_n(80)
+    synth.load_synth(model, 0, "survey")
+    model = model.fuse().eval().to("cuda:0")
+    rng = np.random.RandomState(3)
+    B, h, w, S = 3, 96, 128, 128
+    frames = [torch.from_numpy(rng.randint(0, 256, (B, h, w, 3)).astype(np.uint8)).pin_memory() for _ in range(4)]
+    raw = StreamingDetector(model, (B, 3, S, S), torch.uint8, "cuda:0", raw_frames=(h, w))
+    got = [(d.clone(), c.clone()) for d, c in raw.run(frames)]
+    boxed = []
+    for f in frames:
+        out, _ = dataset.letterbox_batch([im for im in f.to("cuda:0")], S)
+        boxed.append(out.cpu().pin_memory())
+    plain = StreamingDetector(model, (B, 3, S, S), torch.uint8, "cuda:0")
+    want = [(d.clone(), c.clone()) for d, c in plain.run(boxed)]
+    assert len(got) == len(want) == 4
+    for (d0, c0), (d1, c1) in zip(got, want):
+        assert torch.equal(c0, c1)
+        for i in range(B):
+            assert torch.equal(d0[i, :c0[i]], d1[i, :c1[i]])

@@ -395,3 +395,4 @@ def test_arena_never_overlaps_live_buffers(size, batch, hw):
                 assert not (A["offset"] < Bb["offset"] + Bb["bytes"] and Bb["offset"] < A["offset"] + A["bytes"]), \
                     f"{A['tag']} {live[a]} and {Bb['tag']} {live[b]} overlap in the arena"
         assert bufs[a]["offset"] + bufs[a]["bytes"] <= d["workspace_bytes"]
+

@@ -75,6 +75,7 @@ struct ConvParams {
   int dst_ld;         // elements
   int dst_rows_per_img, dst_row_off, hw_out;
   int cout_store;     // channels actually stored (padded to 8 for bf16, 4 for fp32)
+  uint8_t kb_kv[32];  // valid K16 steps of k-block kb (4 unless the block ends a source slice / the real K)
   int out_f32;
   const float* bias;
   const act_t* res;
@@ -572,6 +573,10 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
       const uint32_t c_buf = c_base + (((fast_flow && (ti & 1)) || (alt_epi && grp) || (PAIR && half)) ? c_groups * C_GROUP_BYTES : 0u);
       const uint32_t t_row = tmem_base + ((uint32_t)(qwarp * 32) << 16) + (uint32_t)(acc * (PAIR ? 2 * BN : BN) + half * BN);
       float dist[4];
+      // (measured: keeping the next chunk's tcgen05.ld in flight across the conversion of this one - issue after
+      // the fp32 results exist, reuse the registers - made the halo-patch and residual variants 5-10 % slower and
+      // nothing faster: the epilogue is not what these kernels wait for, and the longer live ranges cost scheduling
+      // freedom.  One load + wait per 16-column chunk it stays.)
       auto do_chunk = [&](int c0, const uint4& rv0, const uint4& rv1, auto with_res) {
         constexpr bool WITH_RES = decltype(with_res)::value;
         uint32_t v[16];
@@ -958,8 +963,6 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
                              ((uint64_t)1 << 16);
     int ti = 0, stage = 0, pstage = 0;
     uint32_t phase = 0, pphase = 0;
-    // K is one contiguous run (gathered im2col rows, or a single TMA-fed source): only its tail is padding
-    const bool k_tail_ok = MODE == MODE_GATHER || P.nseg == 1;
     for (int tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x, ti++) {
       const int acc = ti & 1;
       mbar_wait(tmem_empty_bar(acc), ((uint32_t)(ti >> 1) & 1u) ^ 1u);
@@ -1063,7 +1066,6 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
       const uint32_t dhi = (uint32_t)(desc_hi >> 32);
       const uint32_t a_ring = (ring_base >> 4) | (1u << 16), b_ring = (b_base >> 4) | (1u << 16);
       const uint32_t a_step = A_STAGE_BYTES >> 4, b_step = b_stage_bytes >> 4;
-      const int kv_last = k_tail_ok ? min(BK / 16, (P.K - (num_kb - 1) * BK + 15) >> 4) : BK / 16;
       for (int kb = 0; kb < num_kb; kb++) {
         mbar_wait(full_bar(stage), phase);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -1071,18 +1073,21 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
           const uint32_t da_lo = a_ring + (uint32_t)stage * a_step;
           const uint32_t db_lo = b_ring + (uint32_t)(RES ? kb : stage) * b_step;
           const uint64_t da = ((uint64_t)dhi << 32) | da_lo, db = ((uint64_t)dhi << 32) | db_lo;
+          // K16 steps past the end of a source slice (concat walked as separate K segments, each padded to a
+          // 64-channel block) or past the real K hold zeros: not issued
+          const int kv = kb < 32 ? (int)P.kb_kv[kb] : BK / 16;
           if (kb == 0) {
             umma_bf16(d_tmem, da, db, idesc, 0u);
           } else {
             umma_bf16(d_tmem, da, db, idesc, 1u);
           }
-          if (kb < num_kb - 1 || kv_last == BK / 16) {
+          if (kv == BK / 16) {
 #pragma unroll
             for (int k = 1; k < BK / 16; k++) umma_bf16(d_tmem, da + 2u * k, db + 2u * k, idesc, 1u);
           } else {
 #pragma unroll
             for (int k = 1; k < BK / 16; k++)
-              if (k < kv_last) umma_bf16(d_tmem, da + 2u * k, db + 2u * k, idesc, 1u);
+              if (k < kv) umma_bf16(d_tmem, da + 2u * k, db + 2u * k, idesc, 1u);
           }
           umma_commit(empty_bar(stage));  // frees the smem stage once these MMAs have read it
           if (kb == num_kb - 1) umma_commit(tmem_full_bar(acc));  // accumulator complete -> epilogue
@@ -1474,8 +1479,9 @@ static int make_tmap_nhwc(CUtensorMap* map, const void* base, uint64_t C, uint64
 // a_region: bytes of the A ring when it is not `stages` x 16 KB (PATCH mode), else 0;
 // b_slots: weight slots (num_kb when the weights are resident), 0 = one per stage
 static size_t conv_smem_bytes(int stages, int BN, size_t a_region = 0, int b_slots = 0, int c_bufs = 1) {
+  const int groups = (BN + 63) / 64;
   return 1024 + (a_region ? a_region : (size_t)stages * A_STAGE_BYTES) + (size_t)(b_slots ? b_slots : stages) * BN * 128 +
-         (size_t)((BN + 63) / 64) * C_GROUP_BYTES * c_bufs + NUM_BARS * 8 + 16 + 256 * 4 + 64;
+         (size_t)groups * C_GROUP_BYTES * c_bufs + NUM_BARS * 8 + 16 + 256 * 4 + 64;
 }
 
 static bool patch_eligible(const yb_plan* p, const Op& op) {
@@ -1737,6 +1743,20 @@ static void fill_params(const yb_plan* p, const Op& op, ConvParams& P) {
   P.out_f32 = op.out_f32;
   P.cout = op.dst.C;
   P.cout_store = op.out_f32 ? round_up(op.dst.C, 4) : cpad8(op.dst.C);
+  // valid K16 steps per k-block: TMA-fed sources are padded to 64-channel blocks one by one, everything else is
+  // one run whose tail is padding
+  for (int kb = 0; kb < 32; kb++) P.kb_kv[kb] = BK / 16;
+  if (op.a_tma && !op.dw_fused) {
+    int kb = 0;
+    for (int i = 0; i < op.nseg; i++) {
+      const int blocks = op.seg_kpad[i] / BK, c = cpad8(op.src[i].C);
+      for (int j = 0; j < blocks; j++, kb++)
+        if (kb < 32) P.kb_kv[kb] = (uint8_t)std::max(1, std::min(BK / 16, (c - j * BK + 15) / 16));
+    }
+  } else if (!op.patch) {
+    const int last = op.K_pad / BK - 1;
+    if (last >= 0 && last < 32) P.kb_kv[last] = (uint8_t)std::max(1, std::min(BK / 16, (op.K - last * BK + 15) / 16));
+  }
   const uint8_t* wbase = p->d_weights + cw.info.blob_offset;
   P.w = reinterpret_cast<const act_t*>(wbase);
   P.bias = reinterpret_cast<const float*>(wbase + (size_t)op.N_pad * op.K_pad * 2);

@@ -231,6 +231,10 @@ struct Builder {
             const Slice* dst = nullptr) {
     int c = out_ch / r;
     int H = src_h(srcs[0]), W = src_w(srcs[0]);
+    // (Dense parts - a buffer of its own for every part narrower than 64 bytes per pixel, conv1 storing its two
+    // halves to two tensors, conv2 walking K over 2 + n sources - were built and measured in round 2: the 2.3x DRAM
+    // over-fetch of net.p2.1's 16-channel slices goes away, but the block gets 111 us SLOWER: 32-byte rows are bound
+    // by the TMA engine's row rate on the read and on the write side, not by DRAM.  Dropped)
     int cat = new_buf(H, W, (2 + n) * c, 2, name + ".cat");
     Slice d = sub(cat, 0, 2 * c);
     conv(name + ".conv1", srcs, 2 * c, 1, 1, 1, &d);

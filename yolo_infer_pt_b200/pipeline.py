@@ -10,16 +10,32 @@ pipelined over four CUDA streams:
 `StreamingDetector` owns the buffers and events.  Pinned host batches (or, with `resident=True`, batches that
 already live on the device) go in, padded detections `(det (B, 300, 6) fp32, counts (B,) int32)` come out on
 the host.  PyTorch provides memory, streams and events only; every kernel is libyolob200's.
+
+`raw_frames=(h, w)`: the host batches are the camera / decoder frames themselves - (B, h, w, 3) uint8 HWC BGR, as
+cv2.imread yields them - and the reference's resize + letterbox + BGR->RGB + HWC->CHW (utils/dataset.py:86-103,
+292-313) runs on the device (`yb_letterbox`, bit-exact with cv2) between the copy and the forward: only the raw
+pixels cross PCIe (a 480 x 640 frame is 25 % smaller than its 640 x 640 letterbox), which is what bounds the
+end-to-end rate from one GPU on.
 """
+import ctypes
+
 import torch
 
+from . import _lib
 from .utils import util
 
 
 class StreamingDetector:
     def __init__(self, model, batch_shape, dtype=torch.uint8, device="cuda", conf=0.001, iou=0.65, resident=False,
-                 fuse_filter=True, input_buffers=3):
+                 fuse_filter=True, input_buffers=3, raw_frames=None):
         self.model = model
+        self.raw_frames = raw_frames
+        if raw_frames is not None:
+            if resident or dtype != torch.uint8:
+                raise ValueError("raw_frames needs uint8 host batches")
+            self.input_size = int(batch_shape[-1])
+            if tuple(batch_shape[1:]) != (3, self.input_size, self.input_size):
+                raise ValueError("batch_shape is the model input (B, 3, S, S); frames are (B, h, w, 3)")
         self.device = torch.device(device)
         self.conf, self.iou = conf, iou
         self.resident = resident
@@ -30,8 +46,19 @@ class StreamingDetector:
         # input ring: with three buffers the copy engine always has a free target, so a copy that takes about
         # as long as a forward (PCIe-bound uint8 batches) never waits for the kernels, nor they for it
         self.n_in = 2 if resident else max(2, int(input_buffers))
-        self.inputs = [None] * self.n_in if resident else [torch.empty(batch_shape, dtype=dtype, device=self.device)
+        in_shape = batch_shape if raw_frames is None else (batch_shape[0], int(raw_frames[0]), int(raw_frames[1]), 3)
+        self.inputs = [None] * self.n_in if resident else [torch.empty(in_shape, dtype=dtype, device=self.device)
                                                            for _ in range(self.n_in)]
+        if raw_frames is not None:
+            # letterboxed model inputs (one per input slot) and the per-image descriptors of the frames in each slot
+            # (device pointer, height, width): the slots are static, so the descriptors are built once
+            self.boxed = [torch.empty(batch_shape, dtype=torch.uint8, device=self.device) for _ in range(self.n_in)]
+            frame_bytes = int(raw_frames[0]) * int(raw_frames[1]) * 3
+            self.frame_desc = [torch.tensor([[buf.data_ptr() + i * frame_bytes, int(raw_frames[0]), int(raw_frames[1])]
+                                             for i in range(batch_shape[0])], dtype=torch.int64).to(self.device)
+                               for buf in self.inputs]
+            self.frame_meta = [torch.empty((batch_shape[0], 3), dtype=torch.float64, device=self.device)
+                               for _ in range(self.n_in)]
         self.copied = [torch.cuda.Event() for _ in range(self.n_in)]
         self.consumed = [torch.cuda.Event() for _ in range(self.n_in)]
         self.fwd_done = [torch.cuda.Event() for _ in range(2)]
@@ -68,6 +95,14 @@ class StreamingDetector:
             if not self.resident:
                 self.compute_stream.wait_event(self.copied[islot])
             self.compute_stream.wait_event(self.nms_done[slot])   # the NMS that read this prediction tensor two batches ago
+            if self.raw_frames is not None:
+                # resize + letterbox + BGR->RGB + HWC->CHW of the whole batch, one kernel (bit-exact with cv2)
+                with torch.cuda.device(self.device):
+                    _lib.check(_lib.lib().yb_letterbox(ctypes.c_void_p(self.frame_desc[islot].data_ptr()), x.shape[0],
+                                                       self.input_size, ctypes.c_void_p(self.boxed[islot].data_ptr()),
+                                                       ctypes.c_void_p(self.frame_meta[islot].data_ptr()),
+                                                       ctypes.c_void_p(self.compute_stream.cuda_stream)), "yb_letterbox")
+                x = self.boxed[islot]
             eng = self.model._engine_for(x)
             if self.preds is None:
                 self.preds = [torch.empty_like(eng.out) for _ in range(2)]
