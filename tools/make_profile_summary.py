@@ -24,7 +24,7 @@ def short(name):
 # ---- (1) launch list of `python bench.py --steps 2 --warmup 1`
 per = long_csv(f"{G}/{tag}_launches.csv")
 with open(f"{P}/{tag}_launches_yolo11n_b256.csv", "w") as f:
-    f.write("# ncu --metrics gpu__time_duration.sum --clock-control none: python bench.py --steps 2 --warmup 1 --no-cpu-baseline\n")
+    f.write("# ncu --metrics gpu__time_duration.sum --clock-control none: python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-extras\n")
     f.write("id,kernel,grid,block,duration_us\n")
     agg = collections.defaultdict(lambda: [0, 0.0])
     for k, d in per.items():
