@@ -851,6 +851,8 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
             mbar_wait(empty_bar(s), ph ^ 1u);
             const uint32_t a_s = a_base + (uint32_t)s * A_STAGE_BYTES + sw_off + (uint32_t)rbase * 128u;
             if (k0 < ((K + 15) & ~15)) {   // granules of K16 steps past the real K are never read by the MMA
+              // (through L1 - cp.async.ca, hoping the 2.25x / 9x tap re-reads of a tile hit there - measured slower:
+              // net.p2.0 328 -> 382 us; the carve-out left next to two 113 KB CTAs is too small)
 #pragma unroll
               for (int i = 0; i < 8; i++)  // masked taps are zero-filled; their source is never read
                 cp_async16(a_s + (uint32_t)i * 2048u, img_base + (uint32_t)(offb[i] + deltab),
