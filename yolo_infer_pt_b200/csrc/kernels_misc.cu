@@ -292,7 +292,8 @@ __device__ __forceinline__ void ldmatrix_x4_trans(uint32_t* r, uint32_t addr) {
 template <typename T, int NT, bool SPLIT, bool F16, int MINB = 1>
 __global__ void __launch_bounds__(256, MINB)
     stem_mma_kernel(const T* __restrict__ in, act_t* __restrict__ out, const float* __restrict__ wgt,
-                    int B, int H, int W, int Ho, int Wo, int Cp, int out_ld, float in_scale, int total_tiles) {
+                    int B, int H, int W, int Ho, int Wo, int Cp, int out_ld, float in_scale, int total_tiles,
+                    uint32_t tx_mul, uint32_t tx_shr, uint32_t ty_mul, uint32_t ty_shr) {
   using A16 = Act16<F16>;
   constexpr int EPV = 16 / (int)sizeof(T);
   constexpr bool U8 = sizeof(T) == 1;
@@ -306,6 +307,14 @@ __global__ void __launch_bounds__(256, MINB)
   act_t* stage = reinterpret_cast<act_t*>(zero_rows + STEM_ZERO_B);   // [8 warps][16 px][NT*8]
   pdl_prologue_done();
   const int tiles_x = (Wo + STEM_TW - 1) / STEM_TW, tiles_y = (Ho + STEM_TH - 1) / STEM_TH;
+  // tile -> (image, tile row, tile column) by multiply-high with host-computed magic numbers: the two runtime
+  // divisions (twice per tile and thread: prefetch and compute) were ~12 % of the kernel's instructions
+  auto split_tile = [&](int tl, int& tx, int& ty, int& b) {
+    const int q = tiles_x == 1 ? tl : (int)(__umulhi((uint32_t)tl, tx_mul) >> tx_shr);
+    tx = tl - q * tiles_x;
+    b = tiles_y == 1 ? q : (int)(__umulhi((uint32_t)q, ty_mul) >> ty_shr);
+    ty = q - b * tiles_y;
+  };
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, t = lane & 3;
   if (tid < STEM_ZERO_B / 4) reinterpret_cast<uint32_t*>(zero_rows)[tid] = 0u;
@@ -358,9 +367,8 @@ __global__ void __launch_bounds__(256, MINB)
   uint4 pv[U8 ? NIT : 1];
   uint32_t pb[U8 ? NIT : 1];
   auto fetch_tile = [&](int tl) {
-    const int tx = tl % tiles_x;
-    tl /= tiles_x;
-    const int ty = tl % tiles_y, b = tl / tiles_y;
+    int tx, ty, b;
+    split_tile(tl, tx, ty, b);
     const int gy0 = 2 * ty * STEM_TH - 1, gx0 = 2 * tx * STEM_TW;
 #pragma unroll
     for (int it = 0; it < (U8 ? NIT : 1); it++) {
@@ -427,11 +435,8 @@ __global__ void __launch_bounds__(256, MINB)
   if (U8 && (int)blockIdx.x < total_tiles) fetch_tile(blockIdx.x);
 #pragma unroll 1
   for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-    int bid = tile;
-    const int tx = bid % tiles_x;
-    bid /= tiles_x;
-    const int ty = bid % tiles_y;
-    const int b = bid / tiles_y;
+    int tx, ty, b;
+    split_tile(tile, tx, ty, b);
     if (tile != (int)blockIdx.x) __syncthreads();   // every warp is done with the previous patch
     if (U8) {
       store_tile_u8();
@@ -512,10 +517,11 @@ __global__ void __launch_bounds__(256, MINB)
         }
         __syncwarp();
         const int ox0 = tx * STEM_TW + mi * 16;
+        act_t* orow = out + (((size_t)b * Ho + oy) * Wo + ox0) * out_ld + c0;   // one 64-bit base per 16-pixel block
         for (int c = lane; c < 16 * NT; c += 32) {   // 16-byte chunks of the 16 x (NT*8) tile
           const int px = c / NT, cg = c - px * NT;
           if (ox0 + px < Wo && c0 + cg * 8 < Cp)
-            *reinterpret_cast<uint4*>(out + (((size_t)b * Ho + oy) * Wo + ox0 + px) * out_ld + c0 + cg * 8) =
+            *reinterpret_cast<uint4*>(orow + px * out_ld + cg * 8) =
                 *reinterpret_cast<const uint4*>(wstage + px * NT * 8 + cg * 8);
         }
       }
@@ -562,8 +568,21 @@ static int launch_stem_t(const yb_plan* p, const Op& op, const void* in, float s
     }                                                                                                            \
     const unsigned grid = std::min(blocks, (unsigned)(p->num_sms * occ));                                        \
     YB_CUDA(launch_pdl(stem_mma_kernel<T, NT, SPLIT, F16, MINB>, dim3(grid), dim3(256), smem, st, (const T*)in, out, w, \
-                       p->B, p->H, p->W, op.Hout, op.Wout, Cp, db.C, scale, (int)blocks));                       \
+                       p->B, p->H, p->W, op.Hout, op.Wout, Cp, db.C, scale, (int)blocks, mx.mul, mx.shr, my.mul, my.shr)); \
   } while (0)
+  // q = n / d for n < 2^31: mul = ceil(2^(31 + ceil_log2 d) / d), shr = ceil_log2 d - 1 (as in conv_tc.cu)
+  struct Magic { uint32_t mul = 0, shr = 0; };
+  auto magic = [](int d) {
+    Magic m;
+    if (d <= 1) return m;
+    int lg = 0;
+    while ((1u << lg) < (uint32_t)d) lg++;
+    const int pshift = 31 + lg;
+    m.mul = (uint32_t)((((unsigned long long)1 << pshift) + (unsigned)d - 1) / (unsigned)d);
+    m.shr = (uint32_t)(pshift - 32);
+    return m;
+  };
+  const Magic mx = magic((op.Wout + STEM_TW - 1) / STEM_TW), my = magic((op.Hout + STEM_TH - 1) / STEM_TH);
   static const bool minb4 = getenv("YB_STEM_MINB1") == nullptr;
   if (nt == 3) YB_STEM_MMA(3, 1);
   else if (nt == 4) YB_STEM_MMA(4, 1);
