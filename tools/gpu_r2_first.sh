@@ -3,10 +3,10 @@
 mkdir -p gpurun_out
 rm -f gpurun_out/summary.txt
 for f in parity forward fused_filter nms preprocess metric; do
-  timeout 1500 python -m pytest tests/test_gpu_$f.py -m gpu -q -s > gpurun_out/pytest_$f.log 2>&1
+  timeout 420 python -m pytest tests/test_gpu_$f.py -m gpu -q -s > gpurun_out/pytest_$f.log 2>&1
   echo "pytest $f exit $?" >> gpurun_out/summary.txt
 done
-timeout 900 python bench.py --steps 20 --warmup 5 --profile-json gpurun_out/profile_n256.json > gpurun_out/bench.log 2> gpurun_out/bench.err
+timeout 500 python bench.py --steps 20 --warmup 5 --profile-json gpurun_out/profile_n256.json > gpurun_out/bench.log 2> gpurun_out/bench.err
 echo "bench exit $?" >> gpurun_out/summary.txt
 cat gpurun_out/summary.txt
 grep -hE "widehead|sweep|x@640|n@1280|bench tensor|e2e n@640|passed|failed|Error" gpurun_out/pytest_parity.log | tail -40

@@ -370,6 +370,7 @@ __global__ void __launch_bounds__(256, MINB)
     int tx, ty, b;
     split_tile(tl, tx, ty, b);
     const int gy0 = 2 * ty * STEM_TH - 1, gx0 = 2 * tx * STEM_TW;
+    const uint8_t* img = reinterpret_cast<const uint8_t*>(in) + (size_t)b * 3 * (size_t)H * (size_t)W;
 #pragma unroll
     for (int it = 0; it < (U8 ? NIT : 1); it++) {
       const int i = tid + it * 256;
@@ -379,10 +380,15 @@ __global__ void __launch_bounds__(256, MINB)
       pv[it] = make_uint4(0u, 0u, 0u, 0u);
       pb[it] = 0u;
       if (row < 3 * STEM_IH && (unsigned)gy < (unsigned)H && gx < W) {
-        const uint8_t* src = reinterpret_cast<const uint8_t*>(in) + (((size_t)b * 3 + ci) * H + gy) * (size_t)W + gx;
+        // (one 64-bit image base per tile; the offset inside a 3 x H x W image fits 32 bits)
+        const uint8_t* src = img + (uint32_t)((ci * H + gy) * W + gx);
         pv[it] = __ldg(reinterpret_cast<const uint4*>(src));
-        if (gx > 0) pb[it] = __ldg(src - 1);
+        if (vx == 0 && gx > 0) pb[it] = __ldg(src - 1);   // first vector of the patch row: the byte left of the tile
       }
+      // every other vector's left neighbour is the last byte of the previous lane's vector (NV8 = 8 consecutive
+      // lanes hold one patch row; a masked-out vector is zero, which is also the right value for it)
+      const uint32_t left = __shfl_up_sync(0xffffffffu, pv[it].w >> 24, 1);
+      if (vx != 0) pb[it] = left;
     }
   };
   auto store_tile_u8 = [&]() {
