@@ -349,3 +349,16 @@ def test_second_device_and_current_device_preserved():
         det = util.non_max_suppression(y1, 0.001, 0.65)
         assert torch.cuda.current_device() == 0
     assert torch.equal(y0, y1.cpu()) and det[0].device.index == 1
+
+
+def test_exported_engine_runs_without_the_model(tmp_path):
+    """export_engine / load_engine: the artefact alone gives the same predictions as the model."""
+    from yolo_infer_pt_b200 import export
+    model = _model("n", "survey_widehead")
+    x = synth.synth_images(2, 96, 96, seed=5)
+    path = export.export_engine(model, str(tmp_path / "n.npz"), 2, 96, 96)
+    eng = export.load_engine(path, "cuda:0")
+    y = eng.forward(x.to("cuda:0")).clone()
+    with torch.no_grad():
+        ref = model.to("cuda:0")(x.to("cuda:0"))
+    assert torch.equal(y, ref)

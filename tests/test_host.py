@@ -396,3 +396,27 @@ def test_arena_never_overlaps_live_buffers(size, batch, hw):
                     f"{A['tag']} {live[a]} and {Bb['tag']} {live[b]} overlap in the arena"
         assert bufs[a]["offset"] + bufs[a]["bytes"] <= d["workspace_bytes"]
 
+
+
+def test_engine_export_round_trip(tmp_path):
+    """export_engine -> load_engine (host-only here): the artefact alone reproduces the packed plan, and its CPU
+    replay equals the replay of the engine packed from the model."""
+    from yolo_infer_pt_b200 import export
+    model = nn.yolo_v11_n(80)
+    synth.load_synth(model, 0, "survey_widehead")
+    path = export.export_engine(model, str(tmp_path / "yolo11n_2x64.npz"), 2, 64, 64)
+    eng = export.load_engine(path, host_only=True)
+    ref = Engine(*model._arch, 2, 64, 64, host_only=True)
+    blob = ref.pack_from_model(model)
+    assert np.array_equal(eng.host_blob, blob) and eng.describe() == ref.describe()
+    x = synth.synth_images(2, 64, 64, seed=1)
+    with torch.no_grad():
+        a = PlanReplay(eng.describe(), eng.convs, eng.host_blob).run(x)
+        b = PlanReplay(ref.describe(), ref.convs, blob).run(x)
+    assert torch.equal(a, b)
+    # an artefact from another plan layout is rejected
+    g = dict(np.load(path))
+    g["weight_bytes"] = np.int64(int(g["weight_bytes"]) + 256)
+    np.savez(str(tmp_path / "bad.npz"), **g)
+    with pytest.raises(RuntimeError):
+        export.load_engine(str(tmp_path / "bad.npz"), host_only=True)
