@@ -217,6 +217,31 @@ def test_cuda_graph_replay_equals_stream_launch():
     assert torch.equal(a, b) and torch.equal(b, c)
 
 
+@pytest.mark.parametrize("size,batch,hw", [("n", 16, 320), ("s", 4, 160)])
+def test_stream_lanes_equal_single_stream(size, batch, hw, monkeypatch):
+    """YB_LANES=4: independent branches (head towers against the neck, C3k's parallel 1x1 convs) run on side
+    streams joined by events; the arena only lets buffers share memory when every access is ordered across
+    the lanes.  Output must be bit-identical to the single-stream plan - eager launches, repeated calls (the
+    second call's first kernels must not overtake the first call's side lanes) and CUDA-graph replay."""
+    model = _model(size, "survey_widehead")
+    x = synth.synth_images(batch, hw, hw, seed=21).to("cuda:0")
+    one = Engine(*model._arch, batch, hw, hw, "cuda:0")
+    one.pack_from_model(model)
+    ref = one.forward(x).clone()
+    monkeypatch.setenv("YB_LANES", "4")
+    eng = Engine(*model._arch, batch, hw, hw, "cuda:0")
+    d = eng.describe()
+    assert d["num_lanes"] == 4 and len({op["lane"] for op in d["ops"]}) >= 3
+    eng.pack_from_model(model)
+    for _ in range(4):
+        assert torch.equal(eng.forward(x).clone(), ref)
+    eng.use_graph(True)
+    for _ in range(3):
+        assert torch.equal(eng.forward(x).clone(), ref)
+    det_a, cnt_a = util.nms_padded(ref, 0.25, 0.65)
+    torch.cuda.synchronize()
+
+
 def test_batch_independence():
     """Images are independent (no cross-image op on the path): image i of a batch equals a batch of one."""
     model = _model("n", "survey")

@@ -398,6 +398,64 @@ def test_arena_never_overlaps_live_buffers(size, batch, hw):
 
 
 
+@pytest.mark.parametrize("size,batch,hw,lanes", [("n", 256, 640, 4), ("x", 8, 640, 3), ("s", 3, 320, 2), ("m", 1, 64, 4)])
+def test_stream_lanes_order_every_shared_arena_region(size, batch, hw, lanes, monkeypatch):
+    """YB_LANES > 1: ops run on several streams.  Recompute 'complete before' from the plan (stream order inside a
+    lane + the cross-lane event waits, transitive) and check (1) every data dependency between two ops is ordered,
+    (2) two buffers that share arena memory have ALL their accesses ordered, not just disjoint op-index intervals."""
+    monkeypatch.setenv("YB_LANES", str(lanes))
+    m = getattr(nn, f"yolo_v11_{size}")(80)
+    d = Engine(*m._arch, batch, hw, hw, host_only=True).describe()
+    ops, bufs = d["ops"], d["bufs"]
+    assert d["num_lanes"] == lanes and len({op["lane"] for op in ops}) == lanes
+    n = len(ops)
+    reach = [set() for _ in range(n)]
+    tail = {}
+    for i, op in enumerate(ops):
+        for j in [tail.get(op["lane"])] + list(op["xdeps"]):
+            if j is not None:
+                assert j < i and (j == tail.get(op["lane"]) or ops[j]["signal"])
+                reach[i] |= reach[j] | {j}
+        tail[op["lane"]] = i
+
+    def accesses(i):
+        op = ops[i]
+        rd = [s for s in op["src"]] + ([op["res"]] if op["has_res"] else [])
+        if op.get("dw_fused"):
+            rd += ops[i - 1]["src"]
+        if op["kind"] == 2 and op["dw"][3]:
+            rd.append(op["dst"])
+        if op["kind"] == 5:
+            return [(d["logits_buf"], 0, 10 ** 6, -1, False)]
+        out = [(s["buf"], s["c_off"], s["c_off"] + s["C"], -1, False) for s in rd if s["buf"] >= 0]
+        w = op["dst"]
+        out.append((w["buf"], w["c_off"], w["c_off"] + w["C"], op["dst_row_off"] if op["out_f32"] else -1, True))
+        return out
+
+    acc = [accesses(i) for i in range(n)]
+    touched = {}
+    for i in range(n):
+        for a in acc[i]:
+            touched.setdefault(a[0], []).append(i)
+        for j in range(i):
+            for a in acc[i]:
+                for b in acc[j]:
+                    if a[0] != b[0] or not (a[4] or b[4]) or a[2] <= b[1] or b[2] <= a[1]:
+                        continue
+                    if a[4] and b[4] and a[3] >= 0 and b[3] >= 0 and a[3] != b[3]:
+                        continue
+                    assert j in reach[i], f"{ops[j]['name']} -> {ops[i]['name']} is not ordered"
+    ids = sorted(touched)
+    for a in ids:
+        for b in ids:
+            A, Bb = bufs[a], bufs[b]
+            if a < b and A["offset"] < Bb["offset"] + Bb["bytes"] and Bb["offset"] < A["offset"] + A["bytes"]:
+                first, second = (a, b) if max(touched[a]) < min(touched[b]) else (b, a)
+                for y in touched[second]:
+                    for x in touched[first]:
+                        assert x in reach[y], f"{bufs[first]['tag']} (op {x}) / {bufs[second]['tag']} (op {y}) share memory unordered"
+
+
 def test_engine_export_round_trip(tmp_path):
     """export_engine -> load_engine (host-only here): the artefact alone reproduces the packed plan, and its CPU
     replay equals the replay of the engine packed from the model."""

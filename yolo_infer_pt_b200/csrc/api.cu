@@ -106,14 +106,42 @@ static int run_ops(yb_plan* p, const void* in, int in_dtype, float* out, int raw
   }
   size_t op_i = 0;
   if (ev) YB_CUDA(cudaEventRecord((*ev)[0], st));
+  // Stream lanes (plan.cu): independent branches run on the plan's side streams; cross-lane dependencies are
+  // events, and every side lane joins the caller's stream again before this function returns.  Per-op profiling
+  // and the scalar cross-check path keep everything on the caller's stream.
+  const bool lanes = p->num_lanes > 1 && !ev && p->conv_impl == 0;
+  bool lane_used[YB_MAX_LANES] = {false, false, false, false};
+  if (lanes) {
+    if (p->op_events.size() != p->ops.size()) p->op_events.assign(p->ops.size(), nullptr);
+    for (int l = 1; l < p->num_lanes; l++) {
+      if (!p->lane_streams[l]) YB_CUDA(cudaStreamCreateWithFlags(&p->lane_streams[l], cudaStreamNonBlocking));
+      if (!p->lane_join[l]) YB_CUDA(cudaEventCreateWithFlags(&p->lane_join[l], cudaEventDisableTiming));
+    }
+  }
   for (const Op& op : p->ops) {
+    cudaStream_t os = st;
+    if (lanes) {
+      if (op.lane > 0) os = p->lane_streams[op.lane];
+      for (int d : op.xdeps) YB_CUDA(cudaStreamWaitEvent(os, p->op_events[d], 0));
+      lane_used[op.lane] = true;
+    }
     // a depthwise conv fused into its consumer's kernel is only launched for the scalar cross-check path
-    if (!(op.fused_away && p->conv_impl == 0)) rc = run_one(p, op, in, in_dtype, out, raw, st);
-    if (rc) return rc;
+    if (!(op.fused_away && p->conv_impl == 0)) rc = run_one(p, op, in, in_dtype, out, raw, os);
+    if (rc) break;
+    if (lanes && op.signal) {
+      if (!p->op_events[op_i]) YB_CUDA(cudaEventCreateWithFlags(&p->op_events[op_i], cudaEventDisableTiming));
+      YB_CUDA(cudaEventRecord(p->op_events[op_i], os));
+    }
     op_i++;
     if (ev) YB_CUDA(cudaEventRecord((*ev)[op_i], st));
   }
-  return YB_OK;
+  if (lanes)
+    for (int l = 1; l < p->num_lanes; l++)
+      if (lane_used[l]) {   // (also on the error path: a capture must not end with a forked stream)
+        YB_CUDA(cudaEventRecord(p->lane_join[l], p->lane_streams[l]));
+        YB_CUDA(cudaStreamWaitEvent(st, p->lane_join[l], 0));
+      }
+  return rc;
 }
 
 static int forward_impl(yb_plan* p, const void* in, int in_dtype, float* out, int raw, void* stream) {
@@ -240,6 +268,12 @@ void yb_plan_destroy(yb_plan* plan) {
   for (auto& v : plan->prof_events)
     for (auto& e : v) cudaEventDestroy(e);
   if (plan->capture_stream) cudaStreamDestroy(plan->capture_stream);
+  for (cudaEvent_t e : plan->op_events)
+    if (e) cudaEventDestroy(e);
+  for (int l = 0; l < YB_MAX_LANES; l++) {
+    if (plan->lane_join[l]) cudaEventDestroy(plan->lane_join[l]);
+    if (plan->lane_streams[l]) cudaStreamDestroy(plan->lane_streams[l]);
+  }
   delete plan;
 }
 
@@ -493,7 +527,7 @@ long long yb_plan_describe(const yb_plan* plan, char* buf, size_t capacity) {
     snprintf(t, sizeof(t), "{\"buf\":%d,\"c_off\":%d,\"C\":%d,\"up\":%d}", s.buf, s.c_off, s.C, s.up);
     return std::string(t);
   };
-  snprintf(t, sizeof(t), "{\"act_f16\":%d,", plan->act_f16);
+  snprintf(t, sizeof(t), "{\"act_f16\":%d,\"num_lanes\":%d,", plan->act_f16, plan->num_lanes);
   j += t;
   snprintf(t, sizeof(t), "\"B\":%d,\"H\":%d,\"W\":%d,\"nc\":%d,\"A\":%d,\"logits_buf\":%d,"
            "\"workspace_bytes\":%zu,\"weight_bytes\":%zu,\"lvl_off\":[%d,%d,%d],\"bufs\":[",
@@ -523,6 +557,8 @@ long long yb_plan_describe(const yb_plan* plan, char* buf, size_t capacity) {
     j += t;
     j += "\"src\":[";
     for (int s = 0; s < o.nseg; s++) j += (s ? "," : "") + slice(o.src[s]);
+    j += "],\"lane\":" + std::to_string(o.lane) + ",\"signal\":" + std::to_string(o.signal) + ",\"xdeps\":[";
+    for (size_t s = 0; s < o.xdeps.size(); s++) j += (s ? "," : "") + std::to_string(o.xdeps[s]);
     j += "],\"dst\":" + slice(o.dst) + ",\"res\":" + slice(o.res) + "}";
   }
   j += "]}";

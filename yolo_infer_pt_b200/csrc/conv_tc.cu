@@ -1627,8 +1627,8 @@ int conv_tc_prepare(yb_plan* p, Op& op) {
   op.patch_stages = pst;
   const size_t a_region = op.patch ? (size_t)pst * op.patch_stage_bytes : 0;
   const size_t dw_extra = op.dw_fused ? (size_t)pst * op.patch_stage_bytes + (size_t)10 * num_kb * 64 * 4 : 0;
-  op.smem_bytes = std::max(conv_smem_bytes(st, op.BN, a_region, op.b_resident ? num_kb : 0, cb * halves) + dw_extra,
-                           SMEM_MAX / (occ + 1) + 1024);
+  op.smem_bytes = conv_smem_bytes(st, op.BN, a_region, op.b_resident ? num_kb : 0, cb * halves) + dw_extra;
+  if (getenv("YB_SMEM_EXACT") == nullptr) op.smem_bytes = std::max(op.smem_bytes, SMEM_MAX / (occ + 1) + 1024);
   if (op.smem_bytes > SMEM_MAX) {
     set_error("conv %s: tile needs %zu bytes of shared memory", op.name.c_str(), op.smem_bytes);
     return YB_ERR_UNSUPPORTED;

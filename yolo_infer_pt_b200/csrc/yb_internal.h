@@ -143,6 +143,8 @@ static inline int cpad8(int c) { return round_up(c, 8); }
 // A "slice" is a channel range [c_off, c_off + C) of a buffer; producers write straight into the
 // slice of their consumer's concat buffer, so torch.cat / chunk never exist as kernels.
 // ---------------------------------------------------------------------------------------------
+static constexpr int YB_MAX_LANES = 4;
+
 struct Buf {
   int H = 0, W = 0, C = 0;  // C = total (padded) channels = row stride in elements
   int elem_bytes = 2;
@@ -150,6 +152,7 @@ struct Buf {
   size_t offset = 0;        // byte offset in the workspace arena
   size_t bytes = 0;
   int first_def = 1 << 30, last_use = -1;  // liveness (op indices) for arena reuse
+  std::vector<int> touches;                // every op that reads or writes the buffer (stream-lane aware reuse)
   std::string tag;
 };
 
@@ -204,6 +207,10 @@ struct Op {
   // attention
   int heads = 0, dk = 0, dh = 0;
   float scale = 0.f;
+  // stream lanes (plan.cu): independent branches of the graph are enqueued on separate streams
+  int lane = 0;            // 0 = the caller's stream
+  int signal = 0;          // an op on another lane waits for this one: record an event behind it
+  std::vector<int> xdeps;  // ops on other lanes this op waits for
 };
 
 struct ConvW {
@@ -254,6 +261,11 @@ struct yb_plan {
   int profiling = 0;
   std::vector<std::vector<cudaEvent_t>> prof_events;  // one vector of ops+1 events per recorded forward
   int prof_used = 0;
+  // stream lanes: side streams + the events of cross-lane dependencies (created on first use)
+  int num_lanes = 1;
+  cudaStream_t lane_streams[yb::YB_MAX_LANES] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t lane_join[yb::YB_MAX_LANES] = {nullptr, nullptr, nullptr, nullptr};
+  std::vector<cudaEvent_t> op_events;
 };
 
 namespace yb {
