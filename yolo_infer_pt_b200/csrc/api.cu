@@ -320,7 +320,10 @@ int yb_plan_pack_conv(const yb_plan* plan, int index, const float* w, const floa
         int ci0 = 0;
         for (int s = 0; s < op.nseg; s++) {
           for (int c = 0; c < op.src[s].C; c++) {
-            float v = w[((size_t)co * cin + (ci0 + c)) * k * k + tap];
+            const int ci = ci0 + c;
+            float v = w[((size_t)co * cin + ci) * k * k + tap];
+            if (ci >= op.wfold_dst && ci < op.wfold_dst + op.wfold_n)   // residual folded into this conv (plan.cu, C3k2)
+              v += w[((size_t)co * cin + (ci - op.wfold_dst + op.wfold_src)) * k * k + tap];
             row[kpos + c] = host_to_act16(v, f16);
           }
           ci0 += op.src[s].C;
@@ -557,7 +560,8 @@ long long yb_plan_describe(const yb_plan* plan, char* buf, size_t capacity) {
     j += t;
     j += "\"src\":[";
     for (int s = 0; s < o.nseg; s++) j += (s ? "," : "") + slice(o.src[s]);
-    j += "],\"lane\":" + std::to_string(o.lane) + ",\"signal\":" + std::to_string(o.signal) + ",\"xdeps\":[";
+    j += "],\"wfold\":[" + std::to_string(o.wfold_dst) + "," + std::to_string(o.wfold_src) + "," + std::to_string(o.wfold_n) + "]";
+    j += ",\"lane\":" + std::to_string(o.lane) + ",\"signal\":" + std::to_string(o.signal) + ",\"xdeps\":[";
     for (size_t s = 0; s < o.xdeps.size(); s++) j += (s ? "," : "") + std::to_string(o.xdeps[s]);
     j += "],\"dst\":" + slice(o.dst) + ",\"res\":" + slice(o.res) + "}";
   }

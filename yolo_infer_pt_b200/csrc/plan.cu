@@ -207,11 +207,12 @@ struct Builder {
   }
 
   // Residual bottleneck nn.py:42-49: x + conv2(conv1(x)); the add sits in conv2's epilogue.
-  Slice residual(const std::string& name, const Slice& x, double e, const Slice* dst = nullptr) {
+  // (add = false: the caller folds the `x +` into the weights of the 1x1 conv that consumes x and this output)
+  Slice residual(const std::string& name, const Slice& x, double e, const Slice* dst = nullptr, bool add = true) {
     int c = x.C;
     int h = (int)(c * e);
     Slice t = conv(name + ".conv1", {x}, h, 3, 1, 1);
-    return conv(name + ".conv2", {t}, c, 3, 1, 1, dst, &x);
+    return conv(name + ".conv2", {t}, c, 3, 1, 1, dst, add ? &x : nullptr);
   }
 
   // C3k nn.py:52-63.
@@ -236,6 +237,38 @@ struct Builder {
     // halves to two tensors, conv2 walking K over 2 + n sources - were built and measured in round 2: the 2.3x DRAM
     // over-fetch of net.p2.1's 16-channel slices goes away, but the block gets 111 us SLOWER: 32-byte rows are bound
     // by the TMA engine's row rate on the read and on the write side, not by DRAM.  Dropped)
+    // Narrow parts (c <= 32 channels): conv1's two halves stay together in one buffer and every
+    // bottleneck output gets a dense buffer of its own, conv2 walks K over 1 + n sources.  A 32-byte slice of a
+    // 96-byte pixel costs the whole pixel in DRAM reads (measured: 629 MB for 210 MB of input on net.p2.1), of a
+    // 64-byte pixel only twice the slice.
+    const int split_max = getenv("YB_SPLIT_CAT_MAXC") ? atoi(getenv("YB_SPLIT_CAT_MAXC")) : 32;
+    // The last bottleneck's `x + f(x)` (nn.py:49) is only read by conv2, which also reads x itself as the part in
+    // front of it: W_x x + W_m (x + f) = (W_x + W_m) x + W_m f.  The bottleneck stores f alone (no residual read:
+    // 420 MB of the 735 MB net.p2.1.res_m.0.conv2 pulled through DRAM) and conv2's weights for x are summed when
+    // the blob is packed (yb_plan_pack_conv).  YB_NO_RES_FOLD=1 keeps the add in the bottleneck's epilogue.
+    const bool fold = !use_csp && n >= 1 && getenv("YB_NO_RES_FOLD") == nullptr;
+    auto mark_fold = [&]() {
+      if (!fold) return;
+      Op& o = p->ops.back();
+      o.wfold_dst = n * c;
+      o.wfold_src = (n + 1) * c;
+      o.wfold_n = c;
+    };
+    if (c <= split_max && n <= 3) {
+      int head2 = new_buf(H, W, 2 * c, 2, name + ".cat");
+      Slice d = whole(head2);
+      conv(name + ".conv1", srcs, 2 * c, 1, 1, 1, &d);
+      std::vector<Slice> parts = {whole(head2)};
+      Slice in = sub(head2, c, c);
+      for (int i = 0; i < n; i++) {
+        std::string mn = name + ".res_m." + std::to_string(i);
+        in = use_csp ? csp_module(mn, in, c, nullptr) : residual(mn, in, 0.5, nullptr, !(fold && i == n - 1));
+        parts.push_back(in);
+      }
+      Slice o2 = conv(name + ".conv2", parts, out_ch, 1, 1, 1, dst);
+      mark_fold();
+      return o2;
+    }
     int cat = new_buf(H, W, (2 + n) * c, 2, name + ".cat");
     Slice d = sub(cat, 0, 2 * c);
     conv(name + ".conv1", srcs, 2 * c, 1, 1, 1, &d);
@@ -246,9 +279,11 @@ struct Builder {
       if (use_csp)
         csp_module(mn, in, c, &di);
       else
-        residual(mn, in, 0.5, &di);
+        residual(mn, in, 0.5, &di, !(fold && i == n - 1));
     }
-    return conv(name + ".conv2", {whole(cat)}, out_ch, 1, 1, 1, dst);
+    Slice o2 = conv(name + ".conv2", {whole(cat)}, out_ch, 1, 1, 1, dst);
+    mark_fold();
+    return o2;
   }
 
   // SPPF nn.py:83-94: the 5/9/13 windows equal the three cascaded 5x5 pools (max, -inf padding).

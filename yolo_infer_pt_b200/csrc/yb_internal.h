@@ -207,6 +207,9 @@ struct Op {
   // attention
   int heads = 0, dk = 0, dh = 0;
   float scale = 0.f;
+  // residual folded into the consumer's weights (plan.cu, C3k2): input channels [wfold_dst, +wfold_n) of this conv
+  // take the sum of their own weights and those of channels [wfold_src, +wfold_n) when the blob is packed
+  int wfold_dst = 0, wfold_src = 0, wfold_n = 0;
   // stream lanes (plan.cu): independent branches of the graph are enqueued on separate streams
   int lane = 0;            // 0 = the caller's stream
   int signal = 0;          // an op on another lane waits for this one: record an event behind it
