@@ -185,6 +185,9 @@ def conv_algorithmic_work(desc, batch):
             bytes_ = 2.0 * in_elems + (4.0 if op["out_f32"] else 2.0) * m * cout + 2.0 * cout * cin * op["k"] ** 2
             if op["has_res"]:
                 bytes_ += 2.0 * m * cout
+            # (a bottleneck whose `x +` was folded into this conv's weights: the reference's graph still reads x there -
+            # the algorithmic figure stays SURVEY 8d's, the saved read shows up as time only)
+            bytes_ += 2.0 * m * op.get("wfold", [0, 0, 0])[2]
         work.append((flops, bytes_))
     return work
 

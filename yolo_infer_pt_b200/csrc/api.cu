@@ -472,7 +472,8 @@ long long yb_plan_debug_read(yb_plan* plan, const char* conv_name, float* host_o
     std::vector<uint8_t> tmp(rows * row_bytes);
     YB_CUDA(cudaMemcpy(tmp.data(), buf_ptr(plan, op.dst.buf), tmp.size(), cudaMemcpyDeviceToHost));
     for (size_t r = 0; r < rows; r++) {
-      const uint8_t* rp = tmp.data() + r * row_bytes + (size_t)op.dst.c_off * b.elem_bytes;
+      const uint8_t* rp = tmp.data() + (b.s2d ? buf_row_elem(b, r / b.rows_per_img, r % b.rows_per_img) * b.elem_bytes : r * row_bytes) +
+                          (size_t)op.dst.c_off * b.elem_bytes;
       for (int c = 0; c < C; c++) {
         float v;
         if (b.elem_bytes == 4) {
@@ -501,6 +502,17 @@ int yb_plan_debug_write(yb_plan* plan, int buf_index, const void* host_data, siz
   DeviceGuard guard(plan->device);
   if (guard.rc) return guard.rc;
   YB_CUDA(cudaDeviceSynchronize());
+  const Buf& b = plan->bufs[buf_index];
+  if (b.s2d) {   // host data is (B, H, W, C); the buffer is stored space-to-depth
+    std::vector<uint8_t> tmp(bytes);
+    const size_t px = (size_t)b.C * b.elem_bytes;
+    for (size_t n = 0; n < (size_t)plan->B; n++)
+      for (size_t r = 0; r < (size_t)b.rows_per_img; r++)
+        memcpy(tmp.data() + buf_row_elem(b, n, r) * b.elem_bytes,
+               reinterpret_cast<const uint8_t*>(host_data) + (n * b.rows_per_img + r) * px, px);
+    YB_CUDA(cudaMemcpy(buf_ptr(plan, buf_index), tmp.data(), bytes, cudaMemcpyHostToDevice));
+    return YB_OK;
+  }
   YB_CUDA(cudaMemcpy(buf_ptr(plan, buf_index), host_data, bytes, cudaMemcpyHostToDevice));
   return YB_OK;
 }
@@ -540,9 +552,9 @@ long long yb_plan_describe(const yb_plan* plan, char* buf, size_t capacity) {
   for (size_t i = 0; i < plan->bufs.size(); i++) {
     const Buf& b = plan->bufs[i];
     snprintf(t, sizeof(t), "%s{\"H\":%d,\"W\":%d,\"C\":%d,\"elem_bytes\":%d,\"rows_per_img\":%d,"
-             "\"offset\":%zu,\"bytes\":%zu,\"first_def\":%d,\"last_use\":%d,\"tag\":\"%s\"}",
+             "\"offset\":%zu,\"bytes\":%zu,\"first_def\":%d,\"last_use\":%d,\"s2d\":%d,\"tag\":\"%s\"}",
              i ? "," : "", b.H, b.W, b.C, b.elem_bytes, b.rows_per_img, b.offset, b.bytes, b.first_def,
-             b.last_use, b.tag.c_str());
+             b.last_use, b.s2d, b.tag.c_str());
     j += t;
   }
   j += "],\"ops\":[";
@@ -560,7 +572,7 @@ long long yb_plan_describe(const yb_plan* plan, char* buf, size_t capacity) {
     j += t;
     j += "\"src\":[";
     for (int s = 0; s < o.nseg; s++) j += (s ? "," : "") + slice(o.src[s]);
-    j += "],\"wfold\":[" + std::to_string(o.wfold_dst) + "," + std::to_string(o.wfold_src) + "," + std::to_string(o.wfold_n) + "]";
+    j += "],\"s2d\":" + std::to_string(o.s2d) + ",\"wfold\":[" + std::to_string(o.wfold_dst) + "," + std::to_string(o.wfold_src) + "," + std::to_string(o.wfold_n) + "]";
     j += ",\"lane\":" + std::to_string(o.lane) + ",\"signal\":" + std::to_string(o.signal) + ",\"xdeps\":[";
     for (size_t s = 0; s < o.xdeps.size(); s++) j += (s ? "," : "") + std::to_string(o.xdeps[s]);
     j += "],\"dst\":" + slice(o.dst) + ",\"res\":" + slice(o.res) + "}";

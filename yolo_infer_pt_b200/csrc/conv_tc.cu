@@ -91,6 +91,7 @@ struct ConvParams {
   // 3x3 / stride-1 convs fed from TMA halo patches (mode PATCH): an 18 x 10 pixel patch of `cblk`
   // channels per 16 x 8 output tile; each tap is a shifted UMMA descriptor into the patch
   int patch, cblk, ncb, a_layout;
+  int s2d;              // stride-2 3x3 over a space-to-depth source (16 channels: the four parity blocks are one 64-channel patch)
   int patch_creal;      // real input channels (tap-aligned layers: K steps past them are zero padding and are skipped)
   int pair;             // MODE_PATCH2: 16 x 16 pixel super-tiles = two accumulators sharing every weight k-block
   int patch_tx_bytes, patch_stage_bytes, patch_stages;
@@ -979,6 +980,35 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
         const uint32_t row_bytes = (uint32_t)cblk * 2u;
         const uint64_t adesc_hi = ((uint64_t)((PPW * row_bytes) >> 4) << 32) | ((uint64_t)1 << 46) |
                                   ((uint64_t)P.a_layout << 61);
+        if (P.s2d) {
+          // stride-2 3x3 over a space-to-depth source (16 channels: one 64-channel patch holds the four parity
+          // blocks): original tap (ky, kx) reads parity block (ky != 1, kx != 1) of the pixel one row up / one
+          // column left when ky == 0 / kx == 0 - nine K=16 MMAs, weights in their usual tap-major packing
+          mbar_wait(patch_full_bar(pstage), pphase);
+          if (ti == 0)
+            for (int kb = 0; kb < num_kb; kb++) mbar_wait(full_bar(kb), 0u);
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          {
+            const uint32_t a_lo = ((a_base + (uint32_t)pstage * (uint32_t)P.patch_stage_bytes) >> 4) | (1u << 16);
+            const uint32_t a_hi = (uint32_t)(adesc_hi >> 32), b_hi = (uint32_t)(desc_hi >> 32);
+            const uint32_t b_lo = (b_base >> 4) | (1u << 16), bstep = b_stage_bytes >> 4;
+#pragma unroll
+            for (int t = 0; t < 9; t++) {
+              const int ky = t / 3, kx = t % 3;
+              const int a_off = (((ky != 0) * PPW + (kx != 0)) * 128 + ((ky != 1) * 2 + (kx != 1)) * 32) >> 4;
+              const uint64_t da = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo + (uint32_t)a_off);
+              const uint64_t db = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + (uint32_t)(t / 4) * bstep + 2u * (uint32_t)(t % 4));
+              umma_bf16(d_tmem, da, db, idesc, (uint32_t)(t != 0));
+            }
+            umma_commit(patch_empty_bar(pstage));
+            umma_commit(tmem_full_bar(acc));
+          }
+          if (++pstage == P.patch_stages) {
+            pstage = 0;
+            pphase ^= 1u;
+          }
+          continue;
+        }
         if (RES && ti > 0) {
           // steady state with resident weights: nothing to wait for but the patches
           for (int cb = 0; cb < P.ncb; cb++) {
@@ -1372,7 +1402,8 @@ __global__ void conv_direct_check_kernel(const ConvParams P) {
         int up = P.src_up[s];
         int Hs = P.Hin >> up, Ws = P.Win >> up;
         const act_t* sp =
-            P.src[s] + ((size_t)(img * Hs + (iy >> up)) * Ws + (ix >> up)) * (size_t)P.src_ld[s];
+            P.s2d ? P.src[s] + ((((size_t)img * (Hs >> 1) + (iy >> 1)) * (Ws >> 1) + (ix >> 1)) * 4 + (iy & 1) * 2 + (ix & 1)) * (size_t)P.src_ld[s]
+                  : P.src[s] + ((size_t)(img * Hs + (iy >> up)) * Ws + (ix >> up)) * (size_t)P.src_ld[s];
         for (int c = 0; c < P.src_c[s]; c++)
           acc += Act16<F16>::unpack1(sp[c]) * Act16<F16>::unpack1(wrow[kpos + c]);
       }
@@ -1488,6 +1519,7 @@ static size_t conv_smem_bytes(int stages, int BN, size_t a_region = 0, int b_slo
 
 static bool patch_eligible(const yb_plan* p, const Op& op) {
   if (getenv("YB_NO_PATCH")) return false;
+  if (op.s2d) return true;   // decided with the buffer layout when the plan was built
   if (op.k != 3 || op.stride != 1 || op.nseg != 1 || op.src[0].up || op.out_f32) return false;
   const int C = op.seg_kpad[0];   // channels per tap as packed (a multiple of 64 for tap-aligned layers)
   if (!(C == 8 || C == 16 || C == 32 || (C % 64 == 0 && C > 0))) return false;
@@ -1512,7 +1544,8 @@ int conv_tc_prepare(yb_plan* p, Op& op) {
   // tcgen05.alloc from ever waiting on a co-resident persistent CTA.
   const size_t SMEM_MAX = 227 * 1024;
   // patch layers with tiny N tiles are bound by per-tile latency chains: a third resident CTA hides them
-  const bool tiny_patch = patch_eligible(p, op) && op.BN <= 32 && op.Hout >= 80 && getenv("YB_NO_OCC3") == nullptr;
+  // (space-to-depth sources: 24 KB patches, two CTAs per SM)
+  const bool tiny_patch = patch_eligible(p, op) && !op.s2d && op.BN <= 32 && op.Hout >= 80 && getenv("YB_NO_OCC3") == nullptr;
   int occ = std::min(tiny_patch ? 3 : 2, 512 / tmem_cols_for(op.BN));
   if (op.dw_fused) occ = 1;   // 19-warp CTA (8 depthwise warps): one per SM
   if (const char* e = getenv("YB_OCC")) occ = std::max(1, std::min(occ, atoi(e)));
@@ -1527,6 +1560,7 @@ int conv_tc_prepare(yb_plan* p, Op& op) {
   const int pair_env = getenv("YB_PAIR") ? atoi(getenv("YB_PAIR")) : -1;
   op.pair = (op.patch && op.N_pad == op.BN && 4 * tmem_cols_for(op.BN) / 2 <= 512 && op.Wout >= 16 &&
              (pair_env < 0 ? (op.BN >= 48 && op.Hout >= 160) : pair_env != 0)) ? 1 : 0;
+  if (op.s2d) op.pair = 0;
   if (op.pair) occ = std::min(occ, std::max(1, 512 / tmem_cols_for(2 * op.BN)));
   const int num_kb = op.K_pad / BK;
   const size_t w_bytes = (size_t)num_kb * op.BN * 128;
@@ -1557,7 +1591,7 @@ int conv_tc_prepare(yb_plan* p, Op& op) {
       return false;
     }
     if (op.patch) {
-      const int C = op.seg_kpad[0], cblk = std::min(C, 64);
+      const int C = op.s2d ? 64 : op.seg_kpad[0], cblk = std::min(C, 64);
       op.patch_stage_bytes = round_up(PP_H * (op.pair ? PP2_W : PP_W) * cblk * 2 + 16, 1024);
       for (int pst = MAX_PATCH_STAGES; pst >= 2; pst--) {
         const size_t a_region = (size_t)pst * op.patch_stage_bytes;
@@ -1589,7 +1623,7 @@ int conv_tc_prepare(yb_plan* p, Op& op) {
     if (t.cb == 2 && !cb2_ok) continue;
     if (op.dw_fused && t.cb != dw_cb && cb2_ok) continue;   // (A/B switch YB_DW_CB)
     if (t.occ != occ && !op.dw_fused &&
-        !(op.patch && occ > 1 && w_bytes >= 24 * 1024 && getenv("YB_NO_RESIDENT_OCC1") == nullptr))
+        !(op.patch && occ > 1 && (w_bytes >= 24 * 1024 || op.s2d) && getenv("YB_NO_RESIDENT_OCC1") == nullptr))
       continue;
     if (plan_smem(t.occ, t.res, t.cb, t.min_st, st, pst)) {
       op.b_resident = t.res ? 1 : 0;
@@ -1614,6 +1648,10 @@ int conv_tc_prepare(yb_plan* p, Op& op) {
       set_error("conv %s: fused depthwise tile does not fit shared memory", op.name.c_str());
       return YB_ERR_UNSUPPORTED;
     }
+  }
+  if (op.s2d && !(found && op.b_resident)) {
+    set_error("conv %s: the space-to-depth path needs its weights resident in shared memory", op.name.c_str());
+    return YB_ERR_UNSUPPORTED;
   }
   if (!found && op.patch) {  // patches + streamed weights do not fit: fall back to the gather path
     op.patch = 0;
@@ -1652,6 +1690,10 @@ int conv_tc_prepare(yb_plan* p, Op& op) {
     op.tile2d = 1;
     const Buf& b = p->bufs[op.src[0].buf];
     const uint8_t* base = buf_ptr(p, op.src[0].buf) + (size_t)op.src[0].c_off * 2;
+    if (op.s2d)   // the source as stored: (H/2, W/2, 4C)
+      rc = make_tmap_nhwc(&op.tmap_a[0], base, (uint64_t)4 * b.C, (uint64_t)b.W / 2, (uint64_t)b.H / 2, (uint64_t)p->B,
+                          (uint64_t)4 * b.C, 64, PP_W, PP_H);
+    else
     rc = make_tmap_nhwc(&op.tmap_a[0], base, (uint64_t)op.src[0].C, (uint64_t)b.W, (uint64_t)b.H, (uint64_t)p->B,
                         (uint64_t)b.C, (uint32_t)std::min(op.seg_kpad[0], 64), op.pair ? PP2_W : PP_W, PP_H);
     if (rc) return rc;
@@ -1796,14 +1838,15 @@ static void fill_params(const yb_plan* p, const Op& op, ConvParams& P) {
   P.c_bufs = op.c_bufs;
   // measured: alternate tiles win except on patch layers with >= 32 output channels
   P.alt_epilogue = (getenv("YB_NO_ALT_EPI") || (op.patch && op.BN >= 32) || op.pair) ? 0 : 1;
+  P.s2d = op.s2d;
   if (op.patch) {
-    const int C = op.seg_kpad[0];
+    const int C = op.s2d ? 64 : op.seg_kpad[0];
     P.patch = 1;
     P.cblk = std::min(C, 64);
     P.ncb = (C + 63) / 64;
     P.a_layout = P.cblk == 64 ? 2 : P.cblk == 32 ? 4 : P.cblk == 16 ? 6 : 0;
     P.pair = op.pair;
-    P.patch_creal = op.src[0].C;
+    P.patch_creal = op.s2d ? 64 : op.src[0].C;
     P.patch_tx_bytes = PP_H * (op.pair ? PP2_W : PP_W) * P.cblk * 2;
     P.patch_stage_bytes = op.patch_stage_bytes;
     P.patch_stages = op.patch_stages;

@@ -293,7 +293,7 @@ template <typename T, int NT, bool SPLIT, bool F16, int MINB = 1>
 __global__ void __launch_bounds__(256, MINB)
     stem_mma_kernel(const T* __restrict__ in, act_t* __restrict__ out, const float* __restrict__ wgt,
                     int B, int H, int W, int Ho, int Wo, int Cp, int out_ld, float in_scale, int total_tiles,
-                    uint32_t tx_mul, uint32_t tx_shr, uint32_t ty_mul, uint32_t ty_shr) {
+                    uint32_t tx_mul, uint32_t tx_shr, uint32_t ty_mul, uint32_t ty_shr, int s2d) {
   using A16 = Act16<F16>;
   constexpr int EPV = 16 / (int)sizeof(T);
   constexpr bool U8 = sizeof(T) == 1;
@@ -521,13 +521,19 @@ __global__ void __launch_bounds__(256, MINB)
           *reinterpret_cast<uint32_t*>(wstage + g * NT * 8 + nt * 8 + 2 * t) = A16::pack2(silu_half(d[nt][0]), silu_half(d[nt][1]));
           *reinterpret_cast<uint32_t*>(wstage + (g + 8) * NT * 8 + nt * 8 + 2 * t) = A16::pack2(silu_half(d[nt][2]), silu_half(d[nt][3]));
         }
-        __syncwarp();
         const int ox0 = tx * STEM_TW + mi * 16;
-        act_t* orow = out + (((size_t)b * Ho + oy) * Wo + ox0) * out_ld + c0;   // one 64-bit base per 16-pixel block
+        __syncwarp();
+        // one 64-bit base per 16-pixel block; space-to-depth destination (plan.cu): pixel (y, x) is channel block
+        // (y&1)*2 + (x&1) of pixel (y/2, x/2) of a (Ho/2, Wo/2, 4*out_ld) tensor - a row of 16 pixels lands as 64-byte
+        // halves of eight 128-byte pixels (+33 us on the stem against -104 us on net.p2.0; pairing the two warps of a
+        // row pair through named barriers to store whole 512-byte runs was measured slower: +75 us)
+        act_t* orow = s2d ? out + ((((size_t)b * (Ho >> 1) + (oy >> 1)) * (Wo >> 1) + (ox0 >> 1)) * 4 + (oy & 1) * 2) * out_ld + c0
+                          : out + (((size_t)b * Ho + oy) * Wo + ox0) * out_ld + c0;
         for (int c = lane; c < 16 * NT; c += 32) {   // 16-byte chunks of the 16 x (NT*8) tile
           const int px = c / NT, cg = c - px * NT;
+          const int pxo = s2d ? 2 * px - (px & 1) : px;
           if (ox0 + px < Wo && c0 + cg * 8 < Cp)
-            *reinterpret_cast<uint4*>(orow + px * out_ld + cg * 8) =
+            *reinterpret_cast<uint4*>(orow + pxo * out_ld + cg * 8) =
                 *reinterpret_cast<const uint4*>(wstage + px * NT * 8 + cg * 8);
         }
       }
@@ -574,7 +580,7 @@ static int launch_stem_t(const yb_plan* p, const Op& op, const void* in, float s
     }                                                                                                            \
     const unsigned grid = std::min(blocks, (unsigned)(p->num_sms * occ));                                        \
     YB_CUDA(launch_pdl(stem_mma_kernel<T, NT, SPLIT, F16, MINB>, dim3(grid), dim3(256), smem, st, (const T*)in, out, w, \
-                       p->B, p->H, p->W, op.Hout, op.Wout, Cp, db.C, scale, (int)blocks, mx.mul, mx.shr, my.mul, my.shr)); \
+                       p->B, p->H, p->W, op.Hout, op.Wout, Cp, db.C, scale, (int)blocks, mx.mul, mx.shr, my.mul, my.shr, db.s2d)); \
   } while (0)
   // q = n / d for n < 2^31: mul = ceil(2^(31 + ceil_log2 d) / d), shr = ceil_log2 d - 1 (as in conv_tc.cu)
   struct Magic { uint32_t mul = 0, shr = 0; };

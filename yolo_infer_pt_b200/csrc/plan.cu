@@ -236,12 +236,9 @@ struct Builder {
     // (Dense parts - a buffer of its own for every part narrower than 64 bytes per pixel, conv1 storing its two
     // halves to two tensors, conv2 walking K over 2 + n sources - were built and measured in round 2: the 2.3x DRAM
     // over-fetch of net.p2.1's 16-channel slices goes away, but the block gets 111 us SLOWER: 32-byte rows are bound
-    // by the TMA engine's row rate on the read and on the write side, not by DRAM.  Dropped)
-    // Narrow parts (c <= 32 channels): conv1's two halves stay together in one buffer and every
-    // bottleneck output gets a dense buffer of its own, conv2 walks K over 1 + n sources.  A 32-byte slice of a
-    // 96-byte pixel costs the whole pixel in DRAM reads (measured: 629 MB for 210 MB of input on net.p2.1), of a
-    // 64-byte pixel only twice the slice.
-    const int split_max = getenv("YB_SPLIT_CAT_MAXC") ? atoi(getenv("YB_SPLIT_CAT_MAXC")) : 32;
+    // by the TMA engine's row rate on the read and on the write side, not by DRAM.  A milder split - conv1's two
+    // halves together, every bottleneck output dense, conv2 over 1 + n sources - gained 40 us while the bottleneck
+    // still read its residual, nothing once that read was folded away (below).  Both dropped)
     // The last bottleneck's `x + f(x)` (nn.py:49) is only read by conv2, which also reads x itself as the part in
     // front of it: W_x x + W_m (x + f) = (W_x + W_m) x + W_m f.  The bottleneck stores f alone (no residual read:
     // 420 MB of the 735 MB net.p2.1.res_m.0.conv2 pulled through DRAM) and conv2's weights for x are summed when
@@ -254,21 +251,6 @@ struct Builder {
       o.wfold_src = (n + 1) * c;
       o.wfold_n = c;
     };
-    if (c <= split_max && n <= 3) {
-      int head2 = new_buf(H, W, 2 * c, 2, name + ".cat");
-      Slice d = whole(head2);
-      conv(name + ".conv1", srcs, 2 * c, 1, 1, 1, &d);
-      std::vector<Slice> parts = {whole(head2)};
-      Slice in = sub(head2, c, c);
-      for (int i = 0; i < n; i++) {
-        std::string mn = name + ".res_m." + std::to_string(i);
-        in = use_csp ? csp_module(mn, in, c, nullptr) : residual(mn, in, 0.5, nullptr, !(fold && i == n - 1));
-        parts.push_back(in);
-      }
-      Slice o2 = conv(name + ".conv2", parts, out_ch, 1, 1, 1, dst);
-      mark_fold();
-      return o2;
-    }
     int cat = new_buf(H, W, (2 + n) * c, 2, name + ".cat");
     Slice d = sub(cat, 0, 2 * c);
     conv(name + ".conv1", srcs, 2 * c, 1, 1, 1, &d);
@@ -514,6 +496,26 @@ int build_plan(yb_plan* p) {
     off += (bytes + 255) / 256 * 256;
   }
   p->weight_bytes = off;
+
+  // ---- space-to-depth sources for stride-2 3x3 convs ------------------------------------------------------
+  // A stride-2 conv reads every input pixel 2.25 times through the im2col gather.  Where its source tensor has no
+  // other reader and comes from the stem, the producer stores it as (H/2, W/2, 4C) - channel block = pixel parity -
+  // and the conv becomes a 2x2-tap stride-1 conv over those blocks on the TMA halo-patch path: every original tap
+  // (ky, kx) is one parity block at one of four patch shifts, the weights keep their packing.
+  if (!getenv("YB_NO_S2D") && !getenv("YB_STEM_DIRECT") && !getenv("YB_NO_PATCH")) {
+    int min_hw = 40;
+    if (const char* e = getenv("YB_PATCH_MIN_HW")) min_hw = atoi(e);
+    for (size_t i = 0; i < p->ops.size(); i++) {
+      Op& o = p->ops[i];
+      if (o.kind != OP_CONV || o.k != 3 || o.stride != 2 || o.nseg != 1 || o.src[0].up || o.out_f32) continue;
+      Buf& sb = p->bufs[o.src[0].buf];
+      if (o.src[0].c_off != 0 || o.src[0].C != sb.C || sb.C != 16 || sb.H % 2 || sb.W % 2) continue;
+      if (o.Hout < min_hw || o.Wout < min_hw || o.N_pad != o.BN) continue;
+      if (sb.touches.size() != 2 || sb.touches[0] != 0 || sb.touches[1] != (int)i || p->ops[0].kind != OP_STEM) continue;
+      sb.s2d = 1;
+      o.s2d = 1;
+    }
+  }
 
   // ---- stream lanes (YB_LANES=n, default 1 = off) -------------------------------------------------------
   // Branches of the graph that do not depend on each other (the two towers of every head level against the

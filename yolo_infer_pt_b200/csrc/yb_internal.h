@@ -153,6 +153,9 @@ struct Buf {
   size_t bytes = 0;
   int first_def = 1 << 30, last_use = -1;  // liveness (op indices) for arena reuse
   std::vector<int> touches;                // every op that reads or writes the buffer (stream-lane aware reuse)
+  // space-to-depth storage (plan.cu): the (H, W, C) tensor lives as (H/2, W/2, 4C), channel block (y&1)*2 + (x&1) -
+  // written that way by its producer for a single stride-2 3x3 consumer, which then reads TMA halo patches
+  int s2d = 0;
   std::string tag;
 };
 
@@ -210,6 +213,7 @@ struct Op {
   // residual folded into the consumer's weights (plan.cu, C3k2): input channels [wfold_dst, +wfold_n) of this conv
   // take the sum of their own weights and those of channels [wfold_src, +wfold_n) when the blob is packed
   int wfold_dst = 0, wfold_src = 0, wfold_n = 0;
+  int s2d = 0;             // stride-2 3x3 conv whose source buffer is stored space-to-depth (halo-patch path)
   // stream lanes (plan.cu): independent branches of the graph are enqueued on separate streams
   int lane = 0;            // 0 = the caller's stream
   int signal = 0;          // an op on another lane waits for this one: record an event behind it
@@ -285,4 +289,10 @@ int launch_decode(const yb_plan* p, const float* logits, float* out, cudaStream_
 int conv_tc_prepare(yb_plan* p, Op& op);  // tensor maps + smem attribute, needs bound buffers
 
 inline uint8_t* buf_ptr(const yb_plan* p, int buf) { return p->d_ws + p->bufs[buf].offset; }
+// element offset of logical pixel row r = y * W + x of image n inside a buffer (space-to-depth aware)
+inline size_t buf_row_elem(const Buf& b, size_t n, size_t r) {
+  if (!b.s2d) return (n * (size_t)b.rows_per_img + r) * (size_t)b.C;
+  const size_t y = r / (size_t)b.W, x = r % (size_t)b.W;
+  return ((n * (size_t)(b.H / 2) + y / 2) * (size_t)(b.W / 2) + x / 2) * (size_t)(4 * b.C) + ((y & 1) * 2 + (x & 1)) * (size_t)b.C;
+}
 }  // namespace yb
