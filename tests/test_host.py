@@ -476,6 +476,32 @@ def test_stream_lanes_order_every_shared_arena_region(size, batch, hw, lanes, mo
                         assert x in reach[y], f"{bufs[first]['tag']} (op {x}) / {bufs[second]['tag']} (op {y}) share memory unordered"
 
 
+def test_space_to_depth_sources_are_planned_only_where_they_are_safe(monkeypatch):
+    """Stride-2 3x3 convs read a space-to-depth copy of their source through the halo-patch path when that source
+    has no other reader and its producer can store it that way (stem: 16 channels; 1x1 conv on 8 x 16 tiles: 64)."""
+    def plan(size, hw, batch=2):
+        m = getattr(nn, f"yolo_v11_{size}")(80)
+        return Engine(*m._arch, batch, hw, hw, host_only=True).describe()
+    d = plan("n", 640)
+    ops = {o["name"]: o for o in d["ops"]}
+    assert ops["net.p2.0"]["s2d"] == 1 and ops["net.p3.0"]["s2d"] == 2
+    assert d["bufs"][ops["net.p2.0"]["src"][0]["buf"]]["s2d"] == 1 and d["bufs"][ops["net.p3.0"]["src"][0]["buf"]]["s2d"] == 1
+    # P3 / P4 / N3 / N4 have other readers: their stride-2 consumers keep the gather
+    assert all(ops[n]["s2d"] == 0 for n in ("net.p4.0", "net.p5.0", "fpn.h3", "fpn.h5"))
+    assert sum(b["s2d"] for b in d["bufs"]) == 2
+    for name in ("net.p2.0", "net.p3.0"):   # a space-to-depth buffer has exactly one writer and one reader
+        buf = ops[name]["src"][0]["buf"]
+        users = [o["name"] for o in d["ops"] if o["dst"]["buf"] == buf or any(s["buf"] == buf for s in o["src"])
+                 or (o["has_res"] and o["res"]["buf"] == buf)]
+        assert len(users) == 2 and users[1] == name
+    # 96 x 96 input: the 24 x 24 map of net.p2 is no multiple of the 8 x 16 store tile, and everything is < 40 x 40
+    assert sum(b["s2d"] for b in plan("n", 96)["bufs"]) == 0
+    # other widths (s: 32 / 128 channels, x: 96 / 384) are not covered
+    assert sum(b["s2d"] for b in plan("s", 640)["bufs"]) == 0 and sum(b["s2d"] for b in plan("x", 320)["bufs"]) == 0
+    monkeypatch.setenv("YB_NO_S2D", "1")
+    assert sum(b["s2d"] for b in plan("n", 640)["bufs"]) == 0
+
+
 def test_engine_export_round_trip(tmp_path):
     """export_engine -> load_engine (host-only here): the artefact alone reproduces the packed plan, and its CPU
     replay equals the replay of the engine packed from the model."""

@@ -91,7 +91,8 @@ struct ConvParams {
   // 3x3 / stride-1 convs fed from TMA halo patches (mode PATCH): an 18 x 10 pixel patch of `cblk`
   // channels per 16 x 8 output tile; each tap is a shifted UMMA descriptor into the patch
   int patch, cblk, ncb, a_layout;
-  int s2d;              // stride-2 3x3 over a space-to-depth source (16 channels: the four parity blocks are one 64-channel patch)
+  int s2d;              // stride-2 3x3 over a space-to-depth source: 1 = 16 channels (the four parity blocks are one 64-channel patch), 2 = 64 channels (one patch per parity block)
+  int c_s2d;            // the destination buffer is stored space-to-depth (8 x 16 pixel tiles through a 5-D TMA map)
   int patch_creal;      // real input channels (tap-aligned layers: K steps past them are zero padding and are skipped)
   int pair;             // MODE_PATCH2: 16 x 16 pixel super-tiles = two accumulators sharing every weight k-block
   int patch_tx_bytes, patch_stage_bytes, patch_stages;
@@ -755,7 +756,15 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
           for (uint32_t g = 0; g < c_groups; g++) {
             const int cg0 = n0 + (int)g * 64;
             if (cg0 < P.cout_store) {
-              if (T2D) {
+              if (T2D && !PGEO && P.c_s2d) {
+                // space-to-depth destination: the 8 x 16 pixel tile is the box {64, 2, 8, 2, 4} of {c, x&1, x/2, y&1, n*H/2 + y/2}
+                asm volatile(
+                    "cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4, %5}], [%6];" ::"l"(
+                        (uint64_t)&tmap_c),
+                    "r"(cg0), "r"(0), "r"(tp.ox0 >> 1), "r"(0), "r"(tp.n * (P.Hout >> 1) + (tp.oy0 >> 1)),
+                    "r"(c_buf + g * C_GROUP_BYTES)
+                    : "memory");
+              } else if (T2D) {
                 asm volatile(
                     "cp.async.bulk.tensor.4d.global.shared::cta.bulk_group [%0, {%1, %2, %3, %4}], [%5];" ::"l"(
                         (uint64_t)&tmap_c),
@@ -984,6 +993,39 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
           // stride-2 3x3 over a space-to-depth source (16 channels: one 64-channel patch holds the four parity
           // blocks): original tap (ky, kx) reads parity block (ky != 1, kx != 1) of the pixel one row up / one
           // column left when ky == 0 / kx == 0 - nine K=16 MMAs, weights in their usual tap-major packing
+          if (P.s2d == 2) {
+            // 64 channels: one patch per parity block, loaded in block order; block (py, px) serves the taps with
+            // (ky != 1) == py, (kx != 1) == px - 1 + 2 + 2 + 4 taps of four K=16 steps, weight k-block = tap
+            if (ti == 0)
+              for (int kb = 0; kb < num_kb; kb++) mbar_wait(full_bar(kb), 0u);
+            const uint32_t a_hi = (uint32_t)(adesc_hi >> 32), b_hi = (uint32_t)(desc_hi >> 32);
+            const uint32_t b_lo = (b_base >> 4) | (1u << 16), bstep = b_stage_bytes >> 4;
+#pragma unroll
+            for (int pl = 0; pl < 4; pl++) {
+              mbar_wait(patch_full_bar(pstage), pphase);
+              asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+              const uint32_t a_lo = ((a_base + (uint32_t)pstage * (uint32_t)P.patch_stage_bytes) >> 4) | (1u << 16);
+#pragma unroll
+              for (int t = 0; t < 9; t++) {
+                const int ky = t / 3, kx = t % 3;
+                if (((ky != 1) * 2 + (kx != 1)) != pl) continue;   // compile-time
+                const int a_off = (((ky != 0) * PPW + (kx != 0)) * 128) >> 4;
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                  const uint64_t da = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo + (uint32_t)(a_off + 2 * k));
+                  const uint64_t db = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + (uint32_t)t * bstep + 2u * (uint32_t)k);
+                  umma_bf16(d_tmem, da, db, idesc, (uint32_t)!(pl == 0 && t == 4 && k == 0));
+                }
+              }
+              umma_commit(patch_empty_bar(pstage));
+              if (pl == 3) umma_commit(tmem_full_bar(acc));
+              if (++pstage == P.patch_stages) {
+                pstage = 0;
+                pphase ^= 1u;
+              }
+            }
+            continue;
+          }
           mbar_wait(patch_full_bar(pstage), pphase);
           if (ti == 0)
             for (int kb = 0; kb < num_kb; kb++) mbar_wait(full_bar(kb), 0u);
@@ -1319,7 +1361,7 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
         pre = min(num_kb, S);
         for (int kb = 0; kb < pre; kb++) {
           mbar_expect_tx(full_bar(kb), a_tx + b_stage_bytes);
-          const int kb_w = (PATCH && P.cblk >= 64) ? (kb % 9) * P.ncb + kb / 9 : kb;
+          const int kb_w = (PATCH && P.cblk >= 64 && !P.s2d) ? (kb % 9) * P.ncb + kb / 9 : kb;
           tma_load_2d(b_base + (uint32_t)kb * b_stage_bytes, &tmap_b, kb_w * BK, n0f, full_bar(kb));
         }
       }
@@ -1343,7 +1385,7 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
             else mbar_arrive(full_bar(s));   // im2col layer with resident weights: only the gather feeds this stage
           }
           // PATCH with >= 64 channels consumes k-blocks channel-block-major; they are packed tap-major
-          const int kb_w = (PATCH && P.cblk >= 64) ? (kb % 9) * P.ncb + kb / 9 : kb;
+          const int kb_w = (PATCH && P.cblk >= 64 && !P.s2d) ? (kb % 9) * P.ncb + kb / 9 : kb;
           if (load_b && !early)
             tma_load_2d(b_base + (uint32_t)(RES ? kb : s) * b_stage_bytes, &tmap_b, kb_w * BK, n0, full_bar(s));
           if (MODE == MODE_ATMA) {
@@ -1417,6 +1459,8 @@ __global__ void conv_direct_check_kernel(const ConvParams P) {
     reinterpret_cast<float*>(P.dst)[drow * (size_t)P.dst_ld + n] = x;
   } else {
     if (P.res) x += Act16<F16>::unpack1(P.res[(size_t)m * P.res_ld + n]);
+    if (P.c_s2d)
+      drow = (((size_t)img * (P.Hout >> 1) + (oy >> 1)) * (P.Wout >> 1) + (ox >> 1)) * 4 + (oy & 1) * 2 + (ox & 1);
     reinterpret_cast<act_t*>(P.dst)[drow * (size_t)P.dst_ld + n] = Act16<F16>::pack1(x);
   }
 }
@@ -1504,6 +1548,29 @@ static int make_tmap_nhwc(CUtensorMap* map, const void* base, uint64_t C, uint64
     set_error("cuTensorMapEncodeTiled (4-D NHWC) failed with %d (C=%llu W=%llu H=%llu N=%llu ld=%llu)", (int)r,
               (unsigned long long)C, (unsigned long long)W, (unsigned long long)H, (unsigned long long)N,
               (unsigned long long)ld_elems);
+    return YB_ERR_CUDA;
+  }
+  return YB_OK;
+}
+
+// Store map of a space-to-depth buffer (logical (H, W, C) kept as (H/2, W/2, 4C), channel block (y&1)*2 + (x&1)): dims
+// {c, x&1, x/2, y&1, n*H/2 + y/2}; the box {64, 2, 8, 2, 4} is the 8 x 16 pixel output tile in its usual staging order.
+static int make_tmap_s2d_store(CUtensorMap* map, const void* base, uint64_t C, uint64_t W, uint64_t H, uint64_t N) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled driver entry point not available");
+    return YB_ERR_CUDA;
+  }
+  cuuint64_t dims[5] = {C, 2, W / 2, 2, N * (H / 2)};
+  cuuint64_t strides[4] = {C * 2, 4 * C * 2, 2 * C * 2, (W / 2) * 4 * C * 2};
+  cuuint32_t box[5] = {64, 2, 8, 2, 4};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(map, g_tmap_f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (space-to-depth store) failed with %d (C=%llu W=%llu H=%llu N=%llu)", (int)r,
+              (unsigned long long)C, (unsigned long long)W, (unsigned long long)H, (unsigned long long)N);
     return YB_ERR_CUDA;
   }
   return YB_OK;
@@ -1715,7 +1782,13 @@ int conv_tc_prepare(yb_plan* p, Op& op) {
   if (!op.out_f32) {
     const Buf& db = p->bufs[op.dst.buf];
     const uint8_t* dbase = buf_ptr(p, op.dst.buf) + (size_t)op.dst.c_off * 2;
-    if (op.patch || op.dw_fused)
+    if (db.s2d) {
+      if (!(op.a_tma && op.tile2d && !op.dw_fused && op.N_pad == op.BN)) {
+        set_error("conv %s: cannot store its output space-to-depth", op.name.c_str());
+        return YB_ERR_UNSUPPORTED;
+      }
+      rc = make_tmap_s2d_store(&op.tmap_c, dbase, (uint64_t)db.C, (uint64_t)db.W, (uint64_t)db.H, (uint64_t)p->B);
+    } else if (op.patch || op.dw_fused)
       rc = make_tmap_nhwc(&op.tmap_c, dbase, (uint64_t)cpad8(op.dst.C), (uint64_t)db.W, (uint64_t)db.H,
                           (uint64_t)p->B, (uint64_t)db.C, 64, PT_W, PT_H);
     else if (op.tile2d)
@@ -1839,14 +1912,15 @@ static void fill_params(const yb_plan* p, const Op& op, ConvParams& P) {
   // measured: alternate tiles win except on patch layers with >= 32 output channels
   P.alt_epilogue = (getenv("YB_NO_ALT_EPI") || (op.patch && op.BN >= 32) || op.pair) ? 0 : 1;
   P.s2d = op.s2d;
+  P.c_s2d = (!op.out_f32 && p->bufs[op.dst.buf].s2d) ? 1 : 0;
   if (op.patch) {
     const int C = op.s2d ? 64 : op.seg_kpad[0];
     P.patch = 1;
     P.cblk = std::min(C, 64);
-    P.ncb = (C + 63) / 64;
+    P.ncb = op.s2d == 2 ? 4 : (C + 63) / 64;
     P.a_layout = P.cblk == 64 ? 2 : P.cblk == 32 ? 4 : P.cblk == 16 ? 6 : 0;
     P.pair = op.pair;
-    P.patch_creal = op.s2d ? 64 : op.src[0].C;
+    P.patch_creal = op.s2d == 2 ? 256 : op.s2d ? 64 : op.src[0].C;
     P.patch_tx_bytes = PP_H * (op.pair ? PP2_W : PP_W) * P.cblk * 2;
     P.patch_stage_bytes = op.patch_stage_bytes;
     P.patch_stages = op.patch_stages;

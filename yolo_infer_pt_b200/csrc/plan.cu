@@ -499,21 +499,32 @@ int build_plan(yb_plan* p) {
 
   // ---- space-to-depth sources for stride-2 3x3 convs ------------------------------------------------------
   // A stride-2 conv reads every input pixel 2.25 times through the im2col gather.  Where its source tensor has no
-  // other reader and comes from the stem, the producer stores it as (H/2, W/2, 4C) - channel block = pixel parity -
-  // and the conv becomes a 2x2-tap stride-1 conv over those blocks on the TMA halo-patch path: every original tap
-  // (ky, kx) is one parity block at one of four patch shifts, the weights keep their packing.
+  // other reader, the producer stores it as (H/2, W/2, 4C) - channel block = pixel parity - and the conv becomes a
+  // 2x2-tap stride-1 conv over those blocks on the TMA halo-patch path: every original tap (ky, kx) is one parity
+  // block at one of four patch shifts, the weights keep their packing.  Producers that can store this way: the
+  // stem (plain stores; 16 channels) and a 1x1 conv on 8 x 16 pixel tiles (the same staging tile through a 5-D TMA
+  // map; 64 channels).  YOLO11n: net.p1 -> net.p2.0 and net.p2 -> net.p3.0.
   if (!getenv("YB_NO_S2D") && !getenv("YB_STEM_DIRECT") && !getenv("YB_NO_PATCH")) {
     int min_hw = 40;
     if (const char* e = getenv("YB_PATCH_MIN_HW")) min_hw = atoi(e);
+    const int max_c = getenv("YB_S2D_MAXC") ? atoi(getenv("YB_S2D_MAXC")) : 64;
     for (size_t i = 0; i < p->ops.size(); i++) {
       Op& o = p->ops[i];
       if (o.kind != OP_CONV || o.k != 3 || o.stride != 2 || o.nseg != 1 || o.src[0].up || o.out_f32) continue;
       Buf& sb = p->bufs[o.src[0].buf];
-      if (o.src[0].c_off != 0 || o.src[0].C != sb.C || sb.C != 16 || sb.H % 2 || sb.W % 2) continue;
+      if (o.src[0].c_off != 0 || o.src[0].C != sb.C || (sb.C != 16 && sb.C != 64) || sb.C > max_c || sb.H % 2 || sb.W % 2) continue;
       if (o.Hout < min_hw || o.Wout < min_hw || o.N_pad != o.BN) continue;
-      if (sb.touches.size() != 2 || sb.touches[0] != 0 || sb.touches[1] != (int)i || p->ops[0].kind != OP_STEM) continue;
+      if (sb.touches.size() != 2 || sb.touches[1] != (int)i) continue;
+      const Op& pr = p->ops[sb.touches[0]];
+      if (sb.C == 16) {
+        if (pr.kind != OP_STEM) continue;
+      } else {
+        if (pr.kind != OP_CONV || !pr.a_tma || pr.out_f32 || pr.dw_fused || pr.N_pad != pr.BN || pr.dst.c_off != 0 ||
+            pr.dst.C != sb.C || pr.Hout % 8 || pr.Wout % 16 || getenv("YB_NO_TILE2D"))
+          continue;
+      }
       sb.s2d = 1;
-      o.s2d = 1;
+      o.s2d = sb.C == 16 ? 1 : 2;
     }
   }
 

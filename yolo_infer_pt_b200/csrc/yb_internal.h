@@ -213,7 +213,7 @@ struct Op {
   // residual folded into the consumer's weights (plan.cu, C3k2): input channels [wfold_dst, +wfold_n) of this conv
   // take the sum of their own weights and those of channels [wfold_src, +wfold_n) when the blob is packed
   int wfold_dst = 0, wfold_src = 0, wfold_n = 0;
-  int s2d = 0;             // stride-2 3x3 conv whose source buffer is stored space-to-depth (halo-patch path)
+  int s2d = 0;             // stride-2 3x3 conv whose source buffer is stored space-to-depth (halo-patch path): 1 = 16, 2 = 64 channels
   // stream lanes (plan.cu): independent branches of the graph are enqueued on separate streams
   int lane = 0;            // 0 = the caller's stream
   int signal = 0;          // an op on another lane waits for this one: record an event behind it
