@@ -83,7 +83,8 @@ KEEP = ['Kernel Name', 'gpu__time_duration.sum', 'launch__grid_size', 'launch__b
         'smsp__issue_active.avg.pct', 'sm__inst_executed.sum', 'sm__cycles_elapsed.max',
         'sm__inst_executed_pipe_tma.sum.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_xu.sum.pct_of_peak_sustained_active',
         'sm__inst_executed_pipe_fma.sum.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_lsu.sum.pct_of_peak_sustained_active']
-names = {0: "net.p2.0 (3x3 s2 16->32 @160x160, im2col gather)", 3: "net.p2.1.res_m.0.conv2 (3x3 8->16 +res @160x160, halo patch)",
+names = {0: "net.p2.0 (3x3 s2 16->32 @160x160, im2col gather)" if tag in ("r01", "r02") else "net.p2.0 (3x3 s2 16->32 @160x160, halo patches over the space-to-depth stem output)",
+         3: "net.p2.1.res_m.0.conv2 (3x3 8->16 +res @160x160, halo patch)" if tag in ("r01", "r02") else "net.p2.1.res_m.0.conv2 (3x3 8->16 @160x160, halo patch, residual folded into the consumer's weights)",
          61: "head.box.0.0 (3x3 64->64 @80x80, halo patch, resident weights)", 64: "head.cls.0.1 (dw3x3 + 1x1 64->80 @80x80, fused depthwise)",
          66: "head.cls.0.4 (1x1 80->80 + sigmoid, fp32 planes)"}
 with open(f"{P}/{tag}_ncu_full_conv_gemm_yolo11n_b256.csv", "w") as f:
@@ -112,7 +113,7 @@ with open(f"{P}/{tag}_ncu_sass_evidence.txt", "w") as f:
             src = d[ix['Source']].split()
             op = src[1] if src and src[0].startswith('@') and len(src) > 1 else (src[0] if src else '')
             base = op.split('.')[0]
-            if base in ('UTCHMMA', 'UTMALDG', 'UTMASTG', 'LDTM', 'UTCBAR', 'LDGSTS', 'SYNCS', 'ARRIVES', 'MUFU', 'FFMA2', 'UBLKCP'):
+            if base in ('UTCHMMA', 'UTMALDG', 'UTMASTG', 'LDTM', 'UTCBAR', 'LDGSTS', 'SYNCS', 'ARRIVES', 'MUFU', 'FFMA2', 'HFMA2', 'UBLKCP'):
                 ops[base] += int(float(d[ix['Instructions Executed']] or 0))
         f.write(f"{names[idx]}\n    executed warp-instructions by class: " + ", ".join(f"{k}={v}" for k, v in sorted(ops.items())) + "\n")
 print("wrote", sorted(os.listdir(P)))
