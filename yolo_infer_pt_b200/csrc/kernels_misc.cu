@@ -526,7 +526,8 @@ __global__ void __launch_bounds__(256, MINB)
         // one 64-bit base per 16-pixel block; space-to-depth destination (plan.cu): pixel (y, x) is channel block
         // (y&1)*2 + (x&1) of pixel (y/2, x/2) of a (Ho/2, Wo/2, 4*out_ld) tensor - a row of 16 pixels lands as 64-byte
         // halves of eight 128-byte pixels (+33 us on the stem against -104 us on net.p2.0; pairing the two warps of a
-        // row pair through named barriers to store whole 512-byte runs was measured slower: +75 us)
+        // row pair through named barriers to store whole 512-byte runs was measured slower: +75 us; so was giving each warp a
+        // row pair and half the columns, +57 us: 64 bytes of spills at the kernel's 64 registers)
         act_t* orow = s2d ? out + ((((size_t)b * (Ho >> 1) + (oy >> 1)) * (Wo >> 1) + (ox0 >> 1)) * 4 + (oy & 1) * 2) * out_ld + c0
                           : out + (((size_t)b * Ho + oy) * Wo + ox0) * out_ld + c0;
         for (int c = lane; c < 16 * NT; c += 32) {   // 16-byte chunks of the 16 x (NT*8) tile
