@@ -92,11 +92,16 @@ def bf16_weight_state(model, dtype=torch.bfloat16):
 
 
 @pytest.mark.parametrize("size,hw,act", [("n", 64, torch.float16), ("t", 64, torch.float16), ("s", 64, torch.float16),
-                                         ("m", 64, torch.float16), ("x", 64, torch.bfloat16), ("n", 96, torch.bfloat16)])
+                                         ("m", 64, torch.float16), ("x", 64, torch.bfloat16), ("n", 96, torch.bfloat16),
+                                         ("deep", 64, torch.float16)])
 def test_plan_replay_matches_oracle(size, hw, act):
     """Plan + aliasing + packed weights, replayed in fp32 on the CPU, reproduce the oracle forward
-    run on the same 16-bit-rounded weights — layer by layer and end to end, for both storage types."""
-    model = getattr(nn, f"yolo_v11_{size}")(80)
+    run on the same 16-bit-rounded weights — layer by layer and end to end, for both storage types.
+    ("deep": a C3k2 with two plain bottlenecks - only the last one's residual is folded into conv2's weights.)"""
+    if size == "deep":
+        model = nn.YOLO([3, 16, 32, 64, 128, 256], [2, 2, 1, 1, 1, 2], [False, True], 80)
+    else:
+        model = getattr(nn, f"yolo_v11_{size}")(80)
     synth.load_synth(model, 0)
     eng = Engine(*model._arch, 2, hw, hw, host_only=True, act_dtype=act)
     blob = eng.pack_from_model(model)
@@ -125,7 +130,9 @@ def test_plan_replay_matches_oracle(size, hw, act):
             base, c = o["name"][:-len(".conv2")], o["wfold"][2]
             n = o["wfold"][0] // c
             folded[f"{base}.res_m.{n - 1}.conv2"] = (f"{base}.conv1", c) if n == 1 else (f"{base}.res_m.{n - 2}.conv2", 0)
-    assert folded or size not in ("n", "s")
+    assert folded or size not in ("n", "s", "deep")
+    if size == "deep":
+        assert folded["net.p2.1.res_m.1.conv2"] == ("net.p2.1.res_m.0.conv2", 0)
     for name in [o["name"] for o in desc["ops"] if o["kind"] != 5]:
         if name not in taps_o:
             continue
