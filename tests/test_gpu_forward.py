@@ -219,13 +219,15 @@ def test_cuda_graph_replay_equals_stream_launch():
 
 @pytest.mark.parametrize("size,batch,hw", [("n", 16, 320), ("s", 4, 160)])
 def test_stream_lanes_equal_single_stream(size, batch, hw, monkeypatch):
-    """YB_LANES=4: independent branches (head towers against the neck, C3k's parallel 1x1 convs) run on side
+    """YB_LANES=4 (the default for small batches): independent branches (head towers against the neck, C3k's parallel 1x1 convs) run on side
     streams joined by events; the arena only lets buffers share memory when every access is ordered across
     the lanes.  Output must be bit-identical to the single-stream plan - eager launches, repeated calls (the
     second call's first kernels must not overtake the first call's side lanes) and CUDA-graph replay."""
     model = _model(size, "survey_widehead")
     x = synth.synth_images(batch, hw, hw, seed=21).to("cuda:0")
+    monkeypatch.setenv("YB_LANES", "1")
     one = Engine(*model._arch, batch, hw, hw, "cuda:0")
+    assert one.describe()["num_lanes"] == 1
     one.pack_from_model(model)
     ref = one.forward(x).clone()
     monkeypatch.setenv("YB_LANES", "4")

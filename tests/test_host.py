@@ -483,6 +483,24 @@ def test_stream_lanes_order_every_shared_arena_region(size, batch, hw, lanes, mo
                         assert x in reach[y], f"{bufs[first]['tag']} (op {x}) / {bufs[second]['tag']} (op {y}) share memory unordered"
 
 
+def test_stream_lanes_default_follows_the_batch_size(monkeypatch):
+    """Lanes are a latency tool: on by default up to 16 images of 640 x 640 (measured crossover), one stream above;
+    YB_LANES overrides either way, and with lanes every head level is emitted behind the FPN tensor it reads."""
+    monkeypatch.delenv("YB_LANES", raising=False)
+    arch = nn.yolo_v11_n(80)._arch
+    lanes = lambda b, hw: Engine(*arch, b, hw, hw, host_only=True).describe()["num_lanes"]
+    assert lanes(1, 640) == 4 and lanes(16, 640) == 4 and lanes(64, 320) == 4
+    assert lanes(32, 640) == 1 and lanes(256, 640) == 1 and lanes(8, 1280) == 1
+    names = [o["name"] for o in Engine(*arch, 1, 640, 640, host_only=True).describe()["ops"]]
+    assert names.index("head.box.0.0") < names.index("fpn.h3") < names.index("head.box.1.0") < names.index("fpn.h5")
+    names = [o["name"] for o in Engine(*arch, 256, 640, 640, host_only=True).describe()["ops"]]
+    assert names.index("fpn.h6.conv2") < names.index("head.box.0.0")
+    monkeypatch.setenv("YB_LANES", "1")
+    assert lanes(1, 640) == 1
+    monkeypatch.setenv("YB_LANES", "3")
+    assert lanes(256, 640) == 3
+
+
 def test_space_to_depth_sources_are_planned_only_where_they_are_safe(monkeypatch):
     """Stride-2 3x3 convs read a space-to-depth copy of their source through the halo-patch path when that source
     has no other reader and its producer can store it that way (stem: 16 channels; 1x1 conv on 8 x 16 tiles: 64)."""

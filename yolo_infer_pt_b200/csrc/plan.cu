@@ -422,7 +422,10 @@ int build_plan(yb_plan* p) {
     b.conv(ci + ".4", {c3}, p->nc, 1, 1, 0, &dcls, nullptr, 0, 1, p->lvl_off[i]);
     p->ops.back().head_part = 2;
   };
-  const int lanes_env = getenv("YB_LANES") ? atoi(getenv("YB_LANES")) : 1;
+  // stream lanes (below): on by default where the kernels of one layer do not fill the GPU - measured on the B200, forward
+  // of YOLO11n at 640 x 640: B = 1 -18 %, 4 -12 %, 16 -5 %, 32 and up +1 % (YOLO11x: B = 1 -15 %, 8 -5 %, 16 -1 %)
+  const int lanes_env = getenv("YB_LANES") ? atoi(getenv("YB_LANES"))
+                                           : ((long long)p->B * p->H * p->W <= 16LL * 640 * 640 ? 4 : 1);
   const bool head_last = getenv("YB_HEAD_LAST") ? atoi(getenv("YB_HEAD_LAST")) != 0 : lanes_env <= 1;
   // ---- neck nn.py:203-209 ----
   Slice P5u = P5;
@@ -528,16 +531,17 @@ int build_plan(yb_plan* p) {
     }
   }
 
-  // ---- stream lanes (YB_LANES=n, default 1 = off) -------------------------------------------------------
+  // ---- stream lanes (YB_LANES=n; default 4 for small batches, 1 = one stream otherwise) ---------------------
   // Branches of the graph that do not depend on each other (the two towers of every head level against the
-  // rest of the neck, the two 1x1 convs in front of a C3k) can be enqueued on separate streams.  Dependencies
+  // rest of the neck, the two 1x1 convs in front of a C3k) are enqueued on separate streams.  Dependencies
   // come from the (buffer, channel range, anchor rows) every op reads and writes; an op continues the lane of
   // its latest producer if that producer is still the lane's last op, otherwise it forks onto a lane whose last
   // op is complete anyway (no false ordering), else onto the lane that has been idle longest.
-  // Measured on the B200 (YOLO11n, B = 256, 40-step runs): 42.1-42.4 k img/s with one lane, 42.0-42.2 k with
-  // four - the persistent kernels already fill every SM slot, a dependent kernel launched early by PDL takes
-  // the slots its predecessor frees before another lane's kernel can, and running two chains on half the
-  // slots each sums to the same time.  Kept as a switch; off by default.
+  // Small batches (kernels of a few dozen CTAs, latency-bound): the batch-1 forward of YOLO11n drops from 0.62 to
+  // 0.50 ms.  Large batches (YOLO11n, B = 256: 45.0-45.2 k img/s with one lane, 44.9-45.4 k with four): nothing -
+  // the persistent kernels already fill every SM slot, a dependent kernel launched early by PDL takes the slots
+  // its predecessor frees before another lane's kernel can, and running two chains on half the slots each sums
+  // to the same time.
   const size_t n_ops = p->ops.size();
   const int nl = std::max(1, std::min(YB_MAX_LANES, lanes_env));
   p->num_lanes = nl;
