@@ -295,7 +295,10 @@ def run_ours(args, rank, world, local_rank):
 
     def timed(fn, steps, profile=False):
         sampler = ClockSampler(local_rank)
+        was_graph = eng.graph
         if profile:
+            if was_graph:   # (small batches replay a CUDA graph; the per-op events need stream launches)
+                eng.use_graph(False)
             eng.profile(True)
         barrier()
         torch.cuda.synchronize(dev)
@@ -315,6 +318,8 @@ def run_ours(args, rank, world, local_rank):
         if profile:
             op_ms, _ = eng.profile_read()
             eng.profile(False)
+            if was_graph:
+                eng.use_graph(True)
         if world > 1:
             t = torch.tensor([ms], device=dev)
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)

@@ -507,7 +507,7 @@ int build_plan(yb_plan* p) {
   // block at one of four patch shifts, the weights keep their packing.  Producers that can store this way: the
   // stem (plain stores; 16 channels) and a 1x1 conv on 8 x 16 pixel tiles (the same staging tile through a 5-D TMA
   // map; 64 channels).  YOLO11n: net.p1 -> net.p2.0 and net.p2 -> net.p3.0.
-  if (!getenv("YB_NO_S2D") && !getenv("YB_STEM_DIRECT") && !getenv("YB_NO_PATCH")) {
+  if (!getenv("YB_NO_S2D") && !getenv("YB_STEM_DIRECT") && !getenv("YB_NO_PATCH") && !getenv("YB_NO_RESIDENT")) {   // (needs resident weights)
     int min_hw = 40;
     if (const char* e = getenv("YB_PATCH_MIN_HW")) min_hw = atoi(e);
     const int max_c = getenv("YB_S2D_MAXC") ? atoi(getenv("YB_S2D_MAXC")) : 64;
