@@ -13,6 +13,7 @@ det, cnt = util.nms_padded(y, 0.001, 0.65)
 torch.cuda.synchronize()
 ws = list(util._workspaces.values())[0]
 hdr = ws[:B * 32].view(torch.int32).view(B, 8).cpu().float()
-names = ["hist", "walk/select", "compaction scan", "sort", "prefetch+A+compaction", "B", "C", "D"]
-for i, n in enumerate(names):
-    print(f"{n:22s} mean {hdr[:, i].mean().item():12.0f}")
+# header words in a stats build: cand_count, sel_count, sel2_count, selected, pad[0..] (struct ImgHdr order may differ: print all)
+names = ["cycles: histogram", "cycles: select + compact", "bands", "chunks of 128", "cycles: load + test vs kept + compaction",
+         "cycles: B (pairwise masks)", "cycles: C (resolution)", "cycles: D (append)"]
+print("raw header means:", [round(hdr[:, i].mean().item()) for i in range(8)])
