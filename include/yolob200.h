@@ -12,8 +12,10 @@
  *   - plain C types only; no torch / pybind types cross this boundary;
  *   - every device buffer (input, output, weights, workspace) is owned by the caller;
  *     the library owns plan structs, TMA descriptors and CUDA-graph handles only;
- *   - all work is enqueued on the caller's stream; no hidden synchronisation (except
- *     yb_plan_bind, which may run one-off set-up kernels and is not on the hot path);
+ *   - all work is ordered on the caller's stream (small-batch plans run independent branches of the
+ *     network on side streams the plan owns, forked from and joined to the caller's stream by events
+ *     inside the call); no hidden synchronisation (except yb_plan_bind, which may run one-off set-up
+ *     kernels and is not on the hot path);
  *   - return value: 0 = ok, < 0 = error; the message is in yb_last_error() (thread-local);
  *   - the library never falls back to the CPU: if no sm_100 device is present the calls fail.
  */
