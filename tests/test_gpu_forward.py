@@ -217,21 +217,22 @@ def test_cuda_graph_replay_equals_stream_launch():
     assert torch.equal(a, b) and torch.equal(b, c)
 
 
-@pytest.mark.parametrize("size,batch,hw", [("n", 16, 320), ("s", 4, 160)])
-def test_stream_lanes_equal_single_stream(size, batch, hw, monkeypatch):
+@pytest.mark.parametrize("size,batch,h,w", [("n", 16, 320, 320), ("s", 4, 160, 160), ("n", 1, 640, 640), ("n", 3, 480, 640),
+                                            ("m", 2, 256, 192), ("x", 1, 320, 320)])
+def test_stream_lanes_equal_single_stream(size, batch, h, w, monkeypatch):
     """YB_LANES=4 (the default for small batches): independent branches (head towers against the neck, C3k's parallel 1x1 convs) run on side
     streams joined by events; the arena only lets buffers share memory when every access is ordered across
     the lanes.  Output must be bit-identical to the single-stream plan - eager launches, repeated calls (the
     second call's first kernels must not overtake the first call's side lanes) and CUDA-graph replay."""
     model = _model(size, "survey_widehead")
-    x = synth.synth_images(batch, hw, hw, seed=21).to("cuda:0")
+    x = synth.synth_images(batch, h, w, seed=21).to("cuda:0")
     monkeypatch.setenv("YB_LANES", "1")
-    one = Engine(*model._arch, batch, hw, hw, "cuda:0")
+    one = Engine(*model._arch, batch, h, w, "cuda:0")
     assert one.describe()["num_lanes"] == 1
     one.pack_from_model(model)
     ref = one.forward(x).clone()
     monkeypatch.setenv("YB_LANES", "4")
-    eng = Engine(*model._arch, batch, hw, hw, "cuda:0")
+    eng = Engine(*model._arch, batch, h, w, "cuda:0")
     d = eng.describe()
     assert d["num_lanes"] == 4 and len({op["lane"] for op in d["ops"]}) >= 3
     eng.pack_from_model(model)
