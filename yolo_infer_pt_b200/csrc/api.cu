@@ -284,7 +284,10 @@ int yb_plan_num_outputs(const yb_plan* plan) { return plan ? 4 + plan->nc : 0; }
 int yb_plan_num_convs(const yb_plan* plan) { return plan ? (int)plan->convs.size() : 0; }
 int yb_plan_num_launches(const yb_plan* plan) {
   if (!plan) return 0;
-  return (int)plan->ops.size() - (plan->fuse_decode && plan->conv_impl == 0 ? 1 : 0);
+  int n = (int)plan->ops.size() - (plan->fuse_decode && plan->conv_impl == 0 ? 1 : 0);
+  if (plan->conv_impl == 0)
+    for (const Op& op : plan->ops) n -= op.fused_away;   // depthwise convs computed inside their consumer's kernel
+  return n;
 }
 
 int yb_plan_conv_info(const yb_plan* plan, int index, yb_conv_info* out) {

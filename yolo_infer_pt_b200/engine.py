@@ -142,9 +142,10 @@ class Engine:
 
     def profile_read(self):
         """(mean ms per op over the forwards recorded since the last read, number of forwards)."""
-        ms = np.zeros(self.num_launches + 8, dtype=np.float32)   # one slot per op of the plan
+        n_ops = len(self.describe()["ops"])
+        ms = np.zeros(n_ops, dtype=np.float32)   # one slot per op of the plan
         n = _lib.check(self.L.yb_plan_profile_read(self.plan, ms.ctypes.data, len(ms)), "yb_plan_profile_read")
-        return ms[:len(self.describe()["ops"])], n
+        return ms, n
 
     def set_conv_impl(self, impl):
         _lib.check(self.L.yb_plan_set_conv_impl(self.plan, int(impl)), "yb_plan_set_conv_impl")
