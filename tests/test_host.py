@@ -483,6 +483,32 @@ def test_stream_lanes_order_every_shared_arena_region(size, batch, hw, lanes, mo
                         assert x in reach[y], f"{bufs[first]['tag']} (op {x}) / {bufs[second]['tag']} (op {y}) share memory unordered"
 
 
+def test_plan_decisions_for_the_bench_workload(monkeypatch):
+    """The plan-level choices the measured numbers rest on (YOLO11n, B = 256, 640 x 640): six depthwise convs fused
+    into their 1x1 consumers, five C3k2 residuals folded into the consumer's weights (and only where the block has
+    plain bottlenecks), two space-to-depth sources, one stream, 83 launches per forward (79 of them the tcgen05 conv kernel)."""
+    for v in ("YB_LANES", "YB_NO_S2D", "YB_NO_RES_FOLD", "YB_NO_DWFUSE", "YB_NO_PATCH"):
+        monkeypatch.delenv(v, raising=False)
+    eng = Engine(*nn.yolo_v11_n(80)._arch, 256, 640, 640, host_only=True)
+    d = eng.describe()
+    ops = d["ops"]
+    assert sum(o["fused_away"] for o in ops) == 6 == sum(o["dw_fused"] for o in ops)
+    folded = [o["name"] for o in ops if o["wfold"][2]]
+    assert folded == ["net.p2.1.conv2", "net.p3.1.conv2", "fpn.h1.conv2", "fpn.h2.conv2", "fpn.h4.conv2"]
+    for o in ops:   # a bottleneck whose add was folded has no residual operand; every other Residual keeps it
+        if o["name"].endswith(".res_m.0.conv2") and o["name"].rsplit(".res_m.0.conv2", 1)[0] + ".conv2" in folded:
+            assert not o["has_res"], o["name"]
+        elif ".res_m." in o["name"] and o["name"].endswith(".conv2") and o["k"] == 3:
+            assert o["has_res"], o["name"]
+    assert [o["name"] for o in ops if o["s2d"]] == ["net.p2.0", "net.p3.0"]
+    assert d["num_lanes"] == 1 and eng.num_launches == 83
+    assert sum(1 for o in ops if o["kind"] == 1 and not o["fused_away"]) == 79
+    assert d["workspace_bytes"] < 3.5e9
+    # the x architecture uses C3k blocks everywhere: nothing to fold, nothing stored space-to-depth
+    dx = Engine(*nn.yolo_v11_x(80)._arch, 8, 640, 640, host_only=True).describe()
+    assert not any(o["wfold"][2] or o["s2d"] for o in dx["ops"])
+
+
 def test_stream_lanes_default_follows_the_batch_size(monkeypatch):
     """Lanes are a latency tool: on by default up to 16 images of 640 x 640 (measured crossover), one stream above;
     YB_LANES overrides either way, and with lanes every head level is emitted behind the FPN tensor it reads."""
