@@ -658,13 +658,39 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
           // class scores: plane-major fp32 stores, one anchor per lane -> 128 B per warp store
           float* ob = reinterpret_cast<float*>(P.dst) + ((size_t)n_img * (4 + P.nc) + 4 + nb) * P.A_total +
                       P.dst_row_off + r;
+          // (ncu on head.cls.0.4: this loop was 68 % of the kernel's instructions at ~25 per score - range checks of
+          // __expf / __fdividef, a 64-bit multiply per store address, a branch per class.  Now FMUL + EX2 + FADD + RCP,
+          // a running plane pointer and predicated stores; the candidate count only when a sink is attached.)
           int cnt = 0;
+          const bool sink = P.nms_keys != nullptr;   // uniform
+          float* o = ob;
+          if (nb + 16 <= P.nc) {   // uniform: a whole chunk of classes - no bound check per class, one store predicate
 #pragma unroll
-          for (int j = 0; j < 16; j++) {
-            f[j] = __fdividef(1.f, 1.f + __expf(-f[j]));  // 2-ulp reciprocal: MUFU.RCP + FMUL
-            if (row_ok && nb + j < P.nc) {
-              ob[(size_t)j * P.A_total] = f[j];
-              cnt += f[j] > P.nms_conf ? 1 : 0;
+            for (int j = 0; j < 16; j++) {
+              float t, sg;
+              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(f[j] * -1.4426950408889634f));
+              asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(sg) : "f"(1.f + t));   // 1 / (1 + exp(-x)): inf -> 0, 0 -> 1
+              f[j] = sg;
+              if (row_ok) *o = sg;
+              o += P.A_total;
+            }
+            if (sink) {
+#pragma unroll
+              for (int j = 0; j < 16; j++) cnt += f[j] > P.nms_conf ? 1 : 0;
+              if (!row_ok) cnt = 0;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+              float t, sg;
+              asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(f[j] * -1.4426950408889634f));
+              asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(sg) : "f"(1.f + t));
+              f[j] = sg;
+              if (row_ok && nb + j < P.nc) {
+                *o = sg;
+                cnt += sg > P.nms_conf ? 1 : 0;
+              }
+              o += P.A_total;
             }
           }
           if (P.nms_keys) {
