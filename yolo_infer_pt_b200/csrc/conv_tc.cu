@@ -647,13 +647,17 @@ __global__ void __launch_bounds__(MODE == MODE_DW ? NUM_THREADS_DW : NUM_THREADS
 #pragma unroll
           for (int j = 1; j < 16; j++) mx = fmaxf(mx, f[j]);
           float se = 0.f, sw = 0.f;
+          const float mxl = mx * -1.4426950408889634f;
 #pragma unroll
           for (int j = 0; j < 16; j++) {
-            float e = __expf(f[j] - mx);
+            float e;   // exp(f - mx) as one FFMA + MUFU.EX2 (ncu: __expf's range handling made this line a third of the kernel)
+            asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fmaf(f[j], 1.4426950408889634f, mxl)));
             se += e;
             sw = fmaf((float)j, e, sw);
           }
-          dist[(c0 >> 4) & 3] = sw / se;
+          float rs;
+          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rs) : "f"(se));   // se >= 1 (the maximum contributes exp(0))
+          dist[(c0 >> 4) & 3] = sw * rs;
         } else {
           // class scores: plane-major fp32 stores, one anchor per lane -> 128 B per warp store
           float* ob = reinterpret_cast<float*>(P.dst) + ((size_t)n_img * (4 + P.nc) + 4 + nb) * P.A_total +
