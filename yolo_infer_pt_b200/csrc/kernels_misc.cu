@@ -358,6 +358,11 @@ __global__ void __launch_bounds__(256, MINB)
   const bool single = Cp <= NT * 8;   // one channel group: its fragments stay in registers for all tiles
   if (single) load_weights(0);
   act_t* wstage = stage + warp * 16 * NT * 8;
+  // output store: lane -> (pixel, 16-byte channel chunk) of the warp's 16 x (NT*8) staging tile (NT = 2 / 4: 32 % NT == 0)
+  const int st_px = lane / NT, st_cg = lane - st_px * NT;
+  const int st_src = st_px * NT * 8 + st_cg * 8;
+  const int st_off = (s2d ? 2 * st_px - (st_px & 1) : st_px) * out_ld + st_cg * 8;   // (32 / NT is even: the parity of px is the lane's)
+  bool st_cok = true;
 
   // ---- uint8 staging: a thread owns 16-byte vectors (16 pixels of one input row) whose even / odd
   // pixels are whole 16-byte plane rows; the kx = 0 plane is the kx = 2 plane shifted by one pixel and
@@ -385,10 +390,6 @@ __global__ void __launch_bounds__(256, MINB)
         pv[it] = __ldg(reinterpret_cast<const uint4*>(src));
         if (vx == 0 && gx > 0) pb[it] = __ldg(src - 1);   // first vector of the patch row: the byte left of the tile
       }
-      // every other vector's left neighbour is the last byte of the previous lane's vector (NV8 = 8 consecutive
-      // lanes hold one patch row; a masked-out vector is zero, which is also the right value for it)
-      const uint32_t left = __shfl_up_sync(0xffffffffu, pv[it].w >> 24, 1);
-      if (vx != 0) pb[it] = left;
     }
   };
   auto store_tile_u8 = [&]() {
@@ -396,7 +397,13 @@ __global__ void __launch_bounds__(256, MINB)
     for (int it = 0; it < (U8 ? NIT : 1); it++) {
       const int i = tid + it * 256;
       const int vx = i % NV8, row = i / NV8;
-      if (row >= 3 * STEM_IH) break;
+      // every vector but the first of a patch row takes its left neighbour from the previous lane (NV8 = 8 consecutive
+      // lanes hold one patch row; a masked-out vector is zero, which is also the right value for it).  The shuffle sits
+      // HERE, not behind the loads in fetch_tile: there it made every thread wait for its prefetch on the spot (ncu: 28 %
+      // of the kernel's stall samples, long scoreboard) instead of one tile later.  All lanes take part, hence no break.
+      const uint32_t left = __shfl_up_sync(0xffffffffu, pv[it].w >> 24, 1);
+      if (row >= 3 * STEM_IH) continue;
+      const uint32_t pbv = vx != 0 ? left : pb[it];
       const uint32_t w[4] = {pv[it].x, pv[it].y, pv[it].z, pv[it].w};
       // input column gx0 + 16 vx + j is patch column r = 16 vx + j + 1 (r = 2x + kx)
       uint4 p0, p1, p2;
@@ -414,7 +421,7 @@ __global__ void __launch_bounds__(256, MINB)
           asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(od[k]) : "r"(b), "r"(sc), "r"(off));
         }
         uint32_t hp;
-        asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(hp) : "r"(0x64006400u | pb[it]), "r"(sc), "r"(off));
+        asm("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(hp) : "r"(0x64006400u | pbv), "r"(sc), "r"(off));
         uint32_t sh[4];   // odd pixels shifted by one: (prev, 1), (3, 5), (7, 9), (11, 13)
         asm("prmt.b32 %0, %1, %2, 0x5410;" : "=r"(sh[0]) : "r"(hp), "r"(od[0]));
 #pragma unroll
@@ -426,7 +433,7 @@ __global__ void __launch_bounds__(256, MINB)
       float f[16];
 #pragma unroll
       for (int j = 0; j < 16; j++) f[j] = (float)((w[j >> 2] >> (8 * (j & 3))) & 0xFFu) * PXS;
-      const float fp = (float)pb[it] * PXS;
+      const float fp = (float)pbv * PXS;
       p1 = make_uint4(A16::pack2(f[0], f[2]), A16::pack2(f[4], f[6]), A16::pack2(f[8], f[10]), A16::pack2(f[12], f[14]));
       p2 = make_uint4(A16::pack2(f[1], f[3]), A16::pack2(f[5], f[7]), A16::pack2(f[9], f[11]), A16::pack2(f[13], f[15]));
       p0 = make_uint4(A16::pack2(fp, f[1]), A16::pack2(f[3], f[5]), A16::pack2(f[7], f[9]), A16::pack2(f[11], f[13]));
@@ -491,6 +498,12 @@ __global__ void __launch_bounds__(256, MINB)
 #pragma unroll 1
     for (int c0 = 0; c0 < Cp; c0 += NT * 8) {
       if (!single) load_weights(c0);
+      st_cok = c0 + st_cg * 8 < Cp;
+      // base of this warp's output row in the tile (one 64-bit address per tile and channel pass, 32-bit steps per block)
+      const int tx0 = tx * STEM_TW;
+      act_t* orow0 = s2d ? out + ((((size_t)b * (Ho >> 1) + (oy >> 1)) * (Wo >> 1) + (tx0 >> 1)) * 4 + (oy & 1) * 2) * out_ld + c0
+                         : out + (((size_t)b * Ho + oy) * Wo + tx0) * out_ld + c0;
+      const int opitch = s2d ? 2 * out_ld : out_ld;   // elements per output pixel step along x
 #pragma unroll(STEM_MI_UNROLL)
       for (int mi = 0; mi < STEM_TW / 16; mi++) {
         uint32_t afr[PARTS][2][4];
@@ -528,14 +541,25 @@ __global__ void __launch_bounds__(256, MINB)
         // halves of eight 128-byte pixels (+33 us on the stem against -104 us on net.p2.0; pairing the two warps of a
         // row pair through named barriers to store whole 512-byte runs was measured slower: +75 us; so was giving each warp a
         // row pair and half the columns, +57 us: 64 bytes of spills at the kernel's 64 registers)
-        act_t* orow = s2d ? out + ((((size_t)b * (Ho >> 1) + (oy >> 1)) * (Wo >> 1) + (ox0 >> 1)) * 4 + (oy & 1) * 2) * out_ld + c0
-                          : out + (((size_t)b * Ho + oy) * Wo + ox0) * out_ld + c0;
+        act_t* orow = orow0 + mi * 16 * opitch;
+        if constexpr (NT == 2 || NT == 4) {
+          // 16-byte chunks of the 16 x (NT*8) tile: a lane's channel group and its first pixel never change, so the
+          // offsets are set up once per kernel (this store was 12 % of the kernel's instructions)
+#pragma unroll
+          for (int k = 0; k < 16 * NT / 32; k++) {
+            const int px = st_px + k * (32 / NT);
+            if (ox0 + px < Wo && st_cok)
+              *reinterpret_cast<uint4*>(orow + (s2d ? st_off + k * (32 / NT) * 2 * out_ld : st_off + k * (32 / NT) * out_ld)) =
+                  *reinterpret_cast<const uint4*>(wstage + st_src + k * 32 * 8);
+          }
+        } else {
         for (int c = lane; c < 16 * NT; c += 32) {   // 16-byte chunks of the 16 x (NT*8) tile
           const int px = c / NT, cg = c - px * NT;
           const int pxo = s2d ? 2 * px - (px & 1) : px;
           if (ox0 + px < Wo && c0 + cg * 8 < Cp)
             *reinterpret_cast<uint4*>(orow + pxo * out_ld + cg * 8) =
                 *reinterpret_cast<const uint4*>(wstage + px * NT * 8 + cg * 8);
+        }
         }
       }
     }
