@@ -23,6 +23,12 @@ __device__ __forceinline__ float silu_acc(float x) {  // h + h*tanh(h), h = x/2 
   return fmaf(h, t, h);
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {   // 2^x, one MUFU op: -inf -> 0
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 // Blackwell packed fp32 FMA: two independent fused multiply-adds per instruction (FFMA2).
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
   unsigned long long ra = *reinterpret_cast<unsigned long long*>(&a);
@@ -946,24 +952,30 @@ __global__ void __launch_bounds__(256)
           A16::mma16816(s[nt], qa[ks], *reinterpret_cast<const uint32_t*>(kr + ks * 16),
                          *reinterpret_cast<const uint32_t*>(kr + ks * 16 + 8));
       }
+      // The scores stay unscaled: max(scale * s) = scale * max(s) for scale > 0, and p = 2^(scale * s - m) is one FFMA +
+      // ex2.approx per score (exp2f's range handling and a separate multiply were a third of the kernel's instructions);
+      // keys past N are masked only in the sub-block that holds the boundary.
       float mx0 = -INFINITY, mx1 = -INFINITY;
+      if (kb + 64 > kmax) {   // uniform
+#pragma unroll
+        for (int nt = 0; nt < 8; nt++) {
+          const int key = kb + nt * 8 + 2 * t;
+#pragma unroll
+          for (int e = 0; e < 4; e++)
+            if (key + (e & 1) >= kmax) s[nt][e] = -INFINITY;
+        }
+      }
 #pragma unroll
       for (int nt = 0; nt < 8; nt++) {
-        const int key = kb + nt * 8 + 2 * t;
-#pragma unroll
-        for (int e = 0; e < 4; e++) {
-          const float v = (key + (e & 1) < kmax) ? s[nt][e] * scale_log2e : -INFINITY;
-          s[nt][e] = v;
-          if (e < 2) mx0 = fmaxf(mx0, v);
-          else mx1 = fmaxf(mx1, v);
-        }
+        mx0 = fmaxf(mx0, fmaxf(s[nt][0], s[nt][1]));
+        mx1 = fmaxf(mx1, fmaxf(s[nt][2], s[nt][3]));
       }
       mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
       mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
       mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
       mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-      const float mn0 = fmaxf(m0, mx0), mn1 = fmaxf(m1, mx1);  // finite: every sub-block holds a valid key
-      const float c0 = exp2f(m0 - mn0), c1 = exp2f(m1 - mn1);
+      const float mn0 = fmaxf(m0, mx0 * scale_log2e), mn1 = fmaxf(m1, mx1 * scale_log2e);  // finite: every sub-block holds a valid key
+      const float c0 = ex2_approx(m0 - mn0), c1 = ex2_approx(m1 - mn1);
       m0 = mn0;
       m1 = mn1;
       l0 *= c0;
@@ -978,8 +990,8 @@ __global__ void __launch_bounds__(256)
       uint32_t pa[4][4];
 #pragma unroll
       for (int nt = 0; nt < 8; nt++) {
-        const float p0 = exp2f(s[nt][0] - mn0), p1 = exp2f(s[nt][1] - mn0);
-        const float p2 = exp2f(s[nt][2] - mn1), p3 = exp2f(s[nt][3] - mn1);
+        const float p0 = ex2_approx(fmaf(s[nt][0], scale_log2e, -mn0)), p1 = ex2_approx(fmaf(s[nt][1], scale_log2e, -mn0));
+        const float p2 = ex2_approx(fmaf(s[nt][2], scale_log2e, -mn1)), p3 = ex2_approx(fmaf(s[nt][3], scale_log2e, -mn1));
         l0 += p0 + p1;
         l1 += p2 + p3;
         pa[nt >> 1][(nt & 1) * 2] = A16::pack2(p0, p1);
