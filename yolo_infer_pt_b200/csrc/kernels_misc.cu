@@ -929,14 +929,21 @@ __global__ void __launch_bounds__(256)
   for (int k0 = 0; k0 < N; k0 += ATT_KC) {
     __syncthreads();
     // stage K (KC x 32) and V (KC x 64): 12 granules of 8 channels per key, zero-filled past N
-    for (int i = tid; i < ATT_KC * 12; i += 256) {
-      const int key = i / 12, gr = i - key * 12;
-      const bool ok = k0 + key < N;
-      const act_t* sp = base + (size_t)(ok ? k0 + key : 0) * qkv_ld + 32 + gr * 8;
-      const uint32_t dp = gr < 4 ? ks_s + (uint32_t)(key * ATT_KP + gr * 8) * 2u
-                                 : vs_s + (uint32_t)(key * ATT_VP + (gr - 4) * 8) * 2u;
-      asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dp), "l"(sp), "r"(ok ? 16u : 0u)
-                   : "memory");
+    // (192 threads: a thread keeps its granule and walks the keys in steps of 16 - no division per copy)
+    if (tid < 192) {
+      const int gr = tid % 12, key0 = tid / 12;
+      const uint32_t dp0 = gr < 4 ? ks_s + (uint32_t)(key0 * ATT_KP + gr * 8) * 2u
+                                  : vs_s + (uint32_t)(key0 * ATT_VP + (gr - 4) * 8) * 2u;
+      const uint32_t dstep = (gr < 4 ? (uint32_t)ATT_KP : (uint32_t)ATT_VP) * 16u * 2u;
+      const act_t* sp0 = base + 32 + gr * 8;
+#pragma unroll
+      for (int it = 0; it < ATT_KC / 16; it++) {
+        const int key = key0 + 16 * it;
+        const bool ok = k0 + key < N;
+        const act_t* sp = sp0 + (size_t)(ok ? k0 + key : 0) * qkv_ld;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dp0 + (uint32_t)it * dstep), "l"(sp), "r"(ok ? 16u : 0u)
+                     : "memory");
+      }
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncthreads();
